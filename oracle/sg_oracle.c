@@ -1,0 +1,312 @@
+/*
+ * sg_oracle.c -- CPU restatement of the reference's Monte Carlo sweep path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product:
+ * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this library, and only as the checker or
+ * as the timed CPU baseline.  The product path (spin_glass_anneal_rl_b200)
+ * never links, imports or calls it.
+ *
+ * Parity status: PINNED.  tests/test_oracle_golden.py checks this file
+ * against traces recorded from the reference itself (device='cpu', dense
+ * couplings) by tests/golden/make_golden.py: same seed => same energy
+ * history, best energy, best configuration, final spins and RNG consumption.
+ *
+ * Every function cites the reference lines it restates (paths relative to
+ * /root/reference/spin_glass_rl/).
+ *
+ * RNG model.  The reference draws from torch's global CPU generator
+ * (mt19937).  Measured in this container (torch 2.11): every
+ * torch.randint(0, n, (1,)) consumes exactly one raw 32-bit output x and
+ * returns x % n; every torch.rand(1) consumes one raw output and returns
+ * (x & 0xFFFFFF) * 2^-24.  The oracle therefore takes the RAW 32-bit stream
+ * (produced by the test with numpy's MT19937 seeded the legacy way, which is
+ * bit-identical to torch.manual_seed) and a cursor, and consumes it exactly
+ * where the reference would.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define SGO_RULE_METROPOLIS 0
+#define SGO_RULE_GLAUBER 1
+#define SGO_RULE_HEAT_BATH 2
+
+typedef struct {
+    const uint32_t *raw; /* raw mt19937 outputs                           */
+    int64_t len;         /* number of outputs available                   */
+    int64_t pos;         /* cursor: next output to consume                */
+    int overrun;         /* set if the stream ran dry                     */
+} sgo_stream;
+
+static inline uint32_t sgo_next(sgo_stream *s) {
+    if (s->pos >= s->len) {
+        s->overrun = 1;
+        return 0u;
+    }
+    return s->raw[s->pos++];
+}
+
+/* torch.randint(0, n, (1,)).item()  -- core/spin_dynamics.py:69 */
+static inline int sgo_randint(sgo_stream *s, int n) { return (int)(sgo_next(s) % (uint32_t)n); }
+
+/* torch.rand(1).item() (float32)    -- core/spin_dynamics.py:146,162,181 */
+static inline float sgo_rand(sgo_stream *s) {
+    return (float)(sgo_next(s) & 0xFFFFFFu) * (1.0f / 16777216.0f);
+}
+
+/* fp32 dot as torch.dot does it (fp32 accumulate; summation order is
+ * ATen's own, so float couplings agree to rounding, integer couplings
+ * exactly). */
+static inline float sgo_dotf(const float *a, const float *b, int n) {
+    float acc = 0.0f;
+#pragma omp simd reduction(+ : acc)
+    for (int j = 0; j < n; ++j) acc += a[j] * b[j];
+    return acc;
+}
+
+/* IsingModel.get_local_field(i) -- core/ising_model.py:176-185.
+ * coupling_field = torch.dot(J[i], spins).item()  (fp32, diagonal included)
+ * return coupling_field + h[i].item()              (python double add)      */
+double sgo_local_field(const float *J, int64_t ld, const float *h, const float *spins, int n,
+                       int i) {
+    float cf = sgo_dotf(J + (int64_t)i * ld, spins, n);
+    return (double)cf + (double)h[i];
+}
+
+/* IsingModel.compute_energy() -- core/ising_model.py:149-174.
+ * interaction = -0.5 * torch.dot(s, torch.mv(J, s)).item()
+ * field       = -torch.dot(h, s).item()                                     */
+double sgo_energy(const float *J, int64_t ld, const float *h, const float *spins, int n,
+                  float *scratch) {
+    for (int i = 0; i < n; ++i) scratch[i] = sgo_dotf(J + (int64_t)i * ld, spins, n);
+    double inter = -0.5 * (double)sgo_dotf(spins, scratch, n);
+    double field = -(double)sgo_dotf(h, spins, n);
+    return inter + field;
+}
+
+/* One SpinDynamics.single_spin_update(site) for the three local rules.
+ * Returns 1 if the spin changed ("accepted"), 0 otherwise ("rejected").
+ *   _metropolis_update  core/spin_dynamics.py:131-152
+ *   _glauber_update     core/spin_dynamics.py:154-170
+ *   _heat_bath_update   core/spin_dynamics.py:172-191
+ * flip_spin (core/ising_model.py:125-147) recomputes the same dot and
+ * negates the spin; the recomputation has no observable effect, so only the
+ * baseline timing variant (sgo_sweep with redo_flip_dot=1) performs it.     */
+static inline int sgo_attempt(const float *J, int64_t ld, const float *h, float *spins, int n,
+                              int site, double T, int rule, sgo_stream *st, int redo_flip_dot,
+                              float *u_out, int *drew) {
+    double lf = sgo_local_field(J, ld, h, spins, n, site);
+    *drew = 0;
+    if (rule == SGO_RULE_METROPOLIS) {
+        double dE = 2.0 * (double)spins[site] * lf; /* :135 */
+        int accept;
+        if (dE <= 0.0) { /* :138 */
+            accept = 1;
+        } else {
+            /* :145  torch.exp(torch.tensor(-dE / T)): the double quotient is
+             * rounded to float32, exp is evaluated in float32.              */
+            float p = expf((float)(-dE / T));
+            float u = sgo_rand(st); /* :146, drawn ONLY on this branch */
+            *u_out = u;
+            *drew = 1;
+            accept = ((double)u < (double)p);
+        }
+        if (accept) {
+            if (redo_flip_dot) {
+                volatile double sink = sgo_local_field(J, ld, h, spins, n, site);
+                (void)sink;
+            }
+            spins[site] = -spins[site];
+            return 1;
+        }
+        return 0;
+    }
+    /* Glauber / heat bath: u is ALWAYS drawn (:162, :181). */
+    float arg;
+    if (rule == SGO_RULE_GLAUBER) {
+        arg = (float)(-2.0 * lf / T); /* :159 */
+    } else {
+        double beta = 1.0 / T; /* :177 */
+        arg = (float)(-2.0 * beta * lf); /* :178 */
+    }
+    float prob_up = 1.0f / (1.0f + expf(arg)); /* float32 tensor arithmetic */
+    float u = sgo_rand(st);
+    *u_out = u;
+    *drew = 1;
+    float new_spin = (u < prob_up) ? 1.0f : -1.0f;
+    if (new_spin != spins[site]) {
+        if (redo_flip_dot && rule == SGO_RULE_GLAUBER) {
+            volatile double sink = sgo_local_field(J, ld, h, spins, n, site);
+            (void)sink;
+        }
+        spins[site] = new_spin;
+        return 1;
+    }
+    return 0;
+}
+
+/*
+ * SpinDynamics.sweep() x n_sweeps for ONE replica -- core/spin_dynamics.py:73-94:
+ * n attempts at sites drawn with replacement, then compute_energy().
+ *
+ *   temps[n_sweeps]        temperature used for each sweep (already clamped
+ *                          by set_temperature, core/spin_dynamics.py:57-59)
+ *   energies[n_sweeps]     out: energy after each sweep
+ *   accepted[n_sweeps]     out: accepted attempts in each sweep
+ *   trace_site/trace_u     optional out, n_sweeps*n entries: the site of every
+ *                          attempt and the uniform it consumed (NaN if none)
+ * Returns 0, or -1 if the raw stream ran dry.
+ */
+int sgo_sweeps(const float *J, int64_t ld, const float *h, float *spins, int n, int rule,
+               const double *temps, int n_sweeps, const uint32_t *raw, int64_t raw_len,
+               int64_t *raw_pos, double *energies, int64_t *accepted, int32_t *trace_site,
+               float *trace_u, int redo_flip_dot) {
+    sgo_stream st = {raw, raw_len, *raw_pos, 0};
+    float *scratch = (float *)malloc(sizeof(float) * (size_t)n);
+    for (int sw = 0; sw < n_sweeps; ++sw) {
+        double T = temps[sw];
+        int64_t acc = 0;
+        for (int k = 0; k < n; ++k) {
+            int site = sgo_randint(&st, n);
+            float u = NAN;
+            int drew = 0;
+            acc += sgo_attempt(J, ld, h, spins, n, site, T, rule, &st, redo_flip_dot, &u, &drew);
+            if (trace_site) trace_site[(int64_t)sw * n + k] = site;
+            if (trace_u) trace_u[(int64_t)sw * n + k] = drew ? u : NAN;
+        }
+        if (energies) energies[sw] = sgo_energy(J, ld, h, spins, n, scratch);
+        if (accepted) accepted[sw] = acc;
+    }
+    free(scratch);
+    *raw_pos = st.pos;
+    return st.overrun ? -1 : 0;
+}
+
+/*
+ * The same sweep driven by an explicit per-attempt schedule instead of the raw
+ * stream: sites[k] is visited at attempt k and uniforms[k] is the uniform that
+ * attempt may use.  This is the form the CUDA sweep kernel consumes in its
+ * injected mode (sites are shared by the replicas of a block; one uniform per
+ * attempt per replica), so oracle and kernel can be compared attempt for
+ * attempt.  Metropolis ignores uniforms[k] when dE <= 0, exactly like the
+ * reference (core/spin_dynamics.py:138-142).
+ */
+int sgo_sweeps_scheduled(const float *J, int64_t ld, const float *h, float *spins, int n, int rule,
+                         const double *temps, int n_sweeps, const int32_t *sites,
+                         const float *uniforms, double *energies, int64_t *accepted) {
+    float *scratch = (float *)malloc(sizeof(float) * (size_t)n);
+    for (int sw = 0; sw < n_sweeps; ++sw) {
+        double T = temps[sw];
+        int64_t acc = 0;
+        for (int k = 0; k < n; ++k) {
+            int64_t idx = (int64_t)sw * n + k;
+            int site = sites[idx];
+            float u = uniforms[idx];
+            double lf = sgo_local_field(J, ld, h, spins, n, site);
+            int flip = 0;
+            if (rule == SGO_RULE_METROPOLIS) {
+                double dE = 2.0 * (double)spins[site] * lf;
+                if (dE <= 0.0) {
+                    flip = 1;
+                } else {
+                    float p = expf((float)(-dE / T));
+                    flip = ((double)u < (double)p);
+                }
+            } else {
+                float arg = (rule == SGO_RULE_GLAUBER) ? (float)(-2.0 * lf / T)
+                                                       : (float)(-2.0 * (1.0 / T) * lf);
+                float prob_up = 1.0f / (1.0f + expf(arg));
+                float ns = (u < prob_up) ? 1.0f : -1.0f;
+                flip = (ns != spins[site]);
+            }
+            if (flip) {
+                spins[site] = -spins[site];
+                ++acc;
+            }
+        }
+        if (energies) energies[sw] = sgo_energy(J, ld, h, spins, n, scratch);
+        if (accepted) accepted[sw] = acc;
+    }
+    free(scratch);
+    return 0;
+}
+
+/* Batched energies / local fields, one row per configuration:
+ *   BatchProcessor.process_batch_energies      optimization/high_performance_computing.py:98-165
+ *   VectorizedOperations.vectorized_local_fields   same file :357-372
+ * fields[b][j] = sum_i S[b][i] J[i][j] + h[j];  E[b] = -0.5 sum_j fields'[b][j] S[b][j] - sum_j h[j] S[b][j]
+ * (fields' = fields without h).  Accumulated in double: this is the checker. */
+void sgo_batch_fields_energies(const float *J, int64_t ld, const float *h, const float *S, int n,
+                               int batch, double *fields, double *energies) {
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < batch; ++b) {
+        const float *s = S + (int64_t)b * n;
+        double e_int = 0.0, e_h = 0.0;
+        for (int j = 0; j < n; ++j) {
+            double acc = 0.0;
+            for (int i = 0; i < n; ++i) acc += (double)s[i] * (double)J[(int64_t)i * ld + j];
+            if (fields) fields[(int64_t)b * n + j] = acc + (double)h[j];
+            e_int += acc * (double)s[j];
+            e_h += (double)h[j] * (double)s[j];
+        }
+        if (energies) energies[b] = -0.5 * e_int - e_h;
+    }
+}
+
+/*
+ * CPU baseline: the reference path for many independent replicas, one replica
+ * per OpenMP thread at a time (the reference itself has no replica batching:
+ * R replicas cost R x).  Same arithmetic as sgo_sweeps with the redundant
+ * flip_spin dot included, sites/uniforms from a per-replica xorshift stream
+ * (timing only; not used for parity).  Returns attempts performed.
+ */
+int64_t sgo_baseline_run(const float *J, int64_t ld, const float *h, float *spins, int n,
+                         int n_replicas, int n_sweeps, double T, uint64_t seed, int n_threads,
+                         double *energies_out) {
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+    int64_t total = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : total)
+    for (int r = 0; r < n_replicas; ++r) {
+        float *s = spins + (int64_t)r * n;
+        float *scratch = (float *)malloc(sizeof(float) * (size_t)n);
+        uint64_t x = seed * 0x9E3779B97F4A7C15ull + (uint64_t)(r + 1) * 0xBF58476D1CE4E5B9ull;
+        uint32_t buf[256];
+        for (int sw = 0; sw < n_sweeps; ++sw) {
+            for (int k = 0; k < n; ++k) {
+                /* two raw words per attempt are enough (site, maybe uniform) */
+                for (int q = 0; q < 2; ++q) {
+                    x ^= x << 13;
+                    x ^= x >> 7;
+                    x ^= x << 17;
+                    buf[q] = (uint32_t)(x >> 16);
+                }
+                sgo_stream st = {buf, 2, 0, 0};
+                int site = sgo_randint(&st, n);
+                float u;
+                int drew;
+                (void)sgo_attempt(J, ld, h, s, n, site, T, SGO_RULE_METROPOLIS, &st, 1, &u, &drew);
+            }
+            double e = sgo_energy(J, ld, h, s, n, scratch);
+            if (energies_out) energies_out[r] = e;
+            total += n;
+        }
+        free(scratch);
+    }
+    return total;
+}
+
+int sgo_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
