@@ -1,0 +1,185 @@
+/*
+ * sg_b200.h -- C ABI of the B200-native Ising annealing engine (libsg_b200.so).
+ *
+ * Drop-in boundary for ONE hot path of danieleschmidt/spin-glass-anneal-rl: the
+ * batched Monte Carlo sweep that IsingModel / GPUAnnealer.anneal() /
+ * ParallelTempering.run() drive.  Plain pointers and sizes only; no torch types.
+ * The reference is pure Python, so its "FFI" for this path is the set of device
+ * entry points it declares but can never launch (annealing/cuda_kernels.py) plus
+ * the Python methods that loop around them.  Each entry point below cites the
+ * reference interface it replaces (paths relative to /root/reference/spin_glass_rl/).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative sg_status; the message
+ *     is available from sg_last_error() (thread-local);
+ *   - "dev" pointers are CUDA device pointers on the engine's device, "host"
+ *     pointers are ordinary host memory; functions taking `on_device` accept
+ *     either and copy accordingly;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     all work is enqueued on it and is asynchronous unless a host buffer is
+ *     involved, in which case the call returns after the copy completed;
+ *   - spins are int8 in {-1,+1}, row-major [R][n]; couplings float32 row-major.
+ *   - an engine is not re-entrant; use one engine per host thread / stream
+ *     (the reference's callers fan out over distinct models).
+ */
+#ifndef SG_B200_H
+#define SG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SG_ABI_VERSION 1
+
+typedef enum {
+    SG_OK = 0,
+    SG_ERR_INVALID = -1, /* bad argument / wrong call order   */
+    SG_ERR_CUDA = -2,    /* CUDA runtime error                */
+    SG_ERR_NOMEM = -3,   /* allocation failed                 */
+    SG_ERR_UNSUPPORTED = -4
+} sg_status;
+
+/* update rules: core/spin_dynamics.py:11-16 (UpdateRule; WOLFF is out of scope) */
+#define SG_RULE_METROPOLIS 0 /* _metropolis_update  core/spin_dynamics.py:131-152 */
+#define SG_RULE_GLAUBER 1    /* _glauber_update     core/spin_dynamics.py:154-170 */
+#define SG_RULE_HEAT_BATH 2  /* _heat_bath_update   core/spin_dynamics.py:172-191 */
+
+/* where the acceptance randomness comes from */
+#define SG_RNG_PHILOX 0   /* in-kernel Philox4x32-10 counter RNG (production)          */
+#define SG_RNG_INJECTED 1 /* one caller-supplied float32 uniform per (replica, attempt) */
+
+/* which site each attempt visits (shared by all replicas of a thread block) */
+#define SG_SITES_SEQUENTIAL 0 /* 0,1,...,n-1 every sweep                                   */
+#define SG_SITES_RANDOM 1     /* Philox draw % n, with replacement (core/spin_dynamics.py:69) */
+#define SG_SITES_EXPLICIT 2   /* caller-supplied list (replay of a recorded stream)         */
+
+typedef struct sg_engine sg_engine;
+
+int sg_abi_version(void);
+const char *sg_last_error(void);
+
+/* Engine = one model (J, h) + R replicas resident on one GPU.
+ * Replaces the per-call state the reference rebuilds in
+ * GPUAnnealer._move_model_to_gpu (annealing/gpu_annealer.py:185-197). */
+int sg_create(int device_id, sg_engine **out);
+void sg_destroy(sg_engine *e);
+
+/* IsingModel.set_couplings_from_matrix / set_external_fields
+ * (core/ising_model.py:106-123).  J is n x n float32 with row stride ldJ; it need
+ * not be symmetric: like the reference, the local field of spin i is
+ * sum_j J[i][j] s_j + h[i] (diagonal included, core/ising_model.py:176-185). */
+int sg_set_model_dense(sg_engine *e, int n, const float *J, int64_t ldJ, const float *h,
+                       int on_device, void *stream);
+
+/* Allocate R replicas (spins, local fields, energies, best-so-far, counters). */
+int sg_alloc_replicas(sg_engine *e, int n_replicas, void *stream);
+
+/* IsingModel.set_spins / get_spins (core/ising_model.py:191-198), batched. */
+int sg_set_spins(sg_engine *e, const int8_t *spins, int on_device, void *stream);
+int sg_get_spins(sg_engine *e, int8_t *spins, int on_device, void *stream);
+
+/* Local-field initialisation + energies for all replicas in one pass:
+ *   F = S J^T + h ; E_r = -1/2 sum_i s_ri (F_ri + h_i)
+ * replaces R x IsingModel.compute_energy (core/ising_model.py:149-174) and
+ * CUDAKernelManager.compute_energy_optimized (annealing/cuda_kernels.py:284-324).
+ * Must be called after sg_set_spins and before sg_sweep. */
+int sg_init_fields(sg_engine *e, void *stream);
+
+int sg_get_energies(sg_engine *e, float *energies, int on_device, void *stream);
+int sg_get_fields(sg_engine *e, float *fields, int on_device, void *stream);
+int sg_get_accepted(sg_engine *e, uint64_t *accepted, int on_device, void *stream);
+
+/* Best-so-far per replica (GPUAnnealer best tracking, annealing/gpu_annealer.py:130-131,
+ * 151-153: compared once per sweep).  reset sets best = current. */
+int sg_reset_best(sg_engine *e, void *stream);
+int sg_get_best(sg_engine *e, float *best_energy, int8_t *best_spins, int on_device, void *stream);
+
+typedef struct {
+    uint32_t struct_size;       /* = sizeof(sg_sweep_params)                                  */
+    int32_t n_sweeps;           /* sweeps in this launch; one sweep = n attempts per replica   */
+    int32_t rule;               /* SG_RULE_*                                                   */
+    int32_t rng_mode;           /* SG_RNG_*                                                    */
+    int32_t site_mode;          /* SG_SITES_*                                                  */
+    int32_t replicas_per_block; /* 0 = auto (largest the register file allows)                */
+    /* temperature of replica r in sweep s: temps[s*temps_sweep_stride + r*temps_replica_stride]
+     * (dev, float64).  NULL = the engine's per-replica ladder temperatures (sg_set_ladder). */
+    const double *temps;
+    int64_t temps_sweep_stride;
+    int64_t temps_replica_stride;
+    uint64_t seed;       /* Philox key                                                        */
+    uint64_t sweep_base; /* absolute index of the first sweep (Philox counter; makes results
+                            independent of how a run is cut into launches)                   */
+    /* SG_SITES_EXPLICIT: site of attempt k of sweep s for block b =
+     * sites[b*sites_block_stride + s*sites_sweep_stride + k]   (dev, int32) */
+    const int32_t *sites;
+    int64_t sites_block_stride;
+    int64_t sites_sweep_stride;
+    /* SG_RNG_INJECTED: uniforms[(r*n_sweeps + s)*n + k]   (dev, float32) */
+    const float *uniforms;
+    float *energy_trace; /* optional dev out [n_sweeps][R]: energy after every sweep           */
+    int32_t track_best;  /* compare-and-keep best energy/configuration after every sweep       */
+    int32_t reserved;
+} sg_sweep_params;
+
+/* The sweep: replaces SpinDynamics.sweep() (core/spin_dynamics.py:73-94) looped over
+ * replicas and sweeps, i.e. the body of GPUAnnealer.anneal's loop
+ * (annealing/gpu_annealer.py:139-153), ParallelTempering._parallel_sweeps
+ * (annealing/parallel_tempering.py:191-203) and the never-launched
+ * CUDAKernelManager.metropolis_update_optimized (annealing/cuda_kernels.py:228-282). */
+int sg_sweep(sg_engine *e, const sg_sweep_params *p, void *stream);
+
+/* Parallel tempering ladder: R replicas = n_ladders x n_rungs; rung 0 is the hottest
+ * (ParallelTempering._generate_temperature_ladder, annealing/parallel_tempering.py:146-173).
+ * ladder_temps is a host array [n_rungs]. */
+int sg_set_ladder(sg_engine *e, int n_rungs, const double *ladder_temps, void *stream);
+
+typedef struct {
+    uint32_t struct_size;
+    int32_t parity;          /* first rung of the first pair: 0 or 1 (np.random.randint(0,2)) */
+    int32_t rng_mode;        /* SG_RNG_PHILOX or SG_RNG_INJECTED                               */
+    int32_t reserved;
+    uint64_t seed;
+    uint64_t round;          /* Philox counter                                                 */
+    const double *uniforms;  /* SG_RNG_INJECTED: dev float64 [n_ladders][n_rungs/2] per pair   */
+} sg_exchange_params;
+
+/* Replica exchange between adjacent rungs, p = min(1, exp((b_j-b_i)(E_j-E_i))): replaces
+ * ParallelTempering._nearest_neighbor_exchange/_attempt_single_exchange
+ * (annealing/parallel_tempering.py:214-258) and parallel_tempering_exchange_optimized
+ * (annealing/cuda_kernels.py:326-369).  Temperatures move, configurations stay. */
+int sg_exchange(sg_engine *e, const sg_exchange_params *p, void *stream);
+
+/* rung -> replica map [R], per-replica temperature [R], per-pair statistics
+ * [n_ladders][n_rungs-1] (ParallelTempering.exchange_attempts/accepts). */
+int sg_get_ladder_state(sg_engine *e, int32_t *replica_at_rung, double *replica_temps,
+                        uint32_t *attempts, uint32_t *accepts, int on_device, void *stream);
+
+/* Stand-alone batched energies and local fields for arbitrary configurations:
+ *   BatchProcessor.process_batch_energies          optimization/high_performance_computing.py:98-165
+ *   VectorizedOperations.vectorized_local_fields   optimization/high_performance_computing.py:357-372
+ * spins [batch][n] int8; energies [batch] float32 (may be NULL); fields [batch][n] float32
+ * (may be NULL). */
+int sg_batch_energies(sg_engine *e, int batch, const int8_t *spins, float *energies, float *fields,
+                      int on_device, void *stream);
+
+/* Measured streaming bandwidth of this device for a J-sized buffer, in GB/s: one block per
+ * SM, every block reads the whole buffer `iters` times with 128-bit loads (the sweep's access
+ * pattern; L2-resident when bytes << 126 MB, HBM-bound beyond).  stagger=0: all blocks walk the
+ * rows in the same order (as the sweep does); stagger=1: every block starts elsewhere.  This is
+ * the roofline denominator bench.py normalises the sweep kernel against. */
+int sg_measure_stream_bandwidth(sg_engine *e, int64_t bytes, int iters, int stagger,
+                                double *gbps_out);
+
+/* Layout facts the host side needs (padded row length, resident replicas per block...). */
+int sg_query(sg_engine *e, int32_t *n, int32_t *n_pad, int32_t *n_replicas,
+             int32_t *max_replicas_per_block, int32_t *sm_count);
+
+/* Kernel launch counter (every kernel this library launched on this engine). */
+uint64_t sg_launch_count(sg_engine *e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SG_B200_H */

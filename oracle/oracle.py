@@ -276,8 +276,12 @@ def _converged(energy_history: List[float], tol: float) -> bool:
 def anneal(J, h, spins0, *, n_sweeps: int, T0: float, Tf: float, schedule: str = "geometric",
            schedule_params: Optional[dict] = None, record_interval: int = 10,
            energy_tolerance: float = 1e-8, rule: str = "metropolis",
-           stream: RawStream) -> OracleResult:
-    """GPUAnnealer.anneal on the CPU path, annealing/gpu_annealer.py:96-183."""
+           stream: RawStream, trace: bool = False) -> OracleResult:
+    """GPUAnnealer.anneal on the CPU path, annealing/gpu_annealer.py:96-183.
+
+    trace=True also returns, in ``extra``, the temperature of every sweep and the
+    (site, uniform) of every attempt -- the reference's stream under its own update
+    order, which is what the CUDA kernel is fed in injected mode."""
     sp = dict(schedule_params or {"alpha": 0.95})
     spins = np.ascontiguousarray(np.asarray(spins0, dtype=np.float32)).copy()
     start_pos = stream.pos
@@ -287,6 +291,7 @@ def anneal(J, h, spins0, *, n_sweeps: int, T0: float, Tf: float, schedule: str =
     e_hist, t_hist, a_hist = [best_e], [T0], [0.0]  # :134-136
     n_acc = n_rej = 0
     sweep_energies = []
+    tr_T, tr_site, tr_u = [], [], []
     sweep = -1
     for sweep in range(n_sweeps):  # :139
         rate = n_acc / (n_acc + n_rej) if (n_acc + n_rej) else 0.0
@@ -295,7 +300,11 @@ def anneal(J, h, spins0, *, n_sweeps: int, T0: float, Tf: float, schedule: str =
         else:
             T = schedule_temperature(schedule, sweep, T0, Tf, n_sweeps, **sp)
         T = max(float(T), 1e-10)  # set_temperature clamp, core/spin_dynamics.py:57-59
-        es, acc, _, _ = sweeps(J, h, spins, [T], rule, stream)
+        es, acc, ts, tu = sweeps(J, h, spins, [T], rule, stream, trace=trace)
+        if trace:
+            tr_T.append(T)
+            tr_site.append(ts)
+            tr_u.append(tu)
         n_acc += int(acc[0])
         n_rej += spins.shape[0] - int(acc[0])
         cur = float(es[0])
@@ -308,8 +317,12 @@ def anneal(J, h, spins0, *, n_sweeps: int, T0: float, Tf: float, schedule: str =
             a_hist.append(n_acc / (n_acc + n_rej))
             if _converged(e_hist, energy_tolerance):
                 break
-    return OracleResult(best_cfg, best_e, e_hist, t_hist, a_hist, sweep + 1, spins, sweep_energies,
-                        stream.pos - start_pos)
+    res = OracleResult(best_cfg, best_e, e_hist, t_hist, a_hist, sweep + 1, spins, sweep_energies,
+                       stream.pos - start_pos)
+    if trace:
+        res.extra = {"temps": np.array(tr_T, np.float64), "sites": np.stack(tr_site),
+                     "uniforms": np.stack(tr_u)}
+    return res
 
 
 # --------------------------------------------------------------------------- parallel tempering

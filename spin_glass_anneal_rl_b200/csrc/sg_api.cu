@@ -1,0 +1,596 @@
+// sg_api.cu -- the C ABI of libsg_b200.so (see include/sg_b200.h).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/sg_b200.h"
+#include "sg_internal.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* what, cudaError_t ce = cudaSuccess) {
+    g_err = what;
+    if (ce != cudaSuccess) {
+        g_err += ": ";
+        g_err += cudaGetErrorName(ce);
+        g_err += " (";
+        g_err += cudaGetErrorString(ce);
+        g_err += ")";
+    }
+    return code;
+}
+
+#define SG_CUDA(call)                                                    \
+    do {                                                                 \
+        cudaError_t _e = (call);                                         \
+        if (_e != cudaSuccess) return fail(SG_ERR_CUDA, #call, _e);      \
+    } while (0)
+
+#define SG_REQUIRE(cond, msg)                                   \
+    do {                                                        \
+        if (!(cond)) return fail(SG_ERR_INVALID, msg);          \
+    } while (0)
+
+template <typename T>
+int dev_alloc(T** p, size_t count) {
+    if (*p) {
+        cudaFree(*p);
+        *p = nullptr;
+    }
+    if (count == 0) return SG_OK;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
+    if (e != cudaSuccess) {
+        *p = nullptr;
+        return fail(e == cudaErrorMemoryAllocation ? SG_ERR_NOMEM : SG_ERR_CUDA, "cudaMalloc", e);
+    }
+    return SG_OK;
+}
+
+}  // namespace
+
+struct sg_engine {
+    int device = 0;
+    int sm_count = 0;
+    int n = 0, n_pad = 0, R = 0;
+    float* Jt = nullptr;  // [n][n_pad]
+    float* h = nullptr;   // [n_pad]
+    int8_t* spins = nullptr;
+    float* fields = nullptr;
+    float* energy = nullptr;
+    float* best_energy = nullptr;
+    int8_t* best_spins = nullptr;
+    unsigned long long* accepted = nullptr;
+    bool fields_valid = false;
+    // ladder
+    int K = 0, L = 0;
+    int* rep_at = nullptr;
+    double* rep_temp = nullptr;
+    double* ladder = nullptr;
+    unsigned int* attempts = nullptr;
+    unsigned int* accepts = nullptr;
+    uint64_t launches = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = 0;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true;
+    }
+    ~DeviceGuard() {
+        if (ok) cudaSetDevice(prev);
+    }
+};
+
+// copy `bytes` between a caller buffer (host or device) and an engine device buffer
+int copy_in(void* dst_dev, const void* src, size_t bytes, int on_device, cudaStream_t st) {
+    SG_CUDA(cudaMemcpyAsync(dst_dev, src, bytes,
+                            on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    if (!on_device) SG_CUDA(cudaStreamSynchronize(st));
+    return SG_OK;
+}
+int copy_out(void* dst, const void* src_dev, size_t bytes, int on_device, cudaStream_t st) {
+    SG_CUDA(cudaMemcpyAsync(dst, src_dev, bytes,
+                            on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    if (!on_device) SG_CUDA(cudaStreamSynchronize(st));
+    return SG_OK;
+}
+
+void free_replicas(sg_engine* e) {
+    cudaFree(e->spins); e->spins = nullptr;
+    cudaFree(e->fields); e->fields = nullptr;
+    cudaFree(e->energy); e->energy = nullptr;
+    cudaFree(e->best_energy); e->best_energy = nullptr;
+    cudaFree(e->best_spins); e->best_spins = nullptr;
+    cudaFree(e->accepted); e->accepted = nullptr;
+    e->R = 0;
+    e->fields_valid = false;
+}
+
+void free_ladder(sg_engine* e) {
+    cudaFree(e->rep_at); e->rep_at = nullptr;
+    cudaFree(e->rep_temp); e->rep_temp = nullptr;
+    cudaFree(e->ladder); e->ladder = nullptr;
+    cudaFree(e->attempts); e->attempts = nullptr;
+    cudaFree(e->accepts); e->accepts = nullptr;
+    e->K = e->L = 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sg_abi_version(void) { return SG_ABI_VERSION; }
+
+const char* sg_last_error(void) { return g_err.c_str(); }
+
+int sg_create(int device_id, sg_engine** out) {
+    if (!out) return fail(SG_ERR_INVALID, "sg_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    SG_CUDA(cudaGetDeviceCount(&count));
+    if (device_id < 0 || device_id >= count) return fail(SG_ERR_INVALID, "sg_create: bad device id");
+    cudaDeviceProp prop;
+    SG_CUDA(cudaGetDeviceProperties(&prop, device_id));
+    if (prop.major < 10)
+        return fail(SG_ERR_UNSUPPORTED, "sg_create: this library is built for sm_100a (B200) only");
+    sg_engine* e = new (std::nothrow) sg_engine();
+    if (!e) return fail(SG_ERR_NOMEM, "sg_create: host allocation failed");
+    e->device = device_id;
+    e->sm_count = prop.multiProcessorCount;
+    *out = e;
+    return SG_OK;
+}
+
+void sg_destroy(sg_engine* e) {
+    if (!e) return;
+    DeviceGuard g(e->device);
+    free_replicas(e);
+    free_ladder(e);
+    cudaFree(e->Jt);
+    cudaFree(e->h);
+    delete e;
+}
+
+int sg_set_model_dense(sg_engine* e, int n, const float* J, int64_t ldJ, const float* h,
+                       int on_device, void* stream) {
+    SG_REQUIRE(e && J && h, "sg_set_model_dense: NULL argument");
+    SG_REQUIRE(n >= 1 && ldJ >= n, "sg_set_model_dense: need n >= 1 and ldJ >= n");
+    // padded row length: the smallest size the sweep kernel is instantiated for
+    int n_pad = sg::kColQuantum;
+    while (n_pad < n) n_pad *= 2;
+    if (sg::sweep_max_replicas_per_block(n_pad) == 0)
+        return fail(SG_ERR_UNSUPPORTED, "sg_set_model_dense: dense models support n <= 8192");
+    DeviceGuard g(e->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n != e->n) {
+        free_replicas(e);
+        free_ladder(e);
+    }
+    e->n = n;
+    e->n_pad = n_pad;
+    int rc;
+    if ((rc = dev_alloc(&e->Jt, (size_t)n * n_pad)) != SG_OK) return rc;
+    if ((rc = dev_alloc(&e->h, (size_t)n_pad)) != SG_OK) return rc;
+    const float* Jdev = J;
+    float* tmp = nullptr;
+    if (!on_device) {
+        if ((rc = dev_alloc(&tmp, (size_t)n * ldJ)) != SG_OK) return rc;
+        SG_CUDA(cudaMemcpyAsync(tmp, J, (size_t)n * ldJ * sizeof(float), cudaMemcpyHostToDevice, st));
+        Jdev = tmp;
+    }
+    SG_CUDA(sg::launch_pad_transpose(Jdev, ldJ, n, e->Jt, n_pad, st));
+    e->launches++;
+    SG_CUDA(cudaMemsetAsync(e->h, 0, (size_t)n_pad * sizeof(float), st));
+    SG_CUDA(cudaMemcpyAsync(e->h, h, (size_t)n * sizeof(float),
+                            on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    if (tmp) {
+        SG_CUDA(cudaStreamSynchronize(st));
+        cudaFree(tmp);
+    }
+    e->fields_valid = false;
+    return SG_OK;
+}
+
+int sg_alloc_replicas(sg_engine* e, int n_replicas, void* stream) {
+    SG_REQUIRE(e && e->n > 0, "sg_alloc_replicas: set the model first");
+    SG_REQUIRE(n_replicas >= 1, "sg_alloc_replicas: need n_replicas >= 1");
+    DeviceGuard g(e->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    free_replicas(e);
+    free_ladder(e);
+    const size_t R = (size_t)n_replicas, np = (size_t)e->n_pad;
+    int rc;
+    if ((rc = dev_alloc(&e->spins, R * np)) != SG_OK) return rc;
+    if ((rc = dev_alloc(&e->fields, R * np)) != SG_OK) return rc;
+    if ((rc = dev_alloc(&e->energy, R)) != SG_OK) return rc;
+    if ((rc = dev_alloc(&e->best_energy, R)) != SG_OK) return rc;
+    if ((rc = dev_alloc(&e->best_spins, R * np)) != SG_OK) return rc;
+    if ((rc = dev_alloc(&e->accepted, R)) != SG_OK) return rc;
+    SG_CUDA(cudaMemsetAsync(e->spins, 1, R * np, st));
+    SG_CUDA(cudaMemsetAsync(e->best_spins, 1, R * np, st));
+    SG_CUDA(cudaMemsetAsync(e->accepted, 0, R * sizeof(unsigned long long), st));
+    e->R = n_replicas;
+    e->fields_valid = false;
+    return SG_OK;
+}
+
+int sg_set_spins(sg_engine* e, const int8_t* spins, int on_device, void* stream) {
+    SG_REQUIRE(e && spins && e->R > 0, "sg_set_spins: allocate replicas first");
+    DeviceGuard g(e->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t bytes = (size_t)e->R * e->n;
+    const int8_t* src = spins;
+    int8_t* tmp = nullptr;
+    int rc;
+    if (!on_device) {
+        if ((rc = dev_alloc(&tmp, bytes)) != SG_OK) return rc;
+        SG_CUDA(cudaMemcpyAsync(tmp, spins, bytes, cudaMemcpyHostToDevice, st));
+        src = tmp;
+    }
+    SG_CUDA(sg::launch_pad_spins(src, e->n, e->spins, e->n_pad, e->R, st));
+    e->launches++;
+    if (tmp) {
+        SG_CUDA(cudaStreamSynchronize(st));
+        cudaFree(tmp);
+    }
+    e->fields_valid = false;
+    return SG_OK;
+}
+
+static int get_unpadded_i8(sg_engine* e, const int8_t* src_pad, int8_t* out, int on_device,
+                           cudaStream_t st) {
+    const size_t bytes = (size_t)e->R * e->n;
+    int rc;
+    if (on_device) {
+        SG_CUDA(sg::launch_unpad_spins(src_pad, e->n_pad, out, e->n, e->R, st));
+        e->launches++;
+        return SG_OK;
+    }
+    int8_t* tmp = nullptr;
+    if ((rc = dev_alloc(&tmp, bytes)) != SG_OK) return rc;
+    cudaError_t ce = sg::launch_unpad_spins(src_pad, e->n_pad, tmp, e->n, e->R, st);
+    e->launches++;
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(out, tmp, bytes, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    cudaFree(tmp);
+    if (ce != cudaSuccess) return fail(SG_ERR_CUDA, "get spins", ce);
+    return SG_OK;
+}
+
+int sg_get_spins(sg_engine* e, int8_t* spins, int on_device, void* stream) {
+    SG_REQUIRE(e && spins && e->R > 0, "sg_get_spins: allocate replicas first");
+    DeviceGuard g(e->device);
+    return get_unpadded_i8(e, e->spins, spins, on_device, static_cast<cudaStream_t>(stream));
+}
+
+int sg_reset_best(sg_engine* e, void* stream) {
+    SG_REQUIRE(e && e->R > 0 && e->fields_valid, "sg_reset_best: call sg_init_fields first");
+    DeviceGuard g(e->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SG_CUDA(cudaMemcpyAsync(e->best_energy, e->energy, (size_t)e->R * sizeof(float),
+                            cudaMemcpyDeviceToDevice, st));
+    SG_CUDA(cudaMemcpyAsync(e->best_spins, e->spins, (size_t)e->R * e->n_pad,
+                            cudaMemcpyDeviceToDevice, st));
+    return SG_OK;
+}
+
+int sg_init_fields(sg_engine* e, void* stream) {
+    SG_REQUIRE(e && e->R > 0 && e->Jt, "sg_init_fields: set model and replicas first");
+    DeviceGuard g(e->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SG_CUDA(sg::launch_fields(e->spins, e->n_pad, e->Jt, e->h, e->n, e->n_pad, e->R, e->fields,
+                              e->n_pad, st));
+    SG_CUDA(sg::launch_energies(e->spins, e->n_pad, e->fields, e->n_pad, e->h, e->n, e->R,
+                                e->energy, st));
+    e->launches += 2;
+    e->fields_valid = true;
+    return sg_reset_best(e, stream);
+}
+
+int sg_get_energies(sg_engine* e, float* energies, int on_device, void* stream) {
+    SG_REQUIRE(e && energies && e->R > 0, "sg_get_energies: allocate replicas first");
+    DeviceGuard g(e->device);
+    return copy_out(energies, e->energy, (size_t)e->R * sizeof(float), on_device,
+                    static_cast<cudaStream_t>(stream));
+}
+
+int sg_get_fields(sg_engine* e, float* fields, int on_device, void* stream) {
+    SG_REQUIRE(e && fields && e->R > 0, "sg_get_fields: allocate replicas first");
+    DeviceGuard g(e->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t count = (size_t)e->R * e->n;
+    if (on_device) {
+        SG_CUDA(sg::launch_unpad_f32(e->fields, e->n_pad, fields, e->n, e->R, st));
+        e->launches++;
+        return SG_OK;
+    }
+    float* tmp = nullptr;
+    int rc;
+    if ((rc = dev_alloc(&tmp, count)) != SG_OK) return rc;
+    cudaError_t ce = sg::launch_unpad_f32(e->fields, e->n_pad, tmp, e->n, e->R, st);
+    e->launches++;
+    if (ce == cudaSuccess)
+        ce = cudaMemcpyAsync(fields, tmp, count * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    cudaFree(tmp);
+    if (ce != cudaSuccess) return fail(SG_ERR_CUDA, "sg_get_fields", ce);
+    return SG_OK;
+}
+
+int sg_get_accepted(sg_engine* e, uint64_t* accepted, int on_device, void* stream) {
+    SG_REQUIRE(e && accepted && e->R > 0, "sg_get_accepted: allocate replicas first");
+    DeviceGuard g(e->device);
+    return copy_out(accepted, e->accepted, (size_t)e->R * sizeof(uint64_t), on_device,
+                    static_cast<cudaStream_t>(stream));
+}
+
+int sg_get_best(sg_engine* e, float* best_energy, int8_t* best_spins, int on_device,
+                void* stream) {
+    SG_REQUIRE(e && e->R > 0, "sg_get_best: allocate replicas first");
+    DeviceGuard g(e->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = SG_OK;
+    if (best_energy)
+        rc = copy_out(best_energy, e->best_energy, (size_t)e->R * sizeof(float), on_device, st);
+    if (rc == SG_OK && best_spins) rc = get_unpadded_i8(e, e->best_spins, best_spins, on_device, st);
+    return rc;
+}
+
+int sg_sweep(sg_engine* e, const sg_sweep_params* p, void* stream) {
+    SG_REQUIRE(e && p, "sg_sweep: NULL argument");
+    SG_REQUIRE(p->struct_size == sizeof(sg_sweep_params), "sg_sweep: struct_size mismatch");
+    SG_REQUIRE(e->R > 0 && e->fields_valid, "sg_sweep: call sg_init_fields first");
+    SG_REQUIRE(p->n_sweeps >= 0, "sg_sweep: n_sweeps < 0");
+    SG_REQUIRE(p->rule >= 0 && p->rule <= 2, "sg_sweep: unknown rule");
+    SG_REQUIRE(p->rng_mode == SG_RNG_PHILOX || p->rng_mode == SG_RNG_INJECTED,
+               "sg_sweep: unknown rng_mode");
+    SG_REQUIRE(p->site_mode >= 0 && p->site_mode <= 2, "sg_sweep: unknown site_mode");
+    SG_REQUIRE(p->site_mode != SG_SITES_EXPLICIT || p->sites, "sg_sweep: explicit sites missing");
+    SG_REQUIRE(p->rng_mode != SG_RNG_INJECTED || p->uniforms, "sg_sweep: injected uniforms missing");
+    SG_REQUIRE(p->temps || e->rep_temp, "sg_sweep: no temperatures (pass temps or set a ladder)");
+    if (p->n_sweeps == 0) return SG_OK;
+    DeviceGuard g(e->device);
+    const int gmax = sg::sweep_max_replicas_per_block(e->n_pad);
+    int G = p->replicas_per_block;
+    SG_REQUIRE(G >= 0 && G <= gmax, "sg_sweep: replicas_per_block out of range");
+    if (G == 0) {
+        // fewest waves first, then the fewest replicas per block that achieves it
+        const long long sms = e->sm_count;
+        long long best_cost = -1;
+        for (int cand = 1; cand <= gmax; ++cand) {
+            const long long blocks = (e->R + cand - 1) / cand;
+            const long long waves = (blocks + sms - 1) / sms;
+            const long long cost = waves * (gmax + 2LL * cand);  // per-attempt cost ~ a + b*G
+            if (best_cost < 0 || cost < best_cost) {
+                best_cost = cost;
+                G = cand;
+            }
+        }
+    }
+    sg::SweepDev a{};
+    a.Jt = e->Jt;
+    a.h = e->h;
+    a.spins = e->spins;
+    a.fields = e->fields;
+    a.energy = e->energy;
+    a.best_energy = e->best_energy;
+    a.best_spins = e->best_spins;
+    a.accepted = e->accepted;
+    a.energy_trace = p->energy_trace;
+    if (p->temps) {
+        a.temps = p->temps;
+        a.t_ss = p->temps_sweep_stride;
+        a.t_rs = p->temps_replica_stride;
+    } else {
+        a.temps = e->rep_temp;
+        a.t_ss = 0;
+        a.t_rs = 1;
+    }
+    a.sites = p->sites;
+    a.s_bs = p->sites_block_stride;
+    a.s_ss = p->sites_sweep_stride;
+    a.uniforms = p->uniforms;
+    a.seed = p->seed;
+    a.sweep_base = p->sweep_base;
+    a.n = e->n;
+    a.n_pad = e->n_pad;
+    a.R = e->R;
+    a.G = G;
+    a.n_sweeps = p->n_sweeps;
+    a.rule = p->rule;
+    a.site_mode = p->site_mode;
+    a.track_best = p->track_best ? 1 : 0;
+    const int grid = (e->R + G - 1) / G;
+    SG_CUDA(sg::launch_sweep(a, p->rng_mode == SG_RNG_INJECTED, grid,
+                             static_cast<cudaStream_t>(stream)));
+    e->launches++;
+    return SG_OK;
+}
+
+int sg_set_ladder(sg_engine* e, int n_rungs, const double* ladder_temps, void* stream) {
+    SG_REQUIRE(e && ladder_temps && e->R > 0, "sg_set_ladder: allocate replicas first");
+    SG_REQUIRE(n_rungs >= 1 && e->R % n_rungs == 0,
+               "sg_set_ladder: n_replicas must be a multiple of n_rungs");
+    DeviceGuard g(e->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    free_ladder(e);
+    const int K = n_rungs, L = e->R / n_rungs;
+    int rc;
+    if ((rc = dev_alloc(&e->rep_at, (size_t)e->R)) != SG_OK) return rc;
+    if ((rc = dev_alloc(&e->rep_temp, (size_t)e->R)) != SG_OK) return rc;
+    if ((rc = dev_alloc(&e->ladder, (size_t)K)) != SG_OK) return rc;
+    const size_t nstat = (size_t)L * (K > 1 ? K - 1 : 1);
+    if ((rc = dev_alloc(&e->attempts, nstat)) != SG_OK) return rc;
+    if ((rc = dev_alloc(&e->accepts, nstat)) != SG_OK) return rc;
+    SG_CUDA(cudaMemcpyAsync(e->ladder, ladder_temps, (size_t)K * sizeof(double),
+                            cudaMemcpyHostToDevice, st));
+    SG_CUDA(cudaMemsetAsync(e->attempts, 0, nstat * sizeof(unsigned int), st));
+    SG_CUDA(cudaMemsetAsync(e->accepts, 0, nstat * sizeof(unsigned int), st));
+    SG_CUDA(sg::launch_ladder_init(e->rep_at, e->rep_temp, e->ladder, L, K, st));
+    e->launches++;
+    SG_CUDA(cudaStreamSynchronize(st));  // ladder_temps is a host buffer
+    e->K = K;
+    e->L = L;
+    return SG_OK;
+}
+
+int sg_exchange(sg_engine* e, const sg_exchange_params* p, void* stream) {
+    SG_REQUIRE(e && p, "sg_exchange: NULL argument");
+    SG_REQUIRE(p->struct_size == sizeof(sg_exchange_params), "sg_exchange: struct_size mismatch");
+    SG_REQUIRE(e->K > 0, "sg_exchange: call sg_set_ladder first");
+    SG_REQUIRE(p->parity == 0 || p->parity == 1, "sg_exchange: parity must be 0 or 1");
+    SG_REQUIRE(p->rng_mode != SG_RNG_INJECTED || p->uniforms, "sg_exchange: uniforms missing");
+    DeviceGuard g(e->device);
+    sg::ExchangeDev a{};
+    a.rep_at = e->rep_at;
+    a.rep_temp = e->rep_temp;
+    a.ladder = e->ladder;
+    a.energy = e->energy;
+    a.attempts = e->attempts;
+    a.accepts = e->accepts;
+    a.uniforms = p->uniforms;
+    a.seed = p->seed;
+    a.round = p->round;
+    a.L = e->L;
+    a.K = e->K;
+    a.parity = p->parity;
+    a.inject = (p->rng_mode == SG_RNG_INJECTED);
+    SG_CUDA(sg::launch_exchange(a, static_cast<cudaStream_t>(stream)));
+    e->launches++;
+    return SG_OK;
+}
+
+int sg_get_ladder_state(sg_engine* e, int32_t* replica_at_rung, double* replica_temps,
+                        uint32_t* attempts, uint32_t* accepts, int on_device, void* stream) {
+    SG_REQUIRE(e && e->K > 0, "sg_get_ladder_state: call sg_set_ladder first");
+    DeviceGuard g(e->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t nstat = (size_t)e->L * (e->K > 1 ? e->K - 1 : 1);
+    int rc = SG_OK;
+    if (replica_at_rung)
+        rc = copy_out(replica_at_rung, e->rep_at, (size_t)e->R * sizeof(int), on_device, st);
+    if (rc == SG_OK && replica_temps)
+        rc = copy_out(replica_temps, e->rep_temp, (size_t)e->R * sizeof(double), on_device, st);
+    if (rc == SG_OK && attempts)
+        rc = copy_out(attempts, e->attempts, nstat * sizeof(unsigned int), on_device, st);
+    if (rc == SG_OK && accepts)
+        rc = copy_out(accepts, e->accepts, nstat * sizeof(unsigned int), on_device, st);
+    return rc;
+}
+
+int sg_batch_energies(sg_engine* e, int batch, const int8_t* spins, float* energies, float* fields,
+                      int on_device, void* stream) {
+    SG_REQUIRE(e && spins && e->Jt, "sg_batch_energies: set the model first");
+    SG_REQUIRE(batch >= 1, "sg_batch_energies: batch < 1");
+    DeviceGuard g(e->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t B = (size_t)batch, n = (size_t)e->n, np = (size_t)e->n_pad;
+    int8_t *s_in = nullptr, *s_pad = nullptr;
+    float *f_pad = nullptr, *e_dev = nullptr, *f_out = nullptr;
+    int rc = SG_OK;
+    cudaError_t ce = cudaSuccess;
+    do {
+        if ((rc = dev_alloc(&s_pad, B * np)) != SG_OK) break;
+        if ((rc = dev_alloc(&f_pad, B * np)) != SG_OK) break;
+        if ((rc = dev_alloc(&e_dev, B)) != SG_OK) break;
+        const int8_t* src = spins;
+        if (!on_device) {
+            if ((rc = dev_alloc(&s_in, B * n)) != SG_OK) break;
+            if ((ce = cudaMemcpyAsync(s_in, spins, B * n, cudaMemcpyHostToDevice, st))) break;
+            src = s_in;
+        }
+        if ((ce = sg::launch_pad_spins(src, e->n, s_pad, e->n_pad, batch, st))) break;
+        if ((ce = sg::launch_fields(s_pad, np, e->Jt, e->h, e->n, e->n_pad, batch, f_pad, np, st)))
+            break;
+        if ((ce = sg::launch_energies(s_pad, np, f_pad, np, e->h, e->n, batch, e_dev, st))) break;
+        e->launches += 3;
+        if (energies) {
+            if ((ce = cudaMemcpyAsync(energies, e_dev, B * sizeof(float),
+                                      on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                                      st)))
+                break;
+        }
+        if (fields) {
+            float* dstf = fields;
+            if (!on_device) {
+                if ((rc = dev_alloc(&f_out, B * n)) != SG_OK) break;
+                dstf = f_out;
+            }
+            if ((ce = sg::launch_unpad_f32(f_pad, e->n_pad, dstf, e->n, batch, st))) break;
+            e->launches++;
+            if (!on_device &&
+                (ce = cudaMemcpyAsync(fields, f_out, B * n * sizeof(float), cudaMemcpyDeviceToHost,
+                                      st)))
+                break;
+        }
+        ce = cudaStreamSynchronize(st);  // scratch is freed below
+    } while (0);
+    cudaFree(s_in);
+    cudaFree(s_pad);
+    cudaFree(f_pad);
+    cudaFree(e_dev);
+    cudaFree(f_out);
+    if (rc != SG_OK) return rc;
+    if (ce != cudaSuccess) return fail(SG_ERR_CUDA, "sg_batch_energies", ce);
+    return SG_OK;
+}
+
+int sg_measure_stream_bandwidth(sg_engine* e, int64_t bytes, int iters, int stagger,
+                                double* gbps_out) {
+    SG_REQUIRE(e && gbps_out, "sg_measure_stream_bandwidth: NULL argument");
+    SG_REQUIRE(bytes >= (1 << 20) && iters >= 1, "sg_measure_stream_bandwidth: bytes >= 1 MiB");
+    DeviceGuard g(e->device);
+    const int64_t n_vec = (bytes / 16) / 1024 * 1024;
+    float4* buf = nullptr;
+    float* sink = nullptr;
+    int rc;
+    if ((rc = dev_alloc(&buf, (size_t)n_vec)) != SG_OK) return rc;
+    if ((rc = dev_alloc(&sink, 1)) != SG_OK) {
+        cudaFree(buf);
+        return rc;
+    }
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0);
+    cudaEventCreate(&t1);
+    cudaError_t ce = cudaMemset(buf, 0, (size_t)n_vec * 16);
+    const int grid = e->sm_count;  // one block per SM, like the sweep kernel
+    const int sg_ = stagger ? 1 : 0;
+    if (ce == cudaSuccess) ce = sg::launch_stream_probe(buf, n_vec, 1, sg_, sink, grid, 0);  // warm
+    if (ce == cudaSuccess) ce = cudaEventRecord(t0, 0);
+    if (ce == cudaSuccess) ce = sg::launch_stream_probe(buf, n_vec, iters, sg_, sink, grid, 0);
+    if (ce == cudaSuccess) ce = cudaEventRecord(t1, 0);
+    if (ce == cudaSuccess) ce = cudaEventSynchronize(t1);
+    float ms = 0.0f;
+    if (ce == cudaSuccess) ce = cudaEventElapsedTime(&ms, t0, t1);
+    e->launches += 2;
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    cudaFree(buf);
+    cudaFree(sink);
+    if (ce != cudaSuccess) return fail(SG_ERR_CUDA, "sg_measure_stream_bandwidth", ce);
+    *gbps_out = (double)n_vec * 16.0 * (double)iters * (double)grid / ((double)ms * 1.0e6);
+    return SG_OK;
+}
+
+int sg_query(sg_engine* e, int32_t* n, int32_t* n_pad, int32_t* n_replicas,
+             int32_t* max_replicas_per_block, int32_t* sm_count) {
+    SG_REQUIRE(e, "sg_query: NULL engine");
+    if (n) *n = e->n;
+    if (n_pad) *n_pad = e->n_pad;
+    if (n_replicas) *n_replicas = e->R;
+    if (max_replicas_per_block)
+        *max_replicas_per_block = e->n_pad ? sg::sweep_max_replicas_per_block(e->n_pad) : 0;
+    if (sm_count) *sm_count = e->sm_count;
+    return SG_OK;
+}
+
+uint64_t sg_launch_count(sg_engine* e) { return e ? e->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,72 @@
+// sg_internal.h -- launcher prototypes shared by the translation units of libsg_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sg {
+
+constexpr int kSweepThreads = 256;              // 8 warps: 2 per SM sub-partition, 255 regs each
+constexpr int kColQuantum = 4 * kSweepThreads;  // n_pad is a multiple of this (1024)
+
+// Kernel argument block of the sweep kernel (passed by value).
+struct SweepDev {
+    const float* Jt;          // [n][n_pad]  row i = couplings INTO every j from i:  Jt[i][j] = J[j][i]
+    const float* h;           // [n_pad]
+    int8_t* spins;            // [R][n_pad]
+    float* fields;            // [R][n_pad]
+    float* energy;            // [R]
+    float* best_energy;       // [R]
+    int8_t* best_spins;       // [R][n_pad]
+    unsigned long long* accepted;  // [R]
+    float* energy_trace;      // [n_sweeps][R] or null
+    const double* temps;      // T(s, r) = temps[s*t_ss + r*t_rs]
+    long long t_ss, t_rs;
+    const int* sites;         // explicit site lists
+    long long s_bs, s_ss;
+    const float* uniforms;    // injected uniforms [R][n_sweeps][n]
+    unsigned long long seed, sweep_base;
+    int n, n_pad, R, G, n_sweeps, rule, site_mode, track_best, D;
+};
+
+// Largest number of replicas one block can hold for this padded size (0 = unsupported).
+int sweep_max_replicas_per_block(int n_pad);
+// Dynamic shared memory the sweep kernel needs for (n_pad, G, D).
+size_t sweep_smem_bytes(int n_pad, int g_template, int D);
+// Picks D, sets the smem attribute, launches.  Returns cudaError_t.
+cudaError_t launch_sweep(SweepDev a, bool inject, int grid, cudaStream_t st);
+
+// K2 + helpers (sg_fields.cu)
+cudaError_t launch_pad_transpose(const float* J, int64_t ldJ, int n, float* Jt, int n_pad,
+                                 cudaStream_t st);
+cudaError_t launch_fields(const int8_t* spins, int64_t ld_spins, const float* Jt, const float* h,
+                          int n, int n_pad, int R, float* fields, int64_t ld_fields,
+                          cudaStream_t st);
+cudaError_t launch_energies(const int8_t* spins, int64_t ld_spins, const float* fields,
+                            int64_t ld_fields, const float* h, int n, int R, float* energy,
+                            cudaStream_t st);
+cudaError_t launch_pad_spins(const int8_t* src, int n, int8_t* dst, int n_pad, int R,
+                             cudaStream_t st);
+cudaError_t launch_unpad_spins(const int8_t* src, int n_pad, int8_t* dst, int n, int R,
+                               cudaStream_t st);
+cudaError_t launch_unpad_f32(const float* src, int n_pad, float* dst, int n, int R,
+                             cudaStream_t st);
+cudaError_t launch_stream_probe(const float4* buf, int64_t n_vec, int iters, int stagger,
+                                float* sink, int grid, cudaStream_t st);
+
+// K3 (sg_exchange.cu)
+struct ExchangeDev {
+    int* rep_at;              // [L][K] replica currently at rung k of ladder l
+    double* rep_temp;         // [R]
+    const double* ladder;     // [K]
+    const float* energy;      // [R]
+    unsigned int* attempts;   // [L][K-1]
+    unsigned int* accepts;    // [L][K-1]
+    const double* uniforms;   // injected [L][K/2] or null
+    unsigned long long seed, round;
+    int L, K, parity, inject;
+};
+cudaError_t launch_exchange(ExchangeDev a, cudaStream_t st);
+cudaError_t launch_ladder_init(int* rep_at, double* rep_temp, const double* ladder, int L, int K,
+                               cudaStream_t st);
+
+}  // namespace sg

@@ -1,0 +1,272 @@
+"""Thin object wrapper over the C ABI (include/sg_b200.h).
+
+One ``Engine`` = one Ising model (J, h) plus R replicas resident on one GPU.
+PyTorch is used only as plumbing: device tensors are passed as raw pointers
+(``tensor.data_ptr()``), the launch stream is torch's current stream, and
+host inputs may be numpy arrays or CPU tensors.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ExchangeParams, SweepParams, check
+
+ArrayLike = Union[np.ndarray, torch.Tensor]
+
+
+def _as_host(a: ArrayLike, dtype) -> np.ndarray:
+    if isinstance(a, torch.Tensor):
+        a = a.detach().cpu().numpy()
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Engine:
+    """Replica-batched annealing engine on one B200 (``device`` = CUDA ordinal)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.SGError("no CUDA device: the B200 engine has no CPU fallback")
+        self.device_index = int(device)
+        self.device = torch.device("cuda", self.device_index)
+        h = ctypes.c_void_p()
+        check(self._lib.sg_create(self.device_index, ctypes.byref(h)), "sg_create")
+        self._h = h
+        self.n = 0
+        self.n_replicas = 0
+        self._keep = []  # tensors referenced by in-flight launches
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.sg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self) -> ctypes.c_void_p:
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _ptr(self, t: Optional[torch.Tensor]) -> ctypes.c_void_p:
+        if t is None:
+            return ctypes.c_void_p(0)
+        assert t.is_cuda and t.is_contiguous() and t.device == self.device
+        return ctypes.c_void_p(t.data_ptr())
+
+    def _dev(self, a: ArrayLike, dtype: torch.dtype) -> torch.Tensor:
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.device, dtype=dtype).contiguous()
+        return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device=self.device)
+
+    def synchronize(self) -> None:
+        torch.cuda.current_stream(self.device).synchronize()
+        self._keep.clear()
+
+    # ------------------------------------------------------------------ model / replicas
+    def set_model(self, J: ArrayLike, h: ArrayLike) -> None:
+        """Dense couplings (n x n float32, any symmetry) and external fields."""
+        n = int(J.shape[0])
+        assert tuple(J.shape) == (n, n) and int(h.shape[0]) == n
+        if isinstance(J, torch.Tensor) and J.is_cuda:
+            Jd, hd = self._dev(J, torch.float32), self._dev(h, torch.float32)
+            check(self._lib.sg_set_model_dense(self._h, n, self._ptr(Jd), n, self._ptr(hd), 1,
+                                               self.stream), "sg_set_model_dense")
+            self._keep += [Jd, hd]
+        else:
+            Jh, hh = _as_host(J, np.float32), _as_host(h, np.float32)
+            check(self._lib.sg_set_model_dense(self._h, n, Jh.ctypes.data_as(ctypes.c_void_p), n,
+                                               hh.ctypes.data_as(ctypes.c_void_p), 0, self.stream),
+                  "sg_set_model_dense")
+        if n != self.n:
+            self.n_replicas = 0
+        self.n = n
+
+    def alloc_replicas(self, n_replicas: int) -> None:
+        check(self._lib.sg_alloc_replicas(self._h, int(n_replicas), self.stream),
+              "sg_alloc_replicas")
+        self.n_replicas = int(n_replicas)
+
+    def set_spins(self, spins: ArrayLike) -> None:
+        """spins[R][n] in {-1,+1} (any integer/float dtype)."""
+        assert tuple(spins.shape) == (self.n_replicas, self.n), "spins must be [R, n]"
+        if isinstance(spins, torch.Tensor) and spins.is_cuda:
+            s = self._dev(spins, torch.int8)
+            check(self._lib.sg_set_spins(self._h, self._ptr(s), 1, self.stream), "sg_set_spins")
+            self._keep.append(s)
+        else:
+            s = _as_host(spins, np.int8)
+            check(self._lib.sg_set_spins(self._h, s.ctypes.data_as(ctypes.c_void_p), 0,
+                                         self.stream), "sg_set_spins")
+
+    def init_fields(self) -> None:
+        check(self._lib.sg_init_fields(self._h, self.stream), "sg_init_fields")
+
+    def reset_best(self) -> None:
+        check(self._lib.sg_reset_best(self._h, self.stream), "sg_reset_best")
+
+    # ------------------------------------------------------------------ read-back (device tensors)
+    def spins(self) -> torch.Tensor:
+        out = torch.empty((self.n_replicas, self.n), dtype=torch.int8, device=self.device)
+        check(self._lib.sg_get_spins(self._h, self._ptr(out), 1, self.stream), "sg_get_spins")
+        return out
+
+    def energies(self) -> torch.Tensor:
+        out = torch.empty(self.n_replicas, dtype=torch.float32, device=self.device)
+        check(self._lib.sg_get_energies(self._h, self._ptr(out), 1, self.stream),
+              "sg_get_energies")
+        return out
+
+    def fields(self) -> torch.Tensor:
+        out = torch.empty((self.n_replicas, self.n), dtype=torch.float32, device=self.device)
+        check(self._lib.sg_get_fields(self._h, self._ptr(out), 1, self.stream), "sg_get_fields")
+        return out
+
+    def accepted(self) -> torch.Tensor:
+        out = torch.empty(self.n_replicas, dtype=torch.int64, device=self.device)
+        check(self._lib.sg_get_accepted(self._h, self._ptr(out), 1, self.stream),
+              "sg_get_accepted")
+        return out
+
+    def best(self):
+        e = torch.empty(self.n_replicas, dtype=torch.float32, device=self.device)
+        s = torch.empty((self.n_replicas, self.n), dtype=torch.int8, device=self.device)
+        check(self._lib.sg_get_best(self._h, self._ptr(e), self._ptr(s), 1, self.stream),
+              "sg_get_best")
+        return e, s
+
+    def best_energies(self) -> torch.Tensor:
+        e = torch.empty(self.n_replicas, dtype=torch.float32, device=self.device)
+        check(self._lib.sg_get_best(self._h, self._ptr(e), ctypes.c_void_p(0), 1, self.stream),
+              "sg_get_best")
+        return e
+
+    # ------------------------------------------------------------------ the sweep
+    def sweep(self, n_sweeps: int, temps: Optional[ArrayLike] = None, *,
+              temps_sweep_stride: int = 0, temps_replica_stride: int = 0,
+              rule: str = "metropolis", site_order: str = "random", seed: int = 0,
+              sweep_base: int = 0, sites: Optional[ArrayLike] = None,
+              sites_block_stride: int = 0, sites_sweep_stride: Optional[int] = None,
+              uniforms: Optional[ArrayLike] = None, energy_trace: bool = False,
+              track_best: bool = True, replicas_per_block: int = 0) -> Optional[torch.Tensor]:
+        """Run ``n_sweeps`` sweeps on every replica (one kernel launch).
+
+        temps: float64 array addressed as temps[s*temps_sweep_stride + r*temps_replica_stride]
+        (None = ladder temperatures).  ``uniforms`` switches to injected-uniform mode,
+        ``sites`` to an explicit site list.  Returns the [n_sweeps, R] energy trace if asked.
+        """
+        p = SweepParams()
+        p.struct_size = ctypes.sizeof(SweepParams)
+        p.n_sweeps = int(n_sweeps)
+        p.rule = _lib.SG_RULE[rule]
+        p.replicas_per_block = int(replicas_per_block)
+        p.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        p.sweep_base = int(sweep_base)
+        p.track_best = 1 if track_best else 0
+        keep = []
+        if temps is not None:
+            t = self._dev(temps, torch.float64)
+            keep.append(t)
+            p.temps = t.data_ptr()
+            p.temps_sweep_stride = int(temps_sweep_stride)
+            p.temps_replica_stride = int(temps_replica_stride)
+        if sites is not None:
+            sd = self._dev(sites, torch.int32)
+            keep.append(sd)
+            p.sites = sd.data_ptr()
+            p.site_mode = _lib.SG_SITES["explicit"]
+            p.sites_block_stride = int(sites_block_stride)
+            p.sites_sweep_stride = int(self.n if sites_sweep_stride is None else sites_sweep_stride)
+        else:
+            p.site_mode = _lib.SG_SITES[site_order]
+        if uniforms is not None:
+            u = self._dev(uniforms, torch.float32)
+            assert u.numel() == self.n_replicas * n_sweeps * self.n
+            keep.append(u)
+            p.uniforms = u.data_ptr()
+            p.rng_mode = _lib.SG_RNG_INJECTED
+        else:
+            p.rng_mode = _lib.SG_RNG_PHILOX
+        trace = None
+        if energy_trace:
+            trace = torch.empty((n_sweeps, self.n_replicas), dtype=torch.float32,
+                                device=self.device)
+            p.energy_trace = trace.data_ptr()
+        check(self._lib.sg_sweep(self._h, ctypes.byref(p), self.stream), "sg_sweep")
+        self._keep += keep
+        if len(self._keep) > 256:
+            self.synchronize()
+        return trace
+
+    # ------------------------------------------------------------------ parallel tempering
+    def set_ladder(self, ladder_temps: Sequence[float]) -> None:
+        arr = (ctypes.c_double * len(ladder_temps))(*[float(t) for t in ladder_temps])
+        check(self._lib.sg_set_ladder(self._h, len(ladder_temps), arr, self.stream),
+              "sg_set_ladder")
+        self.n_rungs = len(ladder_temps)
+
+    def exchange(self, parity: int, *, seed: int = 0, round: int = 0,
+                 uniforms: Optional[ArrayLike] = None) -> None:
+        p = ExchangeParams()
+        p.struct_size = ctypes.sizeof(ExchangeParams)
+        p.parity = int(parity)
+        p.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        p.round = int(round)
+        if uniforms is not None:
+            u = self._dev(uniforms, torch.float64)
+            self._keep.append(u)
+            p.uniforms = u.data_ptr()
+            p.rng_mode = _lib.SG_RNG_INJECTED
+        else:
+            p.rng_mode = _lib.SG_RNG_PHILOX
+        check(self._lib.sg_exchange(self._h, ctypes.byref(p), self.stream), "sg_exchange")
+
+    def ladder_state(self):
+        """(replica_at_rung[R], replica_temps[R], attempts[L, K-1], accepts[L, K-1]) on device."""
+        R, K = self.n_replicas, self.n_rungs
+        L = R // K
+        rep_at = torch.empty(R, dtype=torch.int32, device=self.device)
+        temps = torch.empty(R, dtype=torch.float64, device=self.device)
+        att = torch.empty((L, max(K - 1, 1)), dtype=torch.int32, device=self.device)
+        acc = torch.empty((L, max(K - 1, 1)), dtype=torch.int32, device=self.device)
+        check(self._lib.sg_get_ladder_state(self._h, self._ptr(rep_at), self._ptr(temps),
+                                            self._ptr(att), self._ptr(acc), 1, self.stream),
+              "sg_get_ladder_state")
+        return rep_at, temps, att, acc
+
+    # ------------------------------------------------------------------ batched energies
+    def batch_energies(self, spins: ArrayLike, want_fields: bool = False):
+        """Energies (and local fields) of arbitrary configurations spins[B][n]."""
+        B = int(spins.shape[0])
+        s = self._dev(spins, torch.int8)
+        e = torch.empty(B, dtype=torch.float32, device=self.device)
+        f = torch.empty((B, self.n), dtype=torch.float32, device=self.device) if want_fields else None
+        check(self._lib.sg_batch_energies(self._h, B, self._ptr(s), self._ptr(e), self._ptr(f), 1,
+                                          self.stream), "sg_batch_energies")
+        return (e, f) if want_fields else e
+
+    # ------------------------------------------------------------------ facts
+    def query(self) -> dict:
+        v = [ctypes.c_int32() for _ in range(5)]
+        check(self._lib.sg_query(self._h, *[ctypes.byref(x) for x in v]), "sg_query")
+        return dict(n=v[0].value, n_pad=v[1].value, n_replicas=v[2].value,
+                    max_replicas_per_block=v[3].value, sm_count=v[4].value)
+
+    def launch_count(self) -> int:
+        return int(self._lib.sg_launch_count(self._h))
+
+    def measure_stream_bandwidth(self, nbytes: int, iters: int = 20, stagger: bool = False) -> float:
+        out = ctypes.c_double()
+        check(self._lib.sg_measure_stream_bandwidth(self._h, int(nbytes), int(iters),
+                                                    1 if stagger else 0, ctypes.byref(out)),
+              "sg_measure_stream_bandwidth")
+        return out.value
