@@ -161,7 +161,7 @@ void sg_destroy(sg_engine* e) {
 int sg_set_model_dense(sg_engine* e, int n, const float* J, int64_t ldJ, const float* h,
                        int on_device, void* stream) {
     SG_REQUIRE(e && J && h, "sg_set_model_dense: NULL argument");
-    SG_REQUIRE(n >= 1 && ldJ >= n, "sg_set_model_dense: need n >= 1 and ldJ >= n");
+    SG_REQUIRE(n >= 2 && ldJ >= n, "sg_set_model_dense: need n >= 2 and ldJ >= n");
     // padded row length: the smallest size the sweep kernel is instantiated for
     int n_pad = sg::kColQuantum;
     while (n_pad < n) n_pad *= 2;

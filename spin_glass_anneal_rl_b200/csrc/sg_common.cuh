@@ -78,6 +78,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// volatile 64-bit shared-memory accesses for the published-decision ring (polled flags)
+__device__ __forceinline__ unsigned long long ld_volatile_shared_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_shared_u64(unsigned long long* p,
+                                                       unsigned long long v) {
+    asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(smem_u32(p)), "l"(v) : "memory");
+}
+
 // named barriers: producer warps arrive, consumer warp syncs (PTX bar.arrive / bar.sync)
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

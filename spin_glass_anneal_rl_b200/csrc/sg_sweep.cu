@@ -8,27 +8,31 @@
 //   * A block owns G replicas and visits the sites of a sweep in ONE order shared
 //     by its replicas, so row Jt[site][:] is fetched once per attempt and serves
 //     all G replicas.  Rows are streamed L2/HBM -> shared memory by TMA bulk
-//     copies (cp.async.bulk + mbarrier) through a D-stage ring.
+//     copies (cp.async.bulk + mbarrier) through a D-stage ring; a stage is
+//     recycled through an "empty" mbarrier on which every warp arrives.
 //   * The 8 warps keep the local fields f[r][j] = h_j + sum_i J_ji s_ri of all
 //     G replicas RESIDENT IN REGISTERS: thread t owns columns {1024k + 4t + e}.
 //     An accepted flip of spin i in replica r is the rank-1 update
 //     f[r][:] += -2 s_ri * Jt[i][:]  (incremental field update, one FFMA per column).
-//   * The accept decision for the NEXT attempt is made while the current one is
-//     being applied: the warp that owns the next site's column transposes the G
-//     field values of that column through shared memory (lane = replica), adds the
-//     pending update of that single column itself (the same FFMA the owner thread
-//     executes a moment later, so the value is bit-identical), compares against the
-//     pre-computed Metropolis/Glauber threshold and publishes a (flip, sign) mask
-//     that every warp reads after the per-attempt barrier.
-//     (A dedicated 9th decision warp was tried first: 9 warps put 3 warps on one
-//     SM sub-partition and cap every thread at 168 registers, i.e. G = 8.)
+//   * No block-wide barrier inside a sweep.  The accept decisions form a chain
+//     through a ring of published (flip mask, sign mask, tag) words in shared
+//     memory: the warp that owns the column of attempt j+1 prepares everything that
+//     does not depend on attempt j (its G raw field values transposed lane=replica,
+//     the coupling J[site_j][site_j+1], spin bits, thresholds), polls the ring for
+//     decision j, adds the pending contribution of that one flip with the same FFMA
+//     it will execute in its own bulk update a moment later (bit-identical value),
+//     compares, and publishes decision j+1.  Every warp then applies decision j to
+//     its registers at its own pace; warps may drift apart by up to D attempts.
+//     (v1 used a __syncthreads per attempt and cost ~1500 clk/attempt; a dedicated
+//     9th decision warp caps every thread at 168 registers, i.e. G = 8.)
 //   * Thresholds: accept <=> dE < -T ln(u).  The u's come from Philox4x32-10 keyed
-//     on (replica, absolute sweep, attempt) and are produced 32 attempts ahead by
-//     the bulk warps, off the critical path.  In injected mode the caller supplies
-//     the uniforms and the reference's own comparison u < exp(-dE/T) is evaluated.
+//     on (replica, absolute sweep, attempt) and are produced one 32-attempt batch
+//     ahead, off the decision chain.  In injected mode the caller supplies the
+//     uniforms and the reference's own comparison u < exp(-dE/T) is evaluated.
 //   * Spins live as bit planes in shared memory (deciding lane r owns plane r).
-//   * After every sweep the energy of each replica is reduced from the resident
-//     fields, E = -1/2 sum_j s_j (f_j + h_j), and the best configuration is kept.
+//   * After every sweep (block barrier) the energy of each replica is reduced from
+//     the resident fields, E = -1/2 sum_j s_j (f_j + h_j), and the best
+//     configuration is kept.
 #include "sg_common.cuh"
 #include "sg_internal.h"
 
@@ -63,8 +67,11 @@ __device__ __forceinline__ void publish_column(const float (&f)[G][CPT], int c, 
 #undef SG_CASE
 }
 
+constexpr int kRing = 16;   // published-decision ring (must exceed kMaxStages + 1)
+constexpr int kThetaBufs = 3;
+
 struct SmemLayout {
-    size_t jring, sites, sbits, theta, red, xfer, acc, pub, flags, mbar, total;
+    size_t jring, sites, jvtab, sbits, theta, red, xfer, acc, pub, flags, mbar, total;
 };
 
 __host__ __device__ inline SmemLayout make_layout(int n_pad, int G, int D) {
@@ -72,18 +79,20 @@ __host__ __device__ inline SmemLayout make_layout(int n_pad, int G, int D) {
     size_t off = 0;
     L.jring = off; off += (size_t)D * n_pad * sizeof(float);
     L.sites = off; off += 2 * (size_t)n_pad * sizeof(uint16_t);
+    L.jvtab = off; off += (size_t)n_pad * sizeof(float);
     L.sbits = off; off += (size_t)G * (n_pad / 32) * sizeof(uint32_t);
-    L.theta = off; off += 2 * kSB * 32 * sizeof(float);
+    L.theta = off; off += (size_t)kThetaBufs * kSB * 32 * sizeof(float);
     L.red = off;   off += 8 * 32 * sizeof(float);
-    L.xfer = off;  off += 32 * sizeof(float);
+    L.xfer = off;  off += 8 * 32 * sizeof(float);
     L.acc = off;   off += 32 * sizeof(uint32_t);
-    L.pub = off;   off += 4 * sizeof(uint2);
+    L.pub = off;   off += kRing * (32 * sizeof(float) + sizeof(uint32_t));
     L.flags = off; off += 4 * sizeof(uint32_t);
     off = (off + 15) & ~(size_t)15;
-    L.mbar = off;  off += kMaxStages * sizeof(uint64_t);
+    L.mbar = off;  off += (2 * kMaxStages + kRing) * sizeof(uint64_t);
     L.total = off;
     return L;
 }
+
 
 template <int CPT, int G, bool INJECT>
 __global__ void __launch_bounds__(kSweepThreads, 1) sweep_kernel(const SweepDev a) {
@@ -99,11 +108,15 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_kernel(const SweepDev 
     uint32_t* sbits = reinterpret_cast<uint32_t*>(smem + L.sbits);
     float* theta = reinterpret_cast<float*>(smem + L.theta);
     float* red = reinterpret_cast<float*>(smem + L.red);
-    float* xfer = reinterpret_cast<float*>(smem + L.xfer);
+    float* xfer = reinterpret_cast<float*>(smem + L.xfer) + warp * 32;
     uint32_t* acc_s = reinterpret_cast<uint32_t*>(smem + L.acc);
-    uint2* pub = reinterpret_cast<uint2*>(smem + L.pub);
+    float* dpub = reinterpret_cast<float*>(smem + L.pub);  // [kRing][32] field deltas (-2 s) of a decision
+    uint32_t* ampub = reinterpret_cast<uint32_t*>(dpub + kRing * 32);  // [kRing] flip masks
+    float* jvtab = reinterpret_cast<float*>(smem + L.jvtab);
     uint32_t* flags = reinterpret_cast<uint32_t*>(smem + L.flags);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.mbar);
+    uint64_t* empty = full + kMaxStages;
+    uint64_t* pbar = empty + kMaxStages;  // one per slot of the decision ring
 
     const int rep0 = blockIdx.x * a.G;
     const int g_act = min(a.G, a.R - rep0);
@@ -114,7 +127,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_kernel(const SweepDev 
     const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
 
     // ------------------------------------------------------------ helpers
-    auto gen_sites = [&](int s) {  // site table of launch-local sweep s
+    auto gen_sites = [&](int s) {  // site table of launch-local sweep s (all threads)
         uint16_t* tab = sites_s + (size_t)(s & 1) * n_pad;
         if (a.site_mode == 0) {
             for (int i = tid; i < n; i += kSweepThreads) tab[i] = (uint16_t)i;
@@ -134,9 +147,10 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_kernel(const SweepDev 
         }
     };
 
-    auto gen_theta = [&](int s, int bi) {  // thresholds of batch bi of sweep s
+    // thresholds of batch bi of sweep s: warp q produces attempts 4q..4q+3 for lane = replica
+    auto gen_theta = [&](int s, int bi) {
         if (INJECT || s >= n_sweeps) return;
-        const int r = tid & 31, q = tid >> 5;
+        const int r = lane, q = warp;
         const int i0 = bi * kSB + q * 4;
         if (r >= g_act || i0 >= n) return;
         const int rep = rep0 + r;
@@ -145,7 +159,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_kernel(const SweepDev 
         const uint4 x = philox4x32_10(
             make_uint4((uint32_t)rep, (uint32_t)sa, (uint32_t)(sa >> 32), (uint32_t)(i0 >> 2)), key);
         const uint32_t v[4] = {x.x, x.y, x.z, x.w};
-        float* dst = theta + (size_t)((s * nb + bi) & 1) * (kSB * 32) + (q * 4) * 32 + r;
+        float* dst = theta + (size_t)((s * nb + bi) % kThetaBufs) * (kSB * 32) + (q * 4) * 32 + r;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const float u = u01(v[e]);
@@ -161,7 +175,11 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_kernel(const SweepDev 
 
     // ------------------------------------------------------------ prologue
     if (tid == 0) {
-        for (int d = 0; d < D; ++d) mbar_init(&full[d], 1);
+        for (int d = 0; d < D; ++d) {
+            mbar_init(&full[d], 1);
+            mbar_init(&empty[d], kSweepThreads / 32);
+        }
+        for (int d = 0; d < kRing; ++d) mbar_init(&pbar[d], 1);
         fence_mbar_init();
         fence_proxy_async();
     }
@@ -216,120 +234,191 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_kernel(const SweepDev 
     }
     __syncthreads();
 
-    // prefetch cursor (only thread 0 issues TMA)
-    int pf_s = 0, pf_i = 0;
-    auto issue_row = [&](int stage) {
-        const int site = sites_s[(size_t)(pf_s & 1) * n_pad + pf_i];
+    // row of launch-local attempt (ps, pi) -> stage
+    auto issue_row = [&](int stage, int ps, int pi) {
+        const int site = sites_s[(size_t)(ps & 1) * n_pad + pi];
         mbar_arrive_expect_tx(&full[stage], row_bytes);
         bulk_g2s(Jring + (size_t)stage * n_pad, a.Jt + (size_t)site * n_pad, row_bytes,
                  &full[stage]);
-        if (++pf_i == n) { pf_i = 0; ++pf_s; }
     };
     if (tid == 0) {
-        for (int d = 0; d < D && d < total; ++d) issue_row(d);
+        int ps = 0, pi = 0;
+        for (int d = 0; d < D && d < total; ++d) {
+            issue_row(d, ps, pi);
+            if (++pi == n) { pi = 0; ++ps; }
+        }
     }
 
-    // Decision for attempt (s, i) at `site`, executed by the warp that owns the site's
-    // column.  (P, Jv) is the flip that is still being applied: its contribution to this one
-    // column is added here with the same FFMA the owner thread executes in the bulk update.
-    auto decide = [&](int s, int i, int site, uint2 P, float Jv, int slot) {
+    // ---- decision state of this warp (valid between prepare and finish)
+    float dv = 0.0f, dJv = 0.0f, dth = 0.0f, du = 0.0f;
+    double dT = 1.0;
+    uint32_t dw = 0;
+    uint32_t* dwp = nullptr;
+    int dsite = 0;
+    bool dup = false;
+
+    // everything about attempt (s, i) at `site` that does not depend on the previous decision
+    auto prepare = [&](int s, int i, int site) {
         const int ot = (site >> 2) & (kSweepThreads - 1);
-        if ((ot >> 5) != warp) return;
         if ((ot & 31) == lane) publish_column<CPT, G>(f, ((site >> 10) << 2) | (site & 3), xfer);
         __syncwarp();
-        const float v = xfer[lane];
-        bool flip = false, s_up = false;
+        dsite = site;
+        dJv = (i > 0) ? jvtab[i] : 0.0f;  // J[site_i][site_{i-1}]: what the pending flip adds
         if (lane < g_act) {
-            const float d = ((P.x >> lane) & 1u) ? (((P.y >> lane) & 1u) ? -2.0f : 2.0f) : 0.0f;
-            const float v2 = fmaf(d, Jv, v);  // local field of `site` after the pending flip
-            uint32_t* wp = &sbits[lane * W + (site >> 5)];
-            const uint32_t w = *wp;
-            s_up = (w >> (site & 31)) & 1u;
+            dv = xfer[lane];
+            dwp = &sbits[lane * W + (site >> 5)];
             if (!INJECT) {
-                const float th =
-                    theta[(size_t)((s * nb + (i >> 5)) & 1) * (kSB * 32) + (i & 31) * 32 + lane];
+                dth = theta[(size_t)((s * nb + (i >> 5)) % kThetaBufs) * (kSB * 32) +
+                            (i & 31) * 32 + lane];
+            } else {
+                du = a.uniforms[((size_t)(rep0 + lane) * n_sweeps + s) * n + i];
+                dT = a.temps[(long long)s * a.t_ss + (long long)(rep0 + lane) * a.t_rs];
+            }
+        }
+        __syncwarp();  // xfer may be rewritten by this warp's next prepare
+    };
+
+    // finish the prepared decision given the pending delta of the previous attempt (d_prev =
+    // -2 s_old if that attempt flipped this lane's replica, else 0) and publish it as attempt g1
+    auto finish = [&](float d_prev, long long g1) {
+        bool flip = false;
+        dup = false;
+        if (lane < g_act) {
+            const float v2 = fmaf(d_prev, dJv, dv);  // local field of the site after the pending flip
+            dw = *dwp;                               // spin bits (the previous decider may have flipped)
+            dup = (dw >> (dsite & 31)) & 1u;
+            if (!INJECT) {
                 if (a.rule == 0) {
-                    const float x = s_up ? 2.0f * v2 : -2.0f * v2;  // dE = 2 s f
-                    flip = x < th;
+                    const float x = dup ? 2.0f * v2 : -2.0f * v2;  // dE = 2 s f
+                    flip = x < dth;
                 } else {
-                    flip = ((v2 > th) != s_up);
+                    flip = ((v2 > dth) != dup);
                 }
             } else {
-                const float u = a.uniforms[((size_t)(rep0 + lane) * n_sweeps + s) * n + i];
-                const double T_d = a.temps[(long long)s * a.t_ss + (long long)(rep0 + lane) * a.t_rs];
                 if (a.rule == 0) {
-                    const float x = s_up ? 2.0f * v2 : -2.0f * v2;
+                    const float x = dup ? 2.0f * v2 : -2.0f * v2;
                     // reference: dE <= 0 accepts without a draw; else u < exp(float(-dE/T))
-                    flip = (x <= 0.0f) || (u < expf((float)(-(double)x / T_d)));
+                    flip = (x <= 0.0f) || (du < expf((float)(-(double)x / dT)));
                 } else {
-                    const float arg = (a.rule == 1) ? (float)(-2.0 * (double)v2 / T_d)
-                                                    : (float)(-2.0 * (1.0 / T_d) * (double)v2);
+                    const float arg = (a.rule == 1) ? (float)(-2.0 * (double)v2 / dT)
+                                                    : (float)(-2.0 * (1.0 / dT) * (double)v2);
                     const float p_up = 1.0f / (1.0f + expf(arg));
-                    flip = ((u < p_up) != s_up);
+                    flip = ((du < p_up) != dup);
                 }
             }
             if (flip) {
-                *wp = w ^ (1u << (site & 31));
+                *dwp = dw ^ (1u << (dsite & 31));
                 acc_s[lane] += 1u;
             }
         }
+        const int slot1 = (int)(g1 & (kRing - 1));
+        dpub[slot1 * 32 + lane] = flip ? (dup ? -2.0f : 2.0f) : 0.0f;
         const uint32_t am = __ballot_sync(0xFFFFFFFFu, flip);
-        const uint32_t sm = __ballot_sync(0xFFFFFFFFu, s_up);
-        if (lane == 0) pub[slot] = make_uint2(am, sm);
-        __syncwarp();  // xfer is reused by the next decision of this warp
+        __syncwarp();  // every lane's bit-plane / counter / delta store precedes the release below
+        if (lane == 0) {
+            ampub[slot1] = am;
+            mbar_arrive(&pbar[slot1]);  // release: wakes the warps waiting for attempt g1
+        }
     };
 
     // ------------------------------------------------------------ sweeps
     long long g = 0;  // launch-local attempt counter
     int stage = 0;
     uint32_t parity = 0;
+#pragma unroll 1
     for (int s = 0; s < n_sweeps; ++s) {
         const uint16_t* tab = sites_s + (size_t)(s & 1) * n_pad;
         if (s >= 1 && s + 1 < n_sweeps) gen_sites(s + 1);
-
-        // first attempt of the sweep: nothing pending
-        decide(s, 0, tab[0], make_uint2(0u, 0u), 0.0f, (int)(g & 3));
+        // couplings between consecutive sites of this sweep (what a pending flip adds to the
+        // next site's field): gathered once per sweep so the decision chain never waits on TMA
+        for (int i = tid + 1; i < n; i += kSweepThreads)
+            jvtab[i] = a.Jt[(size_t)tab[i - 1] * n_pad + tab[i]];
         __syncthreads();
 
-        for (int i = 0; i < n; ++i) {
-            const uint2 P = pub[g & 3];
-            mbar_wait(&full[stage], parity);
-            const float* Jrow = Jring + (size_t)stage * n_pad;
+        // first attempt of the sweep: nothing pending.  A decision is only published once the
+        // row of its site has landed, so the other warps never wait on the TMA barrier.
+        {
+            const int site0 = tab[0];
+            if ((((site0 >> 2) & (kSweepThreads - 1)) >> 5) == warp) {
+                mbar_wait(&full[stage], parity);
+                prepare(s, 0, site0);
+                finish(0.0f, g);
+            }
+        }
 
+#pragma unroll 1
+        for (int i = 0; i < n; ++i) {
+            const int slot = (int)(g & (kRing - 1));
+            bool own = false;
             if (i + 1 < n) {
                 const int sn = tab[i + 1];
-                decide(s, i + 1, sn, P, Jrow[sn], (int)((g + 1) & 3));
+                own = ((((sn >> 2) & (kSweepThreads - 1)) >> 5) == warp);
+                if (own) {
+                    const int nst = (stage + 1 == D) ? 0 : stage + 1;
+                    mbar_wait(&full[nst], (nst == 0) ? (parity ^ 1u) : parity);  // row of g+1 landed
+                    prepare(s, i + 1, sn);
+                }
             }
+            // decision of attempt g (hardware-suspended wait on the slot's mbarrier)
+            mbar_wait(&pbar[slot], (uint32_t)(g >> 4) & 1u);
+            const uint32_t am = ampub[slot];
+            if (own) finish(dpub[slot * 32 + lane], g + 1);
+
             if ((i & (kSB - 1)) == 0) {  // thresholds for the batch after this one
                 if (i + kSB < n) gen_theta(s, (i >> 5) + 1);
                 else gen_theta(s + 1, 0);
             }
-            if (P.x != 0u) {
-                const float4* Jr4 = reinterpret_cast<const float4*>(Jrow);
+            if (am != 0u) {
+                const float4* Jr4 = reinterpret_cast<const float4*>(Jring + (size_t)stage * n_pad);
+                const float4* d4 = reinterpret_cast<const float4*>(dpub + slot * 32);
                 float4 jv[KCH];
 #pragma unroll
                 for (int k = 0; k < KCH; ++k) jv[k] = Jr4[k * kSweepThreads + tid];
+                // groups of 4 replicas: one uniform branch per group, FMAs with delta 0 for the
+                // replicas of the group that did not flip (no per-replica branches)
 #pragma unroll
-                for (int r = 0; r < G; ++r) {
-                    if (P.x & (1u << r)) {
-                        const float d = (P.y & (1u << r)) ? -2.0f : 2.0f;
+                for (int q = 0; q < (G + 3) / 4; ++q) {
+                    if ((am >> (4 * q)) & 0xFu) {
+                        const float4 dq = d4[q];
+                        const float dd[4] = {dq.x, dq.y, dq.z, dq.w};
 #pragma unroll
-                        for (int k = 0; k < KCH; ++k) {
-                            f[r][4 * k + 0] = fmaf(d, jv[k].x, f[r][4 * k + 0]);
-                            f[r][4 * k + 1] = fmaf(d, jv[k].y, f[r][4 * k + 1]);
-                            f[r][4 * k + 2] = fmaf(d, jv[k].z, f[r][4 * k + 2]);
-                            f[r][4 * k + 3] = fmaf(d, jv[k].w, f[r][4 * k + 3]);
+                        for (int rr = 0; rr < 4; ++rr) {
+                            const int r = 4 * q + rr;
+                            if (r < G) {
+#pragma unroll
+                                for (int k = 0; k < KCH; ++k) {
+                                    f[r][4 * k + 0] = fmaf(dd[rr], jv[k].x, f[r][4 * k + 0]);
+                                    f[r][4 * k + 1] = fmaf(dd[rr], jv[k].y, f[r][4 * k + 1]);
+                                    f[r][4 * k + 2] = fmaf(dd[rr], jv[k].z, f[r][4 * k + 2]);
+                                    f[r][4 * k + 3] = fmaf(dd[rr], jv[k].w, f[r][4 * k + 3]);
+                                }
+                            }
                         }
                     }
                 }
             }
-            __syncthreads();
-            if (tid == 0 && g + D < total) issue_row(stage);
+            // release the stage.  Warp ((g-1) mod 8) re-arms the stage of the PREVIOUS attempt
+            // with the row of attempt g-1+D: one attempt late, so that it rarely has to wait
+            // for the slowest warp (rows are therefore D-1 attempts ahead).
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&empty[stage]);
+                if (g >= 1 && (int)((g - 1) & 7) == warp && g - 1 + D < total) {
+                    const int pst = (stage == 0) ? D - 1 : stage - 1;
+                    const uint32_t ppar = (stage == 0) ? (parity ^ 1u) : parity;
+                    mbar_wait(&empty[pst], ppar);  // all 8 warps are done with attempt g-1
+                    mbar_wait(&full[pst], ppar);   // and its row landed (phase order of `full`)
+                    int pi = i - 1 + D, ps = s;
+                    if (pi >= n) { pi -= n; ++ps; }
+                    issue_row(pst, ps, pi);
+                }
+            }
             ++g;
             if (++stage == D) { stage = 0; parity ^= 1u; }
         }
 
         // ---- end of sweep: energies from the resident fields, best tracking
+        __syncthreads();
         {
             const float4* h4 = reinterpret_cast<const float4*>(a.h);
             float hv[CPT];
@@ -465,6 +554,7 @@ cudaError_t launch_sweep(SweepDev a, bool inject, int grid, cudaStream_t st) {
     int D = kMaxStages;
     while (D > 1 && make_layout(a.n_pad, gt, D).total > 227 * 1024) --D;
     if (D > a.n) D = a.n;
+    if (D < 2) return cudaErrorInvalidValue;  // the ring needs two stages (n >= 2)
     a.D = D;
     switch (a.n_pad / kSweepThreads) {
         case 4: return launch_t<4, kG4>(a, inject, grid, st);
