@@ -54,6 +54,7 @@ typedef enum {
 #define SG_SITES_SEQUENTIAL 0 /* 0,1,...,n-1 every sweep                                   */
 #define SG_SITES_RANDOM 1     /* Philox draw % n, with replacement (core/spin_dynamics.py:69) */
 #define SG_SITES_EXPLICIT 2   /* caller-supplied list (replay of a recorded stream)         */
+#define SG_SITES_RANDOM_PER_BLOCK 3 /* like RANDOM, but an independent stream per thread block */
 
 typedef struct sg_engine sg_engine;
 
@@ -171,6 +172,12 @@ int sg_batch_energies(sg_engine *e, int batch, const int8_t *spins, float *energ
  * the roofline denominator bench.py normalises the sweep kernel against. */
 int sg_measure_stream_bandwidth(sg_engine *e, int64_t bytes, int iters, int stagger,
                                 double *gbps_out);
+
+/* The same measurement for the sweep kernel's actual transport: every block (one per SM)
+ * pulls n_rows rows of row_bytes through a depth-stage shared-memory ring with TMA bulk
+ * copies (cp.async.bulk + mbarrier), no compute.  GB/s aggregated over all SMs. */
+int sg_measure_tma_stream(sg_engine *e, int64_t bytes, int row_bytes, int depth, int n_rows,
+                          int stagger, double *gbps_out);
 
 /* Layout facts the host side needs (padded row length, resident replicas per block...). */
 int sg_query(sg_engine *e, int32_t *n, int32_t *n_pad, int32_t *n_replicas,

@@ -18,7 +18,7 @@ CSRC = os.path.join(_PKG, "csrc")
 
 SG_RULE = {"metropolis": 0, "glauber": 1, "heat_bath": 2}
 SG_RNG_PHILOX, SG_RNG_INJECTED = 0, 1
-SG_SITES = {"sequential": 0, "random": 1, "explicit": 2}
+SG_SITES = {"sequential": 0, "random": 1, "explicit": 2, "random_per_block": 3}
 
 
 class SweepParams(Structure):
@@ -63,6 +63,8 @@ PROTOTYPES = {
                                     c_void_p]),
     "sg_batch_energies": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "sg_measure_stream_bandwidth": (c_int, [c_void_p, c_int64, c_int, c_int, POINTER(c_double)]),
+    "sg_measure_tma_stream": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int,
+                                      POINTER(c_double)]),
     "sg_query": (c_int, [c_void_p, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32),
                          POINTER(c_int32), POINTER(c_int32)]),
     "sg_launch_count": (c_uint64, [c_void_p]),

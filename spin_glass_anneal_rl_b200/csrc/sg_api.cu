@@ -164,9 +164,9 @@ int sg_set_model_dense(sg_engine* e, int n, const float* J, int64_t ldJ, const f
     SG_REQUIRE(n >= 2 && ldJ >= n, "sg_set_model_dense: need n >= 2 and ldJ >= n");
     // padded row length: the smallest size the sweep kernel is instantiated for
     int n_pad = sg::kColQuantum;
-    while (n_pad < n) n_pad *= 2;
+    while (n_pad < n) n_pad += sg::kColQuantum;
     if (sg::sweep_max_replicas_per_block(n_pad) == 0)
-        return fail(SG_ERR_UNSUPPORTED, "sg_set_model_dense: dense models support n <= 8192");
+        return fail(SG_ERR_UNSUPPORTED, "sg_set_model_dense: dense models support n <= 7168");
     DeviceGuard g(e->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (n != e->n) {
@@ -351,11 +351,13 @@ int sg_sweep(sg_engine* e, const sg_sweep_params* p, void* stream) {
     SG_REQUIRE(p->rule >= 0 && p->rule <= 2, "sg_sweep: unknown rule");
     SG_REQUIRE(p->rng_mode == SG_RNG_PHILOX || p->rng_mode == SG_RNG_INJECTED,
                "sg_sweep: unknown rng_mode");
-    SG_REQUIRE(p->site_mode >= 0 && p->site_mode <= 2, "sg_sweep: unknown site_mode");
+    SG_REQUIRE(p->site_mode >= 0 && p->site_mode <= 3, "sg_sweep: unknown site_mode");
     SG_REQUIRE(p->site_mode != SG_SITES_EXPLICIT || p->sites, "sg_sweep: explicit sites missing");
     SG_REQUIRE(p->rng_mode != SG_RNG_INJECTED || p->uniforms, "sg_sweep: injected uniforms missing");
     SG_REQUIRE(p->temps || e->rep_temp, "sg_sweep: no temperatures (pass temps or set a ladder)");
     if (p->n_sweeps == 0) return SG_OK;
+    SG_REQUIRE((long long)p->n_sweeps * e->n < (1LL << 31) - 64,
+               "sg_sweep: n_sweeps * n must stay below 2^31 per launch (cut the run into launches)");
     DeviceGuard g(e->device);
     const int gmax = sg::sweep_max_replicas_per_block(e->n_pad);
     int G = p->replicas_per_block;
@@ -576,6 +578,46 @@ int sg_measure_stream_bandwidth(sg_engine* e, int64_t bytes, int iters, int stag
     cudaFree(sink);
     if (ce != cudaSuccess) return fail(SG_ERR_CUDA, "sg_measure_stream_bandwidth", ce);
     *gbps_out = (double)n_vec * 16.0 * (double)iters * (double)grid / ((double)ms * 1.0e6);
+    return SG_OK;
+}
+
+int sg_measure_tma_stream(sg_engine* e, int64_t bytes, int row_bytes, int depth, int n_rows,
+                          int stagger, double* gbps_out) {
+    SG_REQUIRE(e && gbps_out, "sg_measure_tma_stream: NULL argument");
+    SG_REQUIRE(row_bytes >= 512 && row_bytes % 16 == 0 && depth >= 1 && n_rows >= 1 &&
+                   (size_t)depth * row_bytes + 128 <= 227 * 1024 && bytes >= row_bytes,
+               "sg_measure_tma_stream: bad shape");
+    DeviceGuard g(e->device);
+    const int64_t buf_rows = bytes / row_bytes;
+    float* buf = nullptr;
+    float* sink = nullptr;
+    int rc;
+    if ((rc = dev_alloc(&buf, (size_t)(buf_rows * row_bytes / 4))) != SG_OK) return rc;
+    if ((rc = dev_alloc(&sink, 1)) != SG_OK) {
+        cudaFree(buf);
+        return rc;
+    }
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0);
+    cudaEventCreate(&t1);
+    cudaError_t ce = cudaMemset(buf, 0, (size_t)buf_rows * row_bytes);
+    const int grid = e->sm_count;
+    if (ce == cudaSuccess)
+        ce = sg::launch_tma_probe(buf, buf_rows, row_bytes, n_rows, depth, stagger, sink, grid, 0);
+    if (ce == cudaSuccess) ce = cudaEventRecord(t0, 0);
+    if (ce == cudaSuccess)
+        ce = sg::launch_tma_probe(buf, buf_rows, row_bytes, n_rows, depth, stagger, sink, grid, 0);
+    if (ce == cudaSuccess) ce = cudaEventRecord(t1, 0);
+    if (ce == cudaSuccess) ce = cudaEventSynchronize(t1);
+    float ms = 0.0f;
+    if (ce == cudaSuccess) ce = cudaEventElapsedTime(&ms, t0, t1);
+    e->launches += 2;
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    cudaFree(buf);
+    cudaFree(sink);
+    if (ce != cudaSuccess) return fail(SG_ERR_CUDA, "sg_measure_tma_stream", ce);
+    *gbps_out = (double)row_bytes * n_rows * grid / ((double)ms * 1.0e6);
     return SG_OK;
 }
 

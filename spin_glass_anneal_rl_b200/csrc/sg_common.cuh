@@ -82,6 +82,31 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// shared-memory fetch-add with acquire-release semantics at block scope
+__device__ __forceinline__ uint32_t atom_add_acq_rel_shared(uint32_t* p, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;"
+                 : "=r"(old)
+                 : "r"(smem_u32(p)), "r"(v)
+                 : "memory");
+    return old;
+}
+
+// non-blocking probe (never suspends the thread)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
 // volatile 64-bit shared-memory accesses for the published-decision ring (polled flags)
 __device__ __forceinline__ unsigned long long ld_volatile_shared_u64(const unsigned long long* p) {
     unsigned long long v;

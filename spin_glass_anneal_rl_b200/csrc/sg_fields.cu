@@ -168,7 +168,58 @@ stream_probe_kernel(const float4* __restrict__ buf, int64_t n_vec, int iters, in
     if (acc == 123.456f) sink[0] = acc;  // keep the loads alive
 }
 
+// TMA bulk-copy stream probe: every block pulls `n_rows` rows of `row_bytes` through a
+// `depth`-stage shared-memory ring with cp.async.bulk (no compute), rows taken in the same
+// order by all blocks (stagger=0) or from a per-block offset (stagger=1).
+__global__ void __launch_bounds__(128)
+tma_probe_kernel(const float* __restrict__ buf, int64_t buf_rows, uint32_t row_bytes, int n_rows,
+                 int depth, int stagger, float* __restrict__ sink) {
+    extern __shared__ __align__(128) unsigned char psm[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(psm);
+    float* ring = reinterpret_cast<float*>(psm + 128);
+    const int tid = threadIdx.x;
+    const size_t row_f = row_bytes / 4;
+    const int64_t off = stagger ? ((int64_t)blockIdx.x * 977) % buf_rows : 0;
+    if (tid == 0) {
+        for (int d = 0; d < depth; ++d) mbar_init(&bars[d], 1);
+        fence_mbar_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int d = 0; d < depth && d < n_rows; ++d) {
+            mbar_arrive_expect_tx(&bars[d], row_bytes);
+            bulk_g2s(ring + d * row_f, buf + ((off + d) % buf_rows) * row_f, row_bytes, &bars[d]);
+        }
+    }
+    float acc = 0.0f;
+    int stage = 0;
+    uint32_t parity = 0;
+    for (int r = 0; r < n_rows; ++r) {
+        mbar_wait(&bars[stage], parity);
+        acc += ring[stage * row_f + tid];
+        __syncthreads();
+        if (tid == 0 && r + depth < n_rows) {
+            mbar_arrive_expect_tx(&bars[stage], row_bytes);
+            bulk_g2s(ring + stage * row_f, buf + ((off + r + depth) % buf_rows) * row_f, row_bytes,
+                     &bars[stage]);
+        }
+        if (++stage == depth) { stage = 0; parity ^= 1u; }
+    }
+    if (acc == 123.456f) sink[0] = acc;
+}
+
 }  // namespace
+
+cudaError_t launch_tma_probe(const float* buf, int64_t buf_rows, uint32_t row_bytes, int n_rows,
+                             int depth, int stagger, float* sink, int grid, cudaStream_t st) {
+    const size_t smem = 128 + (size_t)depth * row_bytes;
+    cudaError_t e = cudaFuncSetAttribute(tma_probe_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    tma_probe_kernel<<<grid, 128, smem, st>>>(buf, buf_rows, row_bytes, n_rows, depth, stagger, sink);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_pad_transpose(const float* J, int64_t ldJ, int n, float* Jt, int n_pad,
                                  cudaStream_t st) {

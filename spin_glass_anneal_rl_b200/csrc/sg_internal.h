@@ -6,7 +6,8 @@
 namespace sg {
 
 constexpr int kSweepThreads = 256;              // 8 warps: 2 per SM sub-partition, 255 regs each
-constexpr int kColQuantum = 4 * kSweepThreads;  // n_pad is a multiple of this (1024)
+constexpr int kBulkThreads = 224;               // 7 warps own local-field columns, 1 warp decides
+constexpr int kColQuantum = 4 * kBulkThreads;   // n_pad is a multiple of this (896)
 
 // Kernel argument block of the sweep kernel (passed by value).
 struct SweepDev {
@@ -52,6 +53,9 @@ cudaError_t launch_unpad_f32(const float* src, int n_pad, float* dst, int n, int
                              cudaStream_t st);
 cudaError_t launch_stream_probe(const float4* buf, int64_t n_vec, int iters, int stagger,
                                 float* sink, int grid, cudaStream_t st);
+
+cudaError_t launch_tma_probe(const float* buf, int64_t buf_rows, uint32_t row_bytes, int n_rows,
+                             int depth, int stagger, float* sink, int grid, cudaStream_t st);
 
 // K3 (sg_exchange.cu)
 struct ExchangeDev {

@@ -270,3 +270,11 @@ class Engine:
                                                     1 if stagger else 0, ctypes.byref(out)),
               "sg_measure_stream_bandwidth")
         return out.value
+
+    def measure_tma_stream(self, nbytes: int, row_bytes: int, depth: int = 8, n_rows: int = 4096,
+                           stagger: bool = False) -> float:
+        out = ctypes.c_double()
+        check(self._lib.sg_measure_tma_stream(self._h, int(nbytes), int(row_bytes), int(depth),
+                                              int(n_rows), 1 if stagger else 0, ctypes.byref(out)),
+              "sg_measure_tma_stream")
+        return out.value

@@ -36,15 +36,14 @@ def run(n, R, sweeps, T, G=0, order="random", reps=3):
 
 if __name__ == "__main__":
     eng = Engine(0)
-    for mb in (16, 64, 256):
-        for st in (False, True):
-            print(f"stream probe {mb} MB stagger={st}: {eng.measure_stream_bandwidth(mb << 20, 10, st):.0f} GB/s")
-    run(4096, 148 * 12, 5, 1.0)
-    run(4096, 148 * 12, 5, 0.3)
-    run(4096, 148 * 12, 5, 3.0)
-    run(4096, 148 * 12, 5, 1.0, order="sequential")
-    run(4096, 148 * 6, 5, 1.0, G=6)
+    for rb in (3584, 7168, 17920):
+        for depth in (2, 4, 8, 12):
+            if depth * rb > 200 * 1024: continue
+            a_ = eng.measure_tma_stream(73 << 20, rb, depth, 4096, False)
+            b_ = eng.measure_tma_stream(73 << 20, rb, depth, 4096, True)
+            clk = rb * 148 / (a_ * 1e9) * 1.96e9
+            print(f"tma probe row={rb}B depth={depth}: same-order {a_:.0f} GB/s ({clk:.0f} clk/row/SM), staggered {b_:.0f} GB/s")
+    run(4096, 148 * 10, 5, 1.0)
+    run(4096, 148 * 10, 5, 0.3)
     run(4096, 148 * 1, 5, 1.0, G=1)
     run(4096, 8192, 5, 1.0)
-    run(1024, 148 * 32, 10, 1.0)
-    run(2048, 148 * 24, 10, 1.0)
