@@ -1,0 +1,62 @@
+"""Glue between the host-side model container and the GPU engine.
+
+An ``Engine`` (C-ABI handle: J^T and h resident in HBM) is cached on the model object
+and re-uploaded only when the coupling / field tensors change identity or version --
+the RL environment calls anneal() many times on the same J
+(reference rl_integration/environment.py:318-336).  There is no CPU path: without a
+CUDA device (or without libsg_b200.so) this raises DeviceError.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ..engine import Engine
+from ..utils.exceptions import DeviceError
+
+RULE_NAMES = {"metropolis": "metropolis", "glauber": "glauber", "heat_bath": "heat_bath"}
+
+
+def rule_name(update_rule) -> str:
+    name = getattr(update_rule, "value", update_rule)
+    if name not in RULE_NAMES:
+        raise NotImplementedError(
+            f"update rule {name!r} is not available on the B200 sweep path "
+            "(Metropolis, Glauber and heat bath are; Wolff cluster updates are out of scope)")
+    return name
+
+
+def _signature(model):
+    J, h = model.couplings, model.external_fields
+    return (id(J), J._version, tuple(J.shape), bool(J.is_sparse), id(h), h._version)
+
+
+def engine_for(model, device_index: int = 0) -> Engine:
+    """The engine holding this model's couplings (built / refreshed on demand)."""
+    if not hasattr(model, "couplings") or not hasattr(model, "spins"):
+        raise AttributeError("anneal() needs an IsingModel (couplings / external_fields / spins)")
+    try:
+        cached = getattr(model, "_sg_engine", None)
+        sig = _signature(model)
+        if cached is not None and cached[0] == sig and cached[1].device_index == device_index:
+            return cached[1]
+        eng = cached[1] if cached is not None and cached[1].device_index == device_index \
+            else Engine(device_index)
+        J = model.couplings
+        dense = (J.to_dense() if J.is_sparse else J).to(torch.float32)
+        eng.set_model(dense, model.external_fields.to(torch.float32))
+        model._sg_engine = (sig, eng)
+        return eng
+    except (RuntimeError, OSError) as exc:  # missing library, no GPU, CUDA failure
+        if isinstance(exc, DeviceError):
+            raise
+        raise DeviceError(f"B200 annealing engine unavailable: {exc}") from exc
+
+
+def random_spins(n_replicas: int, n: int, device, generator: torch.Generator) -> torch.Tensor:
+    return (torch.randint(0, 2, (n_replicas, n), device=device, generator=generator,
+                          dtype=torch.int8) * 2 - 1).to(torch.int8)
+
+
+def as_pm1_float(spins_i8: torch.Tensor) -> torch.Tensor:
+    return spins_i8.to(torch.float32).cpu()

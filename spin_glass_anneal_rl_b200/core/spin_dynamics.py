@@ -1,0 +1,107 @@
+"""UpdateRule and a SpinDynamics facade over the GPU sweep.
+
+``UpdateRule`` matches the reference enum (reference core/spin_dynamics.py:11-16).
+``SpinDynamics`` keeps the reference's single-model interface (``sweep``,
+``set_temperature``, ``get_acceptance_rate``, ``n_accepted/n_rejected``,
+``energy_history``, ``run_dynamics``; :19-152, :325-359) but every sweep is one launch of
+the CUDA sweep kernel on one replica; the per-attempt Python loop of the reference
+(:73-94) does not exist here.  WOLFF is declared for API compatibility and rejected.
+"""
+from __future__ import annotations
+
+from enum import Enum
+from typing import Optional
+
+import numpy as np
+import torch
+
+
+class UpdateRule(Enum):
+    METROPOLIS = "metropolis"
+    GLAUBER = "glauber"
+    HEAT_BATH = "heat_bath"
+    WOLFF = "wolff"
+
+
+class SpinDynamics:
+    def __init__(self, model, temperature: float = 1.0,
+                 update_rule: UpdateRule = UpdateRule.METROPOLIS, random_seed: Optional[int] = None):
+        self.model = model
+        self.temperature = temperature
+        self.update_rule = update_rule
+        if random_seed is not None:
+            torch.manual_seed(random_seed)
+            np.random.seed(random_seed)
+        self._seed = int(random_seed) if random_seed is not None else int(torch.initial_seed() & 0x7FFFFFFF)
+        self._sweeps_done = 0
+        self.n_accepted = 0
+        self.n_rejected = 0
+        self.energy_history = []
+        self.magnetization_history = []
+
+    def set_temperature(self, temperature: float) -> None:
+        self.temperature = max(temperature, 1e-10)
+
+    def sweep(self, n_sweeps: int = 1) -> float:
+        """``n_sweeps`` Monte Carlo sweeps (n attempts each) on the GPU; returns the energy."""
+        from ..annealing._backend import engine_for, rule_name
+        eng = engine_for(self.model)
+        n = self.model.n_spins
+        eng.alloc_replicas(1) if eng.n_replicas != 1 else None
+        eng.set_spins(self.model.spins.reshape(1, n))
+        eng.init_fields()
+        acc0 = int(eng.accepted().item())
+        trace = eng.sweep(n_sweeps, np.array([max(self.temperature, 1e-10)]),
+                          rule=rule_name(self.update_rule), site_order="random", seed=self._seed,
+                          sweep_base=self._sweeps_done, energy_trace=True, track_best=False)
+        self._sweeps_done += n_sweeps
+        spins = eng.spins()[0].to(torch.float32).cpu()
+        acc = int(eng.accepted().item()) - acc0
+        self.model.spins = spins.to(self.model.device)
+        self.model._invalidate_cache()
+        self.n_accepted += acc
+        self.n_rejected += n_sweeps * n - acc
+        energies = trace[:, 0].cpu().tolist()
+        self.energy_history.extend(energies)
+        self.magnetization_history.append(float(spins.sum().item()))
+        return float(energies[-1])
+
+    def run_dynamics(self, n_sweeps: int, record_interval: int = 1) -> dict:
+        initial = self.model.compute_energy()
+        self.sweep(n_sweeps)
+        return {"initial_energy": initial, "final_energy": self.model.compute_energy(),
+                "energy_history": self.energy_history.copy(),
+                "acceptance_rate": self.get_acceptance_rate(), "n_sweeps": n_sweeps,
+                "temperature": self.temperature}
+
+    def get_acceptance_rate(self) -> float:
+        total = self.n_accepted + self.n_rejected
+        return self.n_accepted / total if total else 0.0
+
+    @property
+    def accepted_flips(self) -> int:
+        return self.n_accepted
+
+    @accepted_flips.setter
+    def accepted_flips(self, value: int) -> None:
+        self.n_accepted = value
+
+    @property
+    def total_flips(self) -> int:
+        return self.n_accepted + self.n_rejected
+
+    @total_flips.setter
+    def total_flips(self, value: int) -> None:
+        if value < self.n_accepted:
+            raise ValueError("Total flips cannot be less than accepted flips")
+        self.n_rejected = value - self.n_accepted
+
+    def reset_statistics(self) -> None:
+        self.n_accepted = 0
+        self.n_rejected = 0
+        self.energy_history = []
+
+    def __repr__(self) -> str:
+        return (f"SpinDynamics(temperature={self.temperature:.4f}, "
+                f"update_rule={self.update_rule.value}, "
+                f"acceptance_rate={self.get_acceptance_rate():.4f})")

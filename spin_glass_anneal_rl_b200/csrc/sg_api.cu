@@ -73,6 +73,7 @@ struct sg_engine {
     unsigned int* attempts = nullptr;
     unsigned int* accepts = nullptr;
     uint64_t launches = 0;
+    long long* dbg = nullptr;
 };
 
 namespace {
@@ -409,6 +410,7 @@ int sg_sweep(sg_engine* e, const sg_sweep_params* p, void* stream) {
     a.rule = p->rule;
     a.site_mode = p->site_mode;
     a.track_best = p->track_best ? 1 : 0;
+    a.dbg = e->dbg;
     const int grid = (e->R + G - 1) / G;
     SG_CUDA(sg::launch_sweep(a, p->rng_mode == SG_RNG_INJECTED, grid,
                              static_cast<cudaStream_t>(stream)));
@@ -634,5 +636,12 @@ int sg_query(sg_engine* e, int32_t* n, int32_t* n_pad, int32_t* n_replicas,
 }
 
 uint64_t sg_launch_count(sg_engine* e) { return e ? e->launches : 0; }
+
+/* development aid: device buffer of 256*8 int64 clock stamps written by block 0 */
+int sg_debug_set_timeline(sg_engine* e, long long* dev_buf) {
+    if (!e) return SG_ERR_INVALID;
+    e->dbg = dev_buf;
+    return SG_OK;
+}
 
 }  // extern "C"

@@ -27,6 +27,7 @@ struct SweepDev {
     const float* uniforms;    // injected uniforms [R][n_sweeps][n]
     unsigned long long seed, sweep_base;
     int n, n_pad, R, G, n_sweeps, rule, site_mode, track_best, D;
+    long long* dbg;           // optional timeline buffer (development aid), block 0 only
 };
 
 // Largest number of replicas one block can hold for this padded size (0 = unsupported).

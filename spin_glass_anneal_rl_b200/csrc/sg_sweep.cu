@@ -45,6 +45,12 @@
 #include "sg_common.cuh"
 #include "sg_internal.h"
 
+// development aid: -DSG_TIMELINE=1 compiles clock64() stamps into block 0 (tools/timeline.py)
+#ifndef SG_TIMELINE
+#define SG_TIMELINE 0
+#endif
+#define SG_TL (SG_TIMELINE != 0)
+
 namespace sg {
 
 namespace {
@@ -287,6 +293,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_kernel(const SweepDev 
     uint32_t parity = 0;
     int kg = 0;            // launch-global decision-block counter (slot = kg & 3)
     int tbuf0 = 0;         // theta buffer of batch 0 of the current sweep
+    long long tw = 0, tu = 0, tr = 0;  // debug: wait / update / release clocks
 
 #pragma unroll 1
     for (int s = 0; s < n_sweeps; ++s) {
@@ -324,7 +331,9 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_kernel(const SweepDev 
                                     ? a.uniforms[((size_t)(rep0 + lane) * n_sweeps + s) * n + i0 + b]
                                     : 0.0f;
                 }
+                if (SG_TL && a.dbg && blockIdx.x == 0 && lane == 0 && kg < 256) a.dbg[kg * 8 + 1] = clock64();
                 mbar_wait(&rawbar[slot], par);  // raw values + coupling tables of this block
+                if (SG_TL && a.dbg && blockIdx.x == 0 && lane == 0 && kg < 256) a.dbg[kg * 8 + 0] = clock64();
                 float v[kB];
 #pragma unroll
                 for (int b = 0; b < kB; ++b) v[b] = rawp[b * 32];
@@ -398,6 +407,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_kernel(const SweepDev 
                     }
                 }
                 __syncwarp();  // every lane's stores precede the release below
+                if (SG_TL && a.dbg && blockIdx.x == 0 && lane == 0 && kg < 256) a.dbg[kg * 8 + 2] = clock64();
                 if (lane == 0) mbar_arrive(&decbar[slot]);
             }
         } else {
@@ -448,16 +458,21 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_kernel(const SweepDev 
                         if (warp == 0) gen_theta(s, bi, buf, 7);
                     }
                 }
+                if (SG_TL && a.dbg && blockIdx.x == 0 && tid == 0 && kg < 256) a.dbg[kg * 8 + 3] = clock64();
                 mbar_wait(&decbar[slot], (uint32_t)(kg >> 2) & 1u);  // block k decided
+                if (SG_TL && a.dbg && blockIdx.x == 0 && tid == 0 && kg < 256) a.dbg[kg * 8 + 4] = clock64();
                 const uint32_t* amk = amk_s + slot * kB;
                 const float* decb = dec_s + (size_t)slot * kB * 32;
 #pragma unroll 1
                 for (int aa = 0; aa < nbk; ++aa) {
+                    long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+                    if (SG_TL && a.dbg) c0 = clock64();
                     const uint32_t am = amk[aa];
                     // Always wait for the row, even when no replica flipped: this is what keeps a
                     // fast warp from lapping the ring (a stage is re-armed only after all 7 bulk
                     // warps released it, and its barrier completes only after that).
                     mbar_wait(&full[stage], parity);
+                    if (SG_TL && a.dbg) c1 = clock64();
                     if (am != 0u) {
                         const float4* Jr4 = reinterpret_cast<const float4*>(Jring + (size_t)stage * n_pad);
                         const float4* d4 = reinterpret_cast<const float4*>(decb + aa * 32);
@@ -486,6 +501,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_kernel(const SweepDev 
                             }
                         }
                     }
+                    if (SG_TL && a.dbg) c2 = clock64();
                     // release the stage: the LAST bulk warp to finish this attempt re-arms the
                     // stage at once with the row of attempt g + D (rows are D attempts ahead)
                     if (lane == 0) {
@@ -499,10 +515,13 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_kernel(const SweepDev 
                             }
                         }
                     }
+                    if (SG_TL && a.dbg) { c3 = clock64(); tw += c1 - c0; tu += c2 - c1; tr += c3 - c2; }
                     ++g;
                     if (++stage == D) { stage = 0; parity ^= 1u; }
                 }
+                if (SG_TL && a.dbg && blockIdx.x == 0 && tid == 0 && kg < 256) a.dbg[kg * 8 + 5] = clock64();
                 if (k + 2 < nblk) publish_block(k + 2, kg + 2);
+                if (SG_TL && a.dbg && blockIdx.x == 0 && tid == 0 && kg < 256) a.dbg[kg * 8 + 6] = clock64();
             }
         }
         tbuf0 = (tbuf0 + nbat) % kThetaBufs;
@@ -578,6 +597,10 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_kernel(const SweepDev 
         __syncthreads();  // bit planes / flags are modified again by the next sweep
     }
 
+    if (SG_TL && a.dbg && blockIdx.x == 0 && (tid == 0 || tid == 96)) {
+        long long* o = a.dbg + 256 * 8 + (tid ? 4 : 0);
+        o[0] = tw; o[1] = tu; o[2] = tr;
+    }
     // ------------------------------------------------------------ epilogue: state back to HBM
     if (!is_dec) {
 #pragma unroll
