@@ -179,6 +179,12 @@ int sg_measure_stream_bandwidth(sg_engine *e, int64_t bytes, int iters, int stag
 int sg_measure_tma_stream(sg_engine *e, int64_t bytes, int row_bytes, int depth, int n_rows,
                           int stagger, double *gbps_out);
 
+/* Diagnostics for the tensor-core sweep: one rank-16 field update F[r][:] += sum_k
+ * deltas[k][r] * J'[sites16[k]][:] on 16 replicas (J' = sum of the first `planes` bf16 planes of
+ * the model).  Host buffers: sites16 [16], deltas [16][16] (attempt-major), fields [16][n]. */
+int sg_tc_selftest(sg_engine *e, int planes, const int32_t *sites16, const float *deltas,
+                   const float *fields_in, float *fields_out);
+
 /* Layout facts the host side needs (padded row length, resident replicas per block...). */
 int sg_query(sg_engine *e, int32_t *n, int32_t *n_pad, int32_t *n_replicas,
              int32_t *max_replicas_per_block, int32_t *sm_count);

@@ -58,6 +58,8 @@ struct sg_engine {
     int n = 0, n_pad = 0, R = 0;
     float* Jt = nullptr;  // [n][n_pad]
     float* h = nullptr;   // [n_pad]
+    void* Jp = nullptr;   // bf16 planes [3][n][n_tc] of Jt for the tensor-core sweep (n <= 4096)
+    int n_tc = 0;         // plane row length: n rounded up to 128
     int8_t* spins = nullptr;
     float* fields = nullptr;
     float* energy = nullptr;
@@ -156,6 +158,7 @@ void sg_destroy(sg_engine* e) {
     free_ladder(e);
     cudaFree(e->Jt);
     cudaFree(e->h);
+    cudaFree(e->Jp);
     delete e;
 }
 
@@ -191,6 +194,20 @@ int sg_set_model_dense(sg_engine* e, int n, const float* J, int64_t ldJ, const f
     SG_CUDA(cudaMemsetAsync(e->h, 0, (size_t)n_pad * sizeof(float), st));
     SG_CUDA(cudaMemcpyAsync(e->h, h, (size_t)n * sizeof(float),
                             on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    // bf16 planes for the tensor-core sweep (16 replicas x n_tc fp32 fields fill the TMEM)
+    cudaFree(e->Jp);
+    e->Jp = nullptr;
+    e->n_tc = 0;
+    if (n <= 4096) {
+        const int n_tc = (n + 127) / 128 * 128;
+        void* jp = nullptr;
+        cudaError_t ce = cudaMalloc(&jp, (size_t)3 * n * n_tc * 2);
+        if (ce != cudaSuccess) return fail(SG_ERR_NOMEM, "cudaMalloc(planes)", ce);
+        e->Jp = jp;
+        e->n_tc = n_tc;
+        SG_CUDA(sg::launch_split_planes(e->Jt, n, n_pad, e->Jp, n_tc, st));
+        e->launches++;
+    }
     if (tmp) {
         SG_CUDA(cudaStreamSynchronize(st));
         cudaFree(tmp);
@@ -620,6 +637,47 @@ int sg_measure_tma_stream(sg_engine* e, int64_t bytes, int row_bytes, int depth,
     cudaFree(sink);
     if (ce != cudaSuccess) return fail(SG_ERR_CUDA, "sg_measure_tma_stream", ce);
     *gbps_out = (double)row_bytes * n_rows * grid / ((double)ms * 1.0e6);
+    return SG_OK;
+}
+
+int sg_tc_selftest(sg_engine* e, int planes, const int32_t* sites16, const float* deltas,
+                   const float* fields_in, float* fields_out) {
+    SG_REQUIRE(e && sites16 && deltas && fields_in && fields_out, "sg_tc_selftest: NULL argument");
+    SG_REQUIRE(e->Jp, "sg_tc_selftest: no bf16 planes (set a dense model with n <= 4096)");
+    SG_REQUIRE(planes >= 1 && planes <= 3, "sg_tc_selftest: planes must be 1..3");
+    for (int k = 0; k < 16; ++k)
+        SG_REQUIRE(sites16[k] >= 0 && sites16[k] < e->n, "sg_tc_selftest: site out of range");
+    DeviceGuard g(e->device);
+    const size_t nf = (size_t)16 * e->n_tc;
+    int* d_sites = nullptr;
+    float *d_delta = nullptr, *d_in = nullptr, *d_out = nullptr;
+    int rc = SG_OK;
+    cudaError_t ce = cudaSuccess;
+    do {
+        if ((rc = dev_alloc(&d_sites, 16)) != SG_OK) break;
+        if ((rc = dev_alloc(&d_delta, 256)) != SG_OK) break;
+        if ((rc = dev_alloc(&d_in, nf)) != SG_OK) break;
+        if ((rc = dev_alloc(&d_out, nf)) != SG_OK) break;
+        if ((ce = cudaMemcpy(d_sites, sites16, 16 * sizeof(int), cudaMemcpyHostToDevice))) break;
+        if ((ce = cudaMemcpy(d_delta, deltas, 256 * sizeof(float), cudaMemcpyHostToDevice))) break;
+        if ((ce = cudaMemset(d_in, 0, nf * sizeof(float)))) break;
+        if ((ce = cudaMemcpy2D(d_in, (size_t)e->n_tc * 4, fields_in, (size_t)e->n * 4,
+                               (size_t)e->n * 4, 16, cudaMemcpyHostToDevice)))
+            break;
+        if ((ce = sg::launch_tc_selftest(e->Jp, e->n, e->n_tc, planes, d_sites, d_delta, d_in, d_out,
+                                         0)))
+            break;
+        e->launches++;
+        if ((ce = cudaMemcpy2D(fields_out, (size_t)e->n * 4, d_out, (size_t)e->n_tc * 4,
+                               (size_t)e->n * 4, 16, cudaMemcpyDeviceToHost)))
+            break;
+    } while (0);
+    cudaFree(d_sites);
+    cudaFree(d_delta);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (rc != SG_OK) return rc;
+    if (ce != cudaSuccess) return fail(SG_ERR_CUDA, "sg_tc_selftest", ce);
     return SG_OK;
 }
 

@@ -58,6 +58,13 @@ cudaError_t launch_stream_probe(const float4* buf, int64_t n_vec, int iters, int
 cudaError_t launch_tma_probe(const float* buf, int64_t buf_rows, uint32_t row_bytes, int n_rows,
                              int depth, int stagger, float* sink, int grid, cudaStream_t st);
 
+// K1-TC (sg_sweep_tc.cu): bf16 coupling planes and the tensor-core sweep
+cudaError_t launch_split_planes(const float* Jt, int n, int n_pad, void* Jp, int n_tc,
+                                cudaStream_t st);
+cudaError_t launch_tc_selftest(const void* Jp, int n, int n_tc, int planes, const int* sites,
+                               const float* deltas, const float* fields_in, float* fields_out,
+                               cudaStream_t st);
+
 // K3 (sg_exchange.cu)
 struct ExchangeDev {
     int* rep_at;              // [L][K] replica currently at rung k of ladder l
