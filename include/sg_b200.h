@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 1
+#define SG_ABI_VERSION 2
 
 typedef enum {
     SG_OK = 0,
@@ -55,6 +55,11 @@ typedef enum {
 #define SG_SITES_RANDOM 1     /* Philox draw % n, with replacement (core/spin_dynamics.py:69) */
 #define SG_SITES_EXPLICIT 2   /* caller-supplied list (replay of a recorded stream)         */
 #define SG_SITES_RANDOM_PER_BLOCK 3 /* like RANDOM, but an independent stream per thread block */
+
+/* which sweep kernel runs (sg_sweep_params.kernel) */
+#define SG_KERNEL_AUTO 0 /* tensor-core kernel when the model/launch shape allows it, else SIMT   */
+#define SG_KERNEL_SIMT 1 /* register-resident fields, sequential fp32 FMAs (sg_sweep.cu)          */
+#define SG_KERNEL_TC 2   /* TMEM-resident fields, tcgen05 rank-16 block updates (sg_sweep_tc.cu)  */
 
 typedef struct sg_engine sg_engine;
 
@@ -121,6 +126,11 @@ typedef struct {
     const float *uniforms;
     float *energy_trace; /* optional dev out [n_sweeps][R]: energy after every sweep           */
     int32_t track_best;  /* compare-and-keep best energy/configuration after every sweep       */
+    int32_t kernel;      /* SG_KERNEL_*                                                        */
+    /* SG_KERNEL_TC: number of bf16 planes the couplings are summed from: 3 = every fp32 coupling
+     * exactly (default, 0 means 3), 2 = 16 significant bits, 1 = plain bf16.  Integer couplings
+     * |J| <= 256 are exact with 1 plane. */
+    int32_t coupling_planes;
     int32_t reserved;
 } sg_sweep_params;
 

@@ -19,6 +19,7 @@ CSRC = os.path.join(_PKG, "csrc")
 SG_RULE = {"metropolis": 0, "glauber": 1, "heat_bath": 2}
 SG_RNG_PHILOX, SG_RNG_INJECTED = 0, 1
 SG_SITES = {"sequential": 0, "random": 1, "explicit": 2, "random_per_block": 3}
+SG_KERNEL = {"auto": 0, "simt": 1, "tc": 2}
 
 
 class SweepParams(Structure):
@@ -29,7 +30,8 @@ class SweepParams(Structure):
         ("seed", c_uint64), ("sweep_base", c_uint64),
         ("sites", c_void_p), ("sites_block_stride", c_int64), ("sites_sweep_stride", c_int64),
         ("uniforms", c_void_p), ("energy_trace", c_void_p),
-        ("track_best", c_int32), ("reserved", c_int32),
+        ("track_best", c_int32), ("kernel", c_int32), ("coupling_planes", c_int32),
+        ("reserved", c_int32),
     ]
 
 
@@ -108,7 +110,7 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.sg_abi_version() != 1:
+    if lib.sg_abi_version() != 2:
         raise RuntimeError("libsg_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -60,6 +60,10 @@ struct sg_engine {
     float* h = nullptr;   // [n_pad]
     void* Jp = nullptr;   // bf16 planes [3][n][n_tc] of Jt for the tensor-core sweep (n <= 4096)
     int n_tc = 0;         // plane row length: n rounded up to 128
+    void* tc_sites = nullptr;  // per-launch site tables of the tensor-core sweep
+    size_t tc_sites_cap = 0;
+    void* tc_stream = nullptr;  // operand stream (gathered J rows in UMMA layout), <= 1 GiB
+    size_t tc_stream_cap = 0;
     int8_t* spins = nullptr;
     float* fields = nullptr;
     float* energy = nullptr;
@@ -159,6 +163,8 @@ void sg_destroy(sg_engine* e) {
     cudaFree(e->Jt);
     cudaFree(e->h);
     cudaFree(e->Jp);
+    cudaFree(e->tc_sites);
+    cudaFree(e->tc_stream);
     delete e;
 }
 
@@ -428,9 +434,57 @@ int sg_sweep(sg_engine* e, const sg_sweep_params* p, void* stream) {
     a.site_mode = p->site_mode;
     a.track_best = p->track_best ? 1 : 0;
     a.dbg = e->dbg;
+    const bool inject = (p->rng_mode == SG_RNG_INJECTED);
+    SG_REQUIRE(p->kernel >= SG_KERNEL_AUTO && p->kernel <= SG_KERNEL_TC, "sg_sweep: unknown kernel");
+    SG_REQUIRE(p->coupling_planes >= 0 && p->coupling_planes <= 3,
+               "sg_sweep: coupling_planes must be 0..3");
+    const bool tc_ok = e->Jp && sg::sweep_tc_supported(e->n, e->n_tc) &&
+                       p->site_mode != SG_SITES_RANDOM_PER_BLOCK &&
+                       !(p->site_mode == SG_SITES_EXPLICIT && p->sites_block_stride != 0) &&
+                       p->replicas_per_block == 0;
+    bool use_tc = false;
+    if (p->kernel == SG_KERNEL_TC) {
+        SG_REQUIRE(tc_ok, "sg_sweep: the tensor-core kernel needs a dense model with 16 <= n <= 4096, "
+                          "one site order for the grid and replicas_per_block = 0");
+        use_tc = true;
+    } else if (p->kernel == SG_KERNEL_AUTO) {
+        // replay (injected uniforms) stays on the sequential-FMA kernel unless asked otherwise
+        use_tc = tc_ok && !inject;
+    }
+    if (use_tc) {
+        const size_t need = sg::sweep_tc_sites_bytes(e->n, p->n_sweeps);
+        if (need > e->tc_sites_cap) {
+            // the previous table may still be in use by a launch in flight on this stream
+            SG_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+            cudaFree(e->tc_sites);
+            e->tc_sites = nullptr;
+            e->tc_sites_cap = 0;
+            cudaError_t ce = cudaMalloc(&e->tc_sites, need);
+            if (ce != cudaSuccess) return fail(SG_ERR_NOMEM, "cudaMalloc(site tables)", ce);
+            e->tc_sites_cap = need;
+        }
+        const int planes = p->coupling_planes ? p->coupling_planes : 3;
+        const size_t per_sweep = sg::sweep_tc_stream_bytes_per_sweep(e->n, e->n_tc, planes);
+        size_t want = per_sweep * (size_t)p->n_sweeps;
+        const size_t cap_max = (size_t)1 << 30;
+        if (want > cap_max) want = (cap_max / per_sweep ? cap_max / per_sweep : 1) * per_sweep;
+        if (want > e->tc_stream_cap) {
+            SG_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+            cudaFree(e->tc_stream);
+            e->tc_stream = nullptr;
+            e->tc_stream_cap = 0;
+            cudaError_t ce = cudaMalloc(&e->tc_stream, want);
+            if (ce != cudaSuccess) return fail(SG_ERR_NOMEM, "cudaMalloc(operand stream)", ce);
+            e->tc_stream_cap = want;
+        }
+        a.G = 16;
+        SG_CUDA(sg::launch_sweep_tc(a, e->Jp, e->n_tc, planes, inject, e->tc_sites, e->tc_stream,
+                                    e->tc_stream_cap, &e->launches,
+                                    static_cast<cudaStream_t>(stream)));
+        return SG_OK;
+    }
     const int grid = (e->R + G - 1) / G;
-    SG_CUDA(sg::launch_sweep(a, p->rng_mode == SG_RNG_INJECTED, grid,
-                             static_cast<cudaStream_t>(stream)));
+    SG_CUDA(sg::launch_sweep(a, inject, grid, static_cast<cudaStream_t>(stream)));
     e->launches++;
     return SG_OK;
 }
@@ -678,6 +732,19 @@ int sg_tc_selftest(sg_engine* e, int planes, const int32_t* sites16, const float
     cudaFree(d_out);
     if (rc != SG_OK) return rc;
     if (ce != cudaSuccess) return fail(SG_ERR_CUDA, "sg_tc_selftest", ce);
+    return SG_OK;
+}
+
+/* development aid: clocks per tcgen05.mma for an operand layout variant (sg_sweep_tc.cu) */
+int sg_debug_mma_bench(sg_engine* e, int variant, int n_dim, int iters, long long* host_out2) {
+    if (!e || !host_out2) return SG_ERR_INVALID;
+    DeviceGuard g(e->device);
+    long long* d = nullptr;
+    SG_CUDA(cudaMalloc(&d, 16));
+    cudaError_t ce = sg::launch_tc_mma_bench(variant, n_dim, iters, d, 0);
+    if (ce == cudaSuccess) ce = cudaMemcpy(host_out2, d, 16, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (ce != cudaSuccess) return fail(SG_ERR_CUDA, "sg_debug_mma_bench", ce);
     return SG_OK;
 }
 

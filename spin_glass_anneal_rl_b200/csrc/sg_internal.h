@@ -65,6 +65,17 @@ cudaError_t launch_tc_selftest(const void* Jp, int n, int n_tc, int planes, cons
                                const float* deltas, const float* fields_in, float* fields_out,
                                cudaStream_t st);
 
+cudaError_t launch_tc_mma_bench(int variant, int n_dim, int iters, long long* out, cudaStream_t st);
+bool sweep_tc_supported(int n, int n_tc);
+size_t sweep_tc_sites_bytes(int n, int n_sweeps);
+size_t sweep_tc_stream_bytes_per_sweep(int n, int n_tc, int planes);
+// sites_buf: device scratch of sweep_tc_sites_bytes(); stream_buf: device scratch for the operand
+// stream, at least one sweep's worth (the launch is cut into sub-launches of as many sweeps as
+// fit).  Launches the site-table kernel, then (gather, sweep) per sub-launch; counts them.
+cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int planes, bool inject,
+                            void* sites_buf, void* stream_buf, size_t stream_cap,
+                            uint64_t* launches, cudaStream_t st);
+
 // K3 (sg_exchange.cu)
 struct ExchangeDev {
     int* rep_at;              // [L][K] replica currently at rung k of ladder l

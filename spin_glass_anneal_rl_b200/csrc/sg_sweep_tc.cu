@@ -22,17 +22,27 @@
 // of two blocks ago + a 16x16 table of couplings from the previous block's sites + the in-block
 // table, with the same FMAs in the same order as the sequential algorithm.
 //
-// Warp roles (10 warps, 1 block per SM):
+// The J rows of a block must reach shared memory in the UMMA canonical operand layout
+// (A is MN-major: 8 attempts x 8 columns core matrices), which is a 16-byte-granular transpose
+// of 16 randomly chosen rows.  Doing that gather inside the sweep kernel with cp.async (LDGSTS)
+// tops out near 13 B/clk/SM and floods the LSU queue the decision warp depends on (measured),
+// so the gather is done ONCE PER SWEEP FOR THE WHOLE GRID by a separate streaming kernel
+// (tc_gather_kernel: every block visits the sites in the same order, so all 148 SMs consume the
+// same operand stream) and the sweep kernel pulls ready-made 4-tile chunks through a
+// shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier), L2-resident for all
+// blocks but the first that touches a chunk.
+//
+// Warp roles (7 warps, 1 block per SM):
 //   warps 0-3  "quarter" warps (TMEM lane quarter = warp id): read the raw field values of the
 //              16 sites of block k+2 from TMEM (tcgen05.ld), gather the coupling tables, draw the
 //              Philox thresholds; at sweep end reduce the energies from TMEM;
-//   warps 4-7  producers: gather the 16 J rows of a block from L2 into the UMMA canonical
-//              operand layout with 16-byte cp.async (LDGSTS), chunk by chunk (4 tiles x P planes)
-//              through a shared-memory ring; completion is signalled on mbarriers;
-//   warp 8     decision warp (lane = replica): 16 attempts per block in registers, writes the
+//   warp 4     producer (one lane): TMA bulk copies of operand chunks into the ring;
+//   warp 5     decision warp (lane = replica): 16 attempts per block in registers, writes the
 //              B operand (bf16 deltas), flips the spin bit planes;
-//   warp 9     MMA issuer (one lane): tcgen05.mma + tcgen05.commit.
+//   warp 6     MMA issuer (one lane): tcgen05.mma + tcgen05.commit.
 #include <cuda_bf16.h>
+
+#include <cstdlib>
 
 #include "sg_common.cuh"
 #include "sg_internal.h"
@@ -45,10 +55,15 @@ namespace {
 constexpr int kG = 16;             // replicas per block = MMA N
 constexpr int kTileM = 128;        // field columns per MMA
 constexpr int kBlk = 16;           // attempts per block = MMA K
-constexpr int kTileBytes = kTileM * kBlk * 2;   // one (tile, plane) A operand: 4096 B
+#ifndef SG_TC_ASBO
+#define SG_TC_ASBO 128
+#endif
+constexpr uint32_t kASbo = SG_TC_ASBO;          // A: m-group (core matrix) stride (144 = 128 + 16 is legal
+                                                // too but not faster: the MMA rate is A-fetch bound)
+constexpr uint32_t kALbo = 16 * kASbo;          // A: k-group stride
+constexpr int kTileBytes = 2 * kALbo;           // one (tile, plane) A operand
 constexpr int kChunkTiles = 4;     // tiles per ring stage
 constexpr uint32_t kIdesc = tc::make_idesc_bf16(kTileM, kG);
-constexpr uint32_t kALbo = 2048, kASbo = 128;   // A: k-group stride, m-group stride
 constexpr uint32_t kBLbo = 256, kBSbo = 128;    // B: k-group stride, n-group stride
 constexpr int kBopBytes = 512;
 
@@ -92,7 +107,7 @@ __device__ __forceinline__ void gather_chunk(unsigned char* chunk, const __nv_bf
         for (int kg = 0; kg < 2; ++kg) {
             const __nv_bfloat16* row =
                 Jp + (size_t)p * plane_stride + (size_t)site[kg] * n_tc + mg * 8;
-            unsigned char* dst = chunk + p * kTileBytes + mg * 128 + kg * 2048 + kk * 16;
+            unsigned char* dst = chunk + p * kTileBytes + mg * kASbo + kg * kALbo + kk * 16;
 #pragma unroll
             for (int tt = 0; tt < kChunkTiles; ++tt)
                 if (tt < ntiles)
@@ -191,6 +206,694 @@ tc_selftest_kernel(const __nv_bfloat16* __restrict__ Jp, int n, int n_tc,
     if (warp == 0) tc::tmem_dealloc(tbase, 512);
 }
 
+
+// ---------------------------------------------------------------- site tables
+// sites[s][i] (uint16, row length n_s = n rounded up to 16, padding = site 0) for every sweep of
+// a launch; one order for the whole grid (the J rows a block gathers are then L2 hits for all
+// blocks but the first).  Same Philox stream as gen_sites() of sg_sweep.cu.
+__global__ void tc_sites_kernel(int mode, unsigned long long seed, unsigned long long sweep_base,
+                                int n, int n_s, int n_sweeps, const int* __restrict__ explicit_sites,
+                                long long s_ss, uint16_t* __restrict__ out) {
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    const int quads = n_s / 4;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_sweeps * quads;
+         idx += gridDim.x * blockDim.x) {
+        const int s = idx / quads, q = idx - s * quads;
+        uint32_t v[4] = {0u, 0u, 0u, 0u};
+        if (mode == 1) {
+            const unsigned long long sa = sweep_base + (unsigned long long)s;
+            const uint4 x = philox4x32_10(
+                make_uint4(kSiteStreamTag, (uint32_t)sa, (uint32_t)(sa >> 32), (uint32_t)q), key);
+            v[0] = x.x % (uint32_t)n; v[1] = x.y % (uint32_t)n;
+            v[2] = x.z % (uint32_t)n; v[3] = x.w % (uint32_t)n;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int i = q * 4 + e;
+            uint32_t site = 0;
+            if (i < n) {
+                if (mode == 0) site = (uint32_t)i;
+                else if (mode == 1) site = v[e];
+                else site = (uint32_t)explicit_sites[(long long)s * s_ss + i];
+            }
+            out[(size_t)s * n_s + i] = (uint16_t)site;
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------- operand stream
+// Q[(s, block k, chunk c)] = kStage bytes = 4 tiles x P planes, each tile the 128 x 16 A operand
+// of one tcgen05.mma in canonical layout: byte(m, k) = (m/8)*kASbo + (k/8)*kALbo + (k%8)*16 +
+// (m%8)*2, value Jp[p][site_k][tile*128 + m].  One thread moves one 16-byte unit; consecutive
+// threads write consecutive units (coalesced) and read 8 rows x 64 B.
+template <int P>
+__global__ void __launch_bounds__(256)
+tc_gather_kernel(const __nv_bfloat16* __restrict__ Jp, int n, int n_tc,
+                 const uint16_t* __restrict__ sites, int n_s, int s_begin, int n_sub, int nblk,
+                 int nchunk, uint4* __restrict__ Q) {
+    constexpr int kUnitsPerTile = kTileBytes / 16;
+    constexpr int kUnitsPerStage = kChunkTiles * P * kUnitsPerTile;
+    const size_t plane_stride = (size_t)n * n_tc;
+    const int T = n_tc / kTileM;
+    const size_t total = (size_t)n_sub * nblk * nchunk * kUnitsPerStage;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+         g += (size_t)gridDim.x * blockDim.x) {
+        const int u = (int)(g % kUnitsPerStage);
+        const size_t chunk_id = g / kUnitsPerStage;
+        const int c = (int)(chunk_id % nchunk);
+        const size_t blk_id = chunk_id / nchunk;
+        const int k = (int)(blk_id % nblk);
+        const int s_rel = (int)(blk_id / nblk);
+        const int tp = u / kUnitsPerTile, d = u - tp * kUnitsPerTile;
+        const int tt = tp / P, p = tp - tt * P;
+        // d*16 = mg*kASbo + kg*kALbo + kk*16  (kASbo = 128 or 144, kALbo = 16*kASbo)
+        const int off = d * 16;
+        const int kg = off / (int)kALbo, rem = off - kg * (int)kALbo;
+        const int mg = rem / (int)kASbo, rem2 = rem - mg * (int)kASbo;
+        const int kk = rem2 >> 4;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        const int tile = c * kChunkTiles + tt;
+        if (tile < T && kk < 8) {
+            const int site = sites[(size_t)(s_begin + s_rel) * n_s + k * kBlk + kg * 8 + kk];
+            v = *reinterpret_cast<const uint4*>(Jp + (size_t)p * plane_stride + (size_t)site * n_tc +
+                                                tile * kTileM + mg * 8);
+        }
+        Q[g] = v;
+    }
+}
+
+// ---------------------------------------------------------------- the sweep
+constexpr int kTcThreads = 224;
+constexpr int kSlots = 4;
+constexpr int kMaxStagesTc = 8;
+constexpr int kSyncThreads = 160;  // quarter warps + decision warp (named barriers 1..3)
+
+struct TcSmem {
+    size_t ring, bop, sbits, theta, raw, cin, ccr, dup, red, flags, bars, tptr, total;
+};
+
+__host__ __device__ inline TcSmem tc_layout(int n_tc, int P, int NS) {
+    TcSmem L;
+    size_t off = 0;
+    L.ring = off;  off += (size_t)NS * kChunkTiles * P * kTileBytes;
+    L.bop = off;   off += (size_t)kSlots * kBopBytes;
+    L.sbits = off; off += (size_t)kG * (n_tc / 32) * sizeof(uint32_t);
+    L.theta = off; off += (size_t)kSlots * kBlk * kG * sizeof(float);
+    L.raw = off;   off += (size_t)kSlots * kBlk * kG * sizeof(float);
+    L.cin = off;   off += (size_t)kSlots * kBlk * kBlk * sizeof(float);
+    L.ccr = off;   off += (size_t)kSlots * kBlk * kBlk * sizeof(float);
+    L.dup = off;   off += (size_t)kSlots * kBlk * sizeof(uint32_t);
+    L.red = off;   off += 4 * kG * sizeof(float);
+    L.flags = off; off += 4 * sizeof(uint32_t);
+    off = (off + 15) & ~(size_t)15;
+    L.bars = off;  off += (size_t)(2 * kMaxStagesTc + 3 * kSlots) * sizeof(uint64_t);
+    L.tptr = off;  off += 16;
+    L.total = off;
+    return L;
+}
+
+__device__ __forceinline__ void named_sync(int id) { named_bar_sync(id, kSyncThreads); }
+
+// development aid: clock stamps of block 0 (tools/tc_timeline.py); 16 slots per attempt block
+#define SG_STAMP(slot_)                                                              \
+    do {                                                                             \
+        if (a.dbg && blockIdx.x == 0 && lane == 0 && kg < 512) a.dbg[kg * 16 + (slot_)] = clock64(); \
+    } while (0)
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+// 32 spin bits -> 32 int8 (+1 / -1), written as two 16-byte stores
+__device__ __forceinline__ void store_spin_word(int8_t* dst, uint32_t w) {
+    uint32_t o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t nib = (w >> (4 * j)) & 0xFu;
+        uint32_t bytes = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) bytes |= (((nib >> e) & 1u) ? 0x01u : 0xFFu) << (8 * e);
+        o[j] = bytes;
+    }
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+template <int P, bool INJECT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const int n_tc,
+                const uint16_t* __restrict__ sites_g, const int n_s, const int NS,
+                const int tmem_cols, const unsigned char* __restrict__ Q, const int s_begin,
+                const int s_end, const int dbg) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int n = a.n, n_pad = a.n_pad;
+    const int W = n_tc >> 5;
+    const int T = n_tc / kTileM;
+    const int nchunk = (T + kChunkTiles - 1) / kChunkTiles;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    const TcSmem L = tc_layout(n_tc, P, NS);
+    unsigned char* ring = smem + L.ring;
+    unsigned char* bop_s = smem + L.bop;
+    uint32_t* sbits = reinterpret_cast<uint32_t*>(smem + L.sbits);
+    float* theta_s = reinterpret_cast<float*>(smem + L.theta);  // [slot][b][r]
+    float* raw_s = reinterpret_cast<float*>(smem + L.raw);      // [slot][b][r]
+    float* cin_s = reinterpret_cast<float*>(smem + L.cin);      // [slot][a][b]
+    float* ccr_s = reinterpret_cast<float*>(smem + L.ccr);      // [slot][a][b]
+    uint32_t* dup_s = reinterpret_cast<uint32_t*>(smem + L.dup);  // [slot][b]
+    float* red = reinterpret_cast<float*>(smem + L.red);
+    uint32_t* flags = reinterpret_cast<uint32_t*>(smem + L.flags);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);
+    uint64_t* empty = full + kMaxStagesTc;
+    uint64_t* rawbar = empty + kMaxStagesTc;
+    uint64_t* decbar = rawbar + kSlots;
+    uint64_t* mmadone = decbar + kSlots;
+    uint32_t* tptr = reinterpret_cast<uint32_t*>(smem + L.tptr);
+    constexpr int kStageBytes = kChunkTiles * P * kTileBytes;
+
+    const int rep0 = blockIdx.x * kG;
+    const int g_act = min(kG, a.R - rep0);
+    const int n_sweeps = a.n_sweeps;
+    const int nblk = (n + kBlk - 1) / kBlk;
+    const size_t plane_stride = (size_t)n * n_tc;
+    const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+
+    // ------------------------------------------------------------ prologue
+    if (tid == 0) {
+        for (int d = 0; d < NS; ++d) {
+            mbar_init(&full[d], 1);
+            mbar_init(&empty[d], 1);
+        }
+        for (int d = 0; d < kSlots; ++d) {
+            mbar_init(&rawbar[d], 4);
+            mbar_init(&decbar[d], 1);
+            mbar_init(&mmadone[d], 1);
+        }
+        fence_mbar_init();
+        fence_proxy_async();
+    }
+    if (warp == 0) {
+        tc::tmem_alloc(tptr, (uint32_t)tmem_cols);
+        tc::tmem_relinquish();
+    }
+    // spin bit planes from int8 spins
+    for (int w = tid; w < kG * W; w += kTcThreads) {
+        const int r = w / W, word = w - r * W;
+        uint32_t bits = 0xFFFFFFFFu;
+        if (r < g_act) {
+            const uint4* src =
+                reinterpret_cast<const uint4*>(a.spins + (size_t)(rep0 + r) * n_pad + word * 32);
+            const uint4 lo = src[0], hi = src[1];
+            const uint32_t x[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            bits = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t up = (~x[j]) & 0x80808080u;  // byte >= 0  <=> spin up
+                const uint32_t nib =
+                    ((up >> 7) & 1u) | ((up >> 14) & 2u) | ((up >> 21) & 4u) | ((up >> 28) & 8u);
+                bits |= nib << (4 * j);
+            }
+        }
+        sbits[w] = bits;
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tbase = *tptr;
+
+    if (warp < 4) {
+        // resident fields -> TMEM
+        const uint32_t tq = tbase + ((uint32_t)(warp * 32) << 16);
+        for (int t = 0; t < T; ++t) {
+            float v[16];
+            const int col = t * kTileM + warp * 32 + lane;
+#pragma unroll
+            for (int r = 0; r < 16; ++r)
+                v[r] = (r < g_act) ? a.fields[(size_t)(rep0 + r) * n_pad + col] : 0.0f;
+            tc::tmem_st16(tq + t * kG, v);
+        }
+        tc::wait_st();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+
+    if (warp < 4) {
+        // ======================================================== QUARTER WARPS
+        const int q = warp;
+        const uint32_t tq = tbase + ((uint32_t)(q * 32) << 16);
+        int kg = 0;
+#pragma unroll 1
+        for (int s = s_begin; s < s_end; ++s) {
+            const uint16_t* stab = sites_g + (size_t)s * n_s;
+            const unsigned long long sa = a.sweep_base + (unsigned long long)s;
+#pragma unroll 1
+            for (int kb = 0; kb < nblk; ++kb, ++kg) {
+                const int slot = kg & (kSlots - 1);
+                const int i0 = kb * kBlk;
+                const int nbk = min(kBlk, n - i0);
+                if (warp == 0) SG_STAMP(0);
+                const uint4 sq0 = *reinterpret_cast<const uint4*>(stab + i0);
+                const uint4 sq1 = *reinterpret_cast<const uint4*>(stab + i0 + 8);
+                const uint32_t swq[8] = {sq0.x, sq0.y, sq0.z, sq0.w, sq1.x, sq1.y, sq1.z, sq1.w};
+                // --- coupling tables (global gathers, issued before the TMEM wait)
+                {
+                    float* cin = cin_s + slot * kBlk * kBlk;
+                    float* ccr = ccr_s + slot * kBlk * kBlk;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int idx = tid + 128 * j;
+                        const int which = idx >> 8, aa = (idx >> 4) & 15, b = idx & 15;
+                        float val = 0.0f;
+                        if (b < nbk && (which == 0 ? (aa < nbk) : (kb > 0))) {
+                            const int sb = stab[i0 + b];
+                            const int sr = which == 0 ? stab[i0 + aa] : stab[i0 - kBlk + aa];
+                            const __nv_bfloat16* pj = Jp + (size_t)sr * n_tc + sb;
+                            val = __bfloat162float(pj[0]);
+                            if (P > 1) val += __bfloat162float(pj[plane_stride]);
+                            if (P > 2) val += __bfloat162float(pj[2 * plane_stride]);
+                        }
+                        (which == 0 ? cin : ccr)[aa * kBlk + b] = val;
+                    }
+                    if (tid < kBlk) {
+                        uint32_t m = 0;
+                        const int me = stab[i0 + tid];
+                        for (int a2 = 0; a2 < tid; ++a2) m |= (stab[i0 + a2] == me) ? (1u << a2) : 0u;
+                        dup_s[slot * kBlk + tid] = m;
+                    }
+                }
+                // --- thresholds: thread (qq, r) covers attempts 4qq..4qq+3 of the block
+                if (!INJECT && tid < 64) {
+                    const int qq = tid >> 4, r = tid & 15;
+                    const int ia = i0 + qq * 4;
+                    if (r < g_act && ia < n) {
+                        const int rep = rep0 + r;
+                        const float Tm = (float)a.temps[(long long)s * a.t_ss + (long long)rep * a.t_rs];
+                        const uint4 x = philox4x32_10(
+                            make_uint4((uint32_t)rep, (uint32_t)sa, (uint32_t)(sa >> 32),
+                                       (uint32_t)(ia >> 2)), key);
+                        const uint32_t vv[4] = {x.x, x.y, x.z, x.w};
+                        float* dst = theta_s + slot * kBlk * kG + (qq * 4) * kG + r;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float u = u01(vv[e]);
+                            float th;
+                            if (a.rule == 0) th = -__logf(u) * Tm;
+                            else th = 0.5f * Tm * (__logf(u) - __logf(1.0f - u));
+                            dst[e * kG] = th;
+                        }
+                    }
+                }
+                // --- raw field values of the block's sites, as of the end of block kg-2
+                if (warp == 0) SG_STAMP(1);
+                if (kg >= 2) mbar_wait(&mmadone[(kg - 2) & (kSlots - 1)], (uint32_t)((kg - 2) >> 2) & 1u);
+                tc::fence_after_sync();
+                if (warp == 0) SG_STAMP(2);
+                float* rawb = raw_s + slot * kBlk * kG;
+#pragma unroll
+                for (int b = 0; b < kBlk; ++b) {
+                    const int site = (int)((swq[b >> 1] >> (16 * (b & 1))) & 0xFFFFu);
+                    if (b < nbk && ((site >> 5) & 3) == q && !(dbg & 4)) {
+                        float v[16];
+                        tc::tmem_ld16(tq + (site >> 7) * kG, v);
+                        tc::wait_ld();
+                        if (lane == (site & 31)) {
+                            float4* d4 = reinterpret_cast<float4*>(rawb + b * kG);
+                            d4[0] = make_float4(v[0], v[1], v[2], v[3]);
+                            d4[1] = make_float4(v[4], v[5], v[6], v[7]);
+                            d4[2] = make_float4(v[8], v[9], v[10], v[11]);
+                            d4[3] = make_float4(v[12], v[13], v[14], v[15]);
+                        }
+                    }
+                }
+                tc::fence_before_sync();
+                __syncwarp();
+                if (warp == 0) SG_STAMP(3);
+                if (lane == 0) mbar_arrive(&rawbar[slot]);
+            }
+            // ---- end of sweep: energies from the TMEM-resident fields
+            mbar_wait(&mmadone[(kg - 1) & (kSlots - 1)], (uint32_t)((kg - 1) >> 2) & 1u);
+            tc::fence_after_sync();
+            named_sync(1);  // decision warp has flipped the last spins of the sweep
+            {
+                float part[16];
+#pragma unroll
+                for (int r = 0; r < 16; ++r) part[r] = 0.0f;
+                for (int t = 0; t < T; ++t) {
+                    float f[16];
+                    tc::tmem_ld16(tq + t * kG, f);
+                    tc::wait_ld();
+                    const float hv = a.h[t * kTileM + q * 32 + lane];
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) {
+                        const uint32_t w = sbits[r * W + t * 4 + q];
+                        const float tt = f[r] + hv;
+                        part[r] += ((w >> lane) & 1u) ? tt : -tt;
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) part[r] += __shfl_xor_sync(0xFFFFFFFFu, part[r], o);
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) red[q * kG + r] = part[r];
+                }
+            }
+            tc::fence_before_sync();
+            named_sync(2);  // partial sums visible to the decision warp
+            named_sync(3);  // flags[0] = mask of replicas that improved
+            const uint32_t im = flags[0];
+            if (im != 0u) {
+                for (int w = tid; w < kG * W; w += 128) {
+                    const int r = w / W, word = w - r * W;
+                    if ((im >> r) & 1u)
+                        store_spin_word(a.best_spins + (size_t)(rep0 + r) * n_pad + word * 32, sbits[w]);
+                }
+            }
+            named_sync(1);  // bit planes may be modified again
+        }
+        // ---- epilogue: fields and spins back to HBM
+        for (int t = 0; t < T; ++t) {
+            float v[16];
+            tc::tmem_ld16(tq + t * kG, v);
+            tc::wait_ld();
+            const int col = t * kTileM + q * 32 + lane;
+#pragma unroll
+            for (int r = 0; r < 16; ++r)
+                if (r < g_act) a.fields[(size_t)(rep0 + r) * n_pad + col] = v[r];
+        }
+        for (int w = tid; w < kG * W; w += 128) {
+            const int r = w / W, word = w - r * W;
+            if (r < g_act) store_spin_word(a.spins + (size_t)(rep0 + r) * n_pad + word * 32, sbits[w]);
+        }
+    } else if (warp == 4) {
+        // ======================================================== PRODUCER (TMA)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t epar = 1;  // a fresh barrier passes a wait on the "previous" phase
+            const size_t nchunks_total = (size_t)(s_end - s_begin) * nblk * nchunk;
+            int kg = 0, cc = 0;
+#pragma unroll 1
+            for (size_t ci = 0; ci < nchunks_total; ++ci) {
+                if (cc == 0) SG_STAMP(13);
+                mbar_wait(&empty[stage], epar);
+                mbar_arrive_expect_tx(&full[stage], (uint32_t)kStageBytes);
+                if (!(dbg & 1))
+                    bulk_g2s(ring + (size_t)stage * kStageBytes, Q + ci * kStageBytes,
+                             (uint32_t)kStageBytes, &full[stage]);
+                else
+                    bulk_g2s(ring + (size_t)stage * kStageBytes, Q, (uint32_t)kStageBytes,
+                             &full[stage]);
+                if (++stage == NS) { stage = 0; epar ^= 1u; }
+                if (++cc == nchunk) { cc = 0; SG_STAMP(14); ++kg; }
+            }
+        }
+    } else if (warp == 5) {
+        // ======================================================== DECISION WARP
+        const int r = lane & (kG - 1);
+        const bool active = lane < g_act;
+        float best_e = 3.0e38f, cur_e = 0.0f;
+        unsigned int n_acc = 0;
+        if (active) {
+            cur_e = a.energy[rep0 + lane];
+            best_e = a.track_best ? a.best_energy[rep0 + lane] : 3.0e38f;
+        }
+        float pdec[kBlk];
+        uint32_t pam[kBlk];
+#pragma unroll
+        for (int b = 0; b < kBlk; ++b) { pdec[b] = 0.0f; pam[b] = 0u; }
+        int kg = 0;
+#pragma unroll 1
+        for (int s = s_begin; s < s_end; ++s) {
+            const uint16_t* stab = sites_g + (size_t)s * n_s;
+            double dT = 1.0;
+            if (INJECT && active)
+                dT = a.temps[(long long)s * a.t_ss + (long long)(rep0 + lane) * a.t_rs];
+#pragma unroll 1
+            for (int k = 0; k < nblk; ++k, ++kg) {
+                const int slot = kg & (kSlots - 1);
+                const uint32_t par = (uint32_t)(kg >> 2) & 1u;
+                const int i0 = k * kBlk;
+                const int nbk = min(kBlk, n - i0);
+                // the 16 sites of the block (uniform)
+                const uint4 s0 = *reinterpret_cast<const uint4*>(stab + i0);
+                const uint4 s1 = *reinterpret_cast<const uint4*>(stab + i0 + 8);
+                const uint32_t sw[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                int site[kBlk];
+#pragma unroll
+                for (int b = 0; b < kBlk; ++b) site[b] = (int)((sw[b >> 1] >> (16 * (b & 1))) & 0xFFFFu);
+                float uu[kBlk];
+                if (INJECT) {
+#pragma unroll
+                    for (int b = 0; b < kBlk; ++b)
+                        uu[b] = (active && b < nbk)
+                                    ? a.uniforms[((size_t)(rep0 + lane) * n_sweeps + s) * n + i0 + b]
+                                    : 0.0f;
+                }
+                SG_STAMP(4);
+                mbar_wait(&rawbar[slot], par);
+                SG_STAMP(5);
+                const float* rawp = raw_s + slot * kBlk * kG + r;
+                const float* thp = theta_s + slot * kBlk * kG + r;
+                const float* cin = cin_s + slot * kBlk * kBlk;
+                const float* ccr = ccr_s + slot * kBlk * kBlk;
+                float v[kBlk];
+#pragma unroll
+                for (int b = 0; b < kBlk; ++b) v[b] = rawp[b * kG];
+                // flips of the previous block (not yet in the raw values)
+                if (k > 0) {
+#pragma unroll
+                    for (int aa = 0; aa < kBlk; ++aa) {
+                        if (pam[aa] != 0u) {
+                            const float da = pdec[aa];
+                            const float4* row = reinterpret_cast<const float4*>(ccr + aa * kBlk);
+#pragma unroll
+                            for (int b4 = 0; b4 < kBlk / 4; ++b4) {
+                                const float4 c4 = row[b4];
+                                v[4 * b4 + 0] = fmaf(da, c4.x, v[4 * b4 + 0]);
+                                v[4 * b4 + 1] = fmaf(da, c4.y, v[4 * b4 + 1]);
+                                v[4 * b4 + 2] = fmaf(da, c4.z, v[4 * b4 + 2]);
+                                v[4 * b4 + 3] = fmaf(da, c4.w, v[4 * b4 + 3]);
+                            }
+                        }
+                    }
+                }
+                SG_STAMP(6);
+                float th[kBlk];
+                uint32_t w0[kBlk], dup[kBlk];
+#pragma unroll
+                for (int b = 0; b < kBlk; ++b) {
+                    th[b] = INJECT ? 0.0f : thp[b * kG];
+                    w0[b] = sbits[r * W + (site[b] >> 5)];
+                    dup[b] = dup_s[slot * kBlk + b];
+                }
+                // the 16 attempts of the block, strictly in order, registers only
+                uint32_t myflips = 0;
+                float d[kBlk];
+#pragma unroll
+                for (int aa = 0; aa < kBlk; ++aa) {
+                    const bool up = (((w0[aa] >> (site[aa] & 31)) ^ (uint32_t)__popc(myflips & dup[aa])) & 1u) != 0u;
+                    bool flip = false;
+                    const float fv = v[aa];
+                    if (!INJECT) {
+                        if (a.rule == 0) {
+                            const float x = up ? 2.0f * fv : -2.0f * fv;  // dE = 2 s f
+                            flip = x < th[aa];
+                        } else {
+                            flip = ((fv > th[aa]) != up);
+                        }
+                    } else {
+                        if (a.rule == 0) {
+                            const float x = up ? 2.0f * fv : -2.0f * fv;
+                            flip = (x <= 0.0f) || (uu[aa] < expf((float)(-(double)x / dT)));
+                        } else {
+                            const float arg = (a.rule == 1) ? (float)(-2.0 * (double)fv / dT)
+                                                            : (float)(-2.0 * (1.0 / dT) * (double)fv);
+                            const float p_up = 1.0f / (1.0f + expf(arg));
+                            flip = ((uu[aa] < p_up) != up);
+                        }
+                    }
+                    flip = flip && active && (aa < nbk);
+                    const float da = flip ? (up ? -2.0f : 2.0f) : 0.0f;
+                    d[aa] = da;
+                    myflips |= flip ? (1u << aa) : 0u;
+                    const uint32_t am = __ballot_sync(0xFFFFFFFFu, flip);
+                    pam[aa] = am;
+                    if (am != 0u && aa + 1 < kBlk) {
+                        const float* row = cin + aa * kBlk;
+#pragma unroll
+                        for (int b = aa + 1; b < kBlk; ++b) v[b] = fmaf(da, row[b], v[b]);
+                    }
+                }
+                n_acc += (unsigned int)__popc(myflips);
+                SG_STAMP(7);
+                // B operand (K-major bf16): byte(n, k) = (n/8)*128 + (k/8)*256 + (n%8)*16 + (k%8)*2
+                if (lane < kG) {
+                    unsigned char* bo = bop_s + slot * kBopBytes + (lane & 7) * 16 + (lane >> 3) * kBSbo;
+                    *reinterpret_cast<uint4*>(bo) =
+                        make_uint4(pack_bf16x2(d[0], d[1]), pack_bf16x2(d[2], d[3]),
+                                   pack_bf16x2(d[4], d[5]), pack_bf16x2(d[6], d[7]));
+                    *reinterpret_cast<uint4*>(bo + kBLbo) =
+                        make_uint4(pack_bf16x2(d[8], d[9]), pack_bf16x2(d[10], d[11]),
+                                   pack_bf16x2(d[12], d[13]), pack_bf16x2(d[14], d[15]));
+                }
+                // spin bit planes (lane r owns plane r; XOR commutes, so order is irrelevant)
+#pragma unroll
+                for (int aa = 0; aa < kBlk; ++aa)
+                    if ((myflips >> aa) & 1u)
+                        atomicXor(&sbits[r * W + (site[aa] >> 5)], 1u << (site[aa] & 31));
+#pragma unroll
+                for (int b = 0; b < kBlk; ++b) pdec[b] = d[b];
+                fence_proxy_async();  // B operand visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&decbar[slot]);
+                SG_STAMP(8);
+            }
+            // ---- end of sweep: energy, best tracking
+            named_sync(1);
+            named_sync(2);
+            bool improved = false;
+            if (active) {
+                const float acc = red[0 * kG + lane] + red[1 * kG + lane] + red[2 * kG + lane] +
+                                  red[3 * kG + lane];
+                cur_e = -0.5f * acc;
+                if (a.energy_trace) a.energy_trace[(size_t)s * a.R + rep0 + lane] = cur_e;
+                if (a.track_best && cur_e < best_e) {
+                    best_e = cur_e;
+                    improved = true;
+                }
+            }
+            const uint32_t im = __ballot_sync(0xFFFFFFFFu, improved);
+            if (lane == 0) flags[0] = im;
+            named_sync(3);
+            named_sync(1);
+        }
+        if (active) {
+            a.energy[rep0 + lane] = cur_e;
+            if (a.track_best) a.best_energy[rep0 + lane] = best_e;
+            a.accepted[rep0 + lane] += (unsigned long long)n_acc;
+        }
+    } else {
+        // ======================================================== MMA ISSUER
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t fpar = 0;
+            int kg = 0;
+#pragma unroll 1
+            for (int s = s_begin; s < s_end; ++s) {
+#pragma unroll 1
+                for (int k = 0; k < nblk; ++k, ++kg) {
+                    const int slot = kg & (kSlots - 1);
+                    SG_STAMP(9);
+                    mbar_wait(&decbar[slot], (uint32_t)(kg >> 2) & 1u);
+                    SG_STAMP(10);
+                    // raw values of block k+1 must have been read before this block's update lands
+                    if (k + 1 < nblk)
+                        mbar_wait(&rawbar[(kg + 1) & (kSlots - 1)], (uint32_t)((kg + 1) >> 2) & 1u);
+                    const uint64_t bdesc =
+                        tc::make_smem_desc(smem_u32(bop_s + slot * kBopBytes), kBLbo, kBSbo);
+                    SG_STAMP(11);
+#pragma unroll 1
+                    for (int c = 0; c < nchunk; ++c) {
+                        mbar_wait(&full[stage], fpar);
+                        tc::fence_after_sync();
+                        const int nt = min(kChunkTiles, T - c * kChunkTiles);
+                        const uint32_t abase = smem_u32(ring + (size_t)stage * kStageBytes);
+                        for (int tt = 0; tt < ((dbg & 2) ? 0 : nt); ++tt) {
+#pragma unroll
+                            for (int p = 0; p < P; ++p) {
+                                const uint64_t adesc = tc::make_smem_desc(
+                                    abase + (tt * P + p) * kTileBytes, kALbo, kASbo);
+                                tc::mma_bf16_ss(tbase + (c * kChunkTiles + tt) * kG, adesc, bdesc,
+                                                kIdesc, 1u);
+                            }
+                        }
+                        tc::mma_commit(&empty[stage]);
+                        if (++stage == NS) { stage = 0; fpar ^= 1u; }
+                    }
+                    tc::mma_commit(&mmadone[slot]);
+                    SG_STAMP(12);
+                }
+            }
+        }
+    }
+
+    // ------------------------------------------------------------ teardown
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tbase, (uint32_t)tmem_cols);
+}
+
+
+// ---------------------------------------------------------------- MMA issue-rate probe
+// One thread issues `iters` x 32 back-to-back tcgen05.mma (M = 128, K = 16, bf16) on static
+// shared-memory operands, cycling over 32 A tiles and the accumulator columns; reports clocks
+// per MMA.  variant: 0 = A MN-major no swizzle (SBO 128), 1 = same with SBO 144,
+// 2 = A K-major no swizzle, 3 = A K-major 128B swizzle, 4 = A MN-major 128B swizzle.
+__global__ void __launch_bounds__(128, 1)
+tc_mma_bench_kernel(int variant, int n_dim, int iters, long long* out) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tptr;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (160 * 1024) / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) {
+        tc::tmem_alloc(&tptr, 512);
+        tc::tmem_relinquish();
+    }
+    fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tbase = tptr;
+    if (tid == 0) {
+        const uint32_t a0 = smem_u32(smem);            // 32 A tiles, 4608 B apart (128 KB + pad)
+        const uint32_t b0 = smem_u32(smem + 150 * 1024);
+        uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_dim >> 3) << 17) | (8u << 24);
+        uint32_t lbo, sbo, tile = 4608;
+        uint64_t lt = 0;
+        if (variant == 0) { lbo = 2048; sbo = 128; idesc |= (1u << 15); }
+        else if (variant == 1) { lbo = 2304; sbo = 144; idesc |= (1u << 15); }
+        else if (variant == 2) { lbo = 128; sbo = 256; }
+        else if (variant == 3) { lbo = 16; sbo = 1024; lt = 2; tile = 4096; }
+        else { lbo = 1024; sbo = 2048; lt = 2; idesc |= (1u << 15); tile = 4096; }
+        // B: K-major no swizzle, n_dim rows: (n/8)*128 + (k/8)*(n_dim*16)
+        const uint64_t bdesc = tc::make_smem_desc(b0, (uint32_t)n_dim * 16, 128);
+        const int ncol_tiles = 512 / n_dim;
+        const long long t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+            for (int t = 0; t < 32; ++t) {
+                uint64_t adesc;
+                if (variant == 3) {
+                    // 8 tiles of 128 x 64 (16 KB); K = 16 sub-block j = +32 B
+                    adesc = tc::make_smem_desc(a0 + (t >> 2) * 16384 + (t & 3) * 32, lbo, sbo) | (lt << 61);
+                } else {
+                    adesc = tc::make_smem_desc(a0 + t * tile, lbo, sbo) | (lt << 61);
+                }
+                tc::mma_bf16_ss(tbase + (t % ncol_tiles) * n_dim, adesc, bdesc, idesc, 1u);
+            }
+        }
+        const long long t1 = clock64();
+        tc::mma_commit(&bar);
+        mbar_wait(&bar, 0);
+        const long long t2 = clock64();
+        out[0] = t1 - t0;
+        out[1] = t2 - t0;
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tbase, 512);
+}
+
 }  // namespace
 
 cudaError_t launch_split_planes(const float* Jt, int n, int n_pad, void* Jp, int n_tc,
@@ -217,6 +920,99 @@ cudaError_t launch_tc_selftest(const void* Jp, int n, int n_tc, int planes, cons
     else return cudaErrorInvalidValue;
 #undef SG_ST
     return cudaGetLastError();
+}
+
+
+cudaError_t launch_tc_mma_bench(int variant, int n_dim, int iters, long long* out, cudaStream_t st) {
+    const int smem = 160 * 1024;
+    cudaError_t err = cudaFuncSetAttribute(tc_mma_bench_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err != cudaSuccess) return err;
+    tc_mma_bench_kernel<<<1, 128, smem, st>>>(variant, n_dim, iters, out);
+    return cudaGetLastError();
+}
+
+bool sweep_tc_supported(int n, int n_tc) { return n_tc > 0 && n_tc <= 4096 && n >= 16; }
+
+size_t sweep_tc_sites_bytes(int n, int n_sweeps) {
+    const int n_s = (n + 15) / 16 * 16;
+    return (size_t)n_sweeps * n_s * sizeof(uint16_t);
+}
+
+// bytes of operand stream one sweep needs
+size_t sweep_tc_stream_bytes_per_sweep(int n, int n_tc, int planes) {
+    const int nblk = (n + kBlk - 1) / kBlk;
+    const int nchunk = (n_tc / kTileM + kChunkTiles - 1) / kChunkTiles;
+    return (size_t)nblk * nchunk * kChunkTiles * planes * kTileBytes;
+}
+
+cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int planes, bool inject,
+                            void* sites_buf, void* stream_buf, size_t stream_cap,
+                            uint64_t* launches, cudaStream_t st) {
+    if (planes < 1 || planes > 3 || !sweep_tc_supported(a.n, n_tc)) return cudaErrorInvalidValue;
+    if (a.site_mode == 3 || (a.site_mode == 2 && a.s_bs != 0)) return cudaErrorInvalidValue;
+    const int n_s = (a.n + 15) / 16 * 16;
+    uint16_t* sites = static_cast<uint16_t*>(sites_buf);
+    {
+        const int total = a.n_sweeps * (n_s / 4);
+        int grid = (total + 255) / 256;
+        if (grid > 1184) grid = 1184;
+        tc_sites_kernel<<<grid, 256, 0, st>>>(a.site_mode, a.seed, a.sweep_base, a.n, n_s,
+                                              a.n_sweeps, a.sites, a.s_ss, sites);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        ++*launches;
+    }
+    int NS = kMaxStagesTc;
+    while (NS > 2 && tc_layout(n_tc, planes, NS).total > 227 * 1024) --NS;
+    if (const char* ns_env = getenv("SG_TC_STAGES")) {
+        const int v = atoi(ns_env);
+        if (v >= 2 && v <= NS) NS = v;
+    }
+    const size_t smem = tc_layout(n_tc, planes, NS).total;
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    int cols = 32;
+    while (cols < (n_tc / kTileM) * kG) cols *= 2;
+    const int grid = (a.R + kG - 1) / kG;
+    const __nv_bfloat16* J = static_cast<const __nv_bfloat16*>(Jp);
+    const int nblk = (a.n + kBlk - 1) / kBlk;
+    const int nchunk = (n_tc / kTileM + kChunkTiles - 1) / kChunkTiles;
+    const size_t per_sweep = sweep_tc_stream_bytes_per_sweep(a.n, n_tc, planes);
+    const int sub = (int)(stream_cap / per_sweep);
+    if (sub < 1) return cudaErrorInvalidValue;
+    // development aid (timing experiments only, results are wrong): SG_TC_DBG bit0 = constant
+    // operand chunk, bit1 = no MMA, bit2 = no raw TMEM reads
+    const char* dbg_env = getenv("SG_TC_DBG");
+    const int dbg = dbg_env ? atoi(dbg_env) : 0;
+    cudaError_t err = cudaSuccess;
+    for (int s0 = 0; s0 < a.n_sweeps; s0 += sub) {
+        const int s1 = (s0 + sub < a.n_sweeps) ? s0 + sub : a.n_sweeps;
+        const size_t units = (size_t)(s1 - s0) * per_sweep / 16;
+        int ggrid = (int)((units + 255) / 256 < (size_t)148 * 16 ? (units + 255) / 256 : (size_t)148 * 16);
+#define SG_TC(P, INJ)                                                                          \
+    {                                                                                          \
+        tc_gather_kernel<P><<<ggrid, 256, 0, st>>>(J, a.n, n_tc, sites, n_s, s0, s1 - s0, nblk,\
+                                                   nchunk, static_cast<uint4*>(stream_buf));   \
+        err = cudaGetLastError();                                                              \
+        if (err != cudaSuccess) return err;                                                    \
+        err = cudaFuncSetAttribute(sweep_tc_kernel<P, INJ>,                                    \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+        if (err != cudaSuccess) return err;                                                    \
+        sweep_tc_kernel<P, INJ><<<grid, kTcThreads, smem, st>>>(                               \
+            a, J, n_tc, sites, n_s, NS, cols, static_cast<const unsigned char*>(stream_buf),   \
+            s0, s1, dbg);                                                                      \
+    }
+        if (inject) {
+            if (planes == 1) SG_TC(1, true) else if (planes == 2) SG_TC(2, true) else SG_TC(3, true)
+        } else {
+            if (planes == 1) SG_TC(1, false) else if (planes == 2) SG_TC(2, false) else SG_TC(3, false)
+        }
+#undef SG_TC
+        err = cudaGetLastError();
+        if (err != cudaSuccess) return err;
+        *launches += 2;
+    }
+    return err;
 }
 
 }  // namespace sg

@@ -157,7 +157,8 @@ class Engine:
               sweep_base: int = 0, sites: Optional[ArrayLike] = None,
               sites_block_stride: int = 0, sites_sweep_stride: Optional[int] = None,
               uniforms: Optional[ArrayLike] = None, energy_trace: bool = False,
-              track_best: bool = True, replicas_per_block: int = 0) -> Optional[torch.Tensor]:
+              track_best: bool = True, replicas_per_block: int = 0, kernel: str = "auto",
+              coupling_planes: int = 0) -> Optional[torch.Tensor]:
         """Run ``n_sweeps`` sweeps on every replica (one kernel launch).
 
         temps: float64 array addressed as temps[s*temps_sweep_stride + r*temps_replica_stride]
@@ -172,6 +173,8 @@ class Engine:
         p.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         p.sweep_base = int(sweep_base)
         p.track_best = 1 if track_best else 0
+        p.kernel = _lib.SG_KERNEL[kernel]
+        p.coupling_planes = int(coupling_planes)
         keep = []
         if temps is not None:
             t = self._dev(temps, torch.float64)

@@ -1,0 +1,35 @@
+"""Clock-stamp timeline of block 0 of the tensor-core sweep kernel (development aid)."""
+import sys, os, ctypes
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from spin_glass_anneal_rl_b200.engine import Engine
+P = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+n = 4096; R = 148 * 16
+rs = np.random.RandomState(3003)
+Gm = rs.normal(0.0, 1.0 / np.sqrt(n), size=(n, n)).astype(np.float32)
+J = ((Gm + Gm.T) / 2).astype(np.float32); np.fill_diagonal(J, 0)
+eng = Engine(0)
+eng.set_model(torch.from_numpy(J).cuda(), torch.zeros(n, device="cuda"))
+eng.alloc_replicas(R)
+eng.set_spins((torch.randint(0, 2, (R, n), device="cuda") * 2 - 1).to(torch.int8))
+eng.init_fields()
+eng.sweep(1, np.array([1.0]), seed=1, kernel="tc", coupling_planes=P)
+buf = torch.zeros(512 * 16, dtype=torch.int64, device="cuda")
+eng._lib.sg_debug_set_timeline.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+eng._lib.sg_debug_set_timeline(eng._h, ctypes.c_void_p(buf.data_ptr()))
+eng.sweep(2, np.array([1.0]), seed=1, sweep_base=1, kernel="tc", coupling_planes=P)
+torch.cuda.synchronize()
+t = buf.cpu().numpy().reshape(512, 16)
+t0 = t[0, 0]
+names = ["q_start", "q_tabs", "q_mmaok", "q_raw", "d_wait", "d_rawok", "d_cross", "d_dec", "d_done", "m_wait", "m_decok", "m_rawok", "m_done", "p_start", "p_end"]
+print("blk " + " ".join(f"{x:>8s}" for x in names))
+for k in list(range(0, 10)) + list(range(100, 110)) + list(range(254, 262)):
+    print(f"{k:3d} " + " ".join(f"{int(t[k, i] - t0):8d}" for i in range(15)))
+d = t[40:240].astype(np.int64)
+def m(a, b): return float((d[:, a] - d[:, b]).mean())
+print("period", float((d[1:, 12] - d[:-1, 12]).mean()))
+print("quarter: tables+theta", m(1, 0), " wait mma(k-2)", m(2, 1), " raw reads", m(3, 2))
+print("decision: wait raw", m(5, 4), " load+cross", m(6, 5), " 16 attempts", m(7, 6), " epilogue", m(8, 7))
+print("mma: wait dec", m(10, 9), " wait raw(k+1)", m(11, 10), " chunks", m(12, 11))
+print("producer: block issue", m(14, 13))
+print("lags: q_raw(k)->d_rawok(k)", m(5, 3), " d_done(k)->m_decok(k)", m(10, 8), " m_done(k)->q_mmaok(k+2)", float((d[2:, 2] - d[:-2, 12]).mean()))
