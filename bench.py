@@ -7,8 +7,11 @@ One "step" = one pass of the hot path over one batch: `--sweeps` Metropolis swee
 replica of the SK N=4096 instance (cfg3 of BASELINE.json), 8192 replicas PER GPU (weak
 scaling: replicas are independent, no data-path collective; the only collective is the final
 argmin allgather of the best energies).  `value` times the sweep launches with the state
-resident in HBM; `e2e` times the same step through the host-buffer C-ABI path (pinned host
-spins -> device, local-field initialisation, sweeps, best energies -> host).
+resident in HBM (site-table + operand-gather + sweep kernels of the tensor-core path, all
+inside the timed region); `e2e` times the same step through the host-buffer C-ABI path (pinned
+host spins -> device, local-field initialisation, sweeps, best energies -> host).  The roofline
+object is about the dominant kernel alone (sg::sweep_tc_kernel), timed with CUDA events by the
+library around each of its launches.
 
 `--impl reference` times the reference's CPU algorithm (the oracle port in C, all host
 threads, per-attempt dot products + per-sweep O(N^2) energy exactly like the reference's
@@ -157,8 +160,17 @@ def run_ours(args):
     blocks = (R + gmax - 1) // gmax
     launches0 = eng.launch_count()
 
+    kernel = args.kernel
+    planes = args.planes
+
     def step(i):
-        eng.sweep(sweeps, temps, seed=99 + rank, sweep_base=i * sweeps, site_order="random", track_best=True)
+        eng.sweep(sweeps, temps, seed=99 + rank, sweep_base=i * sweeps, site_order="random",
+                  track_best=True, kernel=kernel, coupling_planes=planes)
+
+    use_tc = kernel in ("auto", "tc")
+    if use_tc:
+        gmax = 16
+        blocks = (R + gmax - 1) // gmax
 
     def barrier():
         if world > 1:
@@ -171,6 +183,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     acc0 = eng.accepted().sum().item()
+    eng.set_profiling(True)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     l0 = eng.launch_count()
     ev[0].record()
@@ -180,6 +193,8 @@ def run_ours(args):
     barrier()
     ms_total = ev[0].elapsed_time(ev[1])
     gpu_launches = eng.launch_count() - l0
+    prof = eng.profile()
+    eng.set_profiling(False)
     acc1 = eng.accepted().sum().item()
     clocks = sampler.summary()
 
@@ -218,28 +233,49 @@ def run_ours(args):
     acc_rate = (acc1 - acc0) / (float(R) * n * sweeps * args.steps)
 
     if rank == 0:
-        # roofline of the dominant kernel (sweep): algorithmic J-stream bytes = one padded row of
-        # J per (block, attempt); peak = bandwidth of the same access pattern measured on this box
-        row_bytes = q["n_pad"] * 4
-        bytes_per_launch = float(blocks) * sweeps * n * row_bytes
-        ms_launch = ms_total / max(1, gpu_launches)
+        # roofline of the dominant kernel (the sweep): algorithmic J-stream bytes = every block
+        # streams the 16 coupling rows of every attempt block once (P bf16 planes on the
+        # tensor-core path, one padded fp32 row per attempt on the SIMT path); peak = bandwidth of
+        # the same transport (TMA bulk copies of an L2-resident buffer into a shared-memory ring,
+        # one block per SM) measured on this box
+        if use_tc:
+            n_tc = (n + 127) // 128 * 128
+            bytes_per_sweep_block = float(n) * n_tc * 2 * planes
+            kname = "sg::sweep_tc_kernel"
+            stream_desc = f"{planes} bf16 planes of J in UMMA operand layout ({planes * 2 * n * n_tc / 1e6:.0f} MB per sweep)"
+        else:
+            bytes_per_sweep_block = float(n) * q["n_pad"] * 4
+            kname = "sg::sweep_kernel"
+            stream_desc = "fp32 rows of J (73 MB padded)"
+        n_klaunch = max(1, int(prof["sweep_launches"]))
+        bytes_per_launch = float(blocks) * sweeps * bytes_per_sweep_block * args.steps / n_klaunch
+        ms_launch = prof["sweep_ms"] / n_klaunch
         achieved = bytes_per_launch / (ms_launch * 1e-3) / 1e9
-        l2_peak = eng.measure_tma_stream(J.nbytes + (1 << 20), row_bytes, 8, 4096, False)
+        l2_peak = max(eng.measure_tma_stream(J.nbytes + (1 << 20), 17920, 8, 4096, False),
+                      eng.measure_tma_stream(J.nbytes + (1 << 20), 49152, 4, 2048, False))
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         hbm = float(peaks.get("hbm_gbs", 6650.0))
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_sweep_tc_traffic.json")))[
+                "dram_bytes_per_launch"]
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "achieved": achieved, "peak": l2_peak, "unit": "GB/s",
-                    "frac": achieved / l2_peak, "traffic": None,
-                    "peak_source": "measured on this box: TMA bulk-copy stream of the L2-resident J "
-                                   "(one block per SM, 8-stage ring, sg_measure_tma_stream); J (73 MB "
-                                   "padded) is L2-resident, so the HBM copy peak is not the bound",
+                    "frac": achieved / l2_peak, "traffic": traffic,
+                    "peak_source": "measured on this box (sg_measure_tma_stream): TMA bulk-copy stream of "
+                                   "an L2-resident J-sized buffer, one block per SM; the J stream ("
+                                   + stream_desc + ") is read by all SMs in the same order, so it is "
+                                   "served from the 126 MB L2 and the HBM copy peak is not the bound",
                     "hbm_peak": hbm, "hbm_peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                     "frac_of_hbm_peak": achieved / hbm,
-                    "kernel": "sg::sweep_kernel", "bytes_per_launch": bytes_per_launch,
-                    "ms_per_launch": ms_launch}
+                    "kernel": kname, "bytes_per_launch": bytes_per_launch,
+                    "ms_per_launch": ms_launch, "launches_timed": n_klaunch,
+                    "gather_ms_per_launch": prof["gather_ms"] / max(1, int(prof["gather_launches"]))}
         cpu = None
         if world == 1 or True:
             v, threads, sample = cpu_reference(0, args.cpu_budget)
@@ -251,10 +287,13 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": f"SK dense N={N_SPINS} Gaussian J (cfg3), Metropolis sweep, T={TEMPERATURE}, "
                                    f"{R} replicas/GPU x {sweeps} sweeps per step, shared random site order",
+                       "kernel": "tensor-core (tcgen05, TMEM-resident fields)" if use_tc else "simt",
+                       "coupling_planes": planes if use_tc else None,
                        "replicas_per_gpu": R, "sweeps_per_step": sweeps, "replicas_per_block": gmax,
                        "blocks": blocks, "n_pad": q["n_pad"], "acceptance_rate": acc_rate,
-                       "l2_policy": "inputs (J 73 MB + 170 MB replica state) exceed the 126 MB L2; "
-                                    "no flush between steps", "best_energy": best_global},
+                       "l2_policy": "inputs (J planes 100 MB + operand stream 500 MB + 170 MB replica "
+                                    "state) exceed the 126 MB L2; no flush between steps",
+                       "best_energy": best_global},
             "e2e": {"value": e2e_value, "unit": "attempts/s", "h2d_bytes_per_step": int(R) * n * world,
                     "d2h_bytes_per_step": int(R) * 4 * world, "ms_per_step": ms_e2e},
             "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cpu,
@@ -272,6 +311,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--replicas", type=int, default=REPLICAS_PER_GPU)
     ap.add_argument("--sweeps", type=int, default=5, help="sweeps per step")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "tc", "simt"])
+    ap.add_argument("--planes", type=int, default=3,
+                    help="bf16 planes per coupling on the tensor-core path (3 = exact fp32 couplings)")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline work")
     ap.add_argument("--ref-budget", type=float, default=10.0, help="seconds per reference step")
     args = ap.parse_args()

@@ -199,6 +199,14 @@ int sg_tc_selftest(sg_engine *e, int planes, const int32_t *sites16, const float
 int sg_query(sg_engine *e, int32_t *n, int32_t *n_pad, int32_t *n_replicas,
              int32_t *max_replicas_per_block, int32_t *sm_count);
 
+/* Per-kernel device timing for roofline reporting: while enabled, every sweep-kernel launch (and,
+ * for the tensor-core path, every operand-gather launch) is bracketed by CUDA events on its
+ * stream.  sg_get_profile synchronises, returns the accumulated milliseconds / launch counts since
+ * the last call and resets them. */
+int sg_set_profiling(sg_engine *e, int enable);
+int sg_get_profile(sg_engine *e, double *sweep_ms, uint64_t *sweep_launches, double *gather_ms,
+                   uint64_t *gather_launches);
+
 /* Kernel launch counter (every kernel this library launched on this engine). */
 uint64_t sg_launch_count(sg_engine *e);
 

@@ -68,6 +68,9 @@ PROTOTYPES = {
     "sg_measure_tma_stream": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int,
                                       POINTER(c_double)]),
     "sg_tc_selftest": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sg_set_profiling": (c_int, [c_void_p, c_int]),
+    "sg_get_profile": (c_int, [c_void_p, POINTER(c_double), POINTER(c_uint64), POINTER(c_double),
+                               POINTER(c_uint64)]),
     "sg_query": (c_int, [c_void_p, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32),
                          POINTER(c_int32), POINTER(c_int32)]),
     "sg_launch_count": (c_uint64, [c_void_p]),

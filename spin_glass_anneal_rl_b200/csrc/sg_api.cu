@@ -64,6 +64,8 @@ struct sg_engine {
     size_t tc_sites_cap = 0;
     void* tc_stream = nullptr;  // operand stream (gathered J rows in UMMA layout), <= 1 GiB
     size_t tc_stream_cap = 0;
+    bool profiling = false;
+    sg::KernelTimer timer;
     int8_t* spins = nullptr;
     float* fields = nullptr;
     float* energy = nullptr;
@@ -480,11 +482,14 @@ int sg_sweep(sg_engine* e, const sg_sweep_params* p, void* stream) {
         a.G = 16;
         SG_CUDA(sg::launch_sweep_tc(a, e->Jp, e->n_tc, planes, inject, e->tc_sites, e->tc_stream,
                                     e->tc_stream_cap, &e->launches,
+                                    e->profiling ? &e->timer : nullptr,
                                     static_cast<cudaStream_t>(stream)));
         return SG_OK;
     }
     const int grid = (e->R + G - 1) / G;
+    if (e->profiling) e->timer.begin(0, static_cast<cudaStream_t>(stream));
     SG_CUDA(sg::launch_sweep(a, inject, grid, static_cast<cudaStream_t>(stream)));
+    if (e->profiling) e->timer.end(static_cast<cudaStream_t>(stream));
     e->launches++;
     return SG_OK;
 }
@@ -732,6 +737,30 @@ int sg_tc_selftest(sg_engine* e, int planes, const int32_t* sites16, const float
     cudaFree(d_out);
     if (rc != SG_OK) return rc;
     if (ce != cudaSuccess) return fail(SG_ERR_CUDA, "sg_tc_selftest", ce);
+    return SG_OK;
+}
+
+int sg_set_profiling(sg_engine* e, int enable) {
+    SG_REQUIRE(e, "sg_set_profiling: NULL engine");
+    DeviceGuard g(e->device);
+    double ms[2];
+    unsigned long long cnt[2];
+    e->timer.collect(ms, cnt);
+    e->profiling = enable != 0;
+    return SG_OK;
+}
+
+int sg_get_profile(sg_engine* e, double* sweep_ms, uint64_t* sweep_launches, double* gather_ms,
+                   uint64_t* gather_launches) {
+    SG_REQUIRE(e, "sg_get_profile: NULL engine");
+    DeviceGuard g(e->device);
+    double ms[2];
+    unsigned long long cnt[2];
+    e->timer.collect(ms, cnt);
+    if (sweep_ms) *sweep_ms = ms[0];
+    if (sweep_launches) *sweep_launches = cnt[0];
+    if (gather_ms) *gather_ms = ms[1];
+    if (gather_launches) *gather_launches = cnt[1];
     return SG_OK;
 }
 

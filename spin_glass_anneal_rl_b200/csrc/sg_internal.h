@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 namespace sg {
 
 constexpr int kSweepThreads = 256;              // 8 warps: 2 per SM sub-partition, 255 regs each
@@ -58,6 +60,36 @@ cudaError_t launch_stream_probe(const float4* buf, int64_t n_vec, int iters, int
 cudaError_t launch_tma_probe(const float* buf, int64_t buf_rows, uint32_t row_bytes, int n_rows,
                              int depth, int stagger, float* sink, int grid, cudaStream_t st);
 
+// Optional per-kernel device timing (CUDA events on the launch stream): class 0 = sweep kernel,
+// class 1 = operand gather.  collect() synchronises the events and returns the sums.
+struct KernelTimer {
+    struct Span { cudaEvent_t a, b; int cls; };
+    std::vector<Span> spans;
+    void begin(int cls, cudaStream_t st) {
+        Span s{};
+        s.cls = cls;
+        cudaEventCreate(&s.a);
+        cudaEventCreate(&s.b);
+        cudaEventRecord(s.a, st);
+        spans.push_back(s);
+    }
+    void end(cudaStream_t st) { cudaEventRecord(spans.back().b, st); }
+    void collect(double ms[2], unsigned long long count[2]) {
+        ms[0] = ms[1] = 0.0;
+        count[0] = count[1] = 0;
+        for (Span& s : spans) {
+            float t = 0.0f;
+            cudaEventSynchronize(s.b);
+            cudaEventElapsedTime(&t, s.a, s.b);
+            ms[s.cls] += t;
+            count[s.cls]++;
+            cudaEventDestroy(s.a);
+            cudaEventDestroy(s.b);
+        }
+        spans.clear();
+    }
+};
+
 // K1-TC (sg_sweep_tc.cu): bf16 coupling planes and the tensor-core sweep
 cudaError_t launch_split_planes(const float* Jt, int n, int n_pad, void* Jp, int n_tc,
                                 cudaStream_t st);
@@ -74,7 +106,7 @@ size_t sweep_tc_stream_bytes_per_sweep(int n, int n_tc, int planes);
 // fit).  Launches the site-table kernel, then (gather, sweep) per sub-launch; counts them.
 cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int planes, bool inject,
                             void* sites_buf, void* stream_buf, size_t stream_cap,
-                            uint64_t* launches, cudaStream_t st);
+                            uint64_t* launches, KernelTimer* timer, cudaStream_t st);
 
 // K3 (sg_exchange.cu)
 struct ExchangeDev {

@@ -283,6 +283,48 @@ tc_gather_kernel(const __nv_bfloat16* __restrict__ Jp, int n, int n_tc,
     }
 }
 
+// Decision tables of every attempt block, computed once per sweep for the whole grid:
+//   cin[a][b] = J'[site_a][site_b]                (couplings among the block's own sites)
+//   ccr[a][b] = J'[site_a of block k-1][site_b]   (from the previous block's sites; 0 for k = 0)
+//   dup[b]    = bit mask of the earlier attempts of the block that visit the same site
+// J' = sum of the P planes.  kTabBytes per block, fetched by the sweep kernel with one TMA copy.
+constexpr int kTabBytes = 2 * kBlk * kBlk * 4 + kBlk * 4;  // 2112
+
+template <int P>
+__global__ void __launch_bounds__(256)
+tc_tables_kernel(const __nv_bfloat16* __restrict__ Jp, int n, int n_tc,
+                 const uint16_t* __restrict__ sites, int n_s, int s_begin, int nblk,
+                 unsigned char* __restrict__ tabs) {
+    const int k = blockIdx.x % nblk, s_rel = blockIdx.x / nblk;
+    const uint16_t* stab = sites + (size_t)(s_begin + s_rel) * n_s;
+    const int i0 = k * kBlk;
+    const int nbk = min(kBlk, n - i0);
+    const size_t plane_stride = (size_t)n * n_tc;
+    unsigned char* out = tabs + (size_t)blockIdx.x * kTabBytes;
+    float* cin = reinterpret_cast<float*>(out);
+    float* ccr = cin + kBlk * kBlk;
+    uint32_t* dup = reinterpret_cast<uint32_t*>(ccr + kBlk * kBlk);
+    for (int idx = threadIdx.x; idx < 2 * kBlk * kBlk; idx += blockDim.x) {
+        const int which = idx >> 8, aa = (idx >> 4) & 15, b = idx & 15;
+        float val = 0.0f;
+        if (b < nbk && (which == 0 ? (aa < nbk) : (k > 0))) {
+            const int sb = stab[i0 + b];
+            const int sr = which == 0 ? stab[i0 + aa] : stab[i0 - kBlk + aa];
+            const __nv_bfloat16* pj = Jp + (size_t)sr * n_tc + sb;
+            val = __bfloat162float(pj[0]);
+            if (P > 1) val += __bfloat162float(pj[plane_stride]);
+            if (P > 2) val += __bfloat162float(pj[2 * plane_stride]);
+        }
+        (which == 0 ? cin : ccr)[aa * kBlk + b] = val;
+    }
+    if (threadIdx.x < kBlk) {
+        uint32_t m = 0;
+        const int me = stab[i0 + threadIdx.x];
+        for (int a2 = 0; a2 < (int)threadIdx.x; ++a2) m |= (stab[i0 + a2] == me) ? (1u << a2) : 0u;
+        dup[threadIdx.x] = m;
+    }
+}
+
 // ---------------------------------------------------------------- the sweep
 constexpr int kTcThreads = 224;
 constexpr int kSlots = 4;
@@ -290,7 +332,7 @@ constexpr int kMaxStagesTc = 8;
 constexpr int kSyncThreads = 160;  // quarter warps + decision warp (named barriers 1..3)
 
 struct TcSmem {
-    size_t ring, bop, sbits, theta, raw, cin, ccr, dup, red, flags, bars, tptr, total;
+    size_t ring, bop, sbits, theta, raw, tab, red, flags, bars, tptr, total;
 };
 
 __host__ __device__ inline TcSmem tc_layout(int n_tc, int P, int NS) {
@@ -301,13 +343,11 @@ __host__ __device__ inline TcSmem tc_layout(int n_tc, int P, int NS) {
     L.sbits = off; off += (size_t)kG * (n_tc / 32) * sizeof(uint32_t);
     L.theta = off; off += (size_t)kSlots * kBlk * kG * sizeof(float);
     L.raw = off;   off += (size_t)kSlots * kBlk * kG * sizeof(float);
-    L.cin = off;   off += (size_t)kSlots * kBlk * kBlk * sizeof(float);
-    L.ccr = off;   off += (size_t)kSlots * kBlk * kBlk * sizeof(float);
-    L.dup = off;   off += (size_t)kSlots * kBlk * sizeof(uint32_t);
+    L.tab = off;   off += (size_t)kSlots * kTabBytes;
     L.red = off;   off += 4 * kG * sizeof(float);
     L.flags = off; off += 4 * sizeof(uint32_t);
     off = (off + 15) & ~(size_t)15;
-    L.bars = off;  off += (size_t)(2 * kMaxStagesTc + 3 * kSlots) * sizeof(uint64_t);
+    L.bars = off;  off += (size_t)(2 * kMaxStagesTc + 7 * kSlots) * sizeof(uint64_t);
     L.tptr = off;  off += 16;
     L.total = off;
     return L;
@@ -346,13 +386,16 @@ template <int P, bool INJECT>
 __global__ void __launch_bounds__(kTcThreads, 1)
 sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const int n_tc,
                 const uint16_t* __restrict__ sites_g, const int n_s, const int NS,
-                const int tmem_cols, const unsigned char* __restrict__ Q, const int s_begin,
-                const int s_end, const int dbg) {
+                const int tmem_cols, const unsigned char* __restrict__ Q,
+                const unsigned char* __restrict__ tabs_g, const int s_begin, const int s_end,
+                const int dbg) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int n = a.n, n_pad = a.n_pad;
     const int W = n_tc >> 5;
     const int T = n_tc / kTileM;
     const int nchunk = (T + kChunkTiles - 1) / kChunkTiles;
+    const int hc = (nchunk + 1) >> 1;                   // chunks [0, hc) = half 0, the rest = half 1
+    const int half_cols = hc * kChunkTiles * kTileM;    // field columns below this are in half 0
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     const TcSmem L = tc_layout(n_tc, P, NS);
@@ -361,16 +404,16 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
     uint32_t* sbits = reinterpret_cast<uint32_t*>(smem + L.sbits);
     float* theta_s = reinterpret_cast<float*>(smem + L.theta);  // [slot][b][r]
     float* raw_s = reinterpret_cast<float*>(smem + L.raw);      // [slot][b][r]
-    float* cin_s = reinterpret_cast<float*>(smem + L.cin);      // [slot][a][b]
-    float* ccr_s = reinterpret_cast<float*>(smem + L.ccr);      // [slot][a][b]
-    uint32_t* dup_s = reinterpret_cast<uint32_t*>(smem + L.dup);  // [slot][b]
+    unsigned char* tab_s = smem + L.tab;  // [slot]{cin[16][16], ccr[16][16], dup[16]} (TMA)
     float* red = reinterpret_cast<float*>(smem + L.red);
     uint32_t* flags = reinterpret_cast<uint32_t*>(smem + L.flags);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);
     uint64_t* empty = full + kMaxStagesTc;
-    uint64_t* rawbar = empty + kMaxStagesTc;
-    uint64_t* decbar = rawbar + kSlots;
-    uint64_t* mmadone = decbar + kSlots;
+    uint64_t* tabbar = empty + kMaxStagesTc;   // [slot]     decision tables of a block landed (TMA)
+    uint64_t* thbar = tabbar + kSlots;         // [slot]     thresholds of a block published
+    uint64_t* rbar = thbar + kSlots;           // [slot][2]  raw field values of a half published
+    uint64_t* decbar = rbar + 2 * kSlots;      // [slot]     block decided, B operand written
+    uint64_t* hdone = decbar + kSlots;         // [slot][2]  MMAs of a half of a block completed
     uint32_t* tptr = reinterpret_cast<uint32_t*>(smem + L.tptr);
     constexpr int kStageBytes = kChunkTiles * P * kTileBytes;
 
@@ -388,9 +431,13 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
             mbar_init(&empty[d], 1);
         }
         for (int d = 0; d < kSlots; ++d) {
-            mbar_init(&rawbar[d], 4);
+            mbar_init(&tabbar[d], 1);
+            mbar_init(&thbar[d], 2);
+            mbar_init(&rbar[2 * d], 4);
+            mbar_init(&rbar[2 * d + 1], 4);
             mbar_init(&decbar[d], 1);
-            mbar_init(&mmadone[d], 1);
+            mbar_init(&hdone[2 * d], 1);
+            mbar_init(&hdone[2 * d + 1], 1);
         }
         fence_mbar_init();
         fence_proxy_async();
@@ -459,32 +506,6 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 const uint4 sq0 = *reinterpret_cast<const uint4*>(stab + i0);
                 const uint4 sq1 = *reinterpret_cast<const uint4*>(stab + i0 + 8);
                 const uint32_t swq[8] = {sq0.x, sq0.y, sq0.z, sq0.w, sq1.x, sq1.y, sq1.z, sq1.w};
-                // --- coupling tables (global gathers, issued before the TMEM wait)
-                {
-                    float* cin = cin_s + slot * kBlk * kBlk;
-                    float* ccr = ccr_s + slot * kBlk * kBlk;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int idx = tid + 128 * j;
-                        const int which = idx >> 8, aa = (idx >> 4) & 15, b = idx & 15;
-                        float val = 0.0f;
-                        if (b < nbk && (which == 0 ? (aa < nbk) : (kb > 0))) {
-                            const int sb = stab[i0 + b];
-                            const int sr = which == 0 ? stab[i0 + aa] : stab[i0 - kBlk + aa];
-                            const __nv_bfloat16* pj = Jp + (size_t)sr * n_tc + sb;
-                            val = __bfloat162float(pj[0]);
-                            if (P > 1) val += __bfloat162float(pj[plane_stride]);
-                            if (P > 2) val += __bfloat162float(pj[2 * plane_stride]);
-                        }
-                        (which == 0 ? cin : ccr)[aa * kBlk + b] = val;
-                    }
-                    if (tid < kBlk) {
-                        uint32_t m = 0;
-                        const int me = stab[i0 + tid];
-                        for (int a2 = 0; a2 < tid; ++a2) m |= (stab[i0 + a2] == me) ? (1u << a2) : 0u;
-                        dup_s[slot * kBlk + tid] = m;
-                    }
-                }
                 // --- thresholds: thread (qq, r) covers attempts 4qq..4qq+3 of the block
                 if (!INJECT && tid < 64) {
                     const int qq = tid >> 4, r = tid & 15;
@@ -507,35 +528,45 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                         }
                     }
                 }
-                // --- raw field values of the block's sites, as of the end of block kg-2
+                __syncwarp();
+                if (warp < 2 && lane == 0) mbar_arrive(&thbar[slot]);
                 if (warp == 0) SG_STAMP(1);
-                if (kg >= 2) mbar_wait(&mmadone[(kg - 2) & (kSlots - 1)], (uint32_t)((kg - 2) >> 2) & 1u);
-                tc::fence_after_sync();
-                if (warp == 0) SG_STAMP(2);
+                // --- raw field values of the block's sites, as of the end of block kg-2: the sites
+                // of a column half are read as soon as that half of block kg-2 has landed (the
+                // other half may still be executing), and the same half of block kg-1 is not
+                // issued before the read is done
                 float* rawb = raw_s + slot * kBlk * kG;
 #pragma unroll
-                for (int b = 0; b < kBlk; ++b) {
-                    const int site = (int)((swq[b >> 1] >> (16 * (b & 1))) & 0xFFFFu);
-                    if (b < nbk && ((site >> 5) & 3) == q && !(dbg & 4)) {
-                        float v[16];
-                        tc::tmem_ld16(tq + (site >> 7) * kG, v);
-                        tc::wait_ld();
-                        if (lane == (site & 31)) {
-                            float4* d4 = reinterpret_cast<float4*>(rawb + b * kG);
-                            d4[0] = make_float4(v[0], v[1], v[2], v[3]);
-                            d4[1] = make_float4(v[4], v[5], v[6], v[7]);
-                            d4[2] = make_float4(v[8], v[9], v[10], v[11]);
-                            d4[3] = make_float4(v[12], v[13], v[14], v[15]);
+                for (int h = 0; h < 2; ++h) {
+                    if (kg >= 2)
+                        mbar_wait(&hdone[2 * ((kg - 2) & (kSlots - 1)) + h], (uint32_t)((kg - 2) >> 2) & 1u);
+                    tc::fence_after_sync();
+                    if (warp == 0) SG_STAMP(2 + h);
+#pragma unroll
+                    for (int b = 0; b < kBlk; ++b) {
+                        const int site = (int)((swq[b >> 1] >> (16 * (b & 1))) & 0xFFFFu);
+                        const bool in_h = (site < half_cols) == (h == 0);
+                        if (b < nbk && in_h && ((site >> 5) & 3) == q && !(dbg & 4)) {
+                            float v[16];
+                            tc::tmem_ld16(tq + (site >> 7) * kG, v);
+                            tc::wait_ld();
+                            if (lane == (site & 31)) {
+                                float4* d4 = reinterpret_cast<float4*>(rawb + b * kG);
+                                d4[0] = make_float4(v[0], v[1], v[2], v[3]);
+                                d4[1] = make_float4(v[4], v[5], v[6], v[7]);
+                                d4[2] = make_float4(v[8], v[9], v[10], v[11]);
+                                d4[3] = make_float4(v[12], v[13], v[14], v[15]);
+                            }
                         }
                     }
+                    tc::fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&rbar[2 * slot + h]);
                 }
-                tc::fence_before_sync();
-                __syncwarp();
-                if (warp == 0) SG_STAMP(3);
-                if (lane == 0) mbar_arrive(&rawbar[slot]);
+                if (warp == 0) SG_STAMP(15);
             }
             // ---- end of sweep: energies from the TMEM-resident fields
-            mbar_wait(&mmadone[(kg - 1) & (kSlots - 1)], (uint32_t)((kg - 1) >> 2) & 1u);
+            mbar_wait(&hdone[2 * ((kg - 1) & (kSlots - 1)) + 1], (uint32_t)((kg - 1) >> 2) & 1u);
             tc::fence_after_sync();
             named_sync(1);  // decision warp has flipped the last spins of the sweep
             {
@@ -596,19 +627,31 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
         if (lane == 0) {
             int stage = 0;
             uint32_t epar = 1;  // a fresh barrier passes a wait on the "previous" phase
-            const size_t nchunks_total = (size_t)(s_end - s_begin) * nblk * nchunk;
+            const int nblk_total = (s_end - s_begin) * nblk;
+            const size_t nchunks_total = (size_t)nblk_total * nchunk;
             int kg = 0, cc = 0;
+            // decision tables of block j -> slot j % 4 (the slot's previous user, block j-4, has
+            // been decided long before the operand stream reaches block j-2)
+            auto issue_tables = [&](int j) {
+                if (j >= nblk_total) return;
+                const int sl = j & (kSlots - 1);
+                if (j >= kSlots) mbar_wait(&decbar[sl], (uint32_t)((j - kSlots) >> 2) & 1u);
+                mbar_arrive_expect_tx(&tabbar[sl], (uint32_t)kTabBytes);
+                bulk_g2s(tab_s + sl * kTabBytes, tabs_g + (size_t)j * kTabBytes, (uint32_t)kTabBytes,
+                         &tabbar[sl]);
+            };
+            issue_tables(0);
+            issue_tables(1);
 #pragma unroll 1
             for (size_t ci = 0; ci < nchunks_total; ++ci) {
-                if (cc == 0) SG_STAMP(13);
+                if (cc == 0) {
+                    SG_STAMP(13);
+                    issue_tables(kg + 2);
+                }
                 mbar_wait(&empty[stage], epar);
                 mbar_arrive_expect_tx(&full[stage], (uint32_t)kStageBytes);
-                if (!(dbg & 1))
-                    bulk_g2s(ring + (size_t)stage * kStageBytes, Q + ci * kStageBytes,
-                             (uint32_t)kStageBytes, &full[stage]);
-                else
-                    bulk_g2s(ring + (size_t)stage * kStageBytes, Q, (uint32_t)kStageBytes,
-                             &full[stage]);
+                bulk_g2s(ring + (size_t)stage * kStageBytes, (dbg & 1) ? Q : Q + ci * kStageBytes,
+                         (uint32_t)kStageBytes, &full[stage]);
                 if (++stage == NS) { stage = 0; epar ^= 1u; }
                 if (++cc == nchunk) { cc = 0; SG_STAMP(14); ++kg; }
             }
@@ -624,9 +667,8 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
             best_e = a.track_best ? a.best_energy[rep0 + lane] : 3.0e38f;
         }
         float pdec[kBlk];
-        uint32_t pam[kBlk];
 #pragma unroll
-        for (int b = 0; b < kBlk; ++b) { pdec[b] = 0.0f; pam[b] = 0u; }
+        for (int b = 0; b < kBlk; ++b) pdec[b] = 0.0f;
         int kg = 0;
 #pragma unroll 1
         for (int s = s_begin; s < s_end; ++s) {
@@ -656,42 +698,45 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                                     : 0.0f;
                 }
                 SG_STAMP(4);
-                mbar_wait(&rawbar[slot], par);
-                SG_STAMP(5);
+                mbar_wait(&tabbar[slot], par);
+                mbar_wait(&thbar[slot], par);
                 const float* rawp = raw_s + slot * kBlk * kG + r;
                 const float* thp = theta_s + slot * kBlk * kG + r;
-                const float* cin = cin_s + slot * kBlk * kBlk;
-                const float* ccr = ccr_s + slot * kBlk * kBlk;
+                const float4* cin4 = reinterpret_cast<const float4*>(tab_s + slot * kTabBytes);
+                const float4* ccr4 = cin4 + kBlk * kBlk / 4;
+                const uint32_t* dup_p = reinterpret_cast<const uint32_t*>(tab_s + slot * kTabBytes) + 2 * kBlk * kBlk;
+                // correction for the flips of the previous block (not yet in the raw values)
                 float v[kBlk];
 #pragma unroll
-                for (int b = 0; b < kBlk; ++b) v[b] = rawp[b * kG];
-                // flips of the previous block (not yet in the raw values)
+                for (int b = 0; b < kBlk; ++b) v[b] = 0.0f;
                 if (k > 0) {
 #pragma unroll
                     for (int aa = 0; aa < kBlk; ++aa) {
-                        if (pam[aa] != 0u) {
-                            const float da = pdec[aa];
-                            const float4* row = reinterpret_cast<const float4*>(ccr + aa * kBlk);
+                        const float da = pdec[aa];
 #pragma unroll
-                            for (int b4 = 0; b4 < kBlk / 4; ++b4) {
-                                const float4 c4 = row[b4];
-                                v[4 * b4 + 0] = fmaf(da, c4.x, v[4 * b4 + 0]);
-                                v[4 * b4 + 1] = fmaf(da, c4.y, v[4 * b4 + 1]);
-                                v[4 * b4 + 2] = fmaf(da, c4.z, v[4 * b4 + 2]);
-                                v[4 * b4 + 3] = fmaf(da, c4.w, v[4 * b4 + 3]);
-                            }
+                        for (int b4 = 0; b4 < kBlk / 4; ++b4) {
+                            const float4 c4 = ccr4[aa * 4 + b4];
+                            v[4 * b4 + 0] = fmaf(da, c4.x, v[4 * b4 + 0]);
+                            v[4 * b4 + 1] = fmaf(da, c4.y, v[4 * b4 + 1]);
+                            v[4 * b4 + 2] = fmaf(da, c4.z, v[4 * b4 + 2]);
+                            v[4 * b4 + 3] = fmaf(da, c4.w, v[4 * b4 + 3]);
                         }
                     }
                 }
-                SG_STAMP(6);
                 float th[kBlk];
                 uint32_t w0[kBlk], dup[kBlk];
 #pragma unroll
                 for (int b = 0; b < kBlk; ++b) {
                     th[b] = INJECT ? 0.0f : thp[b * kG];
                     w0[b] = sbits[r * W + (site[b] >> 5)];
-                    dup[b] = dup_s[slot * kBlk + b];
+                    dup[b] = dup_p[b];
                 }
+                SG_STAMP(5);
+                mbar_wait(&rbar[2 * slot], par);
+                mbar_wait(&rbar[2 * slot + 1], par);
+                SG_STAMP(6);
+#pragma unroll
+                for (int b = 0; b < kBlk; ++b) v[b] += rawp[b * kG];
                 // the 16 attempts of the block, strictly in order, registers only
                 uint32_t myflips = 0;
                 float d[kBlk];
@@ -722,12 +767,14 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                     const float da = flip ? (up ? -2.0f : 2.0f) : 0.0f;
                     d[aa] = da;
                     myflips |= flip ? (1u << aa) : 0u;
-                    const uint32_t am = __ballot_sync(0xFFFFFFFFu, flip);
-                    pam[aa] = am;
-                    if (am != 0u && aa + 1 < kBlk) {
-                        const float* row = cin + aa * kBlk;
+                    // bring the later sites of the block up to date (row aa of the in-block table)
 #pragma unroll
-                        for (int b = aa + 1; b < kBlk; ++b) v[b] = fmaf(da, row[b], v[b]);
+                    for (int b4 = (aa + 1) / 4; b4 < kBlk / 4; ++b4) {
+                        const float4 c4 = cin4[aa * 4 + b4];
+                        if (4 * b4 + 0 > aa) v[4 * b4 + 0] = fmaf(da, c4.x, v[4 * b4 + 0]);
+                        if (4 * b4 + 1 > aa) v[4 * b4 + 1] = fmaf(da, c4.y, v[4 * b4 + 1]);
+                        if (4 * b4 + 2 > aa) v[4 * b4 + 2] = fmaf(da, c4.z, v[4 * b4 + 2]);
+                        if (4 * b4 + 3 > aa) v[4 * b4 + 3] = fmaf(da, c4.w, v[4 * b4 + 3]);
                     }
                 }
                 n_acc += (unsigned int)__popc(myflips);
@@ -742,16 +789,18 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                         make_uint4(pack_bf16x2(d[8], d[9]), pack_bf16x2(d[10], d[11]),
                                    pack_bf16x2(d[12], d[13]), pack_bf16x2(d[14], d[15]));
                 }
-                // spin bit planes (lane r owns plane r; XOR commutes, so order is irrelevant)
-#pragma unroll
-                for (int aa = 0; aa < kBlk; ++aa)
-                    if ((myflips >> aa) & 1u)
-                        atomicXor(&sbits[r * W + (site[aa] >> 5)], 1u << (site[aa] & 31));
-#pragma unroll
-                for (int b = 0; b < kBlk; ++b) pdec[b] = d[b];
                 fence_proxy_async();  // B operand visible to the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&decbar[slot]);
+                // spin bit planes (lane r owns plane r; XOR commutes, so order is irrelevant)
+                if (lane < kG) {
+#pragma unroll
+                    for (int aa = 0; aa < kBlk; ++aa)
+                        atomicXor(&sbits[r * W + (site[aa] >> 5)],
+                                  ((myflips >> aa) & 1u) << (site[aa] & 31));
+                }
+#pragma unroll
+                for (int b = 0; b < kBlk; ++b) pdec[b] = d[b];
                 SG_STAMP(8);
             }
             // ---- end of sweep: energy, best tracking
@@ -780,45 +829,57 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
         }
     } else {
         // ======================================================== MMA ISSUER
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t fpar = 0;
-            int kg = 0;
+        // The whole warp runs the loops (descriptor arithmetic stays warp-uniform); one elected
+        // lane issues the tcgen05 instructions.
+        int stage = 0;
+        uint32_t fpar = 0;
+        int kg = 0;
 #pragma unroll 1
-            for (int s = s_begin; s < s_end; ++s) {
+        for (int s = s_begin; s < s_end; ++s) {
 #pragma unroll 1
-                for (int k = 0; k < nblk; ++k, ++kg) {
-                    const int slot = kg & (kSlots - 1);
-                    SG_STAMP(9);
-                    mbar_wait(&decbar[slot], (uint32_t)(kg >> 2) & 1u);
-                    SG_STAMP(10);
-                    // raw values of block k+1 must have been read before this block's update lands
+            for (int k = 0; k < nblk; ++k, ++kg) {
+                const int slot = kg & (kSlots - 1);
+                SG_STAMP(9);
+                mbar_wait(&decbar[slot], (uint32_t)(kg >> 2) & 1u);
+                SG_STAMP(10);
+                const uint64_t bdesc =
+                    tc::make_smem_desc(smem_u32(bop_s + slot * kBopBytes), kBLbo, kBSbo);
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+                    // the raw values of block k+1 in this column half must have been read before
+                    // this block's update of the half is issued
                     if (k + 1 < nblk)
-                        mbar_wait(&rawbar[(kg + 1) & (kSlots - 1)], (uint32_t)((kg + 1) >> 2) & 1u);
-                    const uint64_t bdesc =
-                        tc::make_smem_desc(smem_u32(bop_s + slot * kBopBytes), kBLbo, kBSbo);
-                    SG_STAMP(11);
+                        mbar_wait(&rbar[2 * ((kg + 1) & (kSlots - 1)) + h], (uint32_t)((kg + 1) >> 2) & 1u);
+                    if (h == 0) SG_STAMP(11);
+                    const int c_end = h ? nchunk : hc;
 #pragma unroll 1
-                    for (int c = 0; c < nchunk; ++c) {
+                    for (int c = h ? hc : 0; c < c_end; ++c) {
                         mbar_wait(&full[stage], fpar);
                         tc::fence_after_sync();
-                        const int nt = min(kChunkTiles, T - c * kChunkTiles);
-                        const uint32_t abase = smem_u32(ring + (size_t)stage * kStageBytes);
-                        for (int tt = 0; tt < ((dbg & 2) ? 0 : nt); ++tt) {
+                        const int nt = (dbg & 2) ? 0 : min(kChunkTiles, T - c * kChunkTiles);
+                        const uint64_t adesc0 = tc::make_smem_desc(
+                            smem_u32(ring + (size_t)stage * kStageBytes), kALbo, kASbo);
+                        const uint32_t d0 = tbase + (uint32_t)(c * kChunkTiles * kG);
+                        if (tc::elect_one()) {
 #pragma unroll
-                            for (int p = 0; p < P; ++p) {
-                                const uint64_t adesc = tc::make_smem_desc(
-                                    abase + (tt * P + p) * kTileBytes, kALbo, kASbo);
-                                tc::mma_bf16_ss(tbase + (c * kChunkTiles + tt) * kG, adesc, bdesc,
-                                                kIdesc, 1u);
+                            for (int tt = 0; tt < kChunkTiles; ++tt) {
+                                if (tt < nt) {
+#pragma unroll
+                                    for (int p = 0; p < P; ++p)
+                                        tc::mma_bf16_ss(d0 + tt * kG,
+                                                        adesc0 + (uint64_t)(((tt * P + p) * kTileBytes) >> 4),
+                                                        bdesc, kIdesc, 1u);
+                                }
                             }
+                            tc::mma_commit(&empty[stage]);
                         }
-                        tc::mma_commit(&empty[stage]);
+                        __syncwarp();
                         if (++stage == NS) { stage = 0; fpar ^= 1u; }
                     }
-                    tc::mma_commit(&mmadone[slot]);
-                    SG_STAMP(12);
+                    if (tc::elect_one()) tc::mma_commit(&hdone[2 * slot + h]);
+                    __syncwarp();
                 }
+                SG_STAMP(12);
             }
         }
     }
@@ -855,7 +916,8 @@ tc_mma_bench_kernel(int variant, int n_dim, int iters, long long* out) {
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tbase = tptr;
-    if (tid == 0) {
+    if (warp == 1) {
+        // the whole warp runs the loop (warp-uniform descriptor math); one elected lane issues
         const uint32_t a0 = smem_u32(smem);            // 32 A tiles, 4608 B apart (128 KB + pad)
         const uint32_t b0 = smem_u32(smem + 150 * 1024);
         uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_dim >> 3) << 17) | (8u << 24);
@@ -869,25 +931,25 @@ tc_mma_bench_kernel(int variant, int n_dim, int iters, long long* out) {
         // B: K-major no swizzle, n_dim rows: (n/8)*128 + (k/8)*(n_dim*16)
         const uint64_t bdesc = tc::make_smem_desc(b0, (uint32_t)n_dim * 16, 128);
         const int ncol_tiles = 512 / n_dim;
+        const uint64_t adesc0 = tc::make_smem_desc(a0, lbo, sbo) | (lt << 61);
         const long long t0 = clock64();
         for (int it = 0; it < iters; ++it) {
+#pragma unroll
             for (int t = 0; t < 32; ++t) {
-                uint64_t adesc;
-                if (variant == 3) {
-                    // 8 tiles of 128 x 64 (16 KB); K = 16 sub-block j = +32 B
-                    adesc = tc::make_smem_desc(a0 + (t >> 2) * 16384 + (t & 3) * 32, lbo, sbo) | (lt << 61);
-                } else {
-                    adesc = tc::make_smem_desc(a0 + t * tile, lbo, sbo) | (lt << 61);
-                }
-                tc::mma_bf16_ss(tbase + (t % ncol_tiles) * n_dim, adesc, bdesc, idesc, 1u);
+                const uint64_t adesc = adesc0 + (uint64_t)((variant == 3 ? ((t >> 2) * 16384 + (t & 3) * 32)
+                                                                         : t * tile) >> 4);
+                if (tc::elect_one())
+                    tc::mma_bf16_ss(tbase + (t & (ncol_tiles - 1)) * n_dim, adesc, bdesc, idesc, 1u);
             }
         }
         const long long t1 = clock64();
-        tc::mma_commit(&bar);
+        if (tc::elect_one()) tc::mma_commit(&bar);
         mbar_wait(&bar, 0);
         const long long t2 = clock64();
-        out[0] = t1 - t0;
-        out[1] = t2 - t0;
+        if (tid == 32) {
+            out[0] = t1 - t0;
+            out[1] = t2 - t0;
+        }
     }
     tc::fence_before_sync();
     __syncthreads();
@@ -943,12 +1005,14 @@ size_t sweep_tc_sites_bytes(int n, int n_sweeps) {
 size_t sweep_tc_stream_bytes_per_sweep(int n, int n_tc, int planes) {
     const int nblk = (n + kBlk - 1) / kBlk;
     const int nchunk = (n_tc / kTileM + kChunkTiles - 1) / kChunkTiles;
-    return (size_t)nblk * nchunk * kChunkTiles * planes * kTileBytes;
+    // operand chunks + the decision tables of every block (rounded to 128 B)
+    return (size_t)nblk * nchunk * kChunkTiles * planes * kTileBytes +
+           (((size_t)nblk * kTabBytes + 127) / 128) * 128;
 }
 
 cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int planes, bool inject,
                             void* sites_buf, void* stream_buf, size_t stream_cap,
-                            uint64_t* launches, cudaStream_t st) {
+                            uint64_t* launches, KernelTimer* timer, cudaStream_t st) {
     if (planes < 1 || planes > 3 || !sweep_tc_supported(a.n, n_tc)) return cudaErrorInvalidValue;
     if (a.site_mode == 3 || (a.site_mode == 2 && a.s_bs != 0)) return cudaErrorInvalidValue;
     const int n_s = (a.n + 15) / 16 * 16;
@@ -978,6 +1042,7 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
     const int nblk = (a.n + kBlk - 1) / kBlk;
     const int nchunk = (n_tc / kTileM + kChunkTiles - 1) / kChunkTiles;
     const size_t per_sweep = sweep_tc_stream_bytes_per_sweep(a.n, n_tc, planes);
+    const size_t q_per_sweep = (size_t)nblk * nchunk * kChunkTiles * planes * kTileBytes;
     const int sub = (int)(stream_cap / per_sweep);
     if (sub < 1) return cudaErrorInvalidValue;
     // development aid (timing experiments only, results are wrong): SG_TC_DBG bit0 = constant
@@ -987,20 +1052,27 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
     cudaError_t err = cudaSuccess;
     for (int s0 = 0; s0 < a.n_sweeps; s0 += sub) {
         const int s1 = (s0 + sub < a.n_sweeps) ? s0 + sub : a.n_sweeps;
-        const size_t units = (size_t)(s1 - s0) * per_sweep / 16;
+        const size_t units = (size_t)(s1 - s0) * q_per_sweep / 16;
+        unsigned char* tabs = static_cast<unsigned char*>(stream_buf) + (size_t)sub * q_per_sweep;
         int ggrid = (int)((units + 255) / 256 < (size_t)148 * 16 ? (units + 255) / 256 : (size_t)148 * 16);
 #define SG_TC(P, INJ)                                                                          \
     {                                                                                          \
+        if (timer) timer->begin(1, st);                                                        \
         tc_gather_kernel<P><<<ggrid, 256, 0, st>>>(J, a.n, n_tc, sites, n_s, s0, s1 - s0, nblk,\
                                                    nchunk, static_cast<uint4*>(stream_buf));   \
+        tc_tables_kernel<P><<<(s1 - s0) * nblk, 256, 0, st>>>(J, a.n, n_tc, sites, n_s, s0,    \
+                                                              nblk, tabs);                     \
+        if (timer) timer->end(st);                                                             \
         err = cudaGetLastError();                                                              \
         if (err != cudaSuccess) return err;                                                    \
         err = cudaFuncSetAttribute(sweep_tc_kernel<P, INJ>,                                    \
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
         if (err != cudaSuccess) return err;                                                    \
+        if (timer) timer->begin(0, st);                                                        \
         sweep_tc_kernel<P, INJ><<<grid, kTcThreads, smem, st>>>(                               \
             a, J, n_tc, sites, n_s, NS, cols, static_cast<const unsigned char*>(stream_buf),   \
-            s0, s1, dbg);                                                                      \
+            tabs, s0, s1, dbg);                                                                \
+        if (timer) timer->end(st);                                                             \
     }
         if (inject) {
             if (planes == 1) SG_TC(1, true) else if (planes == 2) SG_TC(2, true) else SG_TC(3, true)
@@ -1010,7 +1082,7 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
 #undef SG_TC
         err = cudaGetLastError();
         if (err != cudaSuccess) return err;
-        *launches += 2;
+        *launches += 3;
     }
     return err;
 }

@@ -115,6 +115,19 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t taddr_d, uint64_t desc_a, u
         : "memory");
 }
 
+// true in exactly one lane of a converged warp (PTX elect.sync)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xFFFFFFFF;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // mbarrier arrive once every tcgen05 operation this thread issued before has completed
 // (implies tcgen05.fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {

@@ -264,6 +264,18 @@ class Engine:
         return dict(n=v[0].value, n_pad=v[1].value, n_replicas=v[2].value,
                     max_replicas_per_block=v[3].value, sm_count=v[4].value)
 
+    def set_profiling(self, enable: bool) -> None:
+        check(self._lib.sg_set_profiling(self._h, 1 if enable else 0), "sg_set_profiling")
+
+    def profile(self) -> dict:
+        """Device time of the sweep / gather kernels since the last call (CUDA events)."""
+        sm, gm = ctypes.c_double(), ctypes.c_double()
+        sc, gc = ctypes.c_uint64(), ctypes.c_uint64()
+        check(self._lib.sg_get_profile(self._h, ctypes.byref(sm), ctypes.byref(sc), ctypes.byref(gm),
+                                       ctypes.byref(gc)), "sg_get_profile")
+        return dict(sweep_ms=sm.value, sweep_launches=sc.value, gather_ms=gm.value,
+                    gather_launches=gc.value)
+
     def launch_count(self) -> int:
         return int(self._lib.sg_launch_count(self._h))
 

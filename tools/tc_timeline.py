@@ -21,15 +21,15 @@ eng.sweep(2, np.array([1.0]), seed=1, sweep_base=1, kernel="tc", coupling_planes
 torch.cuda.synchronize()
 t = buf.cpu().numpy().reshape(512, 16)
 t0 = t[0, 0]
-names = ["q_start", "q_tabs", "q_mmaok", "q_raw", "d_wait", "d_rawok", "d_cross", "d_dec", "d_done", "m_wait", "m_decok", "m_rawok", "m_done", "p_start", "p_end"]
+names = ["q_start", "q_tabs", "q_h0ok", "q_h1ok", "d_start", "d_pre", "d_rawok", "d_dec", "d_done", "m_wait", "m_decok", "m_r0ok", "m_done", "p_start", "p_end", "q_done"]
 print("blk " + " ".join(f"{x:>8s}" for x in names))
-for k in list(range(0, 10)) + list(range(100, 110)) + list(range(254, 262)):
-    print(f"{k:3d} " + " ".join(f"{int(t[k, i] - t0):8d}" for i in range(15)))
+for k in list(range(0, 6)) + list(range(100, 106)) + list(range(254, 260)):
+    print(f"{k:3d} " + " ".join(f"{int(t[k, i] - t0):8d}" for i in range(16)))
 d = t[40:240].astype(np.int64)
 def m(a, b): return float((d[:, a] - d[:, b]).mean())
 print("period", float((d[1:, 12] - d[:-1, 12]).mean()))
-print("quarter: tables+theta", m(1, 0), " wait mma(k-2)", m(2, 1), " raw reads", m(3, 2))
-print("decision: wait raw", m(5, 4), " load+cross", m(6, 5), " 16 attempts", m(7, 6), " epilogue", m(8, 7))
-print("mma: wait dec", m(10, 9), " wait raw(k+1)", m(11, 10), " chunks", m(12, 11))
+print("quarter: tables+theta", m(1, 0), " wait h0(k-2)", m(2, 1), " read h0 + wait h1", m(3, 2), " read h1", m(15, 3))
+print("decision: wait tab", "n/a", " tables+cross prefetch", m(5, 4), " wait raw", m(6, 5), " 16 attempts", m(7, 6), " epilogue", m(8, 7))
+print("mma: wait dec", m(10, 9), " wait r0(k+1)", m(11, 10), " chunks", m(12, 11))
 print("producer: block issue", m(14, 13))
-print("lags: q_raw(k)->d_rawok(k)", m(5, 3), " d_done(k)->m_decok(k)", m(10, 8), " m_done(k)->q_mmaok(k+2)", float((d[2:, 2] - d[:-2, 12]).mean()))
+print("lags: q_done(k)->d_rawok(k)", m(6, 15), " d_done(k)->m_decok(k)", m(10, 8))
