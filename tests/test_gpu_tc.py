@@ -1,0 +1,249 @@
+"""GPU parity of the tensor-core sweep kernel (sg_sweep_tc.cu) through the C ABI.
+
+Integer couplings are exact in the bf16 planes, +-2 x bf16 products are exact and the fp32
+accumulators in tensor memory hold integers exactly, so for integer couplings the tensor-core
+path must be BIT-EXACT against the oracle (replay) and against the sequential-FMA kernel
+(Philox mode, same counters).  For float couplings the accumulation order differs from the
+sequential algorithm; the bar is on the drift of the resident fields / energies against an
+exact recomputation (tolerances written below).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import golden_names, has_cuda, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    if not has_cuda():
+        pytest.skip("needs a CUDA device")
+    from spin_glass_anneal_rl_b200.engine import Engine
+    return Engine(0)
+
+
+def _int_instance(rng, n, amp=2):
+    a = rng.integers(-amp, amp + 1, size=(n, n))
+    J = np.triu(a, 1)
+    J = (J + J.T).astype(np.float32)
+    h = rng.integers(-amp, amp + 1, size=n).astype(np.float32)
+    return J, h
+
+
+def _sk(n, seed=3003):
+    rs = np.random.RandomState(seed)
+    G = rs.normal(0.0, 1.0 / np.sqrt(n), size=(n, n)).astype(np.float32)
+    J = ((G + G.T) / 2).astype(np.float32)
+    np.fill_diagonal(J, 0.0)
+    return J, np.zeros(n, np.float32)
+
+
+def _setup(engine, J, h, S0):
+    engine.set_model(J, h)
+    engine.alloc_replicas(S0.shape[0])
+    engine.set_spins(S0)
+    engine.init_fields()
+
+
+# ------------------------------------------------------------------ the rank-16 update itself
+@pytest.mark.parametrize("n,integer", [(4096, True), (1000, True), (384, False), (4096, False)])
+def test_rank16_update_matches_numpy(engine, n, integer):
+    import torch
+    from spin_glass_anneal_rl_b200._lib import check
+
+    rng = np.random.default_rng(n)
+    if integer:
+        J, _ = _int_instance(rng, n, amp=3)
+    else:
+        J, _ = _sk(n, seed=n)
+    engine.set_model(J, np.zeros(n, np.float32))
+    sites = rng.integers(0, n, size=16).astype(np.int32)
+    deltas = rng.choice([-2.0, 0.0, 2.0], size=(16, 16)).astype(np.float32)
+    f_in = rng.normal(0, 1, size=(16, n)).astype(np.float32)
+    if integer:
+        f_in = np.round(4 * f_in).astype(np.float32)
+
+    def bf16(x):
+        return torch.from_numpy(np.ascontiguousarray(x, np.float32)).to(torch.bfloat16).float().numpy()
+
+    hi = bf16(J)
+    mid = bf16(J - hi)
+    lo = bf16(J - hi - mid)
+    planes = [hi, mid, lo]
+    for P in (1, 2, 3):
+        out = np.empty_like(f_in)
+        check(engine._lib.sg_tc_selftest(engine._h, P, sites.ctypes.data_as(ctypes.c_void_p),
+                                         deltas.ctypes.data_as(ctypes.c_void_p),
+                                         f_in.ctypes.data_as(ctypes.c_void_p),
+                                         out.ctypes.data_as(ctypes.c_void_p)), "sg_tc_selftest")
+        Jq = sum(p.astype(np.float64) for p in planes[:P])
+        ref = f_in.astype(np.float64) + np.einsum("kr,kj->rj", deltas.astype(np.float64), Jq[sites])
+        if integer:
+            assert np.array_equal(out.astype(np.float64), ref)
+        else:
+            assert np.abs(out - ref).max() < 2e-6  # a few ulp of |f| ~ 4
+    assert np.array_equal(sum(p.astype(np.float64) for p in planes), J.astype(np.float64)), \
+        "three bf16 planes must reproduce every fp32 coupling exactly"
+
+
+# ------------------------------------------------------------------ replay against the oracle
+@pytest.mark.parametrize("n,R,ns,rule,planes", [
+    (16, 3, 5, "metropolis", 1), (96, 5, 4, "metropolis", 1), (100, 33, 3, "metropolis", 3),
+    (128, 16, 2, "glauber", 1), (500, 20, 2, "heat_bath", 2), (1024, 17, 2, "metropolis", 1),
+    (4096, 16, 1, "metropolis", 3),
+])
+def test_tc_replay_is_bit_exact_for_integer_couplings(engine, oracle, n, R, ns, rule, planes):
+    rng = np.random.default_rng(n + R)
+    J, h = _int_instance(rng, n)
+    S0 = (rng.integers(0, 2, size=(R, n)) * 2 - 1).astype(np.int8)
+    sites = rng.integers(0, n, size=(ns, n)).astype(np.int32)
+    uni = rng.random((R, ns, n), dtype=np.float32)
+    temps = np.linspace(3.0, 0.5, ns)
+    _setup(engine, J, h, S0)
+    trace = engine.sweep(ns, temps, temps_sweep_stride=1, rule=rule, sites=sites, uniforms=uni,
+                         energy_trace=True, kernel="tc", coupling_planes=planes).cpu().numpy()
+    final = engine.spins().cpu().numpy()
+    acc = engine.accepted().cpu().numpy()
+    best_e, best_s = engine.best()
+    for r in range(R):
+        s = S0[r].astype(np.float32).copy()
+        e0 = oracle.energy(J, h, s)
+        es, ac = oracle.sweeps_scheduled(J, h, s, temps, rule, sites, uni[r])
+        assert np.array_equal(final[r], s.astype(np.int8)), f"replica {r} trajectory differs"
+        assert np.array_equal(trace[:, r].astype(np.float64), es)
+        assert int(acc[r]) == int(ac.sum())
+        assert float(best_e[r]) == min(e0, es.min())
+    Fo, Eo = oracle.batch_fields_energies(J, h, final.astype(np.float32))
+    assert np.array_equal(engine.fields().cpu().numpy().astype(np.float64), Fo)
+    assert np.array_equal(engine.energies().cpu().numpy().astype(np.float64), Eo)
+    assert np.array_equal(engine.batch_energies(best_s).cpu().numpy(), best_e.cpu().numpy())
+
+
+@pytest.mark.parametrize("name", [g for g in golden_names("sa_") if "int" in g or "pm1" in g])
+def test_tc_replays_integer_reference_traces(engine, oracle, name):
+    """The golden traces recorded from the reference (integer couplings) through the TC kernel."""
+    g = load_golden(name)
+    c = g["config"]
+    J, h = g["J"], g["h"]
+    n = J.shape[0]
+    if n < 16 or not (np.all(J == np.round(J)) and np.all(h == np.round(h))):
+        pytest.skip("tensor-core path: integer couplings, n >= 16")
+    stream = oracle.RawStream(oracle.mt_raw_stream(c["seed"], 2 * n * c["n_sweeps"] + 16))
+    ores = oracle.anneal(J, h, g["spins0"], n_sweeps=c["n_sweeps"], T0=c["T0"], Tf=c["Tf"],
+                         schedule=c["schedule"], schedule_params=c["params"],
+                         record_interval=c["record_interval"], energy_tolerance=c["tol"],
+                         rule=c["rule"], stream=stream, trace=True)
+    ns = ores.n_sweeps
+    _setup(engine, J, h, g["spins0"].reshape(1, n).astype(np.int8))
+    uni = np.nan_to_num(ores.extra["uniforms"], nan=0.5).astype(np.float32)
+    trace = engine.sweep(ns, ores.extra["temps"], temps_sweep_stride=1, rule=c["rule"],
+                         sites=ores.extra["sites"].astype(np.int32), uniforms=uni,
+                         energy_trace=True, track_best=True, kernel="tc").cpu().numpy()[:, 0]
+    best_e, best_s = engine.best()
+    assert np.array_equal(engine.spins().cpu().numpy()[0], g["final_spins"])
+    assert np.array_equal(best_s.cpu().numpy()[0], g["best_configuration"])
+    assert float(best_e[0]) == float(g["best_energy"])
+    assert np.array_equal(trace.astype(np.float64), ores.sweep_energies)
+
+
+# ------------------------------------------------------------------ Philox mode: TC == SIMT
+@pytest.mark.parametrize("n,R,ns", [(256, 40, 6), (1000, 64, 3), (4096, 32, 12)])
+def test_tc_equals_simt_kernel_in_philox_mode(engine, n, R, ns):
+    """Same Philox counters, same shared site order, exact fields => identical trajectories.
+    (n = 4096, 12 sweeps also crosses the sub-launch boundary of the operand stream.)"""
+    rng = np.random.default_rng(3 * n + R)
+    J, h = _int_instance(rng, n)
+    S0 = (rng.integers(0, 2, size=(R, n)) * 2 - 1).astype(np.int8)
+    outs = []
+    for kern in ("simt", "tc"):
+        _setup(engine, J, h, S0)
+        tr = engine.sweep(ns, np.array([1.5]), seed=77, sweep_base=5, site_order="random",
+                          energy_trace=True, kernel=kern, coupling_planes=1).cpu().numpy()
+        outs.append((engine.spins().cpu().numpy(), tr, engine.accepted().cpu().numpy(),
+                     engine.best()[0].cpu().numpy(), engine.best()[1].cpu().numpy()))
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+    assert outs[0][2].sum() > 0
+
+
+def test_tc_launch_chunking_is_invisible(engine):
+    rng = np.random.default_rng(11)
+    n, R = 300, 50
+    J, h = _int_instance(rng, n)
+    S0 = (rng.integers(0, 2, size=(R, n)) * 2 - 1).astype(np.int8)
+    temps = np.linspace(3.0, 0.5, 6)
+    outs = []
+    for chunks in ([6], [2, 4], [1, 1, 1, 3]):
+        _setup(engine, J, h, S0)
+        base = 0
+        for c in chunks:
+            engine.sweep(c, temps[base:base + c].copy(), temps_sweep_stride=1, seed=99,
+                         sweep_base=base, site_order="random", kernel="tc")
+            base += c
+        outs.append((engine.spins().cpu().numpy(), engine.energies().cpu().numpy(),
+                     engine.best_energies().cpu().numpy(), engine.accepted().cpu().numpy()))
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert np.array_equal(a, b)
+
+
+def test_tc_sequential_site_order(engine, oracle):
+    rng = np.random.default_rng(5)
+    n, R, ns = 200, 9, 3
+    J, h = _int_instance(rng, n)
+    S0 = (rng.integers(0, 2, size=(R, n)) * 2 - 1).astype(np.int8)
+    uni = rng.random((R, ns, n), dtype=np.float32)
+    _setup(engine, J, h, S0)
+    engine.sweep(ns, np.array([1.2]), site_order="sequential", uniforms=uni, kernel="tc")
+    final = engine.spins().cpu().numpy()
+    sites = np.tile(np.arange(n, dtype=np.int32), (ns, 1))
+    for r in range(R):
+        s = S0[r].astype(np.float32).copy()
+        oracle.sweeps_scheduled(J, h, s, np.full(ns, 1.2), "metropolis", sites, uni[r])
+        assert np.array_equal(final[r], s.astype(np.int8))
+
+
+# ------------------------------------------------------------------ float couplings
+@pytest.mark.parametrize("planes,f_tol,e_tol", [(3, 2e-3, 3e-4), (2, 2e-3, 3e-4)])
+def test_tc_float_couplings_field_drift(engine, planes, f_tol, e_tol):
+    """SK N=4096, Gaussian J: after 10 sweeps (~20k rank-16 updates per field) the TMEM-resident
+    fields stay within f_tol (absolute, |f| ~ 1) of an exact recomputation from the spins and the
+    energies derived from them within e_tol relative.  The engine's best/final energies can be
+    refreshed exactly at any time with sg_init_fields / sg_batch_energies."""
+    import torch
+    n, R = 4096, 32
+    J, h = _sk(n)
+    engine.set_model(J, h)
+    engine.alloc_replicas(R)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    engine.set_spins((torch.randint(0, 2, (R, n), device="cuda", generator=g) * 2 - 1).to(torch.int8))
+    engine.init_fields()
+    engine.sweep(10, np.array([1.0]), seed=3, kernel="tc", coupling_planes=planes)
+    f = engine.fields().double()
+    e = engine.energies().double()
+    e2, f2 = engine.batch_energies(engine.spins(), want_fields=True)
+    assert (f - f2.double()).abs().max().item() < f_tol
+    assert ((e - e2.double()).abs() / e2.double().abs()).max().item() < e_tol
+    # the physics is unchanged: energy per spin after 10 sweeps at T = 1 (SIMT kernel: -0.249)
+    assert abs(e2.mean().item() / n + 0.249) < 0.01
+
+
+def test_tc_auto_dispatch_and_errors(engine):
+    from spin_glass_anneal_rl_b200._lib import SGError
+    rng = np.random.default_rng(0)
+    J, h = _int_instance(rng, 64)
+    S0 = (rng.integers(0, 2, size=(4, 64)) * 2 - 1).astype(np.int8)
+    _setup(engine, J, h, S0)
+    with pytest.raises(SGError):  # per-block site orders cannot share one operand stream
+        engine.sweep(1, np.array([1.0]), site_order="random_per_block", kernel="tc")
+    with pytest.raises(SGError):
+        engine.sweep(1, np.array([1.0]), kernel="tc", coupling_planes=4)
+    # n < 16 has no tensor-core path; auto falls back to the SIMT kernel
+    J8, h8 = _int_instance(rng, 8)
+    _setup(engine, J8, h8, (rng.integers(0, 2, size=(2, 8)) * 2 - 1).astype(np.int8))
+    engine.sweep(2, np.array([1.0]), kernel="auto")
+    with pytest.raises(SGError):
+        engine.sweep(2, np.array([1.0]), kernel="tc")
