@@ -1,0 +1,130 @@
+"""Philox-mode validation (north_star): the GPU sweep in production mode (in-kernel Philox, one
+site order shared by the replicas of a launch) against the CPU oracle of the reference algorithm
+(mt19937 stream, per-replica random sites) on cfg1 (random dense Ising, N = 100).
+
+Different random streams => statistical comparison only: means of final / best energy over
+independent runs, ground-state hit rate, and the acceptance-rate-versus-temperature curve.  The
+tolerances are confidence intervals written in each test (z = 4.5, i.e. a false alarm about once
+in 10^5 runs, so the suite is not flaky)."""
+import numpy as np
+import pytest
+
+from conftest import has_cuda
+
+pytestmark = pytest.mark.gpu
+
+Z = 4.5
+N = 100
+
+
+@pytest.fixture(scope="module")
+def engine():
+    if not has_cuda():
+        pytest.skip("needs a CUDA device")
+    from spin_glass_anneal_rl_b200.engine import Engine
+    return Engine(0)
+
+
+def cfg1_instance():
+    """A ~ N(0,1), J = (A + A^T)/2, zero diagonal, h = 0.5 N(0,1)."""
+    import torch
+    g = torch.Generator().manual_seed(1001)
+    A = torch.randn(N, N, generator=g)
+    J = ((A + A.T) / 2)
+    J.fill_diagonal_(0.0)
+    h = 0.5 * torch.randn(N, generator=g)
+    return J.numpy().astype(np.float32), h.numpy().astype(np.float32)
+
+
+def geometric_temps(ns, T0=5.0, alpha=0.95, Tf=0.01):
+    # GeometricSchedule: T0 * alpha^sweep, floored at Tf (annealing/temperature_scheduler.py:108-125)
+    return np.maximum(T0 * alpha ** np.arange(ns), Tf)
+
+
+def oracle_runs(oracle, J, h, temps, n_runs, seed0=100):
+    finals, bests = [], []
+    ns = len(temps)
+    for s in range(n_runs):
+        raw = oracle.mt_raw_stream(seed0 + s, 2 * N * ns + N + 16)
+        spins = oracle.raw_to_spins(raw[:N]).astype(np.float32)
+        stream = oracle.RawStream(raw, pos=N)
+        es, _, _, _ = oracle.sweeps(J, h, spins, temps, "metropolis", stream)
+        finals.append(es[-1])
+        bests.append(min(es.min(), oracle.energy(J, h, oracle.raw_to_spins(raw[:N]).astype(np.float32))))
+    return np.array(finals), np.array(bests)
+
+
+def gpu_runs(engine, J, h, temps, n_rep, kernel, seed):
+    import torch
+    engine.set_model(J, h)
+    engine.alloc_replicas(n_rep)
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    engine.set_spins((torch.randint(0, 2, (n_rep, N), device="cuda", generator=g) * 2 - 1).to(torch.int8))
+    engine.init_fields()
+    ns = len(temps)
+    # several launches with different site orders: replicas of one launch share the order
+    engine.sweep(ns, temps, temps_sweep_stride=1, seed=seed, site_order="random", kernel=kernel)
+    final = engine.batch_energies(engine.spins()).cpu().numpy().astype(np.float64)
+    best = engine.best_energies().cpu().numpy().astype(np.float64)
+    return final, best
+
+
+def _z(a, b):
+    return abs(a.mean() - b.mean()) / np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b))
+
+
+@pytest.mark.parametrize("kernel", ["simt", "tc"])
+def test_annealing_statistics_match_the_reference_algorithm(engine, oracle, kernel):
+    J, h = cfg1_instance()
+    temps = geometric_temps(160)
+    cf, cb = oracle_runs(oracle, J, h, temps, 256)
+    gf, gb = [], []
+    for launch in range(8):          # 8 independent site orders x 64 replicas
+        f, b = gpu_runs(engine, J, h, temps, 64, kernel, seed=1000 + launch)
+        gf.append(f)
+        gb.append(b)
+    gf, gb = np.concatenate(gf), np.concatenate(gb)
+    assert _z(gf, cf) < Z, (gf.mean(), cf.mean())
+    assert _z(gb, cb) < Z, (gb.mean(), cb.mean())
+    # spread of the final energies agrees as well (F-test-like bound, generous)
+    assert 0.6 < gf.std() / cf.std() < 1.6
+    # ground-state hit rate: best energy over everything seen, within 1e-4 relative
+    e0 = min(gb.min(), cb.min())
+    pg, pc = np.mean(gb <= e0 * (1 - 1e-4)), np.mean(cb <= e0 * (1 - 1e-4))
+    p = (pg * len(gb) + pc * len(cb)) / (len(gb) + len(cb))
+    se = np.sqrt(max(p * (1 - p), 1e-4) * (1 / len(gb) + 1 / len(cb)))
+    assert abs(pg - pc) < Z * se + 0.02, (pg, pc)
+
+
+@pytest.mark.parametrize("kernel", ["simt", "tc"])
+@pytest.mark.parametrize("T", [0.5, 1.0, 2.0, 4.0])
+def test_acceptance_rate_curve(engine, oracle, kernel, T):
+    """Equilibrium acceptance rate at fixed T within 1 % absolute."""
+    import torch
+    J, h = cfg1_instance()
+    burn, meas = 60, 60
+    # oracle: 24 independent replicas
+    acc_c = []
+    for s in range(24):
+        raw = oracle.mt_raw_stream(500 + s, 2 * N * (burn + meas) + N + 16)
+        spins = oracle.raw_to_spins(raw[:N]).astype(np.float32)
+        stream = oracle.RawStream(raw, pos=N)
+        _, acc, _, _ = oracle.sweeps(J, h, spins, np.full(burn + meas, T), "metropolis", stream)
+        acc_c.append(acc[burn:].sum() / (meas * N))
+    acc_c = np.array(acc_c)
+    # GPU: 4 site orders x 96 replicas
+    acc_g = []
+    for launch in range(4):
+        engine.set_model(J, h)
+        engine.alloc_replicas(96)
+        g = torch.Generator(device="cuda").manual_seed(launch)
+        engine.set_spins((torch.randint(0, 2, (96, N), device="cuda", generator=g) * 2 - 1).to(torch.int8))
+        engine.init_fields()
+        engine.sweep(burn, np.array([T]), seed=7 + launch, kernel=kernel)
+        a0 = engine.accepted().cpu().numpy().astype(np.int64)
+        engine.sweep(meas, np.array([T]), seed=7 + launch, sweep_base=burn, kernel=kernel)
+        a1 = engine.accepted().cpu().numpy().astype(np.int64)
+        acc_g.append((a1 - a0) / (meas * N))
+    acc_g = np.concatenate(acc_g)
+    se = np.sqrt(acc_g.var(ddof=1) / len(acc_g) + acc_c.var(ddof=1) / len(acc_c))
+    assert abs(acc_g.mean() - acc_c.mean()) < max(0.01, Z * se), (acc_g.mean(), acc_c.mean())
