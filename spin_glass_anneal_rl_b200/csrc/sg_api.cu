@@ -60,6 +60,11 @@ struct sg_engine {
     float* h = nullptr;   // [n_pad]
     void* Jp = nullptr;   // bf16 planes [3][n][n_tc] of Jt for the tensor-core sweep (n <= 4096)
     int n_tc = 0;         // plane row length: n rounded up to 128
+    void* dig = nullptr;       // fixed-point int8 digits of Jt, tiled for the K2-TC GEMM
+    double* scale = nullptr;   // {2^s, 2^-s} of the fixed-point representation
+    unsigned int* info = nullptr;
+    void* spin_tiles = nullptr;  // spins of the R replicas in UMMA operand tiles (K2-TC scratch)
+    size_t spin_tiles_cap = 0;
     void* tc_sites = nullptr;  // per-launch site tables of the tensor-core sweep
     size_t tc_sites_cap = 0;
     void* tc_stream = nullptr;  // operand stream (gathered J rows in UMMA layout), <= 1 GiB
@@ -167,6 +172,10 @@ void sg_destroy(sg_engine* e) {
     cudaFree(e->Jp);
     cudaFree(e->tc_sites);
     cudaFree(e->tc_stream);
+    cudaFree(e->dig);
+    cudaFree(e->scale);
+    cudaFree(e->info);
+    cudaFree(e->spin_tiles);
     delete e;
 }
 
@@ -202,17 +211,28 @@ int sg_set_model_dense(sg_engine* e, int n, const float* J, int64_t ldJ, const f
     SG_CUDA(cudaMemsetAsync(e->h, 0, (size_t)n_pad * sizeof(float), st));
     SG_CUDA(cudaMemcpyAsync(e->h, h, (size_t)n * sizeof(float),
                             on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    // fixed-point digits for the exact tensor-core field initialisation (K2-TC)
+    {
+        const int n_tc = (n + 127) / 128 * 128;
+        cudaFree(e->dig);
+        e->dig = nullptr;
+        if (!e->scale) SG_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->scale), 2 * sizeof(double)));
+        if (!e->info) SG_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->info), 2 * sizeof(unsigned int)));
+        cudaError_t ce = cudaMalloc(&e->dig, sg::fields_tc_digits_bytes(n, n_tc));
+        if (ce != cudaSuccess) return fail(SG_ERR_NOMEM, "cudaMalloc(digits)", ce);
+        SG_CUDA(sg::launch_fields_tc_prepare(e->Jt, n, n_pad, n_tc, e->info, e->scale, e->dig, st));
+        e->launches += 3;
+    }
     // bf16 planes for the tensor-core sweep (16 replicas x n_tc fp32 fields fill the TMEM)
     cudaFree(e->Jp);
     e->Jp = nullptr;
-    e->n_tc = 0;
+    e->n_tc = (n + 127) / 128 * 128;
     if (n <= 4096) {
         const int n_tc = (n + 127) / 128 * 128;
         void* jp = nullptr;
         cudaError_t ce = cudaMalloc(&jp, (size_t)3 * n * n_tc * 2);
         if (ce != cudaSuccess) return fail(SG_ERR_NOMEM, "cudaMalloc(planes)", ce);
         e->Jp = jp;
-        e->n_tc = n_tc;
         SG_CUDA(sg::launch_split_planes(e->Jt, n, n_pad, e->Jp, n_tc, st));
         e->launches++;
     }
@@ -239,6 +259,7 @@ int sg_alloc_replicas(sg_engine* e, int n_replicas, void* stream) {
     if ((rc = dev_alloc(&e->best_energy, R)) != SG_OK) return rc;
     if ((rc = dev_alloc(&e->best_spins, R * np)) != SG_OK) return rc;
     if ((rc = dev_alloc(&e->accepted, R)) != SG_OK) return rc;
+    SG_CUDA(cudaMemsetAsync(e->fields, 0, R * np * sizeof(float), st));
     SG_CUDA(cudaMemsetAsync(e->spins, 1, R * np, st));
     SG_CUDA(cudaMemsetAsync(e->best_spins, 1, R * np, st));
     SG_CUDA(cudaMemsetAsync(e->accepted, 0, R * sizeof(unsigned long long), st));
@@ -311,11 +332,26 @@ int sg_init_fields(sg_engine* e, void* stream) {
     SG_REQUIRE(e && e->R > 0 && e->Jt, "sg_init_fields: set model and replicas first");
     DeviceGuard g(e->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    SG_CUDA(sg::launch_fields(e->spins, e->n_pad, e->Jt, e->h, e->n, e->n_pad, e->R, e->fields,
-                              e->n_pad, st));
+    if (e->dig && !getenv("SG_K2_SIMT")) {
+        const size_t need = sg::fields_tc_spin_tiles_bytes(e->n, e->R);
+        if (need > e->spin_tiles_cap) {
+            SG_CUDA(cudaStreamSynchronize(st));
+            cudaFree(e->spin_tiles);
+            e->spin_tiles = nullptr;
+            e->spin_tiles_cap = 0;
+            cudaError_t ce = cudaMalloc(&e->spin_tiles, need);
+            if (ce != cudaSuccess) return fail(SG_ERR_NOMEM, "cudaMalloc(spin tiles)", ce);
+            e->spin_tiles_cap = need;
+        }
+        SG_CUDA(sg::launch_fields_tc(e->spins, e->n_pad, e->dig, e->scale, e->h, e->n, e->n_tc, e->R,
+                                     e->spin_tiles, e->fields, e->n_pad, st));
+    } else {
+        SG_CUDA(sg::launch_fields(e->spins, e->n_pad, e->Jt, e->h, e->n, e->n_pad, e->R, e->fields,
+                                  e->n_pad, st));
+    }
     SG_CUDA(sg::launch_energies(e->spins, e->n_pad, e->fields, e->n_pad, e->h, e->n, e->R,
                                 e->energy, st));
-    e->launches += 2;
+    e->launches += 3;
     e->fields_valid = true;
     return sg_reset_best(e, stream);
 }
@@ -573,6 +609,7 @@ int sg_batch_energies(sg_engine* e, int batch, const int8_t* spins, float* energ
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t B = (size_t)batch, n = (size_t)e->n, np = (size_t)e->n_pad;
     int8_t *s_in = nullptr, *s_pad = nullptr;
+    unsigned char* tiles = nullptr;
     float *f_pad = nullptr, *e_dev = nullptr, *f_out = nullptr;
     int rc = SG_OK;
     cudaError_t ce = cudaSuccess;
@@ -587,8 +624,16 @@ int sg_batch_energies(sg_engine* e, int batch, const int8_t* spins, float* energ
             src = s_in;
         }
         if ((ce = sg::launch_pad_spins(src, e->n, s_pad, e->n_pad, batch, st))) break;
-        if ((ce = sg::launch_fields(s_pad, np, e->Jt, e->h, e->n, e->n_pad, batch, f_pad, np, st)))
+        if (e->dig && !getenv("SG_K2_SIMT")) {
+            if ((rc = dev_alloc(&tiles, sg::fields_tc_spin_tiles_bytes(e->n, batch))) != SG_OK) break;
+            if ((ce = cudaMemsetAsync(f_pad, 0, B * np * sizeof(float), st))) break;
+            if ((ce = sg::launch_fields_tc(s_pad, np, e->dig, e->scale, e->h, e->n, e->n_tc, batch,
+                                           tiles, f_pad, np, st)))
+                break;
+        } else if ((ce = sg::launch_fields(s_pad, np, e->Jt, e->h, e->n, e->n_pad, batch, f_pad, np,
+                                           st))) {
             break;
+        }
         if ((ce = sg::launch_energies(s_pad, np, f_pad, np, e->h, e->n, batch, e_dev, st))) break;
         e->launches += 3;
         if (energies) {
@@ -614,6 +659,7 @@ int sg_batch_energies(sg_engine* e, int batch, const int8_t* spins, float* energ
     } while (0);
     cudaFree(s_in);
     cudaFree(s_pad);
+    cudaFree(tiles);
     cudaFree(f_pad);
     cudaFree(e_dev);
     cudaFree(f_out);

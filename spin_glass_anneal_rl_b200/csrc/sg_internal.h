@@ -108,6 +108,15 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
                             void* sites_buf, void* stream_buf, size_t stream_cap,
                             uint64_t* launches, KernelTimer* timer, cudaStream_t st);
 
+// K2-TC (sg_fields_tc.cu): exact field initialisation on the int8 tensor cores
+size_t fields_tc_digits_bytes(int n, int n_tc);
+size_t fields_tc_spin_tiles_bytes(int n, int R);
+cudaError_t launch_fields_tc_prepare(const float* Jt, int n, int n_pad, int n_tc, unsigned int* info,
+                                     double* scale, void* dig, cudaStream_t st);
+cudaError_t launch_fields_tc(const int8_t* spins, int64_t ld_spins, const void* dig,
+                             const double* scale, const float* h, int n, int n_tc, int R,
+                             void* spin_tiles, float* fields, int64_t ld_fields, cudaStream_t st);
+
 // K3 (sg_exchange.cu)
 struct ExchangeDev {
     int* rep_at;              // [L][K] replica currently at rung k of ladder l
