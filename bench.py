@@ -216,6 +216,42 @@ def run_ours(args):
     barrier()
     ms_e2e = t0.elapsed_time(t1) / e2e_steps
 
+    # ---- time to target energy (BASELINE metric, second half): parallel tempering on the same
+    # instance, 64 rungs per ladder, R/64 ladders per GPU, 10 sweeps between exchanges; stop when
+    # the best energy over all replicas of all ranks reaches E_target (0.97 x the Parisi
+    # ground-state energy for Var J = 1/(2N))
+    ttt = None
+    if args.ttt_budget > 0 and R % 64 == 0:
+        e_target = 0.97 * (-0.7632 / np.sqrt(2.0)) * n
+        ladder = np.geomspace(2.0, 0.1, 64)
+        eng.set_spins(spins_dev)
+        eng.init_fields()
+        eng.set_ladder(ladder)
+        barrier()
+        w0 = time.perf_counter()
+        rounds, reached, best_now = 0, False, float("inf")
+        while time.perf_counter() - w0 < args.ttt_budget:
+            for _ in range(4):
+                eng.sweep(10, None, seed=4242 + rank, sweep_base=rounds * 10, site_order="random",
+                          track_best=True, kernel=kernel, coupling_planes=planes)
+                eng.refresh_fields()
+                eng.exchange(rounds & 1, seed=77 + rank, round=rounds)
+                rounds += 1
+            b = eng.best_energies().min().reshape(1).double()
+            if world > 1:
+                dist.all_reduce(b, op=dist.ReduceOp.MIN)
+            best_now = b.item()
+            if best_now <= e_target:
+                reached = True
+                break
+        torch.cuda.synchronize()
+        secs = time.perf_counter() - w0
+        be, bs = eng.best()
+        exact = eng.batch_energies(bs[int(torch.argmin(be).item())].reshape(1, n)).item()
+        ttt = {"e_target": e_target, "reached": reached, "seconds": secs, "sweeps": rounds * 10,
+               "best_energy_exact_local": exact, "ladder": "64 rungs, T geometric 2.0 -> 0.1, "
+               f"{R // 64} ladders/GPU, exchange every 10 sweeps"}
+
     # max over ranks, whole-job aggregate
     t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
     best_local = eng.best_energies().min().reshape(1).double()
@@ -297,7 +333,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "attempts/s", "h2d_bytes_per_step": int(R) * n * world,
                     "d2h_bytes_per_step": int(R) * 4 * world, "ms_per_step": ms_e2e},
             "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cpu,
-            "clocks": clocks,
+            "time_to_target": ttt, "clocks": clocks,
         }))
     if world > 1:
         dist.destroy_process_group()
@@ -311,6 +347,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--replicas", type=int, default=REPLICAS_PER_GPU)
     ap.add_argument("--sweeps", type=int, default=5, help="sweeps per step")
+    ap.add_argument("--ttt-budget", type=float, default=20.0,
+                    help="wall-clock budget (s) of the time-to-target run; 0 skips it")
     ap.add_argument("--kernel", default="auto", choices=["auto", "tc", "simt"])
     ap.add_argument("--planes", type=int, default=3,
                     help="bf16 planes per coupling on the tensor-core path (3 = exact fp32 couplings)")

@@ -93,6 +93,12 @@ int sg_get_spins(sg_engine *e, int8_t *spins, int on_device, void *stream);
  * Must be called after sg_set_spins and before sg_sweep. */
 int sg_init_fields(sg_engine *e, void *stream);
 
+/* Recompute local fields and energies exactly from the current spins WITHOUT touching the
+ * best-so-far records: removes the rounding drift the incremental updates accumulate for
+ * non-integer couplings (the reference recomputes every local field from scratch,
+ * core/ising_model.py:176-185, so it never drifts).  Cheap: one K2 pass. */
+int sg_refresh_fields(sg_engine *e, void *stream);
+
 int sg_get_energies(sg_engine *e, float *energies, int on_device, void *stream);
 int sg_get_fields(sg_engine *e, float *fields, int on_device, void *stream);
 int sg_get_accepted(sg_engine *e, uint64_t *accepted, int on_device, void *stream);

@@ -53,6 +53,7 @@ PROTOTYPES = {
     "sg_set_spins": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "sg_get_spins": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "sg_init_fields": (c_int, [c_void_p, c_void_p]),
+    "sg_refresh_fields": (c_int, [c_void_p, c_void_p]),
     "sg_get_energies": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "sg_get_fields": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "sg_get_accepted": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),

@@ -132,6 +132,9 @@ class GPUAnnealer:
             trace = eng.sweep(k, chunk_t, temps_sweep_stride=1, rule=rule, site_order=cfg.site_order,
                               seed=philox_seed, sweep_base=done, energy_trace=True, track_best=True,
                               replicas_per_block=cfg.replicas_per_block)
+            # incremental field updates drift for non-integer couplings; the reference recomputes
+            # every field from scratch, so refresh them exactly between launches (one K2 pass)
+            eng.refresh_fields()
             done += k
             sweep = last
             if sweep % interval == 0:
@@ -144,7 +147,8 @@ class GPUAnnealer:
                     print(f"Converged at sweep {sweep}")
                     stopped = True
 
-        best_e, best_s = eng.best()
+        _, best_s = eng.best()
+        best_e = eng.batch_energies(best_s)   # exact energies of the best configurations
         r_best = int(torch.argmin(best_e).item())
         final_spins = eng.spins()
         model.spins = final_spins[0].to(torch.float32).to(model.device)

@@ -116,6 +116,7 @@ class ParallelTempering:
             k = nxt - sweep + 1
             eng.sweep(k, None, rule=rule, site_order=c.site_order, seed=int(seed),
                       sweep_base=sweep, track_best=True)
+            eng.refresh_fields()  # exact fields / energies before they feed an exchange decision
             sweep = nxt
             if sweep % ex_iv == 0 and sweep > 0:
                 eng.exchange(int(host_rng.randint(0, 2)), seed=int(seed) ^ 0x5DEECE66D, round=xround)
@@ -133,7 +134,8 @@ class ParallelTempering:
             for r in range(K):
                 self.energy_histories[r] = hist[:, r].tolist()
                 self.temp_histories[r] = [self.temperatures[r]] * hist.shape[0]
-        best_e, best_s = eng.best()
+        _, best_s = eng.best()
+        best_e = eng.batch_energies(best_s)   # exact energies of the best configurations
         r_best = int(torch.argmin(best_e).item())
         accepted = eng.accepted().double()
         rates = (accepted[rep_at[:K].long()] / float(c.n_sweeps * n)).cpu().tolist()

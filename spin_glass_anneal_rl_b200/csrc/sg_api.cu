@@ -328,10 +328,7 @@ int sg_reset_best(sg_engine* e, void* stream) {
     return SG_OK;
 }
 
-int sg_init_fields(sg_engine* e, void* stream) {
-    SG_REQUIRE(e && e->R > 0 && e->Jt, "sg_init_fields: set model and replicas first");
-    DeviceGuard g(e->device);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+static int compute_fields(sg_engine* e, cudaStream_t st) {
     if (e->dig && !getenv("SG_K2_SIMT")) {
         const size_t need = sg::fields_tc_spin_tiles_bytes(e->n, e->R);
         if (need > e->spin_tiles_cap) {
@@ -345,15 +342,31 @@ int sg_init_fields(sg_engine* e, void* stream) {
         }
         SG_CUDA(sg::launch_fields_tc(e->spins, e->n_pad, e->dig, e->scale, e->h, e->n, e->n_tc, e->R,
                                      e->spin_tiles, e->fields, e->n_pad, st));
+        e->launches += 2;
     } else {
         SG_CUDA(sg::launch_fields(e->spins, e->n_pad, e->Jt, e->h, e->n, e->n_pad, e->R, e->fields,
                                   e->n_pad, st));
+        e->launches += 1;
     }
     SG_CUDA(sg::launch_energies(e->spins, e->n_pad, e->fields, e->n_pad, e->h, e->n, e->R,
                                 e->energy, st));
-    e->launches += 3;
+    e->launches += 1;
+    return SG_OK;
+}
+
+int sg_init_fields(sg_engine* e, void* stream) {
+    SG_REQUIRE(e && e->R > 0 && e->Jt, "sg_init_fields: set model and replicas first");
+    DeviceGuard g(e->device);
+    int rc = compute_fields(e, static_cast<cudaStream_t>(stream));
+    if (rc != SG_OK) return rc;
     e->fields_valid = true;
     return sg_reset_best(e, stream);
+}
+
+int sg_refresh_fields(sg_engine* e, void* stream) {
+    SG_REQUIRE(e && e->R > 0 && e->fields_valid, "sg_refresh_fields: call sg_init_fields first");
+    DeviceGuard g(e->device);
+    return compute_fields(e, static_cast<cudaStream_t>(stream));
 }
 
 int sg_get_energies(sg_engine* e, float* energies, int on_device, void* stream) {

@@ -111,6 +111,10 @@ class Engine:
     def init_fields(self) -> None:
         check(self._lib.sg_init_fields(self._h, self.stream), "sg_init_fields")
 
+    def refresh_fields(self) -> None:
+        """Exact fields / energies from the current spins (best-so-far records untouched)."""
+        check(self._lib.sg_refresh_fields(self._h, self.stream), "sg_refresh_fields")
+
     def reset_best(self) -> None:
         check(self._lib.sg_reset_best(self._h, self.stream), "sg_reset_best")
 
