@@ -79,6 +79,15 @@ void sg_destroy(sg_engine *e);
 int sg_set_model_dense(sg_engine *e, int n, const float *J, int64_t ldJ, const float *h,
                        int on_device, void *stream);
 
+/* Sparse couplings (the models the reference's callers build as torch sparse COO,
+ * problems/base.py:107-116; core/ising_model.py:70-80): CSR rows of J, host arrays.  The local
+ * field of spin i is sum over row i + h[i], exactly as for dense models.  Replaces the dense model
+ * of the engine; the sweep then runs the sparse kernel (sg_sweep_csr.cu): one site order per
+ * launch, any n (no 7168 limit), state kept replica-minor.  All other entry points behave the
+ * same (sg_tc_selftest and the kernel / coupling_planes fields of sg_sweep_params do not apply). */
+int sg_set_model_csr(sg_engine *e, int n, int64_t nnz, const int64_t *rowptr, const int32_t *colidx,
+                     const float *val, const float *h, void *stream);
+
 /* Allocate R replicas (spins, local fields, energies, best-so-far, counters). */
 int sg_alloc_replicas(sg_engine *e, int n_replicas, void *stream);
 

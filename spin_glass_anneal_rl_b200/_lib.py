@@ -49,6 +49,8 @@ PROTOTYPES = {
     "sg_create": (c_int, [c_int, POINTER(c_void_p)]),
     "sg_destroy": (None, [c_void_p]),
     "sg_set_model_dense": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
+    "sg_set_model_csr": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p]),
     "sg_alloc_replicas": (c_int, [c_void_p, c_int, c_void_p]),
     "sg_set_spins": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "sg_get_spins": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),

@@ -14,6 +14,8 @@ import torch
 from ..engine import Engine
 from ..utils.exceptions import DeviceError
 
+DENSE_LIMIT = 4096   # above this many spins the model goes to the sparse (CSR) sweep kernel
+
 RULE_NAMES = {"metropolis": "metropolis", "glauber": "glauber", "heat_bath": "heat_bath"}
 
 
@@ -43,8 +45,21 @@ def engine_for(model, device_index: int = 0) -> Engine:
         eng = cached[1] if cached is not None and cached[1].device_index == device_index \
             else Engine(device_index)
         J = model.couplings
-        dense = (J.to_dense() if J.is_sparse else J).to(torch.float32)
-        eng.set_model(dense, model.external_fields.to(torch.float32))
+        n = int(J.shape[0])
+        if n > DENSE_LIMIT:
+            # sparse path (K1-CSR): the 50k-spin scheduling QUBOs and lattices the reference's
+            # callers build as COO (problems/base.py:107-116) cannot be held as dense matrices
+            coo = (J if J.is_sparse else J.to_sparse()).coalesce().cpu()
+            rows, cols = coo.indices()[0].numpy(), coo.indices()[1].numpy()
+            vals = coo.values().to(torch.float32).numpy()
+            order = np.lexsort((cols, rows))
+            rowptr = np.zeros(n + 1, np.int64)
+            np.add.at(rowptr, rows + 1, 1)
+            eng.set_model_csr(np.cumsum(rowptr), cols[order].astype(np.int32), vals[order],
+                              model.external_fields.to(torch.float32).cpu().numpy())
+        else:
+            dense = (J.to_dense() if J.is_sparse else J).to(torch.float32)
+            eng.set_model(dense, model.external_fields.to(torch.float32))
         model._sg_engine = (sig, eng)
         return eng
     except (RuntimeError, OSError) as exc:  # missing library, no GPU, CUDA failure

@@ -3,7 +3,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <algorithm>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "../../include/sg_b200.h"
 #include "sg_internal.h"
@@ -71,6 +74,17 @@ struct sg_engine {
     size_t tc_stream_cap = 0;
     bool profiling = false;
     sg::KernelTimer timer;
+    // sparse (CSR) mode: replica-minor state, see sg_sweep_csr.cu
+    bool csr = false;
+    bool c_symmetric = true;
+    long long *c_rowptr_t = nullptr, *c_rowptr_r = nullptr;
+    int *c_colidx_t = nullptr, *c_colidx_r = nullptr;
+    float *c_val_t = nullptr, *c_val_r = nullptr, *c_diag = nullptr;
+    int8_t *c_spins = nullptr, *c_best = nullptr;
+    float* c_fields = nullptr;
+    int Rp = 0;
+    void* c_sites = nullptr;
+    size_t c_sites_cap = 0;
     int8_t* spins = nullptr;
     float* fields = nullptr;
     float* energy = nullptr;
@@ -127,6 +141,39 @@ void free_replicas(sg_engine* e) {
     e->fields_valid = false;
 }
 
+void free_csr_replicas(sg_engine* e) {
+    cudaFree(e->c_spins); e->c_spins = nullptr;
+    cudaFree(e->c_best); e->c_best = nullptr;
+    cudaFree(e->c_fields); e->c_fields = nullptr;
+    e->Rp = 0;
+}
+
+void free_csr_model(sg_engine* e) {
+    cudaFree(e->c_rowptr_t); e->c_rowptr_t = nullptr;
+    cudaFree(e->c_rowptr_r); e->c_rowptr_r = nullptr;
+    cudaFree(e->c_colidx_t); e->c_colidx_t = nullptr;
+    cudaFree(e->c_colidx_r); e->c_colidx_r = nullptr;
+    cudaFree(e->c_val_t); e->c_val_t = nullptr;
+    cudaFree(e->c_val_r); e->c_val_r = nullptr;
+    cudaFree(e->c_diag); e->c_diag = nullptr;
+    e->csr = false;
+}
+
+sg::CsrDev csr_dev(const sg_engine* e) {
+    sg::CsrDev m{};
+    m.rowptr = e->c_rowptr_t;
+    m.colidx = e->c_colidx_t;
+    m.val = e->c_val_t;
+    m.diag = e->c_diag;
+    m.spins = e->c_spins;
+    m.fields = e->c_fields;
+    m.best_spins = e->c_best;
+    m.Rp = e->Rp;
+    m.symmetric = e->c_symmetric ? 1 : 0;
+    m.h = e->h;
+    return m;
+}
+
 void free_ladder(sg_engine* e) {
     cudaFree(e->rep_at); e->rep_at = nullptr;
     cudaFree(e->rep_temp); e->rep_temp = nullptr;
@@ -137,6 +184,238 @@ void free_ladder(sg_engine* e) {
 }
 
 }  // namespace
+
+
+// ---------------------------------------------------------------- sparse (CSR) mode
+namespace {
+
+template <typename T>
+int upload(T** dst, const T* src, size_t count, cudaStream_t st) {
+    int rc = dev_alloc(dst, count);
+    if (rc != SG_OK) return rc;
+    if (count) SG_CUDA(cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice, st));
+    return SG_OK;
+}
+
+int csr_alloc_replicas(sg_engine* e, int n_replicas, cudaStream_t st) {
+    free_replicas(e);
+    free_csr_replicas(e);
+    free_ladder(e);
+    const size_t R = (size_t)n_replicas, n = (size_t)e->n;
+    const size_t Rp = (R + 31) / 32 * 32;
+    int rc;
+    if ((rc = dev_alloc(&e->c_spins, n * Rp)) != SG_OK) return rc;
+    if ((rc = dev_alloc(&e->c_best, n * Rp)) != SG_OK) return rc;
+    if ((rc = dev_alloc(&e->c_fields, n * Rp)) != SG_OK) return rc;
+    if ((rc = dev_alloc(&e->energy, R)) != SG_OK) return rc;
+    if ((rc = dev_alloc(&e->best_energy, R)) != SG_OK) return rc;
+    if ((rc = dev_alloc(&e->accepted, R)) != SG_OK) return rc;
+    SG_CUDA(cudaMemsetAsync(e->c_spins, 1, n * Rp, st));
+    SG_CUDA(cudaMemsetAsync(e->c_best, 1, n * Rp, st));
+    SG_CUDA(cudaMemsetAsync(e->c_fields, 0, n * Rp * sizeof(float), st));
+    SG_CUDA(cudaMemsetAsync(e->accepted, 0, R * sizeof(unsigned long long), st));
+    e->R = n_replicas;
+    e->Rp = (int)Rp;
+    e->fields_valid = false;
+    return SG_OK;
+}
+
+// caller spins [R][n] (host or device) -> replica-minor buffer dst [n][Rp]
+int csr_put_spins(sg_engine* e, const int8_t* spins, int R, int Rp, int8_t* dst, int on_device,
+                  cudaStream_t st) {
+    const size_t bytes = (size_t)R * e->n;
+    const int8_t* src = spins;
+    int8_t* tmp = nullptr;
+    int rc;
+    if (!on_device) {
+        if ((rc = dev_alloc(&tmp, bytes)) != SG_OK) return rc;
+        SG_CUDA(cudaMemcpyAsync(tmp, spins, bytes, cudaMemcpyHostToDevice, st));
+        src = tmp;
+    }
+    SG_CUDA(sg::launch_to_replica_minor_i8(src, e->n, R, Rp, dst, st));
+    e->launches++;
+    if (tmp) {
+        SG_CUDA(cudaStreamSynchronize(st));
+        cudaFree(tmp);
+    }
+    return SG_OK;
+}
+
+int csr_get_i8(sg_engine* e, const int8_t* src_t, int8_t* out, int on_device, cudaStream_t st) {
+    const size_t bytes = (size_t)e->R * e->n;
+    if (on_device) {
+        SG_CUDA(sg::launch_from_replica_minor_i8(src_t, e->n, e->R, e->Rp, out, st));
+        e->launches++;
+        return SG_OK;
+    }
+    int8_t* tmp = nullptr;
+    int rc;
+    if ((rc = dev_alloc(&tmp, bytes)) != SG_OK) return rc;
+    cudaError_t ce = sg::launch_from_replica_minor_i8(src_t, e->n, e->R, e->Rp, tmp, st);
+    e->launches++;
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(out, tmp, bytes, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    cudaFree(tmp);
+    if (ce != cudaSuccess) return fail(SG_ERR_CUDA, "get spins (csr)", ce);
+    return SG_OK;
+}
+
+int csr_compute_fields(sg_engine* e, cudaStream_t st) {
+    SG_CUDA(sg::launch_csr_fields(csr_dev(e), e->c_rowptr_r, e->c_colidx_r, e->c_val_r, e->h, e->n,
+                                  e->R, e->energy, st));
+    e->launches += 2;
+    return SG_OK;
+}
+
+int csr_reset_best(sg_engine* e, cudaStream_t st) {
+    SG_CUDA(cudaMemcpyAsync(e->best_energy, e->energy, (size_t)e->R * sizeof(float),
+                            cudaMemcpyDeviceToDevice, st));
+    SG_CUDA(cudaMemcpyAsync(e->c_best, e->c_spins, (size_t)e->n * e->Rp, cudaMemcpyDeviceToDevice, st));
+    return SG_OK;
+}
+
+int csr_sweep(sg_engine* e, const sg_sweep_params* p, sg::SweepDev a, cudaStream_t st) {
+    SG_REQUIRE(p->site_mode != SG_SITES_RANDOM_PER_BLOCK && p->replicas_per_block == 0 &&
+                   !(p->site_mode == SG_SITES_EXPLICIT && p->sites_block_stride != 0),
+               "sg_sweep (sparse model): one site order per launch, replicas_per_block = 0");
+    const size_t need = sg::csr_sites_bytes(e->n, p->n_sweeps);
+    if (need > e->c_sites_cap) {
+        SG_CUDA(cudaStreamSynchronize(st));
+        cudaFree(e->c_sites);
+        e->c_sites = nullptr;
+        e->c_sites_cap = 0;
+        cudaError_t ce = cudaMalloc(&e->c_sites, need);
+        if (ce != cudaSuccess) return fail(SG_ERR_NOMEM, "cudaMalloc(site tables)", ce);
+        e->c_sites_cap = need;
+    }
+    a.G = 32;
+    if (e->profiling) e->timer.begin(0, st);
+    SG_CUDA(sg::launch_sweep_csr(csr_dev(e), a, p->rng_mode == SG_RNG_INJECTED, e->c_sites, st));
+    if (e->profiling) e->timer.end(st);
+    e->launches += 2;
+    return SG_OK;
+}
+
+int csr_batch_energies(sg_engine* e, int batch, const int8_t* spins, float* energies, float* fields,
+                       int on_device, cudaStream_t st) {
+    const int Rp = (batch + 31) / 32 * 32;
+    const size_t n = (size_t)e->n;
+    int8_t* s_t = nullptr;
+    float *f_t = nullptr, *e_dev = nullptr, *f_out = nullptr;
+    int rc = SG_OK;
+    cudaError_t ce = cudaSuccess;
+    do {
+        if ((rc = dev_alloc(&s_t, n * Rp)) != SG_OK) break;
+        if ((rc = dev_alloc(&f_t, n * Rp)) != SG_OK) break;
+        if ((rc = dev_alloc(&e_dev, (size_t)batch)) != SG_OK) break;
+        if ((rc = csr_put_spins(e, spins, batch, Rp, s_t, on_device, st)) != SG_OK) break;
+        sg::CsrDev m = csr_dev(e);
+        m.spins = s_t;
+        m.fields = f_t;
+        m.Rp = Rp;
+        if ((ce = sg::launch_csr_fields(m, e->c_rowptr_r, e->c_colidx_r, e->c_val_r, e->h, e->n, batch,
+                                        e_dev, st)))
+            break;
+        e->launches += 2;
+        if (energies &&
+            (ce = cudaMemcpyAsync(energies, e_dev, (size_t)batch * sizeof(float),
+                                  on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st)))
+            break;
+        if (fields) {
+            float* dstf = fields;
+            if (!on_device) {
+                if ((rc = dev_alloc(&f_out, (size_t)batch * n)) != SG_OK) break;
+                dstf = f_out;
+            }
+            if ((ce = sg::launch_from_replica_minor_f32(f_t, e->n, batch, Rp, dstf, st))) break;
+            e->launches++;
+            if (!on_device && (ce = cudaMemcpyAsync(fields, f_out, (size_t)batch * n * sizeof(float),
+                                                    cudaMemcpyDeviceToHost, st)))
+                break;
+        }
+        ce = cudaStreamSynchronize(st);
+    } while (0);
+    cudaFree(s_t);
+    cudaFree(f_t);
+    cudaFree(e_dev);
+    cudaFree(f_out);
+    if (rc != SG_OK) return rc;
+    if (ce != cudaSuccess) return fail(SG_ERR_CUDA, "sg_batch_energies (csr)", ce);
+    return SG_OK;
+}
+
+}  // namespace
+
+extern "C" int sg_set_model_csr(sg_engine* e, int n, int64_t nnz, const int64_t* rowptr,
+                                const int32_t* colidx, const float* val, const float* h,
+                                void* stream) {
+    SG_REQUIRE(e && rowptr && h && (nnz == 0 || (colidx && val)), "sg_set_model_csr: NULL argument");
+    SG_REQUIRE(n >= 2 && nnz >= 0 && rowptr[0] == 0 && rowptr[n] == nnz,
+               "sg_set_model_csr: need n >= 2 and rowptr[0] = 0, rowptr[n] = nnz");
+    for (int64_t k = 0; k < nnz; ++k)
+        SG_REQUIRE(colidx[k] >= 0 && colidx[k] < n, "sg_set_model_csr: column index out of range");
+    DeviceGuard g(e->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // leave dense mode
+    free_replicas(e);
+    free_csr_replicas(e);
+    free_ladder(e);
+    free_csr_model(e);
+    cudaFree(e->Jt); e->Jt = nullptr;
+    cudaFree(e->Jp); e->Jp = nullptr;
+    cudaFree(e->dig); e->dig = nullptr;
+    // transpose on the host: row i of J^T lists the spins j whose field changes when i flips,
+    // with the coupling J[j][i] (the local field of j uses ROW j of J, core/ising_model.py:176-185)
+    std::vector<long long> rp_r(rowptr, rowptr + n + 1), rp_t((size_t)n + 1, 0);
+    std::vector<int> ci_t((size_t)nnz);
+    std::vector<float> v_t((size_t)nnz), diag((size_t)n, 0.0f);
+    for (int64_t k = 0; k < nnz; ++k) rp_t[(size_t)colidx[k] + 1]++;
+    for (int i = 0; i < n; ++i) rp_t[(size_t)i + 1] += rp_t[(size_t)i];
+    {
+        std::vector<long long> cur(rp_t.begin(), rp_t.end() - 1);
+        for (int j = 0; j < n; ++j)
+            for (int64_t k = rowptr[j]; k < rowptr[j + 1]; ++k) {
+                const int i = colidx[k];
+                const long long pos = cur[(size_t)i]++;
+                ci_t[(size_t)pos] = j;
+                v_t[(size_t)pos] = val[k];
+                if (i == j) diag[(size_t)j] += val[k];
+            }
+    }
+    // symmetric?  (rows of J^T come out sorted by column; compare with the sorted rows of J)
+    bool symmetric = true;
+    {
+        std::vector<std::pair<int, float>> row;
+        for (int j = 0; j < n && symmetric; ++j) {
+            const int64_t a0 = rowptr[j], a1 = rowptr[j + 1];
+            if (rp_t[(size_t)j + 1] - rp_t[(size_t)j] != a1 - a0) { symmetric = false; break; }
+            row.clear();
+            for (int64_t k = a0; k < a1; ++k) row.emplace_back(colidx[k], val[k]);
+            std::sort(row.begin(), row.end());
+            for (size_t k = 0; k < row.size(); ++k) {
+                const size_t pos = (size_t)rp_t[(size_t)j] + k;
+                if (ci_t[pos] != row[k].first || v_t[pos] != row[k].second) { symmetric = false; break; }
+            }
+        }
+    }
+    e->c_symmetric = symmetric;
+    int rc;
+    if ((rc = upload(&e->c_rowptr_r, reinterpret_cast<const long long*>(rp_r.data()), (size_t)n + 1, st)) != SG_OK) return rc;
+    if ((rc = upload(&e->c_colidx_r, colidx, (size_t)nnz, st)) != SG_OK) return rc;
+    if ((rc = upload(&e->c_val_r, val, (size_t)nnz, st)) != SG_OK) return rc;
+    if ((rc = upload(&e->c_rowptr_t, reinterpret_cast<const long long*>(rp_t.data()), (size_t)n + 1, st)) != SG_OK) return rc;
+    if ((rc = upload(&e->c_colidx_t, ci_t.data(), (size_t)nnz, st)) != SG_OK) return rc;
+    if ((rc = upload(&e->c_val_t, v_t.data(), (size_t)nnz, st)) != SG_OK) return rc;
+    if ((rc = upload(&e->c_diag, diag.data(), (size_t)n, st)) != SG_OK) return rc;
+    if ((rc = upload(&e->h, h, (size_t)n, st)) != SG_OK) return rc;
+    SG_CUDA(cudaStreamSynchronize(st));  // host vectors go out of scope
+    e->n = n;
+    e->n_pad = n;
+    e->n_tc = 0;
+    e->csr = true;
+    e->fields_valid = false;
+    return SG_OK;
+}
 
 extern "C" {
 
@@ -166,6 +445,9 @@ void sg_destroy(sg_engine* e) {
     if (!e) return;
     DeviceGuard g(e->device);
     free_replicas(e);
+    free_csr_replicas(e);
+    free_csr_model(e);
+    cudaFree(e->c_sites);
     free_ladder(e);
     cudaFree(e->Jt);
     cudaFree(e->h);
@@ -190,10 +472,12 @@ int sg_set_model_dense(sg_engine* e, int n, const float* J, int64_t ldJ, const f
         return fail(SG_ERR_UNSUPPORTED, "sg_set_model_dense: dense models support n <= 7168");
     DeviceGuard g(e->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (n != e->n) {
+    if (n != e->n || e->csr) {
         free_replicas(e);
+        free_csr_replicas(e);
         free_ladder(e);
     }
+    free_csr_model(e);
     e->n = n;
     e->n_pad = n_pad;
     int rc;
@@ -249,6 +533,7 @@ int sg_alloc_replicas(sg_engine* e, int n_replicas, void* stream) {
     SG_REQUIRE(n_replicas >= 1, "sg_alloc_replicas: need n_replicas >= 1");
     DeviceGuard g(e->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (e->csr) return csr_alloc_replicas(e, n_replicas, st);
     free_replicas(e);
     free_ladder(e);
     const size_t R = (size_t)n_replicas, np = (size_t)e->n_pad;
@@ -272,6 +557,10 @@ int sg_set_spins(sg_engine* e, const int8_t* spins, int on_device, void* stream)
     SG_REQUIRE(e && spins && e->R > 0, "sg_set_spins: allocate replicas first");
     DeviceGuard g(e->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (e->csr) {
+        e->fields_valid = false;
+        return csr_put_spins(e, spins, e->R, e->Rp, e->c_spins, on_device, st);
+    }
     const size_t bytes = (size_t)e->R * e->n;
     const int8_t* src = spins;
     int8_t* tmp = nullptr;
@@ -314,6 +603,7 @@ static int get_unpadded_i8(sg_engine* e, const int8_t* src_pad, int8_t* out, int
 int sg_get_spins(sg_engine* e, int8_t* spins, int on_device, void* stream) {
     SG_REQUIRE(e && spins && e->R > 0, "sg_get_spins: allocate replicas first");
     DeviceGuard g(e->device);
+    if (e->csr) return csr_get_i8(e, e->c_spins, spins, on_device, static_cast<cudaStream_t>(stream));
     return get_unpadded_i8(e, e->spins, spins, on_device, static_cast<cudaStream_t>(stream));
 }
 
@@ -321,6 +611,7 @@ int sg_reset_best(sg_engine* e, void* stream) {
     SG_REQUIRE(e && e->R > 0 && e->fields_valid, "sg_reset_best: call sg_init_fields first");
     DeviceGuard g(e->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (e->csr) return csr_reset_best(e, st);
     SG_CUDA(cudaMemcpyAsync(e->best_energy, e->energy, (size_t)e->R * sizeof(float),
                             cudaMemcpyDeviceToDevice, st));
     SG_CUDA(cudaMemcpyAsync(e->best_spins, e->spins, (size_t)e->R * e->n_pad,
@@ -329,6 +620,7 @@ int sg_reset_best(sg_engine* e, void* stream) {
 }
 
 static int compute_fields(sg_engine* e, cudaStream_t st) {
+    if (e->csr) return csr_compute_fields(e, st);
     if (e->dig && !getenv("SG_K2_SIMT")) {
         const size_t need = sg::fields_tc_spin_tiles_bytes(e->n, e->R);
         if (need > e->spin_tiles_cap) {
@@ -355,7 +647,7 @@ static int compute_fields(sg_engine* e, cudaStream_t st) {
 }
 
 int sg_init_fields(sg_engine* e, void* stream) {
-    SG_REQUIRE(e && e->R > 0 && e->Jt, "sg_init_fields: set model and replicas first");
+    SG_REQUIRE(e && e->R > 0 && (e->Jt || e->csr), "sg_init_fields: set model and replicas first");
     DeviceGuard g(e->device);
     int rc = compute_fields(e, static_cast<cudaStream_t>(stream));
     if (rc != SG_OK) return rc;
@@ -381,6 +673,24 @@ int sg_get_fields(sg_engine* e, float* fields, int on_device, void* stream) {
     DeviceGuard g(e->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t count = (size_t)e->R * e->n;
+    if (e->csr) {
+        if (on_device) {
+            SG_CUDA(sg::launch_from_replica_minor_f32(e->c_fields, e->n, e->R, e->Rp, fields, st));
+            e->launches++;
+            return SG_OK;
+        }
+        float* tmpf = nullptr;
+        int rcf;
+        if ((rcf = dev_alloc(&tmpf, count)) != SG_OK) return rcf;
+        cudaError_t cf = sg::launch_from_replica_minor_f32(e->c_fields, e->n, e->R, e->Rp, tmpf, st);
+        e->launches++;
+        if (cf == cudaSuccess)
+            cf = cudaMemcpyAsync(fields, tmpf, count * sizeof(float), cudaMemcpyDeviceToHost, st);
+        if (cf == cudaSuccess) cf = cudaStreamSynchronize(st);
+        cudaFree(tmpf);
+        if (cf != cudaSuccess) return fail(SG_ERR_CUDA, "sg_get_fields (csr)", cf);
+        return SG_OK;
+    }
     if (on_device) {
         SG_CUDA(sg::launch_unpad_f32(e->fields, e->n_pad, fields, e->n, e->R, st));
         e->launches++;
@@ -414,7 +724,9 @@ int sg_get_best(sg_engine* e, float* best_energy, int8_t* best_spins, int on_dev
     int rc = SG_OK;
     if (best_energy)
         rc = copy_out(best_energy, e->best_energy, (size_t)e->R * sizeof(float), on_device, st);
-    if (rc == SG_OK && best_spins) rc = get_unpadded_i8(e, e->best_spins, best_spins, on_device, st);
+    if (rc == SG_OK && best_spins)
+        rc = e->csr ? csr_get_i8(e, e->c_best, best_spins, on_device, st)
+                    : get_unpadded_i8(e, e->best_spins, best_spins, on_device, st);
     return rc;
 }
 
@@ -485,6 +797,7 @@ int sg_sweep(sg_engine* e, const sg_sweep_params* p, void* stream) {
     a.site_mode = p->site_mode;
     a.track_best = p->track_best ? 1 : 0;
     a.dbg = e->dbg;
+    if (e->csr) return csr_sweep(e, p, a, static_cast<cudaStream_t>(stream));
     const bool inject = (p->rng_mode == SG_RNG_INJECTED);
     SG_REQUIRE(p->kernel >= SG_KERNEL_AUTO && p->kernel <= SG_KERNEL_TC, "sg_sweep: unknown kernel");
     SG_REQUIRE(p->coupling_planes >= 0 && p->coupling_planes <= 3,
@@ -616,10 +929,11 @@ int sg_get_ladder_state(sg_engine* e, int32_t* replica_at_rung, double* replica_
 
 int sg_batch_energies(sg_engine* e, int batch, const int8_t* spins, float* energies, float* fields,
                       int on_device, void* stream) {
-    SG_REQUIRE(e && spins && e->Jt, "sg_batch_energies: set the model first");
+    SG_REQUIRE(e && spins && (e->Jt || e->csr), "sg_batch_energies: set the model first");
     SG_REQUIRE(batch >= 1, "sg_batch_energies: batch < 1");
     DeviceGuard g(e->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (e->csr) return csr_batch_energies(e, batch, spins, energies, fields, on_device, st);
     const size_t B = (size_t)batch, n = (size_t)e->n, np = (size_t)e->n_pad;
     int8_t *s_in = nullptr, *s_pad = nullptr;
     unsigned char* tiles = nullptr;

@@ -117,6 +117,33 @@ cudaError_t launch_fields_tc(const int8_t* spins, int64_t ld_spins, const void* 
                              const double* scale, const float* h, int n, int n_tc, int R,
                              void* spin_tiles, float* fields, int64_t ld_fields, cudaStream_t st);
 
+// K1-CSR (sg_sweep_csr.cu): sparse couplings, replica-minor state
+struct CsrDev {
+    const long long* rowptr;  // [n+1]  rows of J^T (= columns of J): whom a flip of `site` touches
+    const int* colidx;        // [nnz]
+    const float* val;         // [nnz]
+    const float* diag;        // [n]    J_ii (0 for the usual models)
+    int8_t* spins;            // [n][Rp]
+    float* fields;            // [n][Rp]
+    int8_t* best_spins;       // [n][Rp]
+    int Rp;                   // replicas padded to 32
+    int symmetric;            // J == J^T: the energy can be carried incrementally
+    const float* h;           // [n] (energy recomputation for asymmetric J)
+};
+size_t csr_sites_bytes(int n, int n_sweeps);
+cudaError_t launch_sweep_csr(const CsrDev& m, const SweepDev& a, bool inject, void* sites_buf,
+                             cudaStream_t st);
+// fields from the rows of J (rowptr_rows...), then energies; m.spins / m.fields / m.Rp are used
+cudaError_t launch_csr_fields(const CsrDev& m, const long long* rowptr_rows, const int* colidx_rows,
+                              const float* val_rows, const float* h, int n, int R, float* energy,
+                              cudaStream_t st);
+cudaError_t launch_to_replica_minor_i8(const int8_t* src, int n, int R, int Rp, int8_t* dst,
+                                       cudaStream_t st);
+cudaError_t launch_from_replica_minor_i8(const int8_t* src, int n, int R, int Rp, int8_t* dst,
+                                         cudaStream_t st);
+cudaError_t launch_from_replica_minor_f32(const float* src, int n, int R, int Rp, float* dst,
+                                          cudaStream_t st);
+
 // K3 (sg_exchange.cu)
 struct ExchangeDev {
     int* rep_at;              // [L][K] replica currently at rung k of ladder l

@@ -87,9 +87,25 @@ class Engine:
             check(self._lib.sg_set_model_dense(self._h, n, Jh.ctypes.data_as(ctypes.c_void_p), n,
                                                hh.ctypes.data_as(ctypes.c_void_p), 0, self.stream),
                   "sg_set_model_dense")
-        if n != self.n:
+        if n != self.n or getattr(self, "_csr", False):
             self.n_replicas = 0
+        self._csr = False
         self.n = n
+
+    def set_model_csr(self, rowptr: ArrayLike, colidx: ArrayLike, val: ArrayLike, h: ArrayLike) -> None:
+        """Sparse couplings as CSR rows of J (host arrays); any number of spins."""
+        rp, ci = _as_host(rowptr, np.int64), _as_host(colidx, np.int32)
+        v, hh = _as_host(val, np.float32), _as_host(h, np.float32)
+        n = int(hh.shape[0])
+        assert rp.shape[0] == n + 1 and ci.shape[0] == v.shape[0] == int(rp[-1])
+        check(self._lib.sg_set_model_csr(self._h, n, int(rp[-1]), rp.ctypes.data_as(ctypes.c_void_p),
+                                         ci.ctypes.data_as(ctypes.c_void_p),
+                                         v.ctypes.data_as(ctypes.c_void_p),
+                                         hh.ctypes.data_as(ctypes.c_void_p), self.stream),
+              "sg_set_model_csr")
+        self.n = n
+        self.n_replicas = 0
+        self._csr = True
 
     def alloc_replicas(self, n_replicas: int) -> None:
         check(self._lib.sg_alloc_replicas(self._h, int(n_replicas), self.stream),

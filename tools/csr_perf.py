@@ -1,0 +1,24 @@
+"""Throughput of the sparse sweep kernel on BASELINE cfg2 (EA L=256, 4096 replicas) and cfg5
+(scheduling 500 x 100, 1024 replicas)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import instances as inst
+from spin_glass_anneal_rl_b200.engine import Engine
+for name, model, R, T, sweeps in (("cfg2 EA L=256", inst.ea_lattice(256), 4096, 1.0, 3),
+                                  ("cfg5 sched 500x100", inst.scheduling_ising(*inst.random_scheduling(500, 100)), 1024, 40.0, 3)):
+    rowptr, colidx, val, h = model
+    n = h.shape[0]
+    eng = Engine(0)
+    eng.set_model_csr(rowptr, colidx, val, h); eng.alloc_replicas(R)
+    eng.set_spins((torch.randint(0, 2, (R, n), device="cuda") * 2 - 1).to(torch.int8)); eng.init_fields()
+    eng.sweep(1, np.array([T]), seed=1); torch.cuda.synchronize()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    a0 = eng.accepted().sum().item()
+    t0.record(); eng.sweep(sweeps, np.array([T]), seed=1, sweep_base=1, track_best=False); t1.record(); torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1); a1 = eng.accepted().sum().item()
+    t0.record(); eng.sweep(sweeps, np.array([T]), seed=1, sweep_base=1 + sweeps, track_best=True); t1.record(); torch.cuda.synchronize()
+    ms2 = t0.elapsed_time(t1)
+    att = R * n * sweeps
+    print(f"{name}: n={n} R={R}: {att / ms / 1e6:.3f} G attempts/s (track_best: {att / ms2 / 1e6:.3f}), acc={(a1 - a0) / att:.3f}, E/N={eng.energies().mean().item() / n:.4f}")
