@@ -85,7 +85,13 @@ def cpu_reference(n_threads, budget_s, sweeps=1):
     from oracle import oracle as orc
     orc.build()
     J, h = sk_instance()
-    threads = n_threads or orc.num_threads()
+    # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which is for the GPU
+    # ranks' host side, not for the CPU baseline)
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    threads = n_threads or max(orc.num_threads(), avail)
     rng = np.random.default_rng(1)
     # calibrate: one replica-sweep per thread
     R = threads
