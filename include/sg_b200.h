@@ -55,6 +55,8 @@ typedef enum {
 #define SG_SITES_RANDOM 1     /* Philox draw % n, with replacement (core/spin_dynamics.py:69) */
 #define SG_SITES_EXPLICIT 2   /* caller-supplied list (replay of a recorded stream)         */
 #define SG_SITES_RANDOM_PER_BLOCK 3 /* like RANDOM, but an independent stream per thread block */
+#define SG_SITES_CHECKERBOARD 4     /* lattice models: all (x+y) even sites in row-major order,
+                                       then all odd ones -- each site once per sweep          */
 
 /* which sweep kernel runs (sg_sweep_params.kernel) */
 #define SG_KERNEL_AUTO 0 /* tensor-core kernel when the model/launch shape allows it, else SIMT   */
@@ -87,6 +89,16 @@ int sg_set_model_dense(sg_engine *e, int n, const float *J, int64_t ldJ, const f
  * same (sg_tc_selftest and the kernel / coupling_planes fields of sg_sweep_params do not apply). */
 int sg_set_model_csr(sg_engine *e, int n, int64_t nnz, const int64_t *rowptr, const int32_t *colidx,
                      const float *val, const float *h, void *stream);
+
+/* 2D +-J lattice (the Edwards-Anderson instances of research/experimental_validation.py:134-180):
+ * L x L spins, spin (x, y) = x * L + y, Jx[x*L+y] couples (x, y) with (x+1 mod L, y), Jy[x*L+y]
+ * couples (x, y) with (x, y+1 mod L); entries -1, 0 (no bond: open boundaries) or +1; host arrays;
+ * h = 0.  Selects the checkerboard multi-spin-coded kernel (sg_sweep_lattice.cu): sg_sweep must
+ * use SG_SITES_CHECKERBOARD; local fields are not materialised (sg_get_fields is unsupported),
+ * everything else behaves the same.  Periodic bonds need an even L. */
+int sg_set_model_lattice2d(sg_engine *e, int L, const int8_t *Jx, const int8_t *Jy, void *stream);
+/* position of site (x, y) in the checkerboard attempt sequence of one sweep (replay tests) */
+int sg_lattice_sequence_index(int L, int x, int y);
 
 /* Allocate R replicas (spins, local fields, energies, best-so-far, counters). */
 int sg_alloc_replicas(sg_engine *e, int n_replicas, void *stream);

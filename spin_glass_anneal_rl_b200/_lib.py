@@ -18,7 +18,7 @@ CSRC = os.path.join(_PKG, "csrc")
 
 SG_RULE = {"metropolis": 0, "glauber": 1, "heat_bath": 2}
 SG_RNG_PHILOX, SG_RNG_INJECTED = 0, 1
-SG_SITES = {"sequential": 0, "random": 1, "explicit": 2, "random_per_block": 3}
+SG_SITES = {"sequential": 0, "random": 1, "explicit": 2, "random_per_block": 3, "checkerboard": 4}
 SG_KERNEL = {"auto": 0, "simt": 1, "tc": 2}
 
 
@@ -51,6 +51,8 @@ PROTOTYPES = {
     "sg_set_model_dense": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
     "sg_set_model_csr": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p]),
+    "sg_set_model_lattice2d": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "sg_lattice_sequence_index": (c_int, [c_int, c_int, c_int]),
     "sg_alloc_replicas": (c_int, [c_void_p, c_int, c_void_p]),
     "sg_set_spins": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "sg_get_spins": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),

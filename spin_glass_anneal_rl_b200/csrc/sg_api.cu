@@ -74,6 +74,11 @@ struct sg_engine {
     size_t tc_stream_cap = 0;
     bool profiling = false;
     sg::KernelTimer timer;
+    // 2D +-J lattice mode: multi-spin-coded bit planes, see sg_sweep_lattice.cu
+    bool lat = false;
+    int l_L = 0, l_bonds = 0;
+    uint32_t *l_lat = nullptr, *l_best = nullptr;
+    uint8_t* l_bond = nullptr;
     // sparse (CSR) mode: replica-minor state, see sg_sweep_csr.cu
     bool csr = false;
     bool c_symmetric = true;
@@ -157,6 +162,26 @@ void free_csr_model(sg_engine* e) {
     cudaFree(e->c_val_r); e->c_val_r = nullptr;
     cudaFree(e->c_diag); e->c_diag = nullptr;
     e->csr = false;
+}
+
+void free_lat_replicas(sg_engine* e) {
+    cudaFree(e->l_lat); e->l_lat = nullptr;
+    cudaFree(e->l_best); e->l_best = nullptr;
+}
+
+void free_lat_model(sg_engine* e) {
+    cudaFree(e->l_bond); e->l_bond = nullptr;
+    e->lat = false;
+}
+
+sg::LatDev lat_dev(const sg_engine* e) {
+    sg::LatDev m{};
+    m.lat = e->l_lat;
+    m.best_lat = e->l_best;
+    m.bond = e->l_bond;
+    m.L = e->l_L;
+    m.n_bonds = e->l_bonds;
+    return m;
 }
 
 sg::CsrDev csr_dev(const sg_engine* e) {
@@ -359,8 +384,10 @@ extern "C" int sg_set_model_csr(sg_engine* e, int n, int64_t nnz, const int64_t*
     // leave dense mode
     free_replicas(e);
     free_csr_replicas(e);
+    free_lat_replicas(e);
     free_ladder(e);
     free_csr_model(e);
+    free_lat_model(e);
     cudaFree(e->Jt); e->Jt = nullptr;
     cudaFree(e->Jp); e->Jp = nullptr;
     cudaFree(e->dig); e->dig = nullptr;
@@ -417,6 +444,181 @@ extern "C" int sg_set_model_csr(sg_engine* e, int n, int64_t nnz, const int64_t*
     return SG_OK;
 }
 
+// ---------------------------------------------------------------- 2D lattice mode
+namespace {
+
+int lat_alloc_replicas(sg_engine* e, int n_replicas, cudaStream_t st) {
+    free_replicas(e);
+    free_csr_replicas(e);
+    free_lat_replicas(e);
+    free_ladder(e);
+    const size_t R = (size_t)n_replicas, W = (R + 31) / 32, n = (size_t)e->n;
+    int rc;
+    if ((rc = dev_alloc(&e->l_lat, W * n)) != SG_OK) return rc;
+    if ((rc = dev_alloc(&e->l_best, W * n)) != SG_OK) return rc;
+    if ((rc = dev_alloc(&e->energy, R)) != SG_OK) return rc;
+    if ((rc = dev_alloc(&e->best_energy, R)) != SG_OK) return rc;
+    if ((rc = dev_alloc(&e->accepted, R)) != SG_OK) return rc;
+    SG_CUDA(cudaMemsetAsync(e->l_lat, 0xFF, W * n * sizeof(uint32_t), st));
+    SG_CUDA(cudaMemsetAsync(e->l_best, 0xFF, W * n * sizeof(uint32_t), st));
+    SG_CUDA(cudaMemsetAsync(e->accepted, 0, R * sizeof(unsigned long long), st));
+    e->R = n_replicas;
+    e->fields_valid = false;
+    return SG_OK;
+}
+
+int lat_put_spins(sg_engine* e, const int8_t* spins, int R, uint32_t* dst, int on_device,
+                  cudaStream_t st) {
+    const size_t bytes = (size_t)R * e->n;
+    const int8_t* src = spins;
+    int8_t* tmp = nullptr;
+    int rc;
+    if (!on_device) {
+        if ((rc = dev_alloc(&tmp, bytes)) != SG_OK) return rc;
+        SG_CUDA(cudaMemcpyAsync(tmp, spins, bytes, cudaMemcpyHostToDevice, st));
+        src = tmp;
+    }
+    SG_CUDA(sg::launch_lat_pack(src, e->n, R, dst, st));
+    e->launches++;
+    if (tmp) {
+        SG_CUDA(cudaStreamSynchronize(st));
+        cudaFree(tmp);
+    }
+    return SG_OK;
+}
+
+int lat_get_spins(sg_engine* e, const uint32_t* src, int8_t* out, int on_device, cudaStream_t st) {
+    const size_t bytes = (size_t)e->R * e->n;
+    if (on_device) {
+        SG_CUDA(sg::launch_lat_unpack(src, e->n, e->R, out, st));
+        e->launches++;
+        return SG_OK;
+    }
+    int8_t* tmp = nullptr;
+    int rc;
+    if ((rc = dev_alloc(&tmp, bytes)) != SG_OK) return rc;
+    cudaError_t ce = sg::launch_lat_unpack(src, e->n, e->R, tmp, st);
+    e->launches++;
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(out, tmp, bytes, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    cudaFree(tmp);
+    if (ce != cudaSuccess) return fail(SG_ERR_CUDA, "get spins (lattice)", ce);
+    return SG_OK;
+}
+
+int lat_compute_energy(sg_engine* e, cudaStream_t st) {
+    SG_CUDA(sg::launch_lat_energy(lat_dev(e), e->l_lat, e->R, e->energy, st));
+    e->launches++;
+    return SG_OK;
+}
+
+int lat_reset_best(sg_engine* e, cudaStream_t st) {
+    const size_t W = ((size_t)e->R + 31) / 32;
+    SG_CUDA(cudaMemcpyAsync(e->best_energy, e->energy, (size_t)e->R * sizeof(float),
+                            cudaMemcpyDeviceToDevice, st));
+    SG_CUDA(cudaMemcpyAsync(e->l_best, e->l_lat, W * e->n * sizeof(uint32_t),
+                            cudaMemcpyDeviceToDevice, st));
+    return SG_OK;
+}
+
+int lat_sweep(sg_engine* e, const sg_sweep_params* p, sg::SweepDev a, cudaStream_t st) {
+    SG_REQUIRE(p->site_mode == SG_SITES_CHECKERBOARD,
+               "sg_sweep (lattice model): site_mode must be SG_SITES_CHECKERBOARD");
+    if (e->profiling) e->timer.begin(0, st);
+    SG_CUDA(sg::launch_sweep_lattice(lat_dev(e), a, p->rng_mode == SG_RNG_INJECTED, &e->launches, st));
+    if (e->profiling) e->timer.end(st);
+    return SG_OK;
+}
+
+int lat_batch_energies(sg_engine* e, int batch, const int8_t* spins, float* energies, float* fields,
+                       int on_device, cudaStream_t st) {
+    SG_REQUIRE(!fields, "sg_batch_energies (lattice model): local fields are not materialised");
+    const size_t W = ((size_t)batch + 31) / 32;
+    uint32_t* tmp_lat = nullptr;
+    float* e_dev = nullptr;
+    int rc = SG_OK;
+    cudaError_t ce = cudaSuccess;
+    do {
+        if ((rc = dev_alloc(&tmp_lat, W * e->n)) != SG_OK) break;
+        if ((rc = dev_alloc(&e_dev, (size_t)batch)) != SG_OK) break;
+        if ((rc = lat_put_spins(e, spins, batch, tmp_lat, on_device, st)) != SG_OK) break;
+        if ((ce = sg::launch_lat_energy(lat_dev(e), tmp_lat, batch, e_dev, st))) break;
+        e->launches++;
+        if (energies &&
+            (ce = cudaMemcpyAsync(energies, e_dev, (size_t)batch * sizeof(float),
+                                  on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st)))
+            break;
+        ce = cudaStreamSynchronize(st);
+    } while (0);
+    cudaFree(tmp_lat);
+    cudaFree(e_dev);
+    if (rc != SG_OK) return rc;
+    if (ce != cudaSuccess) return fail(SG_ERR_CUDA, "sg_batch_energies (lattice)", ce);
+    return SG_OK;
+}
+
+}  // namespace
+
+extern "C" int sg_set_model_lattice2d(sg_engine* e, int L, const int8_t* Jx, const int8_t* Jy,
+                                      void* stream) {
+    SG_REQUIRE(e && Jx && Jy, "sg_set_model_lattice2d: NULL argument");
+    SG_REQUIRE(L >= 2 && L <= 4096, "sg_set_model_lattice2d: need 2 <= L <= 4096");
+    const int n = L * L;
+    std::vector<uint8_t> bond((size_t)n, 0);
+    int n_bonds = 0;
+    bool wraps = false;
+    auto put = [&](int site, int d, int v) {
+        if (v != 0) bond[(size_t)site] |= (uint8_t)((1u << (2 * d)) | ((v < 0 ? 1u : 0u) << (2 * d + 1)));
+    };
+    for (int x = 0; x < L; ++x)
+        for (int y = 0; y < L; ++y) {
+            const int s = x * L + y;
+            const int jx = Jx[s], jy = Jy[s];
+            SG_REQUIRE(jx >= -1 && jx <= 1 && jy >= -1 && jy <= 1,
+                       "sg_set_model_lattice2d: couplings must be -1, 0 or +1");
+            if (jx != 0) {   // (x, y) -- (x + 1 mod L, y)
+                ++n_bonds;
+                wraps |= (x == L - 1);
+                put(s, 1, jx);
+                put(((x + 1) % L) * L + y, 0, jx);
+            }
+            if (jy != 0) {   // (x, y) -- (x, y + 1 mod L)
+                ++n_bonds;
+                wraps |= (y == L - 1);
+                put(s, 3, jy);
+                put(x * L + (y + 1) % L, 2, jy);
+            }
+        }
+    SG_REQUIRE(!(wraps && (L & 1)), "sg_set_model_lattice2d: periodic bonds need an even L (checkerboard)");
+    SG_REQUIRE(!(wraps && L == 2), "sg_set_model_lattice2d: periodic bonds need L > 2");
+    DeviceGuard g(e->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    free_replicas(e);
+    free_csr_replicas(e);
+    free_lat_replicas(e);
+    free_ladder(e);
+    free_csr_model(e);
+    free_lat_model(e);
+    cudaFree(e->Jt); e->Jt = nullptr;
+    cudaFree(e->Jp); e->Jp = nullptr;
+    cudaFree(e->dig); e->dig = nullptr;
+    int rc;
+    if ((rc = upload(&e->l_bond, bond.data(), (size_t)n, st)) != SG_OK) return rc;
+    SG_CUDA(cudaStreamSynchronize(st));
+    e->n = n;
+    e->n_pad = n;
+    e->n_tc = 0;
+    e->l_L = L;
+    e->l_bonds = n_bonds;
+    e->lat = true;
+    e->fields_valid = false;
+    return SG_OK;
+}
+
+extern "C" int sg_lattice_sequence_index(int L, int x, int y) {
+    return sg::lattice_sequence_index(L, x, y);
+}
+
 extern "C" {
 
 int sg_abi_version(void) { return SG_ABI_VERSION; }
@@ -447,6 +649,8 @@ void sg_destroy(sg_engine* e) {
     free_replicas(e);
     free_csr_replicas(e);
     free_csr_model(e);
+    free_lat_replicas(e);
+    free_lat_model(e);
     cudaFree(e->c_sites);
     free_ladder(e);
     cudaFree(e->Jt);
@@ -472,12 +676,14 @@ int sg_set_model_dense(sg_engine* e, int n, const float* J, int64_t ldJ, const f
         return fail(SG_ERR_UNSUPPORTED, "sg_set_model_dense: dense models support n <= 7168");
     DeviceGuard g(e->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (n != e->n || e->csr) {
+    if (n != e->n || e->csr || e->lat) {
         free_replicas(e);
         free_csr_replicas(e);
+        free_lat_replicas(e);
         free_ladder(e);
     }
     free_csr_model(e);
+    free_lat_model(e);
     e->n = n;
     e->n_pad = n_pad;
     int rc;
@@ -534,6 +740,7 @@ int sg_alloc_replicas(sg_engine* e, int n_replicas, void* stream) {
     DeviceGuard g(e->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (e->csr) return csr_alloc_replicas(e, n_replicas, st);
+    if (e->lat) return lat_alloc_replicas(e, n_replicas, st);
     free_replicas(e);
     free_ladder(e);
     const size_t R = (size_t)n_replicas, np = (size_t)e->n_pad;
@@ -560,6 +767,10 @@ int sg_set_spins(sg_engine* e, const int8_t* spins, int on_device, void* stream)
     if (e->csr) {
         e->fields_valid = false;
         return csr_put_spins(e, spins, e->R, e->Rp, e->c_spins, on_device, st);
+    }
+    if (e->lat) {
+        e->fields_valid = false;
+        return lat_put_spins(e, spins, e->R, e->l_lat, on_device, st);
     }
     const size_t bytes = (size_t)e->R * e->n;
     const int8_t* src = spins;
@@ -604,6 +815,7 @@ int sg_get_spins(sg_engine* e, int8_t* spins, int on_device, void* stream) {
     SG_REQUIRE(e && spins && e->R > 0, "sg_get_spins: allocate replicas first");
     DeviceGuard g(e->device);
     if (e->csr) return csr_get_i8(e, e->c_spins, spins, on_device, static_cast<cudaStream_t>(stream));
+    if (e->lat) return lat_get_spins(e, e->l_lat, spins, on_device, static_cast<cudaStream_t>(stream));
     return get_unpadded_i8(e, e->spins, spins, on_device, static_cast<cudaStream_t>(stream));
 }
 
@@ -612,6 +824,7 @@ int sg_reset_best(sg_engine* e, void* stream) {
     DeviceGuard g(e->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (e->csr) return csr_reset_best(e, st);
+    if (e->lat) return lat_reset_best(e, st);
     SG_CUDA(cudaMemcpyAsync(e->best_energy, e->energy, (size_t)e->R * sizeof(float),
                             cudaMemcpyDeviceToDevice, st));
     SG_CUDA(cudaMemcpyAsync(e->best_spins, e->spins, (size_t)e->R * e->n_pad,
@@ -621,6 +834,7 @@ int sg_reset_best(sg_engine* e, void* stream) {
 
 static int compute_fields(sg_engine* e, cudaStream_t st) {
     if (e->csr) return csr_compute_fields(e, st);
+    if (e->lat) return lat_compute_energy(e, st);
     if (e->dig && !getenv("SG_K2_SIMT")) {
         const size_t need = sg::fields_tc_spin_tiles_bytes(e->n, e->R);
         if (need > e->spin_tiles_cap) {
@@ -647,7 +861,7 @@ static int compute_fields(sg_engine* e, cudaStream_t st) {
 }
 
 int sg_init_fields(sg_engine* e, void* stream) {
-    SG_REQUIRE(e && e->R > 0 && (e->Jt || e->csr), "sg_init_fields: set model and replicas first");
+    SG_REQUIRE(e && e->R > 0 && (e->Jt || e->csr || e->lat), "sg_init_fields: set model and replicas first");
     DeviceGuard g(e->device);
     int rc = compute_fields(e, static_cast<cudaStream_t>(stream));
     if (rc != SG_OK) return rc;
@@ -673,6 +887,7 @@ int sg_get_fields(sg_engine* e, float* fields, int on_device, void* stream) {
     DeviceGuard g(e->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t count = (size_t)e->R * e->n;
+    if (e->lat) return fail(SG_ERR_UNSUPPORTED, "sg_get_fields: the lattice kernel keeps no local fields");
     if (e->csr) {
         if (on_device) {
             SG_CUDA(sg::launch_from_replica_minor_f32(e->c_fields, e->n, e->R, e->Rp, fields, st));
@@ -725,8 +940,9 @@ int sg_get_best(sg_engine* e, float* best_energy, int8_t* best_spins, int on_dev
     if (best_energy)
         rc = copy_out(best_energy, e->best_energy, (size_t)e->R * sizeof(float), on_device, st);
     if (rc == SG_OK && best_spins)
-        rc = e->csr ? csr_get_i8(e, e->c_best, best_spins, on_device, st)
-                    : get_unpadded_i8(e, e->best_spins, best_spins, on_device, st);
+        rc = e->csr   ? csr_get_i8(e, e->c_best, best_spins, on_device, st)
+             : e->lat ? lat_get_spins(e, e->l_best, best_spins, on_device, st)
+                      : get_unpadded_i8(e, e->best_spins, best_spins, on_device, st);
     return rc;
 }
 
@@ -738,7 +954,9 @@ int sg_sweep(sg_engine* e, const sg_sweep_params* p, void* stream) {
     SG_REQUIRE(p->rule >= 0 && p->rule <= 2, "sg_sweep: unknown rule");
     SG_REQUIRE(p->rng_mode == SG_RNG_PHILOX || p->rng_mode == SG_RNG_INJECTED,
                "sg_sweep: unknown rng_mode");
-    SG_REQUIRE(p->site_mode >= 0 && p->site_mode <= 3, "sg_sweep: unknown site_mode");
+    SG_REQUIRE(p->site_mode >= 0 && p->site_mode <= 4, "sg_sweep: unknown site_mode");
+    SG_REQUIRE(p->site_mode != SG_SITES_CHECKERBOARD || e->lat,
+               "sg_sweep: SG_SITES_CHECKERBOARD is the order of lattice models only");
     SG_REQUIRE(p->site_mode != SG_SITES_EXPLICIT || p->sites, "sg_sweep: explicit sites missing");
     SG_REQUIRE(p->rng_mode != SG_RNG_INJECTED || p->uniforms, "sg_sweep: injected uniforms missing");
     SG_REQUIRE(p->temps || e->rep_temp, "sg_sweep: no temperatures (pass temps or set a ladder)");
@@ -798,6 +1016,7 @@ int sg_sweep(sg_engine* e, const sg_sweep_params* p, void* stream) {
     a.track_best = p->track_best ? 1 : 0;
     a.dbg = e->dbg;
     if (e->csr) return csr_sweep(e, p, a, static_cast<cudaStream_t>(stream));
+    if (e->lat) return lat_sweep(e, p, a, static_cast<cudaStream_t>(stream));
     const bool inject = (p->rng_mode == SG_RNG_INJECTED);
     SG_REQUIRE(p->kernel >= SG_KERNEL_AUTO && p->kernel <= SG_KERNEL_TC, "sg_sweep: unknown kernel");
     SG_REQUIRE(p->coupling_planes >= 0 && p->coupling_planes <= 3,
@@ -929,11 +1148,12 @@ int sg_get_ladder_state(sg_engine* e, int32_t* replica_at_rung, double* replica_
 
 int sg_batch_energies(sg_engine* e, int batch, const int8_t* spins, float* energies, float* fields,
                       int on_device, void* stream) {
-    SG_REQUIRE(e && spins && (e->Jt || e->csr), "sg_batch_energies: set the model first");
+    SG_REQUIRE(e && spins && (e->Jt || e->csr || e->lat), "sg_batch_energies: set the model first");
     SG_REQUIRE(batch >= 1, "sg_batch_energies: batch < 1");
     DeviceGuard g(e->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (e->csr) return csr_batch_energies(e, batch, spins, energies, fields, on_device, st);
+    if (e->lat) return lat_batch_energies(e, batch, spins, energies, fields, on_device, st);
     const size_t B = (size_t)batch, n = (size_t)e->n, np = (size_t)e->n_pad;
     int8_t *s_in = nullptr, *s_pad = nullptr;
     unsigned char* tiles = nullptr;

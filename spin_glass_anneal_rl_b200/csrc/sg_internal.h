@@ -144,6 +144,21 @@ cudaError_t launch_from_replica_minor_i8(const int8_t* src, int n, int R, int Rp
 cudaError_t launch_from_replica_minor_f32(const float* src, int n, int R, int Rp, float* dst,
                                           cudaStream_t st);
 
+// K1-LAT (sg_sweep_lattice.cu): checkerboard multi-spin-coded sweep for 2D +-J lattices
+struct LatDev {
+    uint32_t* lat;        // [W][n]  bit b of word w = spin of replica 32 w + b (1 = up)
+    uint32_t* best_lat;   // [W][n]
+    const uint8_t* bond;  // [n] bond code: bit 2d present, bit 2d+1 negative; d = up, down, left, right
+    int L;
+    int n_bonds;
+};
+int lattice_sequence_index(int L, int x, int y);
+cudaError_t launch_lat_pack(const int8_t* spins, int n, int R, uint32_t* lat, cudaStream_t st);
+cudaError_t launch_lat_unpack(const uint32_t* lat, int n, int R, int8_t* spins, cudaStream_t st);
+cudaError_t launch_lat_energy(const LatDev& m, const uint32_t* lat, int R, float* energy, cudaStream_t st);
+cudaError_t launch_sweep_lattice(const LatDev& m, const SweepDev& a, bool inject, uint64_t* launches,
+                                 cudaStream_t st);
+
 // K3 (sg_exchange.cu)
 struct ExchangeDev {
     int* rep_at;              // [L][K] replica currently at rung k of ladder l

@@ -107,6 +107,19 @@ class Engine:
         self.n_replicas = 0
         self._csr = True
 
+    def set_model_lattice2d(self, Jx: ArrayLike, Jy: ArrayLike) -> None:
+        """2D +-J lattice: Jx[x, y] couples (x, y)-(x+1, y), Jy[x, y] couples (x, y)-(x, y+1);
+        entries in {-1, 0, +1} (0 = no bond).  Sweeps use site_order="checkerboard"."""
+        jx, jy = _as_host(Jx, np.int8), _as_host(Jy, np.int8)
+        L = int(jx.shape[0])
+        assert jx.shape == (L, L) and jy.shape == (L, L)
+        check(self._lib.sg_set_model_lattice2d(self._h, L, jx.ctypes.data_as(ctypes.c_void_p),
+                                               jy.ctypes.data_as(ctypes.c_void_p), self.stream),
+              "sg_set_model_lattice2d")
+        self.n = L * L
+        self.n_replicas = 0
+        self._csr = True   # not the dense layout
+
     def alloc_replicas(self, n_replicas: int) -> None:
         check(self._lib.sg_alloc_replicas(self._h, int(n_replicas), self.stream),
               "sg_alloc_replicas")

@@ -22,3 +22,16 @@ for name, model, R, T, sweeps in (("cfg2 EA L=256", inst.ea_lattice(256), 4096, 
     ms2 = t0.elapsed_time(t1)
     att = R * n * sweeps
     print(f"{name}: n={n} R={R}: {att / ms / 1e6:.3f} G attempts/s (track_best: {att / ms2 / 1e6:.3f}), acc={(a1 - a0) / att:.3f}, E/N={eng.energies().mean().item() / n:.4f}")
+# ---- cfg2 on the checkerboard multi-spin-coded lattice kernel
+Jx, Jy = inst.ea_lattice_bonds(256)
+n, R = 65536, 4096
+eng = Engine(0)
+eng.set_model_lattice2d(Jx, Jy); eng.alloc_replicas(R)
+eng.set_spins((torch.randint(0, 2, (R, n), device="cuda") * 2 - 1).to(torch.int8)); eng.init_fields()
+temps = np.tile(np.geomspace(3.0, 0.1, 32), R // 32)
+eng.sweep(2, temps, temps_replica_stride=1, seed=1, site_order="checkerboard"); torch.cuda.synchronize()
+t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+for tb in (False, True):
+    t0.record(); eng.sweep(20, temps, temps_replica_stride=1, seed=1, sweep_base=2, site_order="checkerboard", track_best=tb); t1.record(); torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1)
+    print(f"cfg2 EA L=256 lattice kernel: R={R} track_best={tb}: {R * n * 20 / ms / 1e6:.1f} G attempts/s ({ms / 20:.3f} ms/sweep), E/N={eng.energies().mean().item() / n:.4f}")

@@ -114,26 +114,54 @@ def random_scheduling(n_tasks=500, n_agents=100, seed=5005, max_duration=20.0, h
     return dur, due, rate
 
 
-def ea_lattice(L=256, seed=2002):
-    """cfg2: 2D Edwards-Anderson +-J, OPEN boundaries as the reference's generator actually builds
-    it (research/experimental_validation.py:134-180), spin = x * L + y.  Returns CSR + h = 0."""
+def ea_lattice_bonds(L=256, seed=2002, periodic=False):
+    """Bond arrays of the 2D +-J lattice: Jx[x, y] couples (x, y)-(x+1, y), Jy[x, y] couples
+    (x, y)-(x, y+1), int8 in {-1, 0, +1}; open boundaries (zeros in the last row / column) as the
+    reference's generator actually builds it (research/experimental_validation.py:134-180)."""
     rs = np.random.RandomState(seed)
+    Jx = np.zeros((L, L), np.int8)
+    Jy = np.zeros((L, L), np.int8)
+    if periodic:
+        Jx[:] = rs.choice([-1, 1], size=(L, L))
+        Jy[:] = rs.choice([-1, 1], size=(L, L))
+    else:
+        Jx[:L - 1, :] = rs.choice([-1, 1], size=(L - 1, L))
+        Jy[:, :L - 1] = rs.choice([-1, 1], size=(L, L - 1))
+    return Jx, Jy
+
+
+def lattice_csr(Jx, Jy):
+    """CSR rows of the symmetric coupling matrix of a lattice given by its bond arrays."""
+    L = Jx.shape[0]
     n = L * L
-    Jx = rs.choice([-1.0, 1.0], size=(L - 1, L)).astype(np.float32)   # (x, y) -- (x + 1, y)
-    Jy = rs.choice([-1.0, 1.0], size=(L, L - 1)).astype(np.float32)   # (x, y) -- (x, y + 1)
-    rows, cols, vals = [], [], []
     xs, ys = np.meshgrid(np.arange(L), np.arange(L), indexing="ij")
-    a = (xs[:-1] * L + ys[:-1]).ravel(); b = (xs[1:] * L + ys[1:]).ravel()
-    rows += [a, b]; cols += [b, a]; vals += [Jx.ravel(), Jx.ravel()]
-    a = (xs[:, :-1] * L + ys[:, :-1]).ravel(); b = (xs[:, 1:] * L + ys[:, 1:]).ravel()
-    rows += [a, b]; cols += [b, a]; vals += [Jy.ravel(), Jy.ravel()]
-    rows, cols, vals = np.concatenate(rows), np.concatenate(cols), np.concatenate(vals)
+    a = (xs * L + ys).ravel()
+    bx = (((xs + 1) % L) * L + ys).ravel()
+    by = (xs * L + (ys + 1) % L).ravel()
+    rows = np.concatenate([a, bx, a, by])
+    cols = np.concatenate([bx, a, by, a])
+    vals = np.concatenate([Jx.ravel(), Jx.ravel(), Jy.ravel(), Jy.ravel()]).astype(np.float32)
+    keep = vals != 0
+    rows, cols, vals = rows[keep], cols[keep], vals[keep]
     order = np.lexsort((cols, rows))
     rows, cols, vals = rows[order], cols[order], vals[order]
     rowptr = np.zeros(n + 1, np.int64)
     np.add.at(rowptr, rows + 1, 1)
-    rowptr = np.cumsum(rowptr)
-    return rowptr, cols.astype(np.int32), vals.astype(np.float32), np.zeros(n, np.float32)
+    return np.cumsum(rowptr), cols.astype(np.int32), vals, np.zeros(n, np.float32)
+
+
+def ea_lattice(L=256, seed=2002):
+    """cfg2: 2D Edwards-Anderson +-J, open boundaries, spin = x * L + y.  Returns CSR + h = 0."""
+    return lattice_csr(*ea_lattice_bonds(L, seed))
+
+
+def checkerboard_sequence(L):
+    """Site order of one checkerboard sweep: all (x + y) even sites in row-major order, then all
+    odd ones (the order sg_sweep_lattice.cu realises in parallel)."""
+    xs, ys = np.meshgrid(np.arange(L), np.arange(L), indexing="ij")
+    site = (xs * L + ys).ravel()
+    color = ((xs + ys) & 1).ravel()
+    return np.concatenate([site[color == 0], site[color == 1]]).astype(np.int32)
 
 
 def csr_to_dense(rowptr, colidx, val, n):
