@@ -28,7 +28,7 @@ import numpy as np
 import torch
 
 from ..core.spin_dynamics import UpdateRule
-from ._backend import as_pm1_float, engine_for, random_spins, rule_name
+from ._backend import as_pm1_float, engine_for, random_spins, rule_name, site_order_for
 from .result import AnnealingResult
 from .temperature_scheduler import ScheduleType, TemperatureScheduler
 
@@ -129,7 +129,7 @@ class GPUAnnealer:
                 chunk_t = np.array([max(schedule.update(done, acceptance_rate=rate), 1e-10)])
                 last = done
             k = len(chunk_t)
-            trace = eng.sweep(k, chunk_t, temps_sweep_stride=1, rule=rule, site_order=cfg.site_order,
+            trace = eng.sweep(k, chunk_t, temps_sweep_stride=1, rule=rule, site_order=site_order_for(eng, cfg.site_order),
                               seed=philox_seed, sweep_base=done, energy_trace=True, track_best=True,
                               replicas_per_block=cfg.replicas_per_block)
             # incremental field updates drift for non-integer couplings; the reference recomputes

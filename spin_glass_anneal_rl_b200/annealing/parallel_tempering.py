@@ -27,7 +27,7 @@ import numpy as np
 import torch
 
 from ..core.spin_dynamics import UpdateRule
-from ._backend import as_pm1_float, engine_for, random_spins, rule_name
+from ._backend import as_pm1_float, engine_for, random_spins, rule_name, site_order_for
 from .result import AnnealingResult
 
 
@@ -114,7 +114,7 @@ class ParallelTempering:
                     break
                 nxt += 1
             k = nxt - sweep + 1
-            eng.sweep(k, None, rule=rule, site_order=c.site_order, seed=int(seed),
+            eng.sweep(k, None, rule=rule, site_order=site_order_for(eng, c.site_order), seed=int(seed),
                       sweep_base=sweep, track_best=True)
             eng.refresh_fields()  # exact fields / energies before they feed an exchange decision
             sweep = nxt

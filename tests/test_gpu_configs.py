@@ -65,3 +65,33 @@ def test_cfg5_scheduling_sparse_model_goes_to_csr_path():
     assert abs(res.best_energy - e_best) <= 1e-5 * abs(e_best)
     assert res.energy_history[-1] < res.energy_history[0]
     assert torch.equal(model.spins.abs(), torch.ones(n))
+
+
+def test_cfg2_lattice_model_is_detected_and_swept_in_checkerboard_order():
+    """A sparse COO model with the structure of the reference's 2D Edwards-Anderson generator is
+    routed to the multi-spin-coded lattice kernel by the host API."""
+    import spin_glass_anneal_rl_b200 as sg
+    L = 80
+    Jx, Jy = inst.ea_lattice_bonds(L, seed=8)
+    rowptr, colidx, val, h = inst.lattice_csr(Jx, Jy)
+    n = L * L
+    rows = np.repeat(np.arange(n), np.diff(rowptr))
+    model = sg.IsingModel(sg.IsingModelConfig(n_spins=n, use_sparse=True))
+    model.couplings = torch.sparse_coo_tensor(np.stack([rows, colidx]), torch.from_numpy(val), (n, n))
+    cfg = sg.GPUAnnealerConfig(n_sweeps=40, initial_temp=3.0, final_temp=0.2, random_seed=5,
+                               schedule_params={"alpha": 0.93}, n_replicas=96, record_interval=10)
+    res = sg.GPUAnnealer(cfg).anneal(model)
+    assert model._sg_engine[1].kind == "lattice"
+    s = res.best_configuration.numpy().astype(np.float64).reshape(L, L)
+    e = -float((Jx[:-1] * s[:-1] * s[1:]).sum() + (Jy[:, :-1] * s[:, :-1] * s[:, 1:]).sum())
+    assert res.best_energy == e                      # integer energies: exact
+    assert res.best_energy < -1.2 * n                # well below the random-start energy (~0)
+    assert res.energy_history[-1] < res.energy_history[0]
+    # a perturbed copy (one coupling 2.0) is no longer a +-J lattice -> sparse kernel
+    val2 = val.copy()
+    val2[0] = 2.0
+    val2[np.where((rows == colidx[0]) & (colidx == rows[0]))[0][0]] = 2.0
+    model2 = sg.IsingModel(sg.IsingModelConfig(n_spins=n, use_sparse=True))
+    model2.couplings = torch.sparse_coo_tensor(np.stack([rows, colidx]), torch.from_numpy(val2), (n, n))
+    sg.GPUAnnealer(sg.GPUAnnealerConfig(n_sweeps=2, n_replicas=8, random_seed=1)).anneal(model2)
+    assert model2._sg_engine[1].kind == "csr"
