@@ -42,6 +42,7 @@
 //   warp 6     MMA issuer (one lane): tcgen05.mma + tcgen05.commit.
 #include <cuda_bf16.h>
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "sg_common.cuh"
@@ -335,25 +336,81 @@ struct TcSmem {
     size_t ring, bop, sbits, theta, raw, tab, red, flags, bars, tptr, total;
 };
 
-__host__ __device__ inline TcSmem tc_layout(int n_tc, int P, int NS) {
+// C = CTAs per replica group (1, or 2 = a cluster pair that splits the field columns)
+__host__ __device__ inline TcSmem tc_layout(int n_tc, int P, int NS, int C) {
+    const int NG = kG * C;
     TcSmem L;
     size_t off = 0;
     L.ring = off;  off += (size_t)NS * kChunkTiles * P * kTileBytes;
-    L.bop = off;   off += (size_t)kSlots * kBopBytes;
-    L.sbits = off; off += (size_t)kG * (n_tc / 32) * sizeof(uint32_t);
-    L.theta = off; off += (size_t)kSlots * kBlk * kG * sizeof(float);
-    L.raw = off;   off += (size_t)kSlots * kBlk * kG * sizeof(float);
+    L.bop = off;   off += (size_t)kSlots * 32 * NG;
+    L.sbits = off; off += (size_t)NG * (n_tc / 32) * sizeof(uint32_t);
+    L.theta = off; off += (size_t)kSlots * kBlk * NG * sizeof(float);
+    L.raw = off;   off += (size_t)kSlots * kBlk * NG * sizeof(float);
     L.tab = off;   off += (size_t)kSlots * kTabBytes;
-    L.red = off;   off += 4 * kG * sizeof(float);
+    L.red = off;   off += (size_t)C * 4 * NG * sizeof(float);
     L.flags = off; off += 4 * sizeof(uint32_t);
     off = (off + 15) & ~(size_t)15;
-    L.bars = off;  off += (size_t)(2 * kMaxStagesTc + 7 * kSlots) * sizeof(uint64_t);
+    L.bars = off;  off += (size_t)(2 * kMaxStagesTc + 7 * kSlots + 2) * sizeof(uint64_t);
     L.tptr = off;  off += 16;
     L.total = off;
     return L;
 }
 
 __device__ __forceinline__ void named_sync(int id) { named_bar_sync(id, kSyncThreads); }
+
+// ---- thread-block-cluster helpers (C = 2)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n"
+                 "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory location in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t map_to_rank(const void* p, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_f4(uint32_t addr, float4 v) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void st_cluster_f1(uint32_t addr, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+// asynchronous remote stores that count their bytes on an mbarrier of the target CTA
+// (both addresses are shared::cluster addresses of the same CTA): no fence, no remote arrive
+__device__ __forceinline__ void st_async_f4(uint32_t addr, float4 v, uint32_t bar) {
+    asm volatile(
+        "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr),
+        "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void fence_cluster() {
+    asm volatile("fence.acq_rel.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
 
 // development aid: clock stamps of block 0 (tools/tc_timeline.py); 16 slots per attempt block
 #define SG_STAMP(slot_)                                                              \
@@ -382,49 +439,72 @@ __device__ __forceinline__ void store_spin_word(int8_t* dst, uint32_t w) {
     d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
-template <int P, bool INJECT>
+// C = 1: one CTA holds all field columns of 16 replicas.  C = 2: a cluster pair holds 32
+// replicas, CTA `crank` owns the columns [crank * n_tc/2, (crank+1) * n_tc/2) (so each SM streams
+// and multiplies only half of every J row: half the shared-memory traffic per attempt); both
+// CTAs run the same decision warp on identical inputs (raw field values are exchanged through
+// distributed shared memory), so no decision has to cross the cluster.
+template <int P, bool INJECT, int C>
 __global__ void __launch_bounds__(kTcThreads, 1)
 sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const int n_tc,
                 const uint16_t* __restrict__ sites_g, const int n_s, const int NS,
                 const int tmem_cols, const unsigned char* __restrict__ Q,
                 const unsigned char* __restrict__ tabs_g, const int s_begin, const int s_end,
                 const int dbg) {
+    constexpr int NG = kG * C;               // replicas per group = MMA N
+    constexpr int NGRP = NG / 16;            // 16-column TMEM load/store groups per tile
+    constexpr uint32_t IDESC = tc::make_idesc_bf16(kTileM, NG);
+    constexpr int BOP = 32 * NG;             // B operand bytes per slot
+    constexpr uint32_t BLBO = 16 * NG;       // B: k-group stride ((NG/8) n-groups of 128 B)
     extern __shared__ __align__(128) unsigned char smem[];
     const int n = a.n, n_pad = a.n_pad;
     const int W = n_tc >> 5;
-    const int T = n_tc / kTileM;
-    const int nchunk = (T + kChunkTiles - 1) / kChunkTiles;
-    const int hc = (nchunk + 1) >> 1;                   // chunks [0, hc) = half 0, the rest = half 1
-    const int half_cols = hc * kChunkTiles * kTileM;    // field columns below this are in half 0
+    const int T = n_tc / kTileM;             // tiles of the whole model
+    const int Tl = T / C;                    // tiles of this CTA
+    const int nchunk = (T + kChunkTiles - 1) / kChunkTiles;       // chunks per block in Q
+    const int nchunk_l = (Tl + kChunkTiles - 1) / kChunkTiles;    // ... consumed by this CTA
+    const int hc = (nchunk_l + 1) >> 1;                 // local chunks [0, hc) = half 0
+    const int half_cols = hc * kChunkTiles * kTileM;    // local columns below this are in half 0
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t crank = (C == 2) ? cluster_ctarank() : 0u;
+    const uint32_t peer = crank ^ 1u;
+    const int cols_cta = Tl * kTileM;        // field columns per CTA
+    const int col0 = (int)crank * cols_cta;
 
-    const TcSmem L = tc_layout(n_tc, P, NS);
+    const TcSmem L = tc_layout(n_tc, P, NS, C);
     unsigned char* ring = smem + L.ring;
     unsigned char* bop_s = smem + L.bop;
     uint32_t* sbits = reinterpret_cast<uint32_t*>(smem + L.sbits);
     float* theta_s = reinterpret_cast<float*>(smem + L.theta);  // [slot][b][r]
     float* raw_s = reinterpret_cast<float*>(smem + L.raw);      // [slot][b][r]
     unsigned char* tab_s = smem + L.tab;  // [slot]{cin[16][16], ccr[16][16], dup[16]} (TMA)
-    float* red = reinterpret_cast<float*>(smem + L.red);
+    float* red = reinterpret_cast<float*>(smem + L.red);        // [rank][quarter][r]
     uint32_t* flags = reinterpret_cast<uint32_t*>(smem + L.flags);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);
     uint64_t* empty = full + kMaxStagesTc;
     uint64_t* tabbar = empty + kMaxStagesTc;   // [slot]     decision tables of a block landed (TMA)
     uint64_t* thbar = tabbar + kSlots;         // [slot]     thresholds of a block published
-    uint64_t* rbar = thbar + kSlots;           // [slot][2]  raw field values of a half published
-    uint64_t* decbar = rbar + 2 * kSlots;      // [slot]     block decided, B operand written
+    uint64_t* rloc = thbar + kSlots;           // [slot][2]  this CTA's raw reads of a half done
+    uint64_t* rall = rloc + 2 * kSlots;        // [slot]     all raw values of a block published
+    uint64_t* decbar = rall + kSlots;          // [slot]     block decided, B operand written
     uint64_t* hdone = decbar + kSlots;         // [slot][2]  MMAs of a half of a block completed
+    uint64_t* ebar = hdone + 2 * kSlots;       // energy partial sums of a sweep published
     uint32_t* tptr = reinterpret_cast<uint32_t*>(smem + L.tptr);
     constexpr int kStageBytes = kChunkTiles * P * kTileBytes;
 
-    const int rep0 = blockIdx.x * kG;
-    const int g_act = min(kG, a.R - rep0);
+    const int rep0 = (blockIdx.x / C) * NG;
+    const int g_act = min(NG, a.R - rep0);
     const int n_sweeps = a.n_sweeps;
     const int nblk = (n + kBlk - 1) / kBlk;
-    const size_t plane_stride = (size_t)n * n_tc;
     const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
 
     // ------------------------------------------------------------ prologue
+    if (a.dbg && tid == 0 && blockIdx.x < 512) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        a.dbg[8192 + blockIdx.x * 4 + 0] = (long long)gt;
+        a.dbg[8192 + blockIdx.x * 4 + 2] = (long long)clock64();
+    }
     if (tid == 0) {
         for (int d = 0; d < NS; ++d) {
             mbar_init(&full[d], 1);
@@ -432,13 +512,15 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
         }
         for (int d = 0; d < kSlots; ++d) {
             mbar_init(&tabbar[d], 1);
-            mbar_init(&thbar[d], 2);
-            mbar_init(&rbar[2 * d], 4);
-            mbar_init(&rbar[2 * d + 1], 4);
+            mbar_init(&thbar[d], NG / 8);
+            mbar_init(&rloc[2 * d], 4);
+            mbar_init(&rloc[2 * d + 1], 4);
+            mbar_init(&rall[d], 8 + (C - 1));   // 4 warps x 2 halves (+ the expect_tx arrival)
             mbar_init(&decbar[d], 1);
             mbar_init(&hdone[2 * d], 1);
             mbar_init(&hdone[2 * d + 1], 1);
         }
+        mbar_init(ebar, 4 + (C - 1));
         fence_mbar_init();
         fence_proxy_async();
     }
@@ -446,8 +528,8 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
         tc::tmem_alloc(tptr, (uint32_t)tmem_cols);
         tc::tmem_relinquish();
     }
-    // spin bit planes from int8 spins
-    for (int w = tid; w < kG * W; w += kTcThreads) {
+    // spin bit planes from int8 spins (every CTA of a group keeps all NG planes)
+    for (int w = tid; w < NG * W; w += kTcThreads) {
         const int r = w / W, word = w - r * W;
         uint32_t bits = 0xFFFFFFFFu;
         if (r < g_act) {
@@ -468,19 +550,23 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
     }
     tc::fence_before_sync();
     __syncthreads();
+    if (C == 2) cluster_sync_all();   // the peer's barriers exist before anything remote arrives
     tc::fence_after_sync();
     const uint32_t tbase = *tptr;
 
     if (warp < 4) {
         // resident fields -> TMEM
         const uint32_t tq = tbase + ((uint32_t)(warp * 32) << 16);
-        for (int t = 0; t < T; ++t) {
-            float v[16];
-            const int col = t * kTileM + warp * 32 + lane;
+        for (int t = 0; t < Tl; ++t) {
+            const int col = col0 + t * kTileM + warp * 32 + lane;
 #pragma unroll
-            for (int r = 0; r < 16; ++r)
-                v[r] = (r < g_act) ? a.fields[(size_t)(rep0 + r) * n_pad + col] : 0.0f;
-            tc::tmem_st16(tq + t * kG, v);
+            for (int gi = 0; gi < NGRP; ++gi) {
+                float v[16];
+#pragma unroll
+                for (int r = 0; r < 16; ++r)
+                    v[r] = (gi * 16 + r < g_act) ? a.fields[(size_t)(rep0 + gi * 16 + r) * n_pad + col] : 0.0f;
+                tc::tmem_st16(tq + t * NG + gi * 16, v);
+            }
         }
         tc::wait_st();
     }
@@ -493,6 +579,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
         const int q = warp;
         const uint32_t tq = tbase + ((uint32_t)(q * 32) << 16);
         int kg = 0;
+        uint32_t epar = 0;
 #pragma unroll 1
         for (int s = s_begin; s < s_end; ++s) {
             const uint16_t* stab = sites_g + (size_t)s * n_s;
@@ -507,8 +594,8 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 const uint4 sq1 = *reinterpret_cast<const uint4*>(stab + i0 + 8);
                 const uint32_t swq[8] = {sq0.x, sq0.y, sq0.z, sq0.w, sq1.x, sq1.y, sq1.z, sq1.w};
                 // --- thresholds: thread (qq, r) covers attempts 4qq..4qq+3 of the block
-                if (!INJECT && tid < 64) {
-                    const int qq = tid >> 4, r = tid & 15;
+                if (!INJECT && tid < 4 * NG) {
+                    const int qq = tid / NG, r = tid - qq * NG;
                     const int ia = i0 + qq * 4;
                     if (r < g_act && ia < n) {
                         const int rep = rep0 + r;
@@ -517,25 +604,37 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                             make_uint4((uint32_t)rep, (uint32_t)sa, (uint32_t)(sa >> 32),
                                        (uint32_t)(ia >> 2)), key);
                         const uint32_t vv[4] = {x.x, x.y, x.z, x.w};
-                        float* dst = theta_s + slot * kBlk * kG + (qq * 4) * kG + r;
+                        float* dst = theta_s + slot * kBlk * NG + (qq * 4) * NG + r;
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const float u = u01(vv[e]);
                             float th;
                             if (a.rule == 0) th = -__logf(u) * Tm;
                             else th = 0.5f * Tm * (__logf(u) - __logf(1.0f - u));
-                            dst[e * kG] = th;
+                            dst[e * NG] = th;
                         }
                     }
                 }
                 __syncwarp();
-                if (warp < 2 && lane == 0) mbar_arrive(&thbar[slot]);
+                if (warp < NG / 8 && lane == 0) mbar_arrive(&thbar[slot]);
+                if (C == 2 && warp == 0 && lane == 0) {
+                    // the peer will store the raw values of the sites it owns straight into this
+                    // CTA's raw_s[slot], counting bytes on rall[slot]
+                    int n_remote = 0;
+#pragma unroll
+                    for (int b = 0; b < kBlk; ++b) {
+                        const int site = (int)((swq[b >> 1] >> (16 * (b & 1))) & 0xFFFFu);
+                        const int lcr = site - col0;
+                        n_remote += (b < nbk && !(lcr >= 0 && lcr < cols_cta)) ? 1 : 0;
+                    }
+                    mbar_arrive_expect_tx(&rall[slot], (uint32_t)(n_remote * NG * 4));
+                }
                 if (warp == 0) SG_STAMP(1);
-                // --- raw field values of the block's sites, as of the end of block kg-2: the sites
-                // of a column half are read as soon as that half of block kg-2 has landed (the
-                // other half may still be executing), and the same half of block kg-1 is not
-                // issued before the read is done
-                float* rawb = raw_s + slot * kBlk * kG;
+                // --- raw field values of the block's sites in this CTA's columns, as of the end of
+                // block kg-2: the sites of a column half are read as soon as that half of block
+                // kg-2 has landed (the other half may still be executing), and the same half of
+                // block kg-1 is not issued before the read is done
+                float* rawb = raw_s + slot * kBlk * NG;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     if (kg >= 2)
@@ -545,82 +644,119 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
 #pragma unroll
                     for (int b = 0; b < kBlk; ++b) {
                         const int site = (int)((swq[b >> 1] >> (16 * (b & 1))) & 0xFFFFu);
-                        const bool in_h = (site < half_cols) == (h == 0);
-                        if (b < nbk && in_h && ((site >> 5) & 3) == q && !(dbg & 4)) {
-                            float v[16];
-                            tc::tmem_ld16(tq + (site >> 7) * kG, v);
-                            tc::wait_ld();
-                            if (lane == (site & 31)) {
-                                float4* d4 = reinterpret_cast<float4*>(rawb + b * kG);
-                                d4[0] = make_float4(v[0], v[1], v[2], v[3]);
-                                d4[1] = make_float4(v[4], v[5], v[6], v[7]);
-                                d4[2] = make_float4(v[8], v[9], v[10], v[11]);
-                                d4[3] = make_float4(v[12], v[13], v[14], v[15]);
+                        const int lc = site - col0;          // column inside this CTA
+                        const bool mine = (C == 1) || (lc >= 0 && lc < cols_cta);
+                        const bool in_h = (lc < half_cols) == (h == 0);
+                        if (b < nbk && mine && in_h && ((lc >> 5) & 3) == q && !(dbg & 4)) {
+#pragma unroll
+                            for (int gi = 0; gi < NGRP; ++gi) {
+                                float v[16];
+                                tc::tmem_ld16(tq + (lc >> 7) * NG + gi * 16, v);
+                                tc::wait_ld();
+                                if (lane == (lc & 31)) {
+                                    float* dl = rawb + b * NG + gi * 16;
+                                    float4* d4 = reinterpret_cast<float4*>(dl);
+                                    d4[0] = make_float4(v[0], v[1], v[2], v[3]);
+                                    d4[1] = make_float4(v[4], v[5], v[6], v[7]);
+                                    d4[2] = make_float4(v[8], v[9], v[10], v[11]);
+                                    d4[3] = make_float4(v[12], v[13], v[14], v[15]);
+                                    if (C == 2) {
+                                        const uint32_t ra = map_to_rank(dl, peer);
+                                        const uint32_t rb = map_to_rank(&rall[slot], peer);
+                                        st_async_f4(ra, make_float4(v[0], v[1], v[2], v[3]), rb);
+                                        st_async_f4(ra + 16, make_float4(v[4], v[5], v[6], v[7]), rb);
+                                        st_async_f4(ra + 32, make_float4(v[8], v[9], v[10], v[11]), rb);
+                                        st_async_f4(ra + 48, make_float4(v[12], v[13], v[14], v[15]), rb);
+                                    }
+                                }
                             }
                         }
                     }
                     tc::fence_before_sync();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&rbar[2 * slot + h]);
+                    if (lane == 0) {
+                        mbar_arrive(&rloc[2 * slot + h]);
+                        mbar_arrive(&rall[slot]);
+                    }
                 }
                 if (warp == 0) SG_STAMP(15);
             }
-            // ---- end of sweep: energies from the TMEM-resident fields
+            // ---- end of sweep: energy partial sums over this CTA's columns
             mbar_wait(&hdone[2 * ((kg - 1) & (kSlots - 1)) + 1], (uint32_t)((kg - 1) >> 2) & 1u);
             tc::fence_after_sync();
             named_sync(1);  // decision warp has flipped the last spins of the sweep
             {
-                float part[16];
+                float part[NG];
 #pragma unroll
-                for (int r = 0; r < 16; ++r) part[r] = 0.0f;
-                for (int t = 0; t < T; ++t) {
-                    float f[16];
-                    tc::tmem_ld16(tq + t * kG, f);
-                    tc::wait_ld();
-                    const float hv = a.h[t * kTileM + q * 32 + lane];
+                for (int r = 0; r < NG; ++r) part[r] = 0.0f;
+                for (int t = 0; t < Tl; ++t) {
+                    const int colb = col0 + t * kTileM + q * 32;   // first column of this lane group
+                    const float hv = a.h[colb + lane];
 #pragma unroll
-                    for (int r = 0; r < 16; ++r) {
-                        const uint32_t w = sbits[r * W + t * 4 + q];
-                        const float tt = f[r] + hv;
-                        part[r] += ((w >> lane) & 1u) ? tt : -tt;
+                    for (int gi = 0; gi < NGRP; ++gi) {
+                        float f[16];
+                        tc::tmem_ld16(tq + t * NG + gi * 16, f);
+                        tc::wait_ld();
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) {
+                            const uint32_t w = sbits[(gi * 16 + r) * W + (colb >> 5)];
+                            const float tt = f[r] + hv;
+                            part[gi * 16 + r] += ((w >> lane) & 1u) ? tt : -tt;
+                        }
                     }
                 }
 #pragma unroll
-                for (int r = 0; r < 16; ++r) {
+                for (int r = 0; r < NG; ++r) {
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) part[r] += __shfl_xor_sync(0xFFFFFFFFu, part[r], o);
                 }
                 if (lane == 0) {
+                    float* dst = red + ((int)crank * 4 + q) * NG;
 #pragma unroll
-                    for (int r = 0; r < 16; ++r) red[q * kG + r] = part[r];
+                    for (int r = 0; r < NG; ++r) dst[r] = part[r];
+                    if (C == 2) {
+                        if (q == 0) mbar_arrive_expect_tx(ebar, (uint32_t)(4 * NG * 4));
+                        const uint32_t ra = map_to_rank(dst, peer);
+                        const uint32_t rb = map_to_rank(ebar, peer);
+#pragma unroll
+                        for (int r4 = 0; r4 < NG / 4; ++r4)
+                            st_async_f4(ra + 16 * r4, make_float4(part[4 * r4], part[4 * r4 + 1],
+                                                                 part[4 * r4 + 2], part[4 * r4 + 3]), rb);
+                    }
+                    mbar_arrive(ebar);
                 }
             }
             tc::fence_before_sync();
-            named_sync(2);  // partial sums visible to the decision warp
             named_sync(3);  // flags[0] = mask of replicas that improved
             const uint32_t im = flags[0];
-            if (im != 0u) {
-                for (int w = tid; w < kG * W; w += 128) {
+            if (im != 0u && crank == 0) {
+                for (int w = tid; w < NG * W; w += 128) {
                     const int r = w / W, word = w - r * W;
                     if ((im >> r) & 1u)
                         store_spin_word(a.best_spins + (size_t)(rep0 + r) * n_pad + word * 32, sbits[w]);
                 }
             }
             named_sync(1);  // bit planes may be modified again
+            epar ^= 1u;
         }
-        // ---- epilogue: fields and spins back to HBM
-        for (int t = 0; t < T; ++t) {
-            float v[16];
-            tc::tmem_ld16(tq + t * kG, v);
-            tc::wait_ld();
-            const int col = t * kTileM + q * 32 + lane;
+        // ---- epilogue: fields (this CTA's columns) and spins back to HBM
+        for (int t = 0; t < Tl; ++t) {
+            const int col = col0 + t * kTileM + q * 32 + lane;
 #pragma unroll
-            for (int r = 0; r < 16; ++r)
-                if (r < g_act) a.fields[(size_t)(rep0 + r) * n_pad + col] = v[r];
+            for (int gi = 0; gi < NGRP; ++gi) {
+                float v[16];
+                tc::tmem_ld16(tq + t * NG + gi * 16, v);
+                tc::wait_ld();
+#pragma unroll
+                for (int r = 0; r < 16; ++r)
+                    if (gi * 16 + r < g_act) a.fields[(size_t)(rep0 + gi * 16 + r) * n_pad + col] = v[r];
+            }
         }
-        for (int w = tid; w < kG * W; w += 128) {
-            const int r = w / W, word = w - r * W;
-            if (r < g_act) store_spin_word(a.spins + (size_t)(rep0 + r) * n_pad + word * 32, sbits[w]);
+        if (crank == 0) {
+            for (int w = tid; w < NG * W; w += 128) {
+                const int r = w / W, word = w - r * W;
+                if (r < g_act) store_spin_word(a.spins + (size_t)(rep0 + r) * n_pad + word * 32, sbits[w]);
+            }
         }
     } else if (warp == 4) {
         // ======================================================== PRODUCER (TMA)
@@ -628,8 +764,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
             int stage = 0;
             uint32_t epar = 1;  // a fresh barrier passes a wait on the "previous" phase
             const int nblk_total = (s_end - s_begin) * nblk;
-            const size_t nchunks_total = (size_t)nblk_total * nchunk;
-            int kg = 0, cc = 0;
+            int kg = 0;
             // decision tables of block j -> slot j % 4 (the slot's previous user, block j-4, has
             // been decided long before the operand stream reaches block j-2)
             auto issue_tables = [&](int j) {
@@ -643,22 +778,24 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
             issue_tables(0);
             issue_tables(1);
 #pragma unroll 1
-            for (size_t ci = 0; ci < nchunks_total; ++ci) {
-                if (cc == 0) {
-                    SG_STAMP(13);
-                    issue_tables(kg + 2);
+            for (kg = 0; kg < nblk_total; ++kg) {
+                SG_STAMP(13);
+                issue_tables(kg + 2);
+                const unsigned char* src = Q + ((size_t)kg * nchunk + (size_t)crank * nchunk_l) * kStageBytes;
+#pragma unroll 1
+                for (int c = 0; c < nchunk_l; ++c) {
+                    mbar_wait(&empty[stage], epar);
+                    mbar_arrive_expect_tx(&full[stage], (uint32_t)kStageBytes);
+                    bulk_g2s(ring + (size_t)stage * kStageBytes, (dbg & 1) ? Q : src + (size_t)c * kStageBytes,
+                             (uint32_t)kStageBytes, &full[stage]);
+                    if (++stage == NS) { stage = 0; epar ^= 1u; }
                 }
-                mbar_wait(&empty[stage], epar);
-                mbar_arrive_expect_tx(&full[stage], (uint32_t)kStageBytes);
-                bulk_g2s(ring + (size_t)stage * kStageBytes, (dbg & 1) ? Q : Q + ci * kStageBytes,
-                         (uint32_t)kStageBytes, &full[stage]);
-                if (++stage == NS) { stage = 0; epar ^= 1u; }
-                if (++cc == nchunk) { cc = 0; SG_STAMP(14); ++kg; }
+                SG_STAMP(14);
             }
         }
     } else if (warp == 5) {
         // ======================================================== DECISION WARP
-        const int r = lane & (kG - 1);
+        const int r = lane & (NG - 1);
         const bool active = lane < g_act;
         float best_e = 3.0e38f, cur_e = 0.0f;
         unsigned int n_acc = 0;
@@ -670,6 +807,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
 #pragma unroll
         for (int b = 0; b < kBlk; ++b) pdec[b] = 0.0f;
         int kg = 0;
+        uint32_t epar = 0;
 #pragma unroll 1
         for (int s = s_begin; s < s_end; ++s) {
             const uint16_t* stab = sites_g + (size_t)s * n_s;
@@ -700,8 +838,8 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 SG_STAMP(4);
                 mbar_wait(&tabbar[slot], par);
                 mbar_wait(&thbar[slot], par);
-                const float* rawp = raw_s + slot * kBlk * kG + r;
-                const float* thp = theta_s + slot * kBlk * kG + r;
+                const float* rawp = raw_s + slot * kBlk * NG + r;
+                const float* thp = theta_s + slot * kBlk * NG + r;
                 const float4* cin4 = reinterpret_cast<const float4*>(tab_s + slot * kTabBytes);
                 const float4* ccr4 = cin4 + kBlk * kBlk / 4;
                 const uint32_t* dup_p = reinterpret_cast<const uint32_t*>(tab_s + slot * kTabBytes) + 2 * kBlk * kBlk;
@@ -727,16 +865,15 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 uint32_t w0[kBlk], dup[kBlk];
 #pragma unroll
                 for (int b = 0; b < kBlk; ++b) {
-                    th[b] = INJECT ? 0.0f : thp[b * kG];
+                    th[b] = INJECT ? 0.0f : thp[b * NG];
                     w0[b] = sbits[r * W + (site[b] >> 5)];
                     dup[b] = dup_p[b];
                 }
                 SG_STAMP(5);
-                mbar_wait(&rbar[2 * slot], par);
-                mbar_wait(&rbar[2 * slot + 1], par);
+                mbar_wait(&rall[slot], par);
                 SG_STAMP(6);
 #pragma unroll
-                for (int b = 0; b < kBlk; ++b) v[b] += rawp[b * kG];
+                for (int b = 0; b < kBlk; ++b) v[b] += rawp[b * NG];
                 // the 16 attempts of the block, strictly in order, registers only
                 uint32_t myflips = 0;
                 float d[kBlk];
@@ -779,13 +916,13 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 }
                 n_acc += (unsigned int)__popc(myflips);
                 SG_STAMP(7);
-                // B operand (K-major bf16): byte(n, k) = (n/8)*128 + (k/8)*256 + (n%8)*16 + (k%8)*2
-                if (lane < kG) {
-                    unsigned char* bo = bop_s + slot * kBopBytes + (lane & 7) * 16 + (lane >> 3) * kBSbo;
+                // B operand (K-major bf16): byte(n, k) = (n/8)*128 + (k/8)*BLBO + (n%8)*16 + (k%8)*2
+                if (lane < NG) {
+                    unsigned char* bo = bop_s + slot * BOP + (lane & 7) * 16 + (lane >> 3) * kBSbo;
                     *reinterpret_cast<uint4*>(bo) =
                         make_uint4(pack_bf16x2(d[0], d[1]), pack_bf16x2(d[2], d[3]),
                                    pack_bf16x2(d[4], d[5]), pack_bf16x2(d[6], d[7]));
-                    *reinterpret_cast<uint4*>(bo + kBLbo) =
+                    *reinterpret_cast<uint4*>(bo + BLBO) =
                         make_uint4(pack_bf16x2(d[8], d[9]), pack_bf16x2(d[10], d[11]),
                                    pack_bf16x2(d[12], d[13]), pack_bf16x2(d[14], d[15]));
                 }
@@ -793,7 +930,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&decbar[slot]);
                 // spin bit planes (lane r owns plane r; XOR commutes, so order is irrelevant)
-                if (lane < kG) {
+                if (lane < NG) {
 #pragma unroll
                     for (int aa = 0; aa < kBlk; ++aa)
                         atomicXor(&sbits[r * W + (site[aa] >> 5)],
@@ -805,13 +942,18 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
             }
             // ---- end of sweep: energy, best tracking
             named_sync(1);
-            named_sync(2);
+            mbar_wait(ebar, epar);
+            epar ^= 1u;
             bool improved = false;
             if (active) {
-                const float acc = red[0 * kG + lane] + red[1 * kG + lane] + red[2 * kG + lane] +
-                                  red[3 * kG + lane];
+                float acc = 0.0f;
+#pragma unroll
+                for (int rk = 0; rk < C; ++rk) {
+                    const float* pr = red + rk * 4 * NG + lane;
+                    acc += (pr[0] + pr[NG]) + (pr[2 * NG] + pr[3 * NG]);
+                }
                 cur_e = -0.5f * acc;
-                if (a.energy_trace) a.energy_trace[(size_t)s * a.R + rep0 + lane] = cur_e;
+                if (a.energy_trace && crank == 0) a.energy_trace[(size_t)s * a.R + rep0 + lane] = cur_e;
                 if (a.track_best && cur_e < best_e) {
                     best_e = cur_e;
                     improved = true;
@@ -822,7 +964,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
             named_sync(3);
             named_sync(1);
         }
-        if (active) {
+        if (active && crank == 0) {
             a.energy[rep0 + lane] = cur_e;
             if (a.track_best) a.best_energy[rep0 + lane] = best_e;
             a.accepted[rep0 + lane] += (unsigned long long)n_acc;
@@ -842,33 +984,32 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 SG_STAMP(9);
                 mbar_wait(&decbar[slot], (uint32_t)(kg >> 2) & 1u);
                 SG_STAMP(10);
-                const uint64_t bdesc =
-                    tc::make_smem_desc(smem_u32(bop_s + slot * kBopBytes), kBLbo, kBSbo);
+                const uint64_t bdesc = tc::make_smem_desc(smem_u32(bop_s + slot * BOP), BLBO, kBSbo);
 #pragma unroll 1
                 for (int h = 0; h < 2; ++h) {
-                    // the raw values of block k+1 in this column half must have been read before
+                    // this CTA's raw reads of block k+1 in this column half must be done before
                     // this block's update of the half is issued
                     if (k + 1 < nblk)
-                        mbar_wait(&rbar[2 * ((kg + 1) & (kSlots - 1)) + h], (uint32_t)((kg + 1) >> 2) & 1u);
+                        mbar_wait(&rloc[2 * ((kg + 1) & (kSlots - 1)) + h], (uint32_t)((kg + 1) >> 2) & 1u);
                     if (h == 0) SG_STAMP(11);
-                    const int c_end = h ? nchunk : hc;
+                    const int c_end = h ? nchunk_l : hc;
 #pragma unroll 1
                     for (int c = h ? hc : 0; c < c_end; ++c) {
                         mbar_wait(&full[stage], fpar);
                         tc::fence_after_sync();
-                        const int nt = (dbg & 2) ? 0 : min(kChunkTiles, T - c * kChunkTiles);
+                        const int nt = (dbg & 2) ? 0 : min(kChunkTiles, Tl - c * kChunkTiles);
                         const uint64_t adesc0 = tc::make_smem_desc(
                             smem_u32(ring + (size_t)stage * kStageBytes), kALbo, kASbo);
-                        const uint32_t d0 = tbase + (uint32_t)(c * kChunkTiles * kG);
+                        const uint32_t d0 = tbase + (uint32_t)(c * kChunkTiles * NG);
                         if (tc::elect_one()) {
 #pragma unroll
                             for (int tt = 0; tt < kChunkTiles; ++tt) {
                                 if (tt < nt) {
 #pragma unroll
                                     for (int p = 0; p < P; ++p)
-                                        tc::mma_bf16_ss(d0 + tt * kG,
+                                        tc::mma_bf16_ss(d0 + tt * NG,
                                                         adesc0 + (uint64_t)(((tt * P + p) * kTileBytes) >> 4),
-                                                        bdesc, kIdesc, 1u);
+                                                        bdesc, IDESC, 1u);
                                 }
                             }
                             tc::mma_commit(&empty[stage]);
@@ -887,6 +1028,13 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
     // ------------------------------------------------------------ teardown
     tc::fence_before_sync();
     __syncthreads();
+    if (a.dbg && tid == 0 && blockIdx.x < 512) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        a.dbg[8192 + blockIdx.x * 4 + 1] = (long long)gt;
+        a.dbg[8192 + blockIdx.x * 4 + 3] = (long long)clock64();
+    }
+    if (C == 2) cluster_sync_all();   // no CTA exits while its peer may still write into it
     if (warp == 0) tc::tmem_dealloc(tbase, (uint32_t)tmem_cols);
 }
 
@@ -1010,6 +1158,37 @@ size_t sweep_tc_stream_bytes_per_sweep(int n, int n_tc, int planes) {
            (((size_t)nblk * kTabBytes + 127) / 128) * 128;
 }
 
+template <int P, bool INJ, int C>
+static cudaError_t launch_tc_variant(const SweepDev& a, const __nv_bfloat16* J, int n_tc,
+                                     const uint16_t* sites, int n_s, int NS, int cols,
+                                     const unsigned char* Q, const unsigned char* tabs, int s0, int s1,
+                                     int dbg, size_t smem, cudaStream_t st) {
+    cudaError_t err = cudaFuncSetAttribute(sweep_tc_kernel<P, INJ, C>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    const int groups = (a.R + kG * C - 1) / (kG * C);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(groups * C), 1, 1);
+    cfg.blockDim = dim3(kTcThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (C > 1) ? 1 : 0;
+    if (getenv("SG_TC_VERBOSE")) {
+        int ncl = -1;
+        cudaOccupancyMaxActiveClusters(&ncl, sweep_tc_kernel<P, INJ, C>, &cfg);
+        fprintf(stderr, "[sg] sweep_tc C=%d grid=%d smem=%zu NS=%d max active clusters=%d\n", C,
+                groups * C, smem, NS, ncl);
+    }
+    return cudaLaunchKernelEx(&cfg, sweep_tc_kernel<P, INJ, C>, a, J, n_tc, sites, n_s, NS, cols, Q,
+                              tabs, s0, s1, dbg);
+}
+
 cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int planes, bool inject,
                             void* sites_buf, void* stream_buf, size_t stream_cap,
                             uint64_t* launches, KernelTimer* timer, cudaStream_t st) {
@@ -1027,20 +1206,29 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
         if (e != cudaSuccess) return e;
         ++*launches;
     }
+    // C = 1: one CTA per 16 replicas (default).  C = 2 (SG_TC_CLUSTER=2, experimental): a cluster
+    // pair per 32 replicas, each CTA owning half of the field columns -- half the operand bytes
+    // per SM, bit-identical results, but in round 1 still slower end to end (the decision warp and
+    // the TMEM-read round trips are then on the critical path and cluster speed varies with
+    // placement; profiles/r1_notes.md).
+    const int T = n_tc / kTileM;
+    int C = 1;
+    if (const char* c_env = getenv("SG_TC_CLUSTER")) {
+        if (atoi(c_env) == 2 && T % (2 * kChunkTiles) == 0 && a.R > kG) C = 2;
+    }
     int NS = kMaxStagesTc;
-    while (NS > 2 && tc_layout(n_tc, planes, NS).total > 227 * 1024) --NS;
+    while (NS > 2 && tc_layout(n_tc, planes, NS, C).total > 227 * 1024) --NS;
     if (const char* ns_env = getenv("SG_TC_STAGES")) {
         const int v = atoi(ns_env);
         if (v >= 2 && v <= NS) NS = v;
     }
-    const size_t smem = tc_layout(n_tc, planes, NS).total;
+    const size_t smem = tc_layout(n_tc, planes, NS, C).total;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     int cols = 32;
-    while (cols < (n_tc / kTileM) * kG) cols *= 2;
-    const int grid = (a.R + kG - 1) / kG;
+    while (cols < T * kG) cols *= 2;
     const __nv_bfloat16* J = static_cast<const __nv_bfloat16*>(Jp);
     const int nblk = (a.n + kBlk - 1) / kBlk;
-    const int nchunk = (n_tc / kTileM + kChunkTiles - 1) / kChunkTiles;
+    const int nchunk = (T + kChunkTiles - 1) / kChunkTiles;
     const size_t per_sweep = sweep_tc_stream_bytes_per_sweep(a.n, n_tc, planes);
     const size_t q_per_sweep = (size_t)nblk * nchunk * kChunkTiles * planes * kTileBytes;
     const int sub = (int)(stream_cap / per_sweep);
@@ -1054,6 +1242,7 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
         const int s1 = (s0 + sub < a.n_sweeps) ? s0 + sub : a.n_sweeps;
         const size_t units = (size_t)(s1 - s0) * q_per_sweep / 16;
         unsigned char* tabs = static_cast<unsigned char*>(stream_buf) + (size_t)sub * q_per_sweep;
+        const unsigned char* Qc = static_cast<const unsigned char*>(stream_buf);
         int ggrid = (int)((units + 255) / 256 < (size_t)148 * 16 ? (units + 255) / 256 : (size_t)148 * 16);
 #define SG_TC(P, INJ)                                                                          \
     {                                                                                          \
@@ -1065,14 +1254,13 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
         if (timer) timer->end(st);                                                             \
         err = cudaGetLastError();                                                              \
         if (err != cudaSuccess) return err;                                                    \
-        err = cudaFuncSetAttribute(sweep_tc_kernel<P, INJ>,                                    \
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-        if (err != cudaSuccess) return err;                                                    \
         if (timer) timer->begin(0, st);                                                        \
-        sweep_tc_kernel<P, INJ><<<grid, kTcThreads, smem, st>>>(                               \
-            a, J, n_tc, sites, n_s, NS, cols, static_cast<const unsigned char*>(stream_buf),   \
-            tabs, s0, s1, dbg);                                                                \
+        err = (C == 2) ? launch_tc_variant<P, INJ, 2>(a, J, n_tc, sites, n_s, NS, cols, Qc, tabs,\
+                                                      s0, s1, dbg, smem, st)                   \
+                       : launch_tc_variant<P, INJ, 1>(a, J, n_tc, sites, n_s, NS, cols, Qc, tabs,\
+                                                      s0, s1, dbg, smem, st);                  \
         if (timer) timer->end(st);                                                             \
+        if (err != cudaSuccess) return err;                                                    \
     }
         if (inject) {
             if (planes == 1) SG_TC(1, true) else if (planes == 2) SG_TC(2, true) else SG_TC(3, true)

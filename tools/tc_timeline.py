@@ -14,12 +14,18 @@ eng.alloc_replicas(R)
 eng.set_spins((torch.randint(0, 2, (R, n), device="cuda") * 2 - 1).to(torch.int8))
 eng.init_fields()
 eng.sweep(1, np.array([1.0]), seed=1, kernel="tc", coupling_planes=P)
-buf = torch.zeros(512 * 16, dtype=torch.int64, device="cuda")
+buf = torch.zeros(512 * 16 + 2048, dtype=torch.int64, device="cuda")
 eng._lib.sg_debug_set_timeline.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
 eng._lib.sg_debug_set_timeline(eng._h, ctypes.c_void_p(buf.data_ptr()))
 eng.sweep(2, np.array([1.0]), seed=1, sweep_base=1, kernel="tc", coupling_planes=P)
 torch.cuda.synchronize()
-t = buf.cpu().numpy().reshape(512, 16)
+full_buf = buf.cpu().numpy()
+t = full_buf[:512 * 16].reshape(512, 16)
+cta = full_buf[8192:8192 + 4 * 148].reshape(148, 4)
+print('CTA start (us, rel) min/med/max:', (cta[:, 0] - cta[:, 0].min()).min() / 1e3, np.median(cta[:, 0] - cta[:, 0].min()) / 1e3, (cta[:, 0] - cta[:, 0].min()).max() / 1e3)
+dur = (cta[:, 1] - cta[:, 0]) / 1e3
+print('CTA duration us min/med/max:', dur.min(), np.median(dur), dur.max(), ' clocks/ns:', np.median((cta[:, 3] - cta[:, 2]) / np.maximum(1, cta[:, 1] - cta[:, 0])))
+print('durations by CTA (first 16):', np.round(dur[:16], 1))
 t0 = t[0, 0]
 names = ["q_start", "q_tabs", "q_h0ok", "q_h1ok", "d_start", "d_pre", "d_rawok", "d_dec", "d_done", "m_wait", "m_decok", "m_r0ok", "m_done", "p_start", "p_end", "q_done"]
 print("blk " + " ".join(f"{x:>8s}" for x in names))
