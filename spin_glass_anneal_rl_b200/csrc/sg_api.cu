@@ -121,13 +121,7 @@ struct DeviceGuard {
     }
 };
 
-// copy `bytes` between a caller buffer (host or device) and an engine device buffer
-int copy_in(void* dst_dev, const void* src, size_t bytes, int on_device, cudaStream_t st) {
-    SG_CUDA(cudaMemcpyAsync(dst_dev, src, bytes,
-                            on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
-    if (!on_device) SG_CUDA(cudaStreamSynchronize(st));
-    return SG_OK;
-}
+// copy `bytes` from an engine device buffer to a caller buffer (host or device)
 int copy_out(void* dst, const void* src_dev, size_t bytes, int on_device, cudaStream_t st) {
     SG_CUDA(cudaMemcpyAsync(dst, src_dev, bytes,
                             on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));

@@ -189,8 +189,8 @@ lat_energy_kernel(const LatDev m, const uint32_t* __restrict__ lat_all, int R, i
 
 // best tracking: replicas whose energy improved copy their bit into the best lattice
 __global__ void lat_best_kernel(const uint32_t* __restrict__ lat, uint32_t* __restrict__ best_lat, int n,
-                                int R, const float* __restrict__ energy, float* __restrict__ best_energy,
-                                float* __restrict__ energy_trace) {
+                                int R, const float* __restrict__ energy,
+                                const float* __restrict__ best_energy) {
     __shared__ uint32_t mask_s;
     const int w = blockIdx.y;
     if (threadIdx.x < 32) {
@@ -207,7 +207,6 @@ __global__ void lat_best_kernel(const uint32_t* __restrict__ lat, uint32_t* __re
             best_lat[o] = (best_lat[o] & ~mk) | (lat[o] & mk);
         }
     }
-    (void)energy_trace;
 }
 
 // energies are final for this sweep: update best energies (after every block of lat_best_kernel
@@ -288,8 +287,7 @@ cudaError_t launch_sweep_lattice(const LatDev& m, const SweepDev& a, bool inject
             ++*launches;
             if (a.track_best) {
                 dim3 grid(32, W);
-                lat_best_kernel<<<grid, 256, 0, st>>>(m.lat, m.best_lat, n, a.R, a.energy, a.best_energy,
-                                                      nullptr);
+                lat_best_kernel<<<grid, 256, 0, st>>>(m.lat, m.best_lat, n, a.R, a.energy, a.best_energy);
                 ++*launches;
             }
             lat_best_energy_kernel<<<(a.R + 255) / 256, 256, 0, st>>>(

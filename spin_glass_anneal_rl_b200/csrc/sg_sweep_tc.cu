@@ -56,11 +56,9 @@ namespace {
 constexpr int kG = 16;             // replicas per block = MMA N
 constexpr int kTileM = 128;        // field columns per MMA
 constexpr int kBlk = 16;           // attempts per block = MMA K
-#ifndef SG_TC_ASBO
-#define SG_TC_ASBO 128
-#endif
-constexpr uint32_t kASbo = SG_TC_ASBO;          // A: m-group (core matrix) stride (144 = 128 + 16 is legal
-                                                // too but not faster: the MMA rate is A-fetch bound)
+// A operand: m-group (core matrix) stride.  Core matrices need not be 128-byte aligned (144 was
+// tried to spread a k-slice over all banks: bit-exact results, not faster), so keep them dense.
+constexpr uint32_t kASbo = 128;
 constexpr uint32_t kALbo = 16 * kASbo;          // A: k-group stride
 constexpr int kTileBytes = 2 * kALbo;           // one (tile, plane) A operand
 constexpr int kChunkTiles = 4;     // tiles per ring stage
@@ -374,42 +372,13 @@ __device__ __forceinline__ uint32_t map_to_rank(const void* p, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
     return r;
 }
-__device__ __forceinline__ void st_cluster_f4(uint32_t addr, float4 v) {
-    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y),
-                 "f"(v.z), "f"(v.w)
-                 : "memory");
-}
-__device__ __forceinline__ void st_cluster_f1(uint32_t addr, float v) {
-    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
-// asynchronous remote stores that count their bytes on an mbarrier of the target CTA
-// (both addresses are shared::cluster addresses of the same CTA): no fence, no remote arrive
+// asynchronous remote store that counts its bytes on an mbarrier of the target CTA (both
+// addresses are shared::cluster addresses of the same CTA): no fence, no remote arrive
 __device__ __forceinline__ void st_async_f4(uint32_t addr, float4 v, uint32_t bar) {
     asm volatile(
         "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr),
         "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(bar)
         : "memory");
-}
-__device__ __forceinline__ void fence_cluster() {
-    asm volatile("fence.acq_rel.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!ok);
 }
 
 // development aid: clock stamps of block 0 (tools/tc_timeline.py); 16 slots per attempt block
@@ -579,7 +548,6 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
         const int q = warp;
         const uint32_t tq = tbase + ((uint32_t)(q * 32) << 16);
         int kg = 0;
-        uint32_t epar = 0;
 #pragma unroll 1
         for (int s = s_begin; s < s_end; ++s) {
             const uint16_t* stab = sites_g + (size_t)s * n_s;
@@ -737,7 +705,6 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 }
             }
             named_sync(1);  // bit planes may be modified again
-            epar ^= 1u;
         }
         // ---- epilogue: fields (this CTA's columns) and spins back to HBM
         for (int t = 0; t < Tl; ++t) {
@@ -1046,7 +1013,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
 // 2 = A K-major no swizzle, 3 = A K-major 128B swizzle, 4 = A MN-major 128B swizzle.
 __global__ void __launch_bounds__(128, 1)
 tc_mma_bench_kernel(int variant, int n_dim, int iters, long long* out) {
-    extern __shared__ __align__(1024) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tptr;
     const int tid = threadIdx.x, warp = tid >> 5;
