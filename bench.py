@@ -357,7 +357,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--replicas", type=int, default=REPLICAS_PER_GPU)
-    ap.add_argument("--sweeps", type=int, default=5, help="sweeps per step")
+    ap.add_argument("--sweeps", type=int, default=10, help="sweeps per step (= the reference's default exchange_interval)")
     ap.add_argument("--ttt-budget", type=float, default=20.0,
                     help="wall-clock budget (s) of the time-to-target run; 0 skips it")
     ap.add_argument("--kernel", default="auto", choices=["auto", "tc", "simt"])

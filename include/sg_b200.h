@@ -100,6 +100,16 @@ int sg_set_model_lattice2d(sg_engine *e, int L, const int8_t *Jx, const int8_t *
 /* position of site (x, y) in the checkerboard attempt sequence of one sweep (replay tests) */
 int sg_lattice_sequence_index(int L, int x, int y);
 
+/* Block-clique couplings: J_ij = coupling[g] for every pair i != j of group g, 0 between groups --
+ * what the reference's cardinality / one-hot penalties produce (core/constraints.py:126-158; e.g.
+ * SimpleScheduler, problems/simple_scheduler.py:67-127: one group per task).  The local field is
+ * h_i + c_g (S_g - s_i) with S_g the spin sum of the group, so the sweep keeps only spin bits and
+ * integer group sums, in shared memory (sg_sweep_groups.cu); needs 4 n + 64 n_groups bytes <= 227 KB
+ * (SG_ERR_UNSUPPORTED otherwise: use sg_set_model_csr).  Host arrays.  Site orders SEQUENTIAL /
+ * RANDOM / EXPLICIT; sg_get_fields is unsupported; everything else behaves the same. */
+int sg_set_model_groups(sg_engine *e, int n, int n_groups, const int32_t *group_of,
+                        const float *coupling, const float *h, void *stream);
+
 /* Allocate R replicas (spins, local fields, energies, best-so-far, counters). */
 int sg_alloc_replicas(sg_engine *e, int n_replicas, void *stream);
 

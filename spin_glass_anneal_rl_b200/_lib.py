@@ -53,6 +53,7 @@ PROTOTYPES = {
                                  c_void_p]),
     "sg_set_model_lattice2d": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "sg_lattice_sequence_index": (c_int, [c_int, c_int, c_int]),
+    "sg_set_model_groups": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sg_alloc_replicas": (c_int, [c_void_p, c_int, c_void_p]),
     "sg_set_spins": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "sg_get_spins": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),

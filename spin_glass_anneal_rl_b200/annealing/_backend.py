@@ -69,6 +69,34 @@ def _lattice_bonds(rows, cols, vals, h, n):
     return Jx, Jy
 
 
+def _clique_groups(rows, cols, vals, n):
+    """(group_of, coupling) if J_ij is one constant per group for every pair i != j of the group
+    and zero between groups (the one-hot / cardinality penalty structure of
+    core/constraints.py:126-158, e.g. SimpleScheduler), else None."""
+    if rows.size == 0 or np.any(rows == cols):
+        return None
+    order = np.lexsort((cols, rows))
+    rows, cols, vals = rows[order], cols[order], vals[order]
+    deg = np.bincount(rows, minlength=n)
+    rep = np.arange(n)
+    np.minimum.at(rep, rows, cols)                     # smallest member of the neighbourhood
+    if np.any(rep[rows] != rep[cols]):
+        return None
+    uniq, group_of = np.unique(rep, return_inverse=True)
+    size = np.bincount(group_of, minlength=uniq.size)
+    if np.any(deg != size[group_of] - 1):
+        return None
+    if rows.size > 1 and np.any((rows[1:] == rows[:-1]) & (cols[1:] == cols[:-1])):
+        return None
+    coupling = np.zeros(uniq.size, np.float32)
+    coupling[group_of[rows]] = vals
+    if np.any(coupling[group_of[rows]] != vals):
+        return None
+    if 4 * n + 64 * uniq.size > 227 * 1024:
+        return None
+    return group_of.astype(np.int32), coupling
+
+
 def site_order_for(eng: Engine, requested: str) -> str:
     """Lattice models are swept in checkerboard order (every site once per sweep)."""
     return "checkerboard" if getattr(eng, "kind", "dense") == "lattice" else requested
@@ -95,9 +123,13 @@ def engine_for(model, device_index: int = 0) -> Engine:
             vals = coo.values().to(torch.float32).numpy()
             hh = model.external_fields.to(torch.float32).cpu().numpy()
             bonds = _lattice_bonds(rows, cols, vals, hh, n)
+            groups = None if bonds is not None else _clique_groups(rows, cols, vals, n)
             if bonds is not None:
                 eng.set_model_lattice2d(*bonds)
                 eng.kind = "lattice"
+            elif groups is not None:
+                eng.set_model_groups(groups[0], groups[1], hh)
+                eng.kind = "groups"
             else:
                 order = np.lexsort((cols, rows))
                 rowptr = np.zeros(n + 1, np.int64)

@@ -77,6 +77,11 @@ struct sg_engine {
     // 2D +-J lattice mode: multi-spin-coded bit planes, see sg_sweep_lattice.cu
     bool lat = false;
     int l_L = 0, l_bonds = 0;
+    // block-clique ("groups") mode shares the bit-plane buffers of lattice mode (lat == true too)
+    bool grp = false;
+    int g_n = 0;
+    int* g_group_of = nullptr;
+    float* g_coupling = nullptr;
     uint32_t *l_lat = nullptr, *l_best = nullptr;
     uint8_t* l_bond = nullptr;
     // sparse (CSR) mode: replica-minor state, see sg_sweep_csr.cu
@@ -165,7 +170,21 @@ void free_lat_replicas(sg_engine* e) {
 
 void free_lat_model(sg_engine* e) {
     cudaFree(e->l_bond); e->l_bond = nullptr;
+    cudaFree(e->g_group_of); e->g_group_of = nullptr;
+    cudaFree(e->g_coupling); e->g_coupling = nullptr;
     e->lat = false;
+    e->grp = false;
+}
+
+sg::GrpDev grp_dev(const sg_engine* e) {
+    sg::GrpDev m{};
+    m.group_of = e->g_group_of;
+    m.coupling = e->g_coupling;
+    m.h = e->h;
+    m.words = e->l_lat;
+    m.best_words = e->l_best;
+    m.n_groups = e->g_n;
+    return m;
 }
 
 sg::LatDev lat_dev(const sg_engine* e) {
@@ -501,6 +520,11 @@ int lat_get_spins(sg_engine* e, const uint32_t* src, int8_t* out, int on_device,
 }
 
 int lat_compute_energy(sg_engine* e, cudaStream_t st) {
+    if (e->grp) {
+        SG_CUDA(sg::launch_groups_energy(grp_dev(e), e->l_lat, e->n, e->R, e->energy, st));
+        e->launches++;
+        return SG_OK;
+    }
     SG_CUDA(sg::launch_lat_energy(lat_dev(e), e->l_lat, e->R, e->energy, st));
     e->launches++;
     return SG_OK;
@@ -516,6 +540,28 @@ int lat_reset_best(sg_engine* e, cudaStream_t st) {
 }
 
 int lat_sweep(sg_engine* e, const sg_sweep_params* p, sg::SweepDev a, cudaStream_t st) {
+    if (e->grp) {
+        SG_REQUIRE(p->site_mode <= SG_SITES_EXPLICIT && p->replicas_per_block == 0 &&
+                       !(p->site_mode == SG_SITES_EXPLICIT && p->sites_block_stride != 0),
+                   "sg_sweep (group model): one site order per launch, replicas_per_block = 0");
+        const size_t need = sg::csr_sites_bytes(e->n, p->n_sweeps);
+        if (need > e->c_sites_cap) {
+            SG_CUDA(cudaStreamSynchronize(st));
+            cudaFree(e->c_sites);
+            e->c_sites = nullptr;
+            e->c_sites_cap = 0;
+            cudaError_t ce = cudaMalloc(&e->c_sites, need);
+            if (ce != cudaSuccess) return fail(SG_ERR_NOMEM, "cudaMalloc(site tables)", ce);
+            e->c_sites_cap = need;
+        }
+        SG_CUDA(sg::launch_sites_table(a, static_cast<int*>(e->c_sites), st));
+        if (e->profiling) e->timer.begin(0, st);
+        SG_CUDA(sg::launch_sweep_groups(grp_dev(e), a, p->rng_mode == SG_RNG_INJECTED,
+                                        static_cast<const int*>(e->c_sites), st));
+        if (e->profiling) e->timer.end(st);
+        e->launches += 2;
+        return SG_OK;
+    }
     SG_REQUIRE(p->site_mode == SG_SITES_CHECKERBOARD,
                "sg_sweep (lattice model): site_mode must be SG_SITES_CHECKERBOARD");
     if (e->profiling) e->timer.begin(0, st);
@@ -536,7 +582,11 @@ int lat_batch_energies(sg_engine* e, int batch, const int8_t* spins, float* ener
         if ((rc = dev_alloc(&tmp_lat, W * e->n)) != SG_OK) break;
         if ((rc = dev_alloc(&e_dev, (size_t)batch)) != SG_OK) break;
         if ((rc = lat_put_spins(e, spins, batch, tmp_lat, on_device, st)) != SG_OK) break;
-        if ((ce = sg::launch_lat_energy(lat_dev(e), tmp_lat, batch, e_dev, st))) break;
+        if (e->grp) {
+            if ((ce = sg::launch_groups_energy(grp_dev(e), tmp_lat, e->n, batch, e_dev, st))) break;
+        } else if ((ce = sg::launch_lat_energy(lat_dev(e), tmp_lat, batch, e_dev, st))) {
+            break;
+        }
         e->launches++;
         if (energies &&
             (ce = cudaMemcpyAsync(energies, e_dev, (size_t)batch * sizeof(float),
@@ -605,6 +655,42 @@ extern "C" int sg_set_model_lattice2d(sg_engine* e, int L, const int8_t* Jx, con
     e->l_L = L;
     e->l_bonds = n_bonds;
     e->lat = true;
+    e->fields_valid = false;
+    return SG_OK;
+}
+
+extern "C" int sg_set_model_groups(sg_engine* e, int n, int n_groups, const int32_t* group_of,
+                                   const float* coupling, const float* h, void* stream) {
+    SG_REQUIRE(e && group_of && coupling && h, "sg_set_model_groups: NULL argument");
+    SG_REQUIRE(n >= 2 && n_groups >= 1 && n_groups <= n, "sg_set_model_groups: bad sizes");
+    for (int i = 0; i < n; ++i)
+        SG_REQUIRE(group_of[i] >= 0 && group_of[i] < n_groups, "sg_set_model_groups: group id out of range");
+    if (sg::groups_smem_bytes(n, n_groups) > 227 * 1024)
+        return fail(SG_ERR_UNSUPPORTED,
+                    "sg_set_model_groups: 4 n + 64 n_groups bytes must fit in 227 KB of shared memory "
+                    "(use sg_set_model_csr)");
+    DeviceGuard g(e->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    free_replicas(e);
+    free_csr_replicas(e);
+    free_lat_replicas(e);
+    free_ladder(e);
+    free_csr_model(e);
+    free_lat_model(e);
+    cudaFree(e->Jt); e->Jt = nullptr;
+    cudaFree(e->Jp); e->Jp = nullptr;
+    cudaFree(e->dig); e->dig = nullptr;
+    int rc;
+    if ((rc = upload(&e->g_group_of, reinterpret_cast<const int*>(group_of), (size_t)n, st)) != SG_OK) return rc;
+    if ((rc = upload(&e->g_coupling, coupling, (size_t)n_groups, st)) != SG_OK) return rc;
+    if ((rc = upload(&e->h, h, (size_t)n, st)) != SG_OK) return rc;
+    SG_CUDA(cudaStreamSynchronize(st));
+    e->n = n;
+    e->n_pad = n;
+    e->n_tc = 0;
+    e->g_n = n_groups;
+    e->lat = true;
+    e->grp = true;
     e->fields_valid = false;
     return SG_OK;
 }
@@ -949,7 +1035,7 @@ int sg_sweep(sg_engine* e, const sg_sweep_params* p, void* stream) {
     SG_REQUIRE(p->rng_mode == SG_RNG_PHILOX || p->rng_mode == SG_RNG_INJECTED,
                "sg_sweep: unknown rng_mode");
     SG_REQUIRE(p->site_mode >= 0 && p->site_mode <= 4, "sg_sweep: unknown site_mode");
-    SG_REQUIRE(p->site_mode != SG_SITES_CHECKERBOARD || e->lat,
+    SG_REQUIRE(p->site_mode != SG_SITES_CHECKERBOARD || (e->lat && !e->grp),
                "sg_sweep: SG_SITES_CHECKERBOARD is the order of lattice models only");
     SG_REQUIRE(p->site_mode != SG_SITES_EXPLICIT || p->sites, "sg_sweep: explicit sites missing");
     SG_REQUIRE(p->rng_mode != SG_RNG_INJECTED || p->uniforms, "sg_sweep: injected uniforms missing");

@@ -159,6 +159,23 @@ cudaError_t launch_lat_energy(const LatDev& m, const uint32_t* lat, int R, float
 cudaError_t launch_sweep_lattice(const LatDev& m, const SweepDev& a, bool inject, uint64_t* launches,
                                  cudaStream_t st);
 
+// K1-GRP (sg_sweep_groups.cu): block-clique couplings, state in shared memory as group sums
+struct GrpDev {
+    const int* group_of;      // [n]
+    const float* coupling;    // [n_groups]  J_ij = coupling[g] for i != j in group g
+    const float* h;           // [n]
+    uint32_t* words;          // [W][n] spin bit planes (as in lattice mode)
+    uint32_t* best_words;     // [W][n]
+    int n_groups;
+};
+size_t groups_smem_bytes(int n, int n_groups);
+cudaError_t launch_sweep_groups(const GrpDev& m, const SweepDev& a, bool inject, const int* sites,
+                                cudaStream_t st);
+cudaError_t launch_groups_energy(const GrpDev& m, const uint32_t* words, int n, int R, float* energy,
+                                 cudaStream_t st);
+// int32 site table [n_sweeps][n] for the sparse / group kernels (same Philox stream as the others)
+cudaError_t launch_sites_table(const SweepDev& a, int* out, cudaStream_t st);
+
 // K3 (sg_exchange.cu)
 struct ExchangeDev {
     int* rep_at;              // [L][K] replica currently at rung k of ladder l

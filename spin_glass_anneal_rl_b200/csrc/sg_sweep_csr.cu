@@ -246,14 +246,18 @@ __global__ void from_replica_minor_kernel(const T* __restrict__ src, int n, int 
 
 size_t csr_sites_bytes(int n, int n_sweeps) { return (size_t)n_sweeps * n * sizeof(int); }
 
-cudaError_t launch_sweep_csr(const CsrDev& m, const SweepDev& a, bool inject, void* sites_buf,
-                             cudaStream_t st) {
-    int* sites = static_cast<int*>(sites_buf);
+cudaError_t launch_sites_table(const SweepDev& a, int* out, cudaStream_t st) {
     const long long total = (long long)a.n_sweeps * ((a.n + 3) / 4);
     int grid = (int)((total + 255) / 256 < 2368 ? (total + 255) / 256 : 2368);
     csr_sites_kernel<<<grid, 256, 0, st>>>(a.site_mode, a.seed, a.sweep_base, a.n, a.n_sweeps,
-                                           a.sites, a.s_ss, sites);
-    cudaError_t e = cudaGetLastError();
+                                           a.sites, a.s_ss, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sweep_csr(const CsrDev& m, const SweepDev& a, bool inject, void* sites_buf,
+                             cudaStream_t st) {
+    int* sites = static_cast<int*>(sites_buf);
+    cudaError_t e = launch_sites_table(a, sites, st);
     if (e != cudaSuccess) return e;
     const int groups = (a.R + 31) / 32;
     const int blocks = (groups + kCsrWarps - 1) / kCsrWarps;

@@ -120,6 +120,18 @@ class Engine:
         self.n_replicas = 0
         self._csr = True   # not the dense layout
 
+    def set_model_groups(self, group_of: ArrayLike, coupling: ArrayLike, h: ArrayLike) -> None:
+        """Block-clique couplings: J_ij = coupling[g] for i != j in the same group g."""
+        go, cp, hh = _as_host(group_of, np.int32), _as_host(coupling, np.float32), _as_host(h, np.float32)
+        check(self._lib.sg_set_model_groups(self._h, int(hh.shape[0]), int(cp.shape[0]),
+                                            go.ctypes.data_as(ctypes.c_void_p),
+                                            cp.ctypes.data_as(ctypes.c_void_p),
+                                            hh.ctypes.data_as(ctypes.c_void_p), self.stream),
+              "sg_set_model_groups")
+        self.n = int(hh.shape[0])
+        self.n_replicas = 0
+        self._csr = True   # not the dense layout
+
     def alloc_replicas(self, n_replicas: int) -> None:
         check(self._lib.sg_alloc_replicas(self._h, int(n_replicas), self.stream),
               "sg_alloc_replicas")

@@ -44,7 +44,7 @@ def test_cfg4_tsp64_dense_model():
     assert len(res.energy_history) == len(res.temperature_history) == 1 + 6
 
 
-def test_cfg5_scheduling_sparse_model_goes_to_csr_path():
+def test_cfg5_scheduling_sparse_model_through_the_api():
     """500 tasks x 100 agents = 50 000 spins, block cliques: a torch sparse COO model, as
     problems/base.py builds them; dense J would be 10 GB."""
     import spin_glass_anneal_rl_b200 as sg

@@ -35,3 +35,14 @@ for tb in (False, True):
     t0.record(); eng.sweep(20, temps, temps_replica_stride=1, seed=1, sweep_base=2, site_order="checkerboard", track_best=tb); t1.record(); torch.cuda.synchronize()
     ms = t0.elapsed_time(t1)
     print(f"cfg2 EA L=256 lattice kernel: R={R} track_best={tb}: {R * n * 20 / ms / 1e6:.1f} G attempts/s ({ms / 20:.3f} ms/sweep), E/N={eng.energies().mean().item() / n:.4f}")
+# ---- cfg5 on the block-clique (group-sum) kernel
+rowptr, colidx, val, h = inst.scheduling_ising(*inst.random_scheduling(500, 100))
+n, R = 50000, 1024
+eng = Engine(0)
+eng.set_model_groups((np.arange(n) // 100).astype(np.int32), np.full(500, 50.0, np.float32), h); eng.alloc_replicas(R)
+eng.set_spins((torch.randint(0, 2, (R, n), device="cuda") * 2 - 1).to(torch.int8)); eng.init_fields()
+eng.sweep(2, np.array([40.0]), seed=1); torch.cuda.synchronize()
+for tb in (False, True):
+    t0.record(); eng.sweep(20, np.array([40.0]), seed=1, sweep_base=2, track_best=tb); t1.record(); torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1)
+    print(f"cfg5 sched 500x100 groups kernel: R={R} track_best={tb}: {R * n * 20 / ms / 1e6:.2f} G attempts/s ({ms / 20:.3f} ms/sweep), E/N={eng.energies().mean().item() / n:.3f}")

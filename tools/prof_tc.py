@@ -5,7 +5,7 @@ import numpy as np, torch
 from spin_glass_anneal_rl_b200.engine import Engine
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 R = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
-sw = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+sw = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 P = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 rs = np.random.RandomState(3003)
 Gm = rs.normal(0.0, 1.0 / np.sqrt(n), size=(n, n)).astype(np.float32)

@@ -45,7 +45,7 @@ def to_bytes(v, unit):
     return float(v.replace(",", "")) * m[unit]
 with open(os.path.join(out_dir, f"{tag}_sweep_tc_ncu.txt"), "w") as f:
     f.write(f"# ncu --set full --clock-control none --import-source on -k regex:sweep_tc  python tools/prof_tc.py\n")
-    f.write(f"# (SK N=4096, 8192 replicas, 5 sweeps per launch, 3 planes: the bench's launch shape)\n")
+    f.write(f"# (SK N=4096, 8192 replicas, 10 sweeps per launch, 3 planes: the bench launch shape)\n")
     f.write(f"kernel: {d[h.index('Kernel Name')]}\n")
     for w in want:
         if w in h:
@@ -58,7 +58,7 @@ with open(os.path.join(out_dir, f"{tag}_sweep_tc_ncu.txt"), "w") as f:
 rd, wr = to_bytes(*get("dram__bytes_read.sum")), to_bytes(*get("dram__bytes_write.sum"))
 dur_v, dur_u = get("gpu__time_duration.sum")
 json.dump({"kernel": "sg::sweep_tc_kernel", "source": f"profiles/{tag}_sweep_tc_ncu.txt",
-           "shape": "SK N=4096, 8192 replicas, 5 sweeps per launch, 3 bf16 planes",
+           "shape": "SK N=4096, 8192 replicas, 10 sweeps per launch, 3 bf16 planes",
            "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr,
            "ncu_duration": f"{dur_v} {dur_u}"},
           open(os.path.join(out_dir, f"{tag}_sweep_tc_traffic.json"), "w"), indent=1)
