@@ -85,3 +85,72 @@ def global_argmin(best_energy: torch.Tensor, best_spins: torch.Tensor,
 def rank_seed(seed: Optional[int], rank: int) -> Optional[int]:
     """Independent Philox keys per rank (replica ids are local to a rank)."""
     return None if seed is None else int(seed) * 1_000_003 + rank
+
+
+@dataclass
+class MultiGPUConfig:
+    """Mirror of the reference's MultiGPUConfig (annealing/multi_gpu.py:20-43) for the fields that
+    mean something here.  ``strategy`` "data_parallel" = independent multi-start replicas,
+    "replica_exchange" = whole temperature ladders per GPU; ``communication_backend`` is what
+    torch.distributed was initialised with by the launcher (torchrun), "nccl" on GPUs."""
+    n_replicas: int = 8192            # over all GPUs
+    strategy: str = "data_parallel"
+    communication_backend: str = "nccl"
+    n_rungs: int = 64                 # ladder length for replica_exchange
+
+    def __post_init__(self):
+        if self.strategy not in ("data_parallel", "replica_exchange"):
+            raise ValueError(f"Unknown strategy: {self.strategy} (model_parallel would split the "
+                             "couplings across GPUs, which changes the model; it is not offered)")
+        if self.communication_backend not in ("nccl", "gloo", "mpi"):
+            raise ValueError(f"Unknown communication backend: {self.communication_backend}")
+
+
+class MultiGPUAnnealer:
+    """One process per GPU (torchrun): every rank anneals its shard of the replicas on its own
+    B200 with no data-path collective; the best configuration over all ranks is found with one
+    all_gather + one broadcast at the end.  Without an initialised process group it is a
+    single-GPU annealer.  ``anneal(model)`` returns the same AnnealingResult on every rank."""
+
+    def __init__(self, config: MultiGPUConfig, annealer_config=None):
+        self.config = config
+        self.annealer_config = annealer_config
+        init = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size() if init else 1
+        self.rank = dist.get_rank() if init else 0
+
+    def shard(self) -> ReplicaShard:
+        rungs = self.config.n_rungs if self.config.strategy == "replica_exchange" else 1
+        return shard_replicas(self.config.n_replicas, self.world, self.rank, rungs)
+
+    def anneal(self, model, update_rule=None):
+        import copy
+        from ..core.spin_dynamics import UpdateRule
+        from .gpu_annealer import GPUAnnealer, GPUAnnealerConfig
+        from .parallel_tempering import ParallelTempering, ParallelTemperingConfig
+        from .result import AnnealingResult
+        rule = update_rule or UpdateRule.METROPOLIS
+        sh = self.shard()
+        local_device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        if self.config.strategy == "replica_exchange":
+            cfg = copy.copy(self.annealer_config) if self.annealer_config else ParallelTemperingConfig()
+            cfg.n_replicas, cfg.n_ladders = self.config.n_rungs, max(1, sh.n_ladders)
+            cfg.random_seed = rank_seed(cfg.random_seed, self.rank)
+            cfg.device_index = local_device
+            res = ParallelTempering(cfg).run(model, rule)
+        else:
+            cfg = copy.copy(self.annealer_config) if self.annealer_config else GPUAnnealerConfig()
+            cfg.n_replicas = max(1, sh.count)
+            cfg.random_seed = rank_seed(cfg.random_seed, self.rank)
+            cfg.device_index = local_device
+            res = GPUAnnealer(cfg).anneal(model, rule)
+        dev = torch.device("cuda", local_device) if torch.cuda.is_available() else torch.device("cpu")
+        e, s, gid = global_argmin(torch.tensor([res.best_energy], dtype=torch.float64, device=dev),
+                                  res.best_configuration.to(dev).reshape(1, -1), sh)
+        return AnnealingResult(best_configuration=s.cpu(), best_energy=float(e),
+                               energy_history=res.energy_history,
+                               temperature_history=res.temperature_history,
+                               acceptance_rate_history=res.acceptance_rate_history,
+                               total_time=res.total_time, n_sweeps=res.n_sweeps,
+                               algorithm=res.algorithm + f"+{self.world}gpu", device=str(dev),
+                               random_seed=res.random_seed)

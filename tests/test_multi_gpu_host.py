@@ -73,3 +73,14 @@ def test_global_argmin_without_process_group():
     s = torch.arange(12, dtype=torch.int8).reshape(3, 4)
     be, cfg, gid = global_argmin(e, s, shard_replicas(6, 2, 1, 1))
     assert be == -1.0 and torch.equal(cfg, s[1]) and gid == 3 + 1
+
+
+def test_multi_gpu_config_validation():
+    from spin_glass_anneal_rl_b200.annealing.multi_gpu import MultiGPUAnnealer, MultiGPUConfig
+    with pytest.raises(ValueError):
+        MultiGPUConfig(strategy="model_parallel")
+    with pytest.raises(ValueError):
+        MultiGPUConfig(communication_backend="smoke-signals")
+    a = MultiGPUAnnealer(MultiGPUConfig(n_replicas=128, strategy="replica_exchange", n_rungs=16))
+    sh = a.shard()
+    assert (a.world, a.rank, sh.count, sh.n_ladders) == (1, 0, 128, 8)
