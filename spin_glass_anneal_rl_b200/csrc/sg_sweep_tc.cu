@@ -283,11 +283,12 @@ tc_gather_kernel(const __nv_bfloat16* __restrict__ Jp, int n, int n_tc,
 }
 
 // Decision tables of every attempt block, computed once per sweep for the whole grid:
-//   cin[a][b] = J'[site_a][site_b]                (couplings among the block's own sites)
-//   ccr[a][b] = J'[site_a of block k-1][site_b]   (from the previous block's sites; 0 for k = 0)
-//   dup[b]    = bit mask of the earlier attempts of the block that visit the same site
+//   cin[a][b]  = J'[site_a][site_b]                (couplings among the block's own sites)
+//   ccr1[a][b] = J'[site_a of block k-1][site_b]   (from the previous block's sites; 0 for k = 0)
+//   ccr2[a][b] = J'[site_a of block k-2][site_b]   (two blocks back; 0 for k < 2; cluster variant)
+//   dup[b]     = bit mask of the earlier attempts of the block that visit the same site
 // J' = sum of the P planes.  kTabBytes per block, fetched by the sweep kernel with one TMA copy.
-constexpr int kTabBytes = 2 * kBlk * kBlk * 4 + kBlk * 4;  // 2112
+constexpr int kTabBytes = 3 * kBlk * kBlk * 4 + kBlk * 4;  // 3136
 
 template <int P>
 __global__ void __launch_bounds__(256)
@@ -301,20 +302,19 @@ tc_tables_kernel(const __nv_bfloat16* __restrict__ Jp, int n, int n_tc,
     const size_t plane_stride = (size_t)n * n_tc;
     unsigned char* out = tabs + (size_t)blockIdx.x * kTabBytes;
     float* cin = reinterpret_cast<float*>(out);
-    float* ccr = cin + kBlk * kBlk;
-    uint32_t* dup = reinterpret_cast<uint32_t*>(ccr + kBlk * kBlk);
-    for (int idx = threadIdx.x; idx < 2 * kBlk * kBlk; idx += blockDim.x) {
+    uint32_t* dup = reinterpret_cast<uint32_t*>(cin + 3 * kBlk * kBlk);
+    for (int idx = threadIdx.x; idx < 3 * kBlk * kBlk; idx += blockDim.x) {
         const int which = idx >> 8, aa = (idx >> 4) & 15, b = idx & 15;
         float val = 0.0f;
-        if (b < nbk && (which == 0 ? (aa < nbk) : (k > 0))) {
+        if (b < nbk && (which == 0 ? (aa < nbk) : (k >= which))) {
             const int sb = stab[i0 + b];
-            const int sr = which == 0 ? stab[i0 + aa] : stab[i0 - kBlk + aa];
+            const int sr = stab[i0 - which * kBlk + aa];
             const __nv_bfloat16* pj = Jp + (size_t)sr * n_tc + sb;
             val = __bfloat162float(pj[0]);
             if (P > 1) val += __bfloat162float(pj[plane_stride]);
             if (P > 2) val += __bfloat162float(pj[2 * plane_stride]);
         }
-        (which == 0 ? cin : ccr)[aa * kBlk + b] = val;
+        cin[which * kBlk * kBlk + aa * kBlk + b] = val;
     }
     if (threadIdx.x < kBlk) {
         uint32_t m = 0;
@@ -374,6 +374,15 @@ __device__ __forceinline__ uint32_t map_to_rank(const void* p, uint32_t rank) {
 }
 // asynchronous remote store that counts its bytes on an mbarrier of the target CTA (both
 // addresses are shared::cluster addresses of the same CTA): no fence, no remote arrive
+// bulk copy from this CTA's shared memory into a peer CTA's, bytes counted on the peer's mbarrier
+__device__ __forceinline__ void bulk_s2peer(uint32_t dst_cluster_addr, const void* src, uint32_t bytes,
+                                            uint32_t bar_cluster_addr) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            dst_cluster_addr),
+        "r"(smem_u32(src)), "r"(bytes), "r"(bar_cluster_addr)
+        : "memory");
+}
 __device__ __forceinline__ void st_async_f4(uint32_t addr, float4 v, uint32_t bar) {
     asm volatile(
         "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr),
@@ -420,6 +429,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 const int tmem_cols, const unsigned char* __restrict__ Q,
                 const unsigned char* __restrict__ tabs_g, const int s_begin, const int s_end,
                 const int dbg) {
+    constexpr int LAG = C;                   // raw field values are read LAG+1 blocks before use
     constexpr int NG = kG * C;               // replicas per group = MMA N
     constexpr int NGRP = NG / 16;            // 16-column TMEM load/store groups per tile
     constexpr uint32_t IDESC = tc::make_idesc_bf16(kTileM, NG);
@@ -599,14 +609,16 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 }
                 if (warp == 0) SG_STAMP(1);
                 // --- raw field values of the block's sites in this CTA's columns, as of the end of
-                // block kg-2: the sites of a column half are read as soon as that half of block
-                // kg-2 has landed (the other half may still be executing), and the same half of
-                // block kg-1 is not issued before the read is done
+                // block kg-LAG-1: the sites of a column half are read as soon as that half of that
+                // block has landed (the other half may still be executing), and the same half of
+                // block kg-LAG is not issued before the read is done.  (LAG = 2 in the cluster
+                // variant gives the cross-CTA exchange and the decision a whole block of slack.)
                 float* rawb = raw_s + slot * kBlk * NG;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    if (kg >= 2)
-                        mbar_wait(&hdone[2 * ((kg - 2) & (kSlots - 1)) + h], (uint32_t)((kg - 2) >> 2) & 1u);
+                    if (kg >= LAG + 1)
+                        mbar_wait(&hdone[2 * ((kg - LAG - 1) & (kSlots - 1)) + h],
+                                  (uint32_t)((kg - LAG - 1) >> 2) & 1u);
                     tc::fence_after_sync();
                     if (warp == 0) SG_STAMP(2 + h);
 #pragma unroll
@@ -629,12 +641,12 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                                     d4[2] = make_float4(v[8], v[9], v[10], v[11]);
                                     d4[3] = make_float4(v[12], v[13], v[14], v[15]);
                                     if (C == 2) {
-                                        const uint32_t ra = map_to_rank(dl, peer);
-                                        const uint32_t rb = map_to_rank(&rall[slot], peer);
-                                        st_async_f4(ra, make_float4(v[0], v[1], v[2], v[3]), rb);
-                                        st_async_f4(ra + 16, make_float4(v[4], v[5], v[6], v[7]), rb);
-                                        st_async_f4(ra + 32, make_float4(v[8], v[9], v[10], v[11]), rb);
-                                        st_async_f4(ra + 48, make_float4(v[12], v[13], v[14], v[15]), rb);
+                                        // the 64 bytes just written go to the same place in the
+                                        // peer's shared memory (one DSMEM bulk copy, bytes counted
+                                        // on the peer's rall[slot])
+                                        fence_proxy_async();
+                                        bulk_s2peer(map_to_rank(dl, peer), dl, 64u,
+                                                    map_to_rank(&rall[slot], peer));
                                     }
                                 }
                             }
@@ -742,12 +754,12 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 bulk_g2s(tab_s + sl * kTabBytes, tabs_g + (size_t)j * kTabBytes, (uint32_t)kTabBytes,
                          &tabbar[sl]);
             };
-            issue_tables(0);
-            issue_tables(1);
+#pragma unroll
+            for (int j = 0; j <= LAG; ++j) issue_tables(j);
 #pragma unroll 1
             for (kg = 0; kg < nblk_total; ++kg) {
                 SG_STAMP(13);
-                issue_tables(kg + 2);
+                issue_tables(kg + LAG + 1);
                 const unsigned char* src = Q + ((size_t)kg * nchunk + (size_t)crank * nchunk_l) * kStageBytes;
 #pragma unroll 1
                 for (int c = 0; c < nchunk_l; ++c) {
@@ -770,9 +782,11 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
             cur_e = a.energy[rep0 + lane];
             best_e = a.track_best ? a.best_energy[rep0 + lane] : 3.0e38f;
         }
-        float pdec[kBlk];
+        float pdec[LAG][kBlk];   // deltas of the previous LAG blocks ([0] = most recent)
 #pragma unroll
-        for (int b = 0; b < kBlk; ++b) pdec[b] = 0.0f;
+        for (int l = 0; l < LAG; ++l)
+#pragma unroll
+            for (int b = 0; b < kBlk; ++b) pdec[l][b] = 0.0f;
         int kg = 0;
         uint32_t epar = 0;
 #pragma unroll 1
@@ -808,23 +822,27 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 const float* rawp = raw_s + slot * kBlk * NG + r;
                 const float* thp = theta_s + slot * kBlk * NG + r;
                 const float4* cin4 = reinterpret_cast<const float4*>(tab_s + slot * kTabBytes);
-                const float4* ccr4 = cin4 + kBlk * kBlk / 4;
-                const uint32_t* dup_p = reinterpret_cast<const uint32_t*>(tab_s + slot * kTabBytes) + 2 * kBlk * kBlk;
-                // correction for the flips of the previous block (not yet in the raw values)
+                const uint32_t* dup_p = reinterpret_cast<const uint32_t*>(tab_s + slot * kTabBytes) + 3 * kBlk * kBlk;
+                // correction for the flips of the previous LAG blocks (not yet in the raw values),
+                // oldest block first
                 float v[kBlk];
 #pragma unroll
                 for (int b = 0; b < kBlk; ++b) v[b] = 0.0f;
-                if (k > 0) {
 #pragma unroll
-                    for (int aa = 0; aa < kBlk; ++aa) {
-                        const float da = pdec[aa];
+                for (int l = LAG; l >= 1; --l) {
+                    if (k >= l) {
+                        const float4* ccr4 = cin4 + l * (kBlk * kBlk / 4);
 #pragma unroll
-                        for (int b4 = 0; b4 < kBlk / 4; ++b4) {
-                            const float4 c4 = ccr4[aa * 4 + b4];
-                            v[4 * b4 + 0] = fmaf(da, c4.x, v[4 * b4 + 0]);
-                            v[4 * b4 + 1] = fmaf(da, c4.y, v[4 * b4 + 1]);
-                            v[4 * b4 + 2] = fmaf(da, c4.z, v[4 * b4 + 2]);
-                            v[4 * b4 + 3] = fmaf(da, c4.w, v[4 * b4 + 3]);
+                        for (int aa = 0; aa < kBlk; ++aa) {
+                            const float da = pdec[l - 1][aa];
+#pragma unroll
+                            for (int b4 = 0; b4 < kBlk / 4; ++b4) {
+                                const float4 c4 = ccr4[aa * 4 + b4];
+                                v[4 * b4 + 0] = fmaf(da, c4.x, v[4 * b4 + 0]);
+                                v[4 * b4 + 1] = fmaf(da, c4.y, v[4 * b4 + 1]);
+                                v[4 * b4 + 2] = fmaf(da, c4.z, v[4 * b4 + 2]);
+                                v[4 * b4 + 3] = fmaf(da, c4.w, v[4 * b4 + 3]);
+                            }
                         }
                     }
                 }
@@ -904,7 +922,11 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                                   ((myflips >> aa) & 1u) << (site[aa] & 31));
                 }
 #pragma unroll
-                for (int b = 0; b < kBlk; ++b) pdec[b] = d[b];
+                for (int l = LAG - 1; l >= 1; --l)
+#pragma unroll
+                    for (int b = 0; b < kBlk; ++b) pdec[l][b] = pdec[l - 1][b];
+#pragma unroll
+                for (int b = 0; b < kBlk; ++b) pdec[0][b] = d[b];
                 SG_STAMP(8);
             }
             // ---- end of sweep: energy, best tracking
@@ -954,10 +976,11 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 const uint64_t bdesc = tc::make_smem_desc(smem_u32(bop_s + slot * BOP), BLBO, kBSbo);
 #pragma unroll 1
                 for (int h = 0; h < 2; ++h) {
-                    // this CTA's raw reads of block k+1 in this column half must be done before
+                    // this CTA's raw reads of block k+LAG in this column half must be done before
                     // this block's update of the half is issued
-                    if (k + 1 < nblk)
-                        mbar_wait(&rloc[2 * ((kg + 1) & (kSlots - 1)) + h], (uint32_t)((kg + 1) >> 2) & 1u);
+                    if (k + LAG < nblk)
+                        mbar_wait(&rloc[2 * ((kg + LAG) & (kSlots - 1)) + h],
+                                  (uint32_t)((kg + LAG) >> 2) & 1u);
                     if (h == 0) SG_STAMP(11);
                     const int c_end = h ? nchunk_l : hc;
 #pragma unroll 1

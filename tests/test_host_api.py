@@ -220,3 +220,49 @@ def test_install_as_spin_glass_rl():
     assert D.METROPOLIS.value == "metropolis"
     for k in [k for k in sys.modules if k.startswith("spin_glass_rl")]:
         del sys.modules[k]
+
+
+# ------------------------------------------------------------------ structure detection (host logic)
+def _coo(n, rowptr, colidx, val):
+    rows = np.repeat(np.arange(n), np.diff(rowptr))
+    return rows, colidx.astype(np.int64), val
+
+
+def test_lattice_and_clique_structure_detection():
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import instances as inst
+    from spin_glass_anneal_rl_b200.annealing._backend import _clique_groups, _lattice_bonds
+
+    # 2D +-J lattice, open and periodic
+    for periodic in (False, True):
+        Jx, Jy = inst.ea_lattice_bonds(12, seed=3, periodic=periodic)
+        rowptr, colidx, val, h = inst.lattice_csr(Jx, Jy)
+        rows, cols, vals = _coo(144, rowptr, colidx, val)
+        got = _lattice_bonds(rows, cols, vals, h, 144)
+        assert got is not None and np.array_equal(got[0], Jx) and np.array_equal(got[1], Jy)
+        assert _clique_groups(rows, cols, vals, 144) is None
+    # not a lattice: a field, a non-unit coupling, an asymmetric entry, a long-range bond
+    Jx, Jy = inst.ea_lattice_bonds(12, seed=3)
+    rowptr, colidx, val, h = inst.lattice_csr(Jx, Jy)
+    rows, cols, vals = _coo(144, rowptr, colidx, val)
+    assert _lattice_bonds(rows, cols, vals, h + 1.0, 144) is None
+    v2 = vals.copy(); v2[0] = 2.0
+    assert _lattice_bonds(rows, cols, v2, h, 144) is None
+    assert _lattice_bonds(rows[1:], cols[1:], vals[1:], h, 144) is None
+    c2 = cols.copy(); c2[0] = 77
+    assert _lattice_bonds(rows, c2, vals, h, 144) is None
+
+    # block cliques (scheduler) and things that are not
+    rowptr, colidx, val, h = inst.scheduling_ising(*inst.random_scheduling(7, 5, seed=2))
+    rows, cols, vals = _coo(35, rowptr, colidx, val)
+    group_of, coupling = _clique_groups(rows, cols, vals, 35)
+    assert np.array_equal(group_of, np.arange(35) // 5) and np.all(coupling == 50.0)
+    assert _lattice_bonds(rows, cols, vals, np.zeros(35, np.float32), 35) is None
+    v3 = vals.copy(); v3[3] = 49.0
+    assert _clique_groups(rows, cols, v3, 35) is None               # not constant inside a group
+    assert _clique_groups(rows[:-1], cols[:-1], vals[:-1], 35) is None   # a missing pair
+    # two overlapping clique families (TSP rows and columns) are not disjoint groups
+    J, _ = inst.tsp_ising(inst.random_tsp(5, 1))
+    r, c = np.nonzero(J)
+    assert _clique_groups(r, c, J[r, c], 25) is None
