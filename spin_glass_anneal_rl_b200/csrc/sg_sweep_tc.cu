@@ -341,7 +341,7 @@ __host__ __device__ inline TcSmem tc_layout(int n_tc, int P, int NS, int C) {
     size_t off = 0;
     L.ring = off;  off += (size_t)NS * kChunkTiles * P * kTileBytes;
     L.bop = off;   off += (size_t)kSlots * 32 * NG;
-    L.sbits = off; off += (size_t)NG * (n_tc / 32) * sizeof(uint32_t);
+    L.sbits = off; off += (size_t)NG * (n_tc / 32 + 1) * sizeof(uint32_t);   // stride W + 1: no bank conflicts
     L.theta = off; off += (size_t)kSlots * kBlk * NG * sizeof(float);
     L.raw = off;   off += (size_t)kSlots * kBlk * NG * sizeof(float);
     L.tab = off;   off += (size_t)kSlots * kTabBytes;
@@ -437,7 +437,9 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
     constexpr uint32_t BLBO = 16 * NG;       // B: k-group stride ((NG/8) n-groups of 128 B)
     extern __shared__ __align__(128) unsigned char smem[];
     const int n = a.n, n_pad = a.n_pad;
-    const int W = n_tc >> 5;
+    const int W = n_tc >> 5;                 // spin words per replica
+    const int Wp = W + 1;                    // padded stride of a bit plane (lane = replica reads
+                                             // word x of 32 planes: odd stride = 32 distinct banks)
     const int T = n_tc / kTileM;             // tiles of the whole model
     const int Tl = T / C;                    // tiles of this CTA
     const int nchunk = (T + kChunkTiles - 1) / kChunkTiles;       // chunks per block in Q
@@ -525,7 +527,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 bits |= nib << (4 * j);
             }
         }
-        sbits[w] = bits;
+        sbits[r * Wp + word] = bits;
     }
     tc::fence_before_sync();
     __syncthreads();
@@ -649,6 +651,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                                                     map_to_rank(&rall[slot], peer));
                                     }
                                 }
+
                             }
                         }
                     }
@@ -679,7 +682,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                         tc::wait_ld();
 #pragma unroll
                         for (int r = 0; r < 16; ++r) {
-                            const uint32_t w = sbits[(gi * 16 + r) * W + (colb >> 5)];
+                            const uint32_t w = sbits[(gi * 16 + r) * Wp + (colb >> 5)];
                             const float tt = f[r] + hv;
                             part[gi * 16 + r] += ((w >> lane) & 1u) ? tt : -tt;
                         }
@@ -713,7 +716,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 for (int w = tid; w < NG * W; w += 128) {
                     const int r = w / W, word = w - r * W;
                     if ((im >> r) & 1u)
-                        store_spin_word(a.best_spins + (size_t)(rep0 + r) * n_pad + word * 32, sbits[w]);
+                        store_spin_word(a.best_spins + (size_t)(rep0 + r) * n_pad + word * 32, sbits[r * Wp + word]);
                 }
             }
             named_sync(1);  // bit planes may be modified again
@@ -734,7 +737,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
         if (crank == 0) {
             for (int w = tid; w < NG * W; w += 128) {
                 const int r = w / W, word = w - r * W;
-                if (r < g_act) store_spin_word(a.spins + (size_t)(rep0 + r) * n_pad + word * 32, sbits[w]);
+                if (r < g_act) store_spin_word(a.spins + (size_t)(rep0 + r) * n_pad + word * 32, sbits[r * Wp + word]);
             }
         }
     } else if (warp == 4) {
@@ -851,7 +854,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
 #pragma unroll
                 for (int b = 0; b < kBlk; ++b) {
                     th[b] = INJECT ? 0.0f : thp[b * NG];
-                    w0[b] = sbits[r * W + (site[b] >> 5)];
+                    w0[b] = sbits[r * Wp + (site[b] >> 5)];
                     dup[b] = dup_p[b];
                 }
                 SG_STAMP(5);
@@ -918,7 +921,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 if (lane < NG) {
 #pragma unroll
                     for (int aa = 0; aa < kBlk; ++aa)
-                        atomicXor(&sbits[r * W + (site[aa] >> 5)],
+                        atomicXor(&sbits[r * Wp + (site[aa] >> 5)],
                                   ((myflips >> aa) & 1u) << (site[aa] & 31));
                 }
 #pragma unroll

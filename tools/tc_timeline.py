@@ -14,7 +14,7 @@ eng.alloc_replicas(R)
 eng.set_spins((torch.randint(0, 2, (R, n), device="cuda") * 2 - 1).to(torch.int8))
 eng.init_fields()
 eng.sweep(1, np.array([1.0]), seed=1, kernel="tc", coupling_planes=P)
-buf = torch.zeros(512 * 16 + 2048, dtype=torch.int64, device="cuda")
+buf = torch.zeros(512 * 16 + 2048 + 512, dtype=torch.int64, device="cuda")
 eng._lib.sg_debug_set_timeline.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
 eng._lib.sg_debug_set_timeline(eng._h, ctypes.c_void_p(buf.data_ptr()))
 eng.sweep(2, np.array([1.0]), seed=1, sweep_base=1, kernel="tc", coupling_planes=P)
