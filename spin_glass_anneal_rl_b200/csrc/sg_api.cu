@@ -1115,7 +1115,7 @@ int sg_sweep(sg_engine* e, const sg_sweep_params* p, void* stream) {
         use_tc = tc_ok && !inject;
     }
     if (use_tc) {
-        const size_t need = sg::sweep_tc_sites_bytes(e->n, p->n_sweeps);
+        const size_t need = sg::sweep_tc_sites_bytes(e->n, p->n_sweeps, e->R);
         if (need > e->tc_sites_cap) {
             // the previous table may still be in use by a launch in flight on this stream
             SG_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));

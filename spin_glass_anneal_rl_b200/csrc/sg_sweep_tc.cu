@@ -391,6 +391,10 @@ __device__ __forceinline__ void st_async_f4(uint32_t addr, float4 v, uint32_t ba
 }
 
 // development aid: clock stamps of block 0 (tools/tc_timeline.py); 16 slots per attempt block
+#define SG_ISTAMP(slot_)                                                             \
+    do {                                                                             \
+        if (a.dbg && blockIdx.x == 0 && tid == 0 && it == cid) a.dbg[10240 + (slot_)] = clock64(); \
+    } while (0)
 #define SG_STAMP(slot_)                                                              \
     do {                                                                             \
         if (a.dbg && blockIdx.x == 0 && lane == 0 && kg < 512) a.dbg[kg * 16 + (slot_)] = clock64(); \
@@ -417,6 +421,63 @@ __device__ __forceinline__ void store_spin_word(int8_t* dst, uint32_t w) {
     d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
+// Persistent-CTA work list of the sweep kernel.
+struct TcItems {
+    int n_groups, s_begin, s_end, spi, n_cta;
+    __host__ __device__ int n_chunks() const { return (s_end - s_begin + spi - 1) / spi; }
+    __host__ __device__ int count() const { return n_groups * n_chunks(); }
+};
+struct TcItem {
+    int ch, g, s_lo, s_hi;
+};
+__host__ __device__ inline TcItem tc_item(const TcItems& w, int it) {
+    TcItem x;
+    x.ch = it / w.n_groups;
+    x.g = it - x.ch * w.n_groups;
+    x.s_lo = w.s_begin + x.ch * w.spi;
+    x.s_hi = (x.s_lo + w.spi < w.s_end) ? x.s_lo + w.spi : w.s_end;
+    return x;
+}
+// walks the attempt blocks of a CTA's items in execution order (the TMA producer runs ahead of
+// the other warps across item boundaries; it needs no group state, only the stream position)
+struct TcBlockWalk {
+    int s, s_hi, k, ch, g, n_chunks, dch, dg;   // no division on the per-block path
+    __device__ void start(const TcItems& w, int cid) {
+        n_chunks = w.n_chunks();
+        dch = w.n_cta / w.n_groups;
+        dg = w.n_cta - dch * w.n_groups;
+        ch = cid / w.n_groups;
+        g = cid - ch * w.n_groups;
+        k = 0;
+        set_sweeps(w);
+    }
+    __device__ void set_sweeps(const TcItems& w) {
+        s = w.s_begin + ch * w.spi;
+        s_hi = (s + w.spi < w.s_end) ? s + w.spi : w.s_end;
+    }
+    __device__ bool valid() const { return ch < n_chunks; }
+    __device__ void next(const TcItems& w, int nblk) {
+        if (++k < nblk) return;
+        k = 0;
+        if (++s < s_hi) return;
+        ch += dch;
+        g += dg;
+        if (g >= w.n_groups) { g -= w.n_groups; ++ch; }
+        set_sweeps(w);
+    }
+    __device__ size_t stream_block(const TcItems& w, int nblk) const {
+        return (size_t)(s - w.s_begin) * nblk + k;
+    }
+};
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // C = 1: one CTA holds all field columns of 16 replicas.  C = 2: a cluster pair holds 32
 // replicas, CTA `crank` owns the columns [crank * n_tc/2, (crank+1) * n_tc/2) (so each SM streams
 // and multiplies only half of every J row: half the shared-memory traffic per attempt); both
@@ -428,7 +489,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 const uint16_t* __restrict__ sites_g, const int n_s, const int NS,
                 const int tmem_cols, const unsigned char* __restrict__ Q,
                 const unsigned char* __restrict__ tabs_g, const int s_begin, const int s_end,
-                const int dbg) {
+                const int spi, int* __restrict__ done_g, const int dbg) {
     constexpr int LAG = C;                   // raw field values are read LAG+1 blocks before use
     constexpr int NG = kG * C;               // replicas per group = MMA N
     constexpr int NGRP = NG / 16;            // 16-column TMEM load/store groups per tile
@@ -473,11 +534,17 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
     uint32_t* tptr = reinterpret_cast<uint32_t*>(smem + L.tptr);
     constexpr int kStageBytes = kChunkTiles * P * kTileBytes;
 
-    const int rep0 = (blockIdx.x / C) * NG;
-    const int g_act = min(NG, a.R - rep0);
     const int n_sweeps = a.n_sweeps;
     const int nblk = (n + kBlk - 1) / kBlk;
     const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+    // Work items: (sweep chunk ch, replica group g), numbered chunk-major; CTA (or cluster) c runs
+    // items c, c + n_cta, ...  A group's state (fields, spins, energies) lives in HBM between its
+    // items; done_g[g] counts the chunks of group g that are complete.  With one chunk per group
+    // (spi = all sweeps, n_cta = groups) this is the plain one-CTA-per-group launch.
+    const TcItems items{(a.R + NG - 1) / NG, s_begin, s_end, spi, (int)(gridDim.x / C)};
+    const int cid = (int)(blockIdx.x / C);
+    const int n_items = items.count();
+    const int n_chunks = items.n_chunks();
 
     // ------------------------------------------------------------ prologue
     if (a.dbg && tid == 0 && blockIdx.x < 512) {
@@ -509,26 +576,6 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
         tc::tmem_alloc(tptr, (uint32_t)tmem_cols);
         tc::tmem_relinquish();
     }
-    // spin bit planes from int8 spins (every CTA of a group keeps all NG planes)
-    for (int w = tid; w < NG * W; w += kTcThreads) {
-        const int r = w / W, word = w - r * W;
-        uint32_t bits = 0xFFFFFFFFu;
-        if (r < g_act) {
-            const uint4* src =
-                reinterpret_cast<const uint4*>(a.spins + (size_t)(rep0 + r) * n_pad + word * 32);
-            const uint4 lo = src[0], hi = src[1];
-            const uint32_t x[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-            bits = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const uint32_t up = (~x[j]) & 0x80808080u;  // byte >= 0  <=> spin up
-                const uint32_t nib =
-                    ((up >> 7) & 1u) | ((up >> 14) & 2u) | ((up >> 21) & 4u) | ((up >> 28) & 8u);
-                bits |= nib << (4 * j);
-            }
-        }
-        sbits[r * Wp + word] = bits;
-    }
     tc::fence_before_sync();
     __syncthreads();
     if (C == 2) cluster_sync_all();   // the peer's barriers exist before anything remote arrives
@@ -536,32 +583,86 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
     const uint32_t tbase = *tptr;
 
     if (warp < 4) {
-        // resident fields -> TMEM
-        const uint32_t tq = tbase + ((uint32_t)(warp * 32) << 16);
-        for (int t = 0; t < Tl; ++t) {
-            const int col = col0 + t * kTileM + warp * 32 + lane;
-#pragma unroll
-            for (int gi = 0; gi < NGRP; ++gi) {
-                float v[16];
-#pragma unroll
-                for (int r = 0; r < 16; ++r)
-                    v[r] = (gi * 16 + r < g_act) ? a.fields[(size_t)(rep0 + gi * 16 + r) * n_pad + col] : 0.0f;
-                tc::tmem_st16(tq + t * NG + gi * 16, v);
-            }
-        }
-        tc::wait_st();
-    }
-    tc::fence_before_sync();
-    __syncthreads();
-    tc::fence_after_sync();
-
-    if (warp < 4) {
         // ======================================================== QUARTER WARPS
         const int q = warp;
         const uint32_t tq = tbase + ((uint32_t)(q * 32) << 16);
         int kg = 0;
 #pragma unroll 1
-        for (int s = s_begin; s < s_end; ++s) {
+        for (int it = cid; it < n_items; it += items.n_cta) {
+        const TcItem item = tc_item(items, it);
+        const int rep0 = item.g * NG;
+        const int g_act = min(NG, a.R - rep0);
+        // ---- item prologue: the group's previous chunk is complete, then state HBM -> SM
+        SG_ISTAMP(0);
+        if (item.ch > 0 && tid == 0) {
+            while (ld_acquire_gpu(done_g + item.g) < item.ch) __nanosleep(256);
+        }
+        named_sync(2);
+        SG_ISTAMP(1);
+        // spin bit planes from int8 spins (every CTA of a group keeps all NG planes); four words
+        // (eight 16-byte loads) in flight per thread
+        for (int w0 = tid; w0 < NG * W; w0 += 4 * 128) {
+            uint4 lo[4], hi[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int w = w0 + u * 128;
+                const int r = w / W, word = w - r * W;
+                lo[u] = hi[u] = make_uint4(0u, 0u, 0u, 0u);
+                if (w < NG * W && r < g_act) {
+                    const uint4* src =
+                        reinterpret_cast<const uint4*>(a.spins + (size_t)(rep0 + r) * n_pad + word * 32);
+                    lo[u] = __ldcg(src);
+                    hi[u] = __ldcg(src + 1);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int w = w0 + u * 128;
+                const int r = w / W, word = w - r * W;
+                if (w >= NG * W) break;
+                uint32_t bits = 0xFFFFFFFFu;
+                if (r < g_act) {
+                    const uint32_t x[8] = {lo[u].x, lo[u].y, lo[u].z, lo[u].w, hi[u].x, hi[u].y, hi[u].z, hi[u].w};
+                    bits = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t up = (~x[j]) & 0x80808080u;  // byte >= 0  <=> spin up
+                        const uint32_t nib =
+                            ((up >> 7) & 1u) | ((up >> 14) & 2u) | ((up >> 21) & 4u) | ((up >> 28) & 8u);
+                        bits |= nib << (4 * j);
+                    }
+                }
+                sbits[r * Wp + word] = bits;
+            }
+        }
+        SG_ISTAMP(2);
+        // resident fields -> TMEM, two tiles (32 loads per thread) in flight
+        for (int t = 0; t < Tl; t += 2) {
+            float v[2][NGRP][16];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int col = col0 + (t + u) * kTileM + q * 32 + lane;
+#pragma unroll
+                for (int gi = 0; gi < NGRP; ++gi)
+#pragma unroll
+                    for (int r = 0; r < 16; ++r)
+                        v[u][gi][r] = (t + u < Tl && gi * 16 + r < g_act)
+                                          ? __ldcg(a.fields + (size_t)(rep0 + gi * 16 + r) * n_pad + col) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (t + u < Tl) {
+#pragma unroll
+                    for (int gi = 0; gi < NGRP; ++gi) tc::tmem_st16(tq + (t + u) * NG + gi * 16, v[u][gi]);
+                }
+        }
+        tc::wait_st();
+        tc::fence_before_sync();
+        named_sync(2);   // bit planes complete (decision warp reads them)
+        tc::fence_after_sync();
+        SG_ISTAMP(3);
+#pragma unroll 1
+        for (int s = item.s_lo; s < item.s_hi; ++s) {
             const uint16_t* stab = sites_g + (size_t)s * n_s;
             const unsigned long long sa = a.sweep_base + (unsigned long long)s;
 #pragma unroll 1
@@ -721,7 +822,8 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
             }
             named_sync(1);  // bit planes may be modified again
         }
-        // ---- epilogue: fields (this CTA's columns) and spins back to HBM
+        // ---- item epilogue: fields (this CTA's columns) and spins back to HBM
+        SG_ISTAMP(4);
         for (int t = 0; t < Tl; ++t) {
             const int col = col0 + t * kTileM + q * 32 + lane;
 #pragma unroll
@@ -731,7 +833,8 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 tc::wait_ld();
 #pragma unroll
                 for (int r = 0; r < 16; ++r)
-                    if (gi * 16 + r < g_act) a.fields[(size_t)(rep0 + gi * 16 + r) * n_pad + col] = v[r];
+                    if (gi * 16 + r < g_act)
+                        __stcg(a.fields + (size_t)(rep0 + gi * 16 + r) * n_pad + col, v[r]);
             }
         }
         if (crank == 0) {
@@ -740,30 +843,43 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 if (r < g_act) store_spin_word(a.spins + (size_t)(rep0 + r) * n_pad + word * 32, sbits[r * Wp + word]);
             }
         }
+        SG_ISTAMP(5);
+        __threadfence();
+        SG_ISTAMP(6);
+        named_sync(2);   // every store of the item (quarter warps and decision warp) is fenced
+        SG_ISTAMP(7);
+        if (tid == 0 && n_chunks > 1) st_release_gpu(done_g + item.g, item.ch + 1);
+        }  // items
     } else if (warp == 4) {
         // ======================================================== PRODUCER (TMA)
         if (lane == 0) {
             int stage = 0;
             uint32_t epar = 1;  // a fresh barrier passes a wait on the "previous" phase
-            const int nblk_total = (s_end - s_begin) * nblk;
             int kg = 0;
-            // decision tables of block j -> slot j % 4 (the slot's previous user, block j-4, has
-            // been decided long before the operand stream reaches block j-2)
-            auto issue_tables = [&](int j) {
-                if (j >= nblk_total) return;
-                const int sl = j & (kSlots - 1);
-                if (j >= kSlots) mbar_wait(&decbar[sl], (uint32_t)((j - kSlots) >> 2) & 1u);
+            TcBlockWalk wt, wq;   // table prefetch position (LAG+1 blocks ahead) and stream position
+            wt.start(items, cid);
+            wq.start(items, cid);
+            int jt = 0;
+            // decision tables of the CTA's block j -> slot j % 4 (the slot's previous user, block
+            // j-4, has been decided long before the operand stream reaches block j-2)
+            auto issue_tables = [&]() {
+                if (!wt.valid()) return;
+                const int sl = jt & (kSlots - 1);
+                if (jt >= kSlots) mbar_wait(&decbar[sl], (uint32_t)((jt - kSlots) >> 2) & 1u);
                 mbar_arrive_expect_tx(&tabbar[sl], (uint32_t)kTabBytes);
-                bulk_g2s(tab_s + sl * kTabBytes, tabs_g + (size_t)j * kTabBytes, (uint32_t)kTabBytes,
-                         &tabbar[sl]);
+                bulk_g2s(tab_s + sl * kTabBytes, tabs_g + wt.stream_block(items, nblk) * kTabBytes,
+                         (uint32_t)kTabBytes, &tabbar[sl]);
+                wt.next(items, nblk);
+                ++jt;
             };
 #pragma unroll
-            for (int j = 0; j <= LAG; ++j) issue_tables(j);
+            for (int j = 0; j <= LAG; ++j) issue_tables();
 #pragma unroll 1
-            for (kg = 0; kg < nblk_total; ++kg) {
+            for (; wq.valid(); wq.next(items, nblk), ++kg) {
                 SG_STAMP(13);
-                issue_tables(kg + LAG + 1);
-                const unsigned char* src = Q + ((size_t)kg * nchunk + (size_t)crank * nchunk_l) * kStageBytes;
+                issue_tables();
+                const unsigned char* src =
+                    Q + (wq.stream_block(items, nblk) * nchunk + (size_t)crank * nchunk_l) * kStageBytes;
 #pragma unroll 1
                 for (int c = 0; c < nchunk_l; ++c) {
                     mbar_wait(&empty[stage], epar);
@@ -778,13 +894,6 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
     } else if (warp == 5) {
         // ======================================================== DECISION WARP
         const int r = lane & (NG - 1);
-        const bool active = lane < g_act;
-        float best_e = 3.0e38f, cur_e = 0.0f;
-        unsigned int n_acc = 0;
-        if (active) {
-            cur_e = a.energy[rep0 + lane];
-            best_e = a.track_best ? a.best_energy[rep0 + lane] : 3.0e38f;
-        }
         float pdec[LAG][kBlk];   // deltas of the previous LAG blocks ([0] = most recent)
 #pragma unroll
         for (int l = 0; l < LAG; ++l)
@@ -793,7 +902,21 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
         int kg = 0;
         uint32_t epar = 0;
 #pragma unroll 1
-        for (int s = s_begin; s < s_end; ++s) {
+        for (int it = cid; it < n_items; it += items.n_cta) {
+        const TcItem item = tc_item(items, it);
+        const int rep0 = item.g * NG;
+        const int g_act = min(NG, a.R - rep0);
+        const bool active = lane < g_act;
+        named_sync(2);   // the group's previous chunk is complete
+        float best_e = 3.0e38f, cur_e = 0.0f;
+        unsigned int n_acc = 0;
+        if (active) {
+            cur_e = __ldcg(a.energy + rep0 + lane);
+            best_e = a.track_best ? __ldcg(a.best_energy + rep0 + lane) : 3.0e38f;
+        }
+        named_sync(2);   // bit planes loaded
+#pragma unroll 1
+        for (int s = item.s_lo; s < item.s_hi; ++s) {
             const uint16_t* stab = sites_g + (size_t)s * n_s;
             double dT = 1.0;
             if (INJECT && active)
@@ -957,10 +1080,13 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
             named_sync(1);
         }
         if (active && crank == 0) {
-            a.energy[rep0 + lane] = cur_e;
-            if (a.track_best) a.best_energy[rep0 + lane] = best_e;
-            a.accepted[rep0 + lane] += (unsigned long long)n_acc;
+            __stcg(a.energy + rep0 + lane, cur_e);
+            if (a.track_best) __stcg(a.best_energy + rep0 + lane, best_e);
+            __stcg(a.accepted + rep0 + lane, __ldcg(a.accepted + rep0 + lane) + (unsigned long long)n_acc);
         }
+        __threadfence();
+        named_sync(2);   // item complete (tid 0 publishes the group's progress)
+        }  // items
     } else {
         // ======================================================== MMA ISSUER
         // The whole warp runs the loops (descriptor arithmetic stays warp-uniform); one elected
@@ -968,8 +1094,13 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
         int stage = 0;
         uint32_t fpar = 0;
         int kg = 0;
+        int n_own = 0;   // sweeps this CTA runs, over all of its items
+        for (int it = cid; it < n_items; it += items.n_cta) {
+            const TcItem item = tc_item(items, it);
+            n_own += item.s_hi - item.s_lo;
+        }
 #pragma unroll 1
-        for (int s = s_begin; s < s_end; ++s) {
+        for (int s = 0; s < n_own; ++s) {
 #pragma unroll 1
             for (int k = 0; k < nblk; ++k, ++kg) {
                 const int slot = kg & (kSlots - 1);
@@ -994,6 +1125,9 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                         const uint64_t adesc0 = tc::make_smem_desc(
                             smem_u32(ring + (size_t)stage * kStageBytes), kALbo, kASbo);
                         const uint32_t d0 = tbase + (uint32_t)(c * kChunkTiles * NG);
+                        // (the issue pattern is not the limit here: a branch-free block of 12 MMAs
+                        // issues at 48 clocks per MMA in isolation, tools/mma_bench.py, but the phase
+                        // is bound by shared-memory bandwidth -- TMA writes plus operand reads)
                         if (tc::elect_one()) {
 #pragma unroll
                             for (int tt = 0; tt < kChunkTiles; ++tt) {
@@ -1038,14 +1172,18 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
 // per MMA.  variant: 0 = A MN-major no swizzle (SBO 128), 1 = same with SBO 144,
 // 2 = A K-major no swizzle, 3 = A K-major 128B swizzle, 4 = A MN-major 128B swizzle.
 __global__ void __launch_bounds__(128, 1)
-tc_mma_bench_kernel(int variant, int n_dim, int iters, long long* out) {
+tc_mma_bench_kernel(int variant_in, int n_dim, int iters, long long* out) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
+    __shared__ uint64_t cbar;                  // sink of the periodic commits
+    const int commit_every = variant_in >> 4;  // 0 = only the final commit
+    const int variant = variant_in & 15;
     __shared__ uint32_t tptr;
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int i = tid; i < (160 * 1024) / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
         mbar_init(&bar, 1);
+        mbar_init(&cbar, 1);
         fence_mbar_init();
     }
     if (warp == 0) {
@@ -1074,13 +1212,66 @@ tc_mma_bench_kernel(int variant, int n_dim, int iters, long long* out) {
         const int ncol_tiles = 512 / n_dim;
         const uint64_t adesc0 = tc::make_smem_desc(a0, lbo, sbo) | (lt << 61);
         const long long t0 = clock64();
-        for (int it = 0; it < iters; ++it) {
+        auto adesc_of = [&](int t) {
+            return adesc0 + (uint64_t)((variant == 3 ? ((t >> 2) * 16384 + (t & 3) * 32) : t * tile) >> 4);
+        };
+        if (commit_every == 0) {
+            for (int it = 0; it < iters; ++it) {
 #pragma unroll
-            for (int t = 0; t < 32; ++t) {
-                const uint64_t adesc = adesc0 + (uint64_t)((variant == 3 ? ((t >> 2) * 16384 + (t & 3) * 32)
-                                                                         : t * tile) >> 4);
-                if (tc::elect_one())
-                    tc::mma_bf16_ss(tbase + (t & (ncol_tiles - 1)) * n_dim, adesc, bdesc, idesc, 1u);
+                for (int t = 0; t < 32; ++t) {
+                    if (tc::elect_one())
+                        tc::mma_bf16_ss(tbase + (t & (ncol_tiles - 1)) * n_dim, adesc_of(t), bdesc, idesc, 1u);
+                }
+            }
+        } else if (commit_every == 14) {
+            // the fix: one election per MMA, descriptors computed in converged code
+            for (int it = 0; it < iters; ++it) {
+#pragma unroll 1
+                for (int c = 0; c < 8; ++c) {
+                    const int t0c = (c * 12) & 31;
+                    const uint64_t ad0 = adesc_of(t0c & 16);
+                    const uint32_t dd0 = tbase + (uint32_t)((t0c & (ncol_tiles - 1)) * n_dim);
+#pragma unroll
+                    for (int t = 0; t < 12; ++t) {
+                        if (tc::elect_one())
+                            tc::mma_bf16_ss(dd0 + (t & 3) * n_dim, ad0 + (uint64_t)((t * 4608) >> 4), bdesc, idesc, 1u);
+                    }
+                    if (tc::elect_one()) tc::mma_commit(&cbar);
+                    __syncwarp();
+                }
+            }
+        } else if (commit_every == 12 || commit_every == 13) {
+            // the sweep kernel's issue pattern: one elected lane issues 12 MMAs (4 tiles x 3 planes)
+            // and (12) a commit, then the warp reconverges
+            for (int it = 0; it < iters; ++it) {
+#pragma unroll 1
+                for (int c = 0; c < 8; ++c) {
+                    const int t0c = (c * 12) & 31;
+                    const uint64_t ad0 = adesc_of(t0c & 16);
+                    const uint32_t dd0 = tbase + (uint32_t)((t0c & (ncol_tiles - 1)) * n_dim);
+                    if (tc::elect_one()) {
+#pragma unroll
+                        for (int t = 0; t < 12; ++t)
+                            tc::mma_bf16_ss(dd0 + (t & 3) * n_dim, ad0 + (uint64_t)((t * 4608) >> 4), bdesc, idesc, 1u);
+                        if (commit_every == 12) tc::mma_commit(&cbar);
+                    }
+                    __syncwarp();
+                }
+            }
+        } else {
+            for (int it = 0; it < iters; ++it) {
+#pragma unroll 1
+                for (int c = 0; c < 16; ++c) {
+                    if (tc::elect_one()) {
+#pragma unroll
+                        for (int t = 0; t < 6; ++t) {
+                            const int tt = (c * 6 + t) & 31;
+                            tc::mma_bf16_ss(tbase + (tt & (ncol_tiles - 1)) * n_dim, adesc_of(tt), bdesc, idesc, 1u);
+                        }
+                        if (commit_every == 6) tc::mma_commit(&cbar);
+                    }
+                    __syncwarp();
+                }
             }
         }
         const long long t1 = clock64();
@@ -1088,8 +1279,10 @@ tc_mma_bench_kernel(int variant, int n_dim, int iters, long long* out) {
         mbar_wait(&bar, 0);
         const long long t2 = clock64();
         if (tid == 32) {
-            out[0] = t1 - t0;
-            out[1] = t2 - t0;
+            // variants 12/13 and 6/7 issue 96 MMAs per iteration, the plain loop 32
+            const int per_it = commit_every ? 96 : 32;
+            out[0] = (t1 - t0) * 32 / per_it;
+            out[1] = (t2 - t0) * 32 / per_it;
         }
     }
     tc::fence_before_sync();
@@ -1137,9 +1330,10 @@ cudaError_t launch_tc_mma_bench(int variant, int n_dim, int iters, long long* ou
 
 bool sweep_tc_supported(int n, int n_tc) { return n_tc > 0 && n_tc <= 4096 && n >= 16; }
 
-size_t sweep_tc_sites_bytes(int n, int n_sweeps) {
+size_t sweep_tc_sites_bytes(int n, int n_sweeps, int R) {
     const int n_s = (n + 15) / 16 * 16;
-    return (size_t)n_sweeps * n_s * sizeof(uint16_t);
+    return (((size_t)n_sweeps * n_s * sizeof(uint16_t) + 15) & ~(size_t)15) +
+           (size_t)((R + kG - 1) / kG) * sizeof(int);
 }
 
 // bytes of operand stream one sweep needs
@@ -1151,17 +1345,46 @@ size_t sweep_tc_stream_bytes_per_sweep(int n, int n_tc, int planes) {
            (((size_t)nblk * kTabBytes + 127) / 128) * 128;
 }
 
+// Sweeps per work item for `groups` replica groups on `n_cta` persistent CTAs: the chunking whose
+// most loaded CTA finishes first (an item costs its sweeps plus ~3% of a sweep for moving the
+// group's state through HBM); ties go to the longer items.
+static int tc_pick_spi(int groups, int S, int n_sm) {
+    if (groups <= n_sm || S <= 1) return S;
+    int best_spi = S;
+    double best_cost = 1e300;
+    for (int spi = S; spi >= 1; --spi) {
+        const int chunks = (S + spi - 1) / spi;
+        const long long n_items = (long long)groups * chunks;
+        const int n_cta = (int)(n_items < n_sm ? n_items : n_sm);
+        double worst = 0.0;
+        for (int c = 0; c < n_cta; ++c) {
+            double load = 0.0;
+            for (long long it = c; it < n_items; it += n_cta) {
+                const int ch = (int)(it / groups);
+                const int len = (ch * spi + spi <= S) ? spi : S - ch * spi;
+                load += len + 0.03;
+            }
+            if (load > worst) worst = load;
+        }
+        if (worst < best_cost - 1e-9) {
+            best_cost = worst;
+            best_spi = spi;
+        }
+    }
+    return best_spi;
+}
+
 template <int P, bool INJ, int C>
 static cudaError_t launch_tc_variant(const SweepDev& a, const __nv_bfloat16* J, int n_tc,
                                      const uint16_t* sites, int n_s, int NS, int cols,
                                      const unsigned char* Q, const unsigned char* tabs, int s0, int s1,
-                                     int dbg, size_t smem, cudaStream_t st) {
+                                     int spi, int grid_groups, int* done, int dbg, size_t smem,
+                                     cudaStream_t st) {
     cudaError_t err = cudaFuncSetAttribute(sweep_tc_kernel<P, INJ, C>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    const int groups = (a.R + kG * C - 1) / (kG * C);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(groups * C), 1, 1);
+    cfg.gridDim = dim3((unsigned)(grid_groups * C), 1, 1);
     cfg.blockDim = dim3(kTcThreads, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
@@ -1175,11 +1398,11 @@ static cudaError_t launch_tc_variant(const SweepDev& a, const __nv_bfloat16* J, 
     if (getenv("SG_TC_VERBOSE")) {
         int ncl = -1;
         cudaOccupancyMaxActiveClusters(&ncl, sweep_tc_kernel<P, INJ, C>, &cfg);
-        fprintf(stderr, "[sg] sweep_tc C=%d grid=%d smem=%zu NS=%d max active clusters=%d\n", C,
-                groups * C, smem, NS, ncl);
+        fprintf(stderr, "[sg] sweep_tc C=%d grid=%d smem=%zu NS=%d sweeps/item=%d max active clusters=%d\n",
+                C, grid_groups * C, smem, NS, spi, ncl);
     }
     return cudaLaunchKernelEx(&cfg, sweep_tc_kernel<P, INJ, C>, a, J, n_tc, sites, n_s, NS, cols, Q,
-                              tabs, s0, s1, dbg);
+                              tabs, s0, s1, spi, done, dbg);
 }
 
 cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int planes, bool inject,
@@ -1230,10 +1453,38 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
     // operand chunk, bit1 = no MMA, bit2 = no raw TMEM reads
     const char* dbg_env = getenv("SG_TC_DBG");
     const int dbg = dbg_env ? atoi(dbg_env) : 0;
+    const char* spi_s = getenv("SG_TC_SPI");
+    const int spi_env = spi_s ? atoi(spi_s) : -1;
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (const char* sm_env = getenv("SG_TC_SM")) {   // tests: pretend the GPU has fewer SMs
+        const int v = atoi(sm_env);
+        if (v >= 1 && v < n_sm) n_sm = v;
+    }
+    // per-group progress counters live behind the site tables
+    int* done = reinterpret_cast<int*>(static_cast<unsigned char*>(sites_buf) +
+                                       (((size_t)a.n_sweeps * n_s * sizeof(uint16_t) + 15) & ~(size_t)15));
     cudaError_t err = cudaSuccess;
     for (int s0 = 0; s0 < a.n_sweeps; s0 += sub) {
         const int s1 = (s0 + sub < a.n_sweeps) ? s0 + sub : a.n_sweeps;
         const size_t units = (size_t)(s1 - s0) * q_per_sweep / 16;
+        // persistent CTAs over (sweep chunk, replica group) items when there are more groups than
+        // SMs: no partial last wave (SG_TC_SPI=0 forces one CTA per group for all sweeps)
+        const int groups = (a.R + kG * C - 1) / (kG * C);
+        int spi = s1 - s0, grid_groups = groups;
+        if (C == 1 && groups > n_sm) {
+            spi = tc_pick_spi(groups, s1 - s0, n_sm);
+            if (spi_env > 0) spi = spi_env < s1 - s0 ? spi_env : s1 - s0;
+            if (spi_env == 0) spi = s1 - s0;
+            const int chunks = (s1 - s0 + spi - 1) / spi;
+            if (chunks > 1) {
+                const long long n_items = (long long)groups * chunks;
+                grid_groups = (int)(n_items < n_sm ? n_items : n_sm);
+                err = cudaMemsetAsync(done, 0, (size_t)groups * sizeof(int), st);
+                if (err != cudaSuccess) return err;
+            }
+        }
         unsigned char* tabs = static_cast<unsigned char*>(stream_buf) + (size_t)sub * q_per_sweep;
         const unsigned char* Qc = static_cast<const unsigned char*>(stream_buf);
         int ggrid = (int)((units + 255) / 256 < (size_t)148 * 16 ? (units + 255) / 256 : (size_t)148 * 16);
@@ -1249,9 +1500,9 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
         if (err != cudaSuccess) return err;                                                    \
         if (timer) timer->begin(0, st);                                                        \
         err = (C == 2) ? launch_tc_variant<P, INJ, 2>(a, J, n_tc, sites, n_s, NS, cols, Qc, tabs,\
-                                                      s0, s1, dbg, smem, st)                   \
+                                                      s0, s1, spi, grid_groups, done, dbg, smem, st) \
                        : launch_tc_variant<P, INJ, 1>(a, J, n_tc, sites, n_s, NS, cols, Qc, tabs,\
-                                                      s0, s1, dbg, smem, st);                  \
+                                                      s0, s1, spi, grid_groups, done, dbg, smem, st); \
         if (timer) timer->end(st);                                                             \
         if (err != cudaSuccess) return err;                                                    \
     }

@@ -169,6 +169,55 @@ def test_tc_equals_simt_kernel_in_philox_mode(engine, n, R, ns):
     assert outs[0][2].sum() > 0
 
 
+@pytest.mark.parametrize("n_sm,spi", [(2, None), (3, 1), (5, 2), (2, 0)])
+def test_tc_work_item_schedule_is_invisible(engine, monkeypatch, n_sm, spi):
+    """More replica groups than SMs: persistent CTAs walk (sweep chunk, group) items and hand a
+    group's state from CTA to CTA through HBM (progress flags, acquire/release).  Pretending the
+    GPU has 2..5 SMs forces that path on a small problem; the trajectories must not change."""
+    rng = np.random.default_rng(1234)
+    n, R, ns = 200, 16 * 7 + 5, 7          # 8 groups, the last one ragged
+    J, h = _int_instance(rng, n)
+    S0 = (rng.integers(0, 2, size=(R, n)) * 2 - 1).astype(np.int8)
+    temps = np.linspace(2.5, 0.4, ns)
+
+    def run():
+        _setup(engine, J, h, S0)
+        tr = engine.sweep(ns, temps, temps_sweep_stride=1, seed=5, sweep_base=3, site_order="random",
+                          energy_trace=True, kernel="tc").cpu().numpy()
+        return (engine.spins().cpu().numpy(), tr, engine.accepted().cpu().numpy(),
+                engine.best()[0].cpu().numpy(), engine.best()[1].cpu().numpy(),
+                engine.fields().cpu().numpy())
+
+    ref = run()                              # 8 groups <= SMs: one CTA per group
+    monkeypatch.setenv("SG_TC_SM", str(n_sm))
+    if spi is not None:
+        monkeypatch.setenv("SG_TC_SPI", str(spi))
+    out = run()
+    for a, b in zip(ref, out):
+        assert np.array_equal(a, b)
+
+
+def test_tc_full_size_many_waves_matches_one_cta_per_group(engine, monkeypatch):
+    """Headline shape (n = 4096, more groups than SMs): the work-item schedule and the plain
+    one-CTA-per-group launch give identical results."""
+    rng = np.random.default_rng(77)
+    n, R, ns = 4096, 16 * 160, 4
+    J, h = _int_instance(rng, n, amp=1)
+    S0 = (rng.integers(0, 2, size=(R, n)) * 2 - 1).astype(np.int8)
+    outs = []
+    for spi in ("0", None):
+        if spi is None:
+            monkeypatch.delenv("SG_TC_SPI", raising=False)
+        else:
+            monkeypatch.setenv("SG_TC_SPI", spi)
+        _setup(engine, J, h, S0)
+        engine.sweep(ns, np.array([1.2]), seed=9, site_order="random", kernel="tc", coupling_planes=1)
+        outs.append((engine.spins().cpu().numpy(), engine.energies().cpu().numpy(),
+                     engine.accepted().cpu().numpy(), engine.best()[0].cpu().numpy()))
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+
+
 def test_tc_launch_chunking_is_invisible(engine):
     rng = np.random.default_rng(11)
     n, R = 300, 50

@@ -12,3 +12,9 @@ for v in range(5):
         rc = f(eng._h, v, nd, 8, out)
         f(eng._h, v, nd, 8, out)
         print(f"{names[v]:16s} N={nd:3d}: rc={rc} issue {out[0] / 256:.1f} clk/MMA, complete {out[1] / 256:.1f} clk/MMA")
+for ce, label in ((0, "32 per elect, no commit"), (13, "12 per elect, no commit"), (12, "12 per elect + commit"), (14, "12 x (elect, MMA) + commit"),
+                  (7, "6 per elect, no commit"), (6, "6 per elect + commit")):
+    out = (ctypes.c_longlong * 2)()
+    f(eng._h, ce * 16, 16, 8, out)
+    f(eng._h, ce * 16, 16, 8, out)
+    print(f"MN nosw N=16, {label}: issue {out[0] / 256:.1f} clk/MMA, complete {out[1] / 256:.1f} clk/MMA")

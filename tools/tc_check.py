@@ -112,6 +112,6 @@ if what in ("all", "drift"):
 if what in ("all", "perf"):
     for P in (3, 2, 1):
         perf(planes=P)
-    perf(R=8192, planes=3); perf(R=8192, planes=2); perf(T=0.3, planes=3)
+    perf(R=8192, planes=3, sweeps=10); perf(R=8192, planes=2, sweeps=10); perf(T=0.3, planes=3)
 print("TC CHECK", "PASS" if ok else "FAIL")
 sys.exit(0 if ok else 1)

@@ -26,6 +26,10 @@ print('CTA start (us, rel) min/med/max:', (cta[:, 0] - cta[:, 0].min()).min() / 
 dur = (cta[:, 1] - cta[:, 0]) / 1e3
 print('CTA duration us min/med/max:', dur.min(), np.median(dur), dur.max(), ' clocks/ns:', np.median((cta[:, 3] - cta[:, 2]) / np.maximum(1, cta[:, 1] - cta[:, 0])))
 print('durations by CTA (first 16):', np.round(dur[:16], 1))
+ist = full_buf[10240:10248]
+if ist[7] > 0:
+    print("item phases (clk): dep wait", ist[1] - ist[0], " bit planes", ist[2] - ist[1], " fields->TMEM", ist[3] - ist[2],
+          " sweeps", ist[4] - ist[3], " state->HBM", ist[5] - ist[4], " fence", ist[6] - ist[5], " sync", ist[7] - ist[6])
 t0 = t[0, 0]
 names = ["q_start", "q_tabs", "q_h0ok", "q_h1ok", "d_start", "d_pre", "d_rawok", "d_dec", "d_done", "m_wait", "m_decok", "m_r0ok", "m_done", "p_start", "p_end", "q_done"]
 print("blk " + " ".join(f"{x:>8s}" for x in names))
