@@ -337,9 +337,13 @@ def run_ours(args):
                        "kernel": "tensor-core (tcgen05, TMEM-resident fields)" if use_tc else "simt",
                        "coupling_planes": planes if use_tc else None,
                        "replicas_per_gpu": R, "sweeps_per_step": sweeps, "replicas_per_block": gmax,
-                       "blocks": blocks, "n_pad": q["n_pad"], "acceptance_rate": acc_rate,
-                       "l2_policy": "inputs (J planes 100 MB + operand stream 500 MB + 170 MB replica "
-                                    "state) exceed the 126 MB L2; no flush between steps",
+                       "replica_groups": blocks,
+                       "schedule": ("one persistent CTA per SM walks (sweep chunk, replica group) work "
+                                    "items; a group's fields/spins move through HBM between its items")
+                                   if use_tc and blocks > q["sm_count"] else "one CTA per replica group",
+                       "n_pad": q["n_pad"], "acceptance_rate": acc_rate,
+                       "l2_policy": f"inputs (J planes 100 MB + operand stream {sweeps * 100} MB per step + "
+                                    "170 MB replica state) exceed the 126 MB L2; no flush between steps",
                        "best_energy": best_global},
             "e2e": {"value": e2e_value, "unit": "attempts/s", "h2d_bytes_per_step": int(R) * n * world,
                     "d2h_bytes_per_step": int(R) * 4 * world, "ms_per_step": ms_e2e},
