@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 2
+#define SG_ABI_VERSION 3
 
 typedef enum {
     SG_OK = 0,
@@ -169,6 +169,11 @@ typedef struct {
      * |J| <= 256 are exact with 1 plane. */
     int32_t coupling_planes;
     int32_t reserved;
+    /* optional dev out [R][n] (float32, caller-zeroed): every accepted flip adds its energy change
+     * 2 s_i f_i to entry (replica, site) -- the third return value of
+     * CUDAKernelManager.metropolis_update_optimized (annealing/cuda_kernels.py:228-282, 371-397).
+     * Dense models on the sequential-FMA kernel only (kernel = SG_KERNEL_SIMT or replay). */
+    float *site_energy_changes;
 } sg_sweep_params;
 
 /* The sweep: replaces SpinDynamics.sweep() (core/spin_dynamics.py:73-94) looped over
@@ -198,6 +203,23 @@ typedef struct {
  * (annealing/parallel_tempering.py:214-258) and parallel_tempering_exchange_optimized
  * (annealing/cuda_kernels.py:326-369).  Temperatures move, configurations stay. */
 int sg_exchange(sg_engine *e, const sg_exchange_params *p, void *stream);
+
+/* The exchange in the shape of the reference's operator,
+ * CUDAKernelManager.parallel_tempering_exchange_optimized(spins_arrays, energies, temperatures)
+ * (annealing/cuda_kernels.py:326-369; the loop that runs upstream is
+ * _parallel_tempering_fallback, :405-436): ONE ordered pass over the pairs (i, i+1),
+ * i = 0 .. n_replicas-2, each pair seeing the energies the previous swap left;
+ * p = exp((1/T[i+1] - 1/T[i]) * (E[i] - E[i+1])) in float32 as written there, one uniform per
+ * pair; an accepted pair swaps rows i and i+1 of `rows` and the two energies IN PLACE
+ * (temperatures stay with the index).  `rows` is any device matrix of n_replicas rows of
+ * row_bytes bytes, row_stride_bytes apart (float32 or int8 spins); energies, temperatures and
+ * the optional uniforms[n_replicas-1] are device float32 (uniforms NULL: Philox keyed on
+ * seed / round).  No engine needed.  Synchronises `stream`; *n_accepted (host) = number of
+ * accepted pairs. */
+int sg_exchange_chain(int device, void *rows, int64_t row_stride_bytes, int64_t row_bytes,
+                      int n_replicas, float *energies, const float *temperatures,
+                      const float *uniforms, uint64_t seed, uint64_t round, int32_t *n_accepted,
+                      void *stream);
 
 /* rung -> replica map [R], per-replica temperature [R], per-pair statistics
  * [n_ladders][n_rungs-1] (ParallelTempering.exchange_attempts/accepts). */

@@ -18,6 +18,9 @@ around them, citing the reference lines (paths relative to
 * ``temperature_ladder``    <- annealing/parallel_tempering.py:146-173
 * ``parallel_tempering``    <- annealing/parallel_tempering.py:82-144, 175-258, 295-313
 * ``result_postprocess``    <- annealing/result.py:37-77
+* ``operator_*``            <- annealing/cuda_kernels.py:371-436 (the loops behind the
+  CUDAKernelManager entry points), pinned by ``tests/golden/op_*.npz``
+  (``tests/golden/make_operator_golden.py``)
 """
 from __future__ import annotations
 
@@ -190,6 +193,74 @@ def sweeps_scheduled(J, h, spins: np.ndarray, temps, rule: str, sites, uniforms)
                                _p(uniforms, ctypes.c_float), _p(energies, ctypes.c_double),
                                _p(accepted, ctypes.c_int64))
     return energies, accepted
+
+
+# --------------------------------------------------------------------------- operator API
+def operator_metropolis_update(J, h, spins, temperature: float, n_updates: int, *,
+                               uniforms=None, uniform_stream=None):
+    """CUDAKernelManager._metropolis_update_fallback (annealing/cuda_kernels.py:371-397), float32.
+
+    ``n_updates`` passes over the sites in index order; local field WITHOUT the diagonal term;
+    dE = 2 s_i lf; accept iff dE <= 0 or u < exp(-dE / T).  The reference draws a uniform only
+    when dE > 0: ``uniform_stream`` (1-D) is consumed like that, in order; ``uniforms``
+    ([n_updates, n]) gives attempt (p, i) its own value instead (what the CUDA path takes).
+    Returns (spins, accepted, energy_changes[n], positional uniforms [n_updates, n] -- the stream
+    values placed at the attempts that consumed them, 0.5 elsewhere)."""
+    J = _f32(J)
+    h = _f32(h)
+    s = np.array(spins, dtype=np.float32)
+    n = s.shape[0]
+    T = np.float32(temperature)
+    changes = np.zeros(n, dtype=np.float32)
+    placed = np.full((n_updates, n), 0.5, dtype=np.float32)
+    accepted = 0
+    pos = 0
+    for p in range(n_updates):
+        for i in range(n):
+            lf = np.float32(h[i] + np.sum(J[i] * s, dtype=np.float32) - J[i, i] * s[i])
+            dE = np.float32(np.float32(2.0) * s[i] * lf)
+            take = dE <= 0
+            if not take:
+                if uniforms is not None:
+                    u = np.float32(uniforms[p][i])
+                else:
+                    u = np.float32(uniform_stream[pos])
+                    pos += 1
+                placed[p, i] = u
+                take = float(u) < float(np.exp(np.float32(-dE / T)))
+            if take:
+                s[i] = -s[i]
+                changes[i] += dE
+                accepted += 1
+    return s, accepted, changes, placed
+
+
+def operator_energy(J, h, spins) -> float:
+    """CUDAKernelManager._compute_energy_fallback (annealing/cuda_kernels.py:398-403):
+    -1/2 sum_ij s_i J_ij s_j - sum_i h_i s_i, diagonal included (accumulated in double here)."""
+    J = np.asarray(J, dtype=np.float64)
+    h = np.asarray(h, dtype=np.float64)
+    s = np.asarray(spins, dtype=np.float64)
+    return float(-0.5 * s @ J @ s - h @ s)
+
+
+def operator_exchange(spins_arrays, energies, temperatures, uniforms):
+    """CUDAKernelManager._parallel_tempering_fallback (annealing/cuda_kernels.py:405-436), float32:
+    one ordered pass over (i, i+1); p = exp((1/T[i+1] - 1/T[i]) * (E[i] - E[i+1])); a uniform per
+    pair; rows and energies swapped in place.  Returns (rows, energies, accepted)."""
+    S = np.array(spins_arrays)
+    E = np.array(energies, dtype=np.float32)
+    T = np.asarray(temperatures, dtype=np.float32)
+    accepted = 0
+    for i in range(S.shape[0] - 1):
+        beta1 = np.float32(1.0) / T[i]
+        beta2 = np.float32(1.0) / T[i + 1]
+        prob = np.exp(np.float32((beta2 - beta1) * (E[i] - E[i + 1])))
+        if float(np.float32(uniforms[i])) < float(prob):
+            S[[i, i + 1]] = S[[i + 1, i]]
+            E[[i, i + 1]] = E[[i + 1, i]]
+            accepted += 1
+    return S, E, accepted
 
 
 # --------------------------------------------------------------------------- schedules

@@ -31,7 +31,7 @@ class SweepParams(Structure):
         ("sites", c_void_p), ("sites_block_stride", c_int64), ("sites_sweep_stride", c_int64),
         ("uniforms", c_void_p), ("energy_trace", c_void_p),
         ("track_best", c_int32), ("kernel", c_int32), ("coupling_planes", c_int32),
-        ("reserved", c_int32),
+        ("reserved", c_int32), ("site_energy_changes", c_void_p),
     ]
 
 
@@ -54,6 +54,8 @@ PROTOTYPES = {
     "sg_set_model_lattice2d": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "sg_lattice_sequence_index": (c_int, [c_int, c_int, c_int]),
     "sg_set_model_groups": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sg_exchange_chain": (c_int, [c_int, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p,
+                                  c_uint64, c_uint64, POINTER(c_int32), c_void_p]),
     "sg_alloc_replicas": (c_int, [c_void_p, c_int, c_void_p]),
     "sg_set_spins": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "sg_get_spins": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
@@ -119,7 +121,7 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.sg_abi_version() != 2:
+    if lib.sg_abi_version() != 3:
         raise RuntimeError("libsg_b200.so ABI version mismatch")
     _lib = lib
     return lib

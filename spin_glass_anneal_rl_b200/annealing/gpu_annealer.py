@@ -73,8 +73,15 @@ class GPUAnnealer:
             print(f"Using GPU: {torch.cuda.get_device_name(config.device_index)}")
         else:
             print("CUDA not available: anneal() needs a B200 (there is no CPU path)")
-        self.cuda_kernels = None     # reference attribute (CUDAKernelManager); the C ABI replaced it
-        self.memory_optimizer = None
+        # reference attributes (gpu_annealer.py:84-90): the per-call operator interface, kept for
+        # callers that use it directly; anneal() itself runs the batched launches below
+        if self.use_cuda:
+            from .cuda_kernels import CUDAKernelManager, GPUMemoryOptimizer
+            self.cuda_kernels = CUDAKernelManager(self.device)
+            self.memory_optimizer = GPUMemoryOptimizer(self.device)
+        else:
+            self.cuda_kernels = None
+            self.memory_optimizer = None
         self.total_flips = 0
         self.total_time = 0.0
         self._launch_seed = 0

@@ -65,7 +65,11 @@ class ParallelTempering:
         self.n_threads = config.n_threads or min(config.n_replicas, 8)
         self.use_cuda = torch.cuda.is_available()
         self.device = torch.device("cuda", config.device_index) if self.use_cuda else torch.device("cpu")
-        self.cuda_kernels = None
+        if self.use_cuda:   # reference parallel_tempering.py:77-80
+            from .cuda_kernels import CUDAKernelManager
+            self.cuda_kernels = CUDAKernelManager(self.device)
+        else:
+            self.cuda_kernels = None
         self._final_spins = None
 
     def _generate_temperature_ladder(self) -> List[float]:

@@ -1095,6 +1095,10 @@ int sg_sweep(sg_engine* e, const sg_sweep_params* p, void* stream) {
     a.site_mode = p->site_mode;
     a.track_best = p->track_best ? 1 : 0;
     a.dbg = e->dbg;
+    a.site_de = p->site_energy_changes;
+    SG_REQUIRE(!a.site_de || (!e->csr && !e->lat && p->kernel != SG_KERNEL_TC &&
+                              (p->kernel == SG_KERNEL_SIMT || p->rng_mode == SG_RNG_INJECTED)),
+               "sg_sweep: site_energy_changes needs a dense model on the sequential-FMA kernel");
     if (e->csr) return csr_sweep(e, p, a, static_cast<cudaStream_t>(stream));
     if (e->lat) return lat_sweep(e, p, a, static_cast<cudaStream_t>(stream));
     const bool inject = (p->rng_mode == SG_RNG_INJECTED);
@@ -1205,6 +1209,32 @@ int sg_exchange(sg_engine* e, const sg_exchange_params* p, void* stream) {
     a.inject = (p->rng_mode == SG_RNG_INJECTED);
     SG_CUDA(sg::launch_exchange(a, static_cast<cudaStream_t>(stream)));
     e->launches++;
+    return SG_OK;
+}
+
+int sg_exchange_chain(int device, void* rows, int64_t row_stride_bytes, int64_t row_bytes,
+                      int n_replicas, float* energies, const float* temperatures,
+                      const float* uniforms, uint64_t seed, uint64_t round, int32_t* n_accepted,
+                      void* stream) {
+    SG_REQUIRE(rows && energies && temperatures && n_accepted, "sg_exchange_chain: NULL argument");
+    SG_REQUIRE(n_replicas >= 1 && row_bytes >= 1 && row_stride_bytes >= row_bytes,
+               "sg_exchange_chain: bad shape");
+    *n_accepted = 0;
+    if (n_replicas == 1) return SG_OK;
+    DeviceGuard g(device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t head = sg::exchange_chain_header_bytes(n_replicas);
+    void* scratch = nullptr;
+    cudaError_t ce = cudaMallocAsync(&scratch, head + (size_t)n_replicas * (size_t)row_bytes, st);
+    if (ce != cudaSuccess) return fail(SG_ERR_NOMEM, "cudaMallocAsync(exchange scratch)", ce);
+    ce = sg::launch_exchange_chain(rows, row_stride_bytes, row_bytes, n_replicas, energies,
+                                   temperatures, uniforms, seed, round, scratch, st);
+    if (ce == cudaSuccess)
+        ce = cudaMemcpyAsync(n_accepted, static_cast<int*>(scratch) + n_replicas, sizeof(int),
+                             cudaMemcpyDeviceToHost, st);
+    cudaFreeAsync(scratch, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    if (ce != cudaSuccess) return fail(SG_ERR_CUDA, "sg_exchange_chain", ce);
     return SG_OK;
 }
 

@@ -58,7 +58,106 @@ __global__ void ladder_init_kernel(int* rep_at, double* rep_temp, const double* 
     rep_temp[t] = ladder[t % K];
 }
 
+// ---- the reference's operator form of the exchange (annealing/cuda_kernels.py:326-369 with the
+// loop that actually runs, _parallel_tempering_fallback :405-436): ONE pass over the pairs
+// (i, i+1), i = 0 .. R-2, in order, each using the energies left by the previous swap;
+// p = exp((1/T[i+1] - 1/T[i]) * (E[i] - E[i+1])) in float32 exactly as written there (note the
+// sign: it is the inverse of ParallelTempering._attempt_single_exchange's), a uniform is drawn
+// for every pair, configurations AND energies are swapped, temperatures stay with the index.
+// The pass is a dependency chain over R-1 scalars: one thread decides it and records where every
+// row has to come from; the rows are then moved by the whole grid.
+__global__ void exchange_chain_decide_kernel(float* __restrict__ energies, const float* __restrict__ temps,
+                                             const float* __restrict__ uniforms, unsigned long long seed,
+                                             unsigned long long round, int R, int* __restrict__ src,
+                                             int* __restrict__ accepted) {
+    if (threadIdx.x != 0) return;
+    int acc = 0;
+    // (e_cur, s_cur): energy and original index of the row that sits at position i when pair i
+    // is examined -- row i itself, or the row a chain of accepted swaps has carried there
+    float e_cur = energies[0];
+    int s_cur = 0;
+    for (int i = 0; i + 1 < R; ++i) {
+        const float beta1 = 1.0f / temps[i];
+        const float beta2 = 1.0f / temps[i + 1];
+        const float e_next = energies[i + 1];
+        const float prob = expf((beta2 - beta1) * (e_cur - e_next));
+        float u;
+        if (uniforms) {
+            u = uniforms[i];
+        } else {
+            const uint4 x = philox4x32_10(
+                make_uint4(0xC4A1E8C4u, (uint32_t)round, (uint32_t)(round >> 32), (uint32_t)i),
+                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+            u = u01(x.x);
+        }
+        if (u < prob) {
+            // rows i and i+1 trade places: position i keeps what was at i+1, the row that was
+            // at i moves on to i+1 and meets the next pair
+            energies[i] = e_next;
+            src[i] = i + 1;
+            ++acc;
+        } else {
+            energies[i] = e_cur;
+            src[i] = s_cur;
+            e_cur = e_next;
+            s_cur = i + 1;
+        }
+    }
+    energies[R - 1] = e_cur;
+    src[R - 1] = s_cur;
+    *accepted = acc;
+}
+
+// dst row i <- src row map[i] (map == nullptr: identity), only rows that moved
+__global__ void move_rows_kernel(unsigned char* __restrict__ dst, long long dst_stride,
+                                 const unsigned char* __restrict__ src, long long src_stride,
+                                 long long row_bytes, const int* __restrict__ map_to_src,
+                                 const int* __restrict__ moved_ref, int vec16) {
+    const int row = blockIdx.y;
+    const int from = map_to_src ? map_to_src[row] : row;
+    if (moved_ref[row] == row) return;
+    unsigned char* d = dst + (size_t)row * dst_stride;
+    const unsigned char* s = src + (size_t)from * src_stride;
+    if (vec16) {
+        const long long nv = row_bytes >> 4;
+        for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nv;
+             v += (long long)gridDim.x * blockDim.x)
+            reinterpret_cast<uint4*>(d)[v] = reinterpret_cast<const uint4*>(s)[v];
+    } else {
+        for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < row_bytes;
+             v += (long long)gridDim.x * blockDim.x)
+            d[v] = s[v];
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_exchange_chain(void* rows, long long row_stride, long long row_bytes, int R,
+                                  float* energies, const float* temps, const float* uniforms,
+                                  unsigned long long seed, unsigned long long round, void* scratch,
+                                  cudaStream_t st) {
+    // scratch: [R] int source map, [1] int count (16-byte padded), then R * row_bytes of rows
+    int* src = static_cast<int*>(scratch);
+    int* acc = src + R;
+    unsigned char* tmp = static_cast<unsigned char*>(scratch) + exchange_chain_header_bytes(R);
+    exchange_chain_decide_kernel<<<1, 32, 0, st>>>(energies, temps, uniforms, seed, round, R, src, acc);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const int vec16 = (row_bytes % 16 == 0 && row_stride % 16 == 0 &&
+                       reinterpret_cast<uintptr_t>(rows) % 16 == 0) ? 1 : 0;
+    const long long units = vec16 ? row_bytes / 16 : row_bytes;
+    int gx = (int)((units + 255) / 256);
+    if (gx > 64) gx = 64;
+    if (gx < 1) gx = 1;
+    dim3 grid((unsigned)gx, (unsigned)R);
+    move_rows_kernel<<<grid, 256, 0, st>>>(tmp, row_bytes, static_cast<const unsigned char*>(rows),
+                                           row_stride, row_bytes, src, src, vec16);
+    move_rows_kernel<<<grid, 256, 0, st>>>(static_cast<unsigned char*>(rows), row_stride, tmp, row_bytes,
+                                           row_bytes, nullptr, src, vec16);
+    return cudaGetLastError();
+}
+
+size_t exchange_chain_header_bytes(int R) { return (((size_t)R + 1) * sizeof(int) + 15) & ~(size_t)15; }
 
 cudaError_t launch_exchange(ExchangeDev a, cudaStream_t st) {
     const int npairs = (a.K - a.parity) / 2;

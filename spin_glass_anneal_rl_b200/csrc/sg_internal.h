@@ -30,6 +30,7 @@ struct SweepDev {
     unsigned long long seed, sweep_base;
     int n, n_pad, R, G, n_sweeps, rule, site_mode, track_best, D;
     long long* dbg;           // optional timeline buffer (development aid), block 0 only
+    float* site_de;           // optional [R][n]: sum of the accepted energy changes per site
 };
 
 // Largest number of replicas one block can hold for this padded size (0 = unsupported).
@@ -189,6 +190,12 @@ struct ExchangeDev {
     int L, K, parity, inject;
 };
 cudaError_t launch_exchange(ExchangeDev a, cudaStream_t st);
+// operator-form exchange (one ordered pass over adjacent pairs, rows swapped in place)
+size_t exchange_chain_header_bytes(int R);
+cudaError_t launch_exchange_chain(void* rows, long long row_stride, long long row_bytes, int R,
+                                  float* energies, const float* temps, const float* uniforms,
+                                  unsigned long long seed, unsigned long long round, void* scratch,
+                                  cudaStream_t st);
 cudaError_t launch_ladder_init(int* rep_at, double* rep_temp, const double* ladder, int L, int K,
                                cudaStream_t st);
 

@@ -393,6 +393,8 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_kernel(const SweepDev 
                         if (flip) {
                             *wp = w ^ (1u << (site & 31));
                             ++n_acc;
+                            if (a.site_de)   // operator output: accepted dE accumulated per site
+                                a.site_de[(size_t)(rep0 + lane) * n + site] += up ? 2.0f * fv : -2.0f * fv;
                         }
                     }
                     const float da = flip ? (up ? -2.0f : 2.0f) : 0.0f;

@@ -203,8 +203,12 @@ class Engine:
               sites_block_stride: int = 0, sites_sweep_stride: Optional[int] = None,
               uniforms: Optional[ArrayLike] = None, energy_trace: bool = False,
               track_best: bool = True, replicas_per_block: int = 0, kernel: str = "auto",
-              coupling_planes: int = 0) -> Optional[torch.Tensor]:
+              coupling_planes: int = 0,
+              site_energy_changes: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
         """Run ``n_sweeps`` sweeps on every replica (one kernel launch).
+
+        ``site_energy_changes``: optional device float32 [R, n] accumulator of the accepted
+        energy changes per site (sequential-FMA kernel only).
 
         temps: float64 array addressed as temps[s*temps_sweep_stride + r*temps_replica_stride]
         (None = ladder temperatures).  ``uniforms`` switches to injected-uniform mode,
@@ -249,6 +253,13 @@ class Engine:
             trace = torch.empty((n_sweeps, self.n_replicas), dtype=torch.float32,
                                 device=self.device)
             p.energy_trace = trace.data_ptr()
+        if site_energy_changes is not None:
+            d = site_energy_changes
+            if (d.device != self.device or d.dtype != torch.float32 or not d.is_contiguous()
+                    or d.numel() != self.n_replicas * self.n):
+                raise ValueError("site_energy_changes must be a contiguous device float32 [R, n] tensor")
+            keep.append(d)
+            p.site_energy_changes = d.data_ptr()
         check(self._lib.sg_sweep(self._h, ctypes.byref(p), self.stream), "sg_sweep")
         self._keep += keep
         if len(self._keep) > 256:

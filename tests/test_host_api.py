@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"libsg_b200.so lacks {name}"
     assert declared == set(_lib.PROTOTYPES), (declared ^ set(_lib.PROTOTYPES))
-    assert _lib.load().sg_abi_version() == 2
+    assert _lib.load().sg_abi_version() == 3
 
 
 def test_param_structs_match_header_layout(tmp_path):
