@@ -7,6 +7,13 @@ coupling_strength, external_field_strength, use_sparse, device)`` and an
 sparse COO, both triangles stored) and ``external_fields`` are ordinary, publicly
 mutable torch tensors on the host.  H = -1/2 s^T J s - h^T s.
 
+``set_coupling`` on a sparse model is O(1): the reference densifies and re-sparsifies the whole
+matrix per call (core/ising_model.py:94-99), which makes its own problem encoders
+(problems/routing.py:275-294, core/constraints.py:360-388: one call per pair) take ~4 million
+N^2 round trips for a 64-city TSP.  Here the writes are queued and folded into the COO tensor in
+one vectorised pass the next time ``couplings`` is read, with the same last-write-wins and
+zero-removal result.
+
 The model is only the container the callers build; every sweep runs on the GPU
 engine (annealing/_backend.py uploads J, h once and keeps them resident).  Unlike the
 reference, the sparse representation works for every method: the reference slices a
@@ -18,6 +25,7 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import Dict
 
+import numpy as np
 import torch
 
 
@@ -44,6 +52,7 @@ class IsingModel:
         self.n_spins = config.n_spins
         self.device = torch.device(config.device)
         self.spins = _random_spins(self.n_spins, self.device)
+        self._pending: Dict[int, float] = {}   # queued set_coupling writes: i * n + j -> strength
         if config.use_sparse:
             self.couplings = torch.sparse_coo_tensor(
                 torch.empty((2, 0), dtype=torch.long), torch.empty(0),
@@ -55,6 +64,41 @@ class IsingModel:
         self._cache_valid = False
 
     # ------------------------------------------------------------------ couplings / fields
+    @property
+    def couplings(self) -> torch.Tensor:
+        """Dense [n, n] or sparse COO tensor; publicly readable and assignable like the
+        reference's attribute.  Reading folds the queued ``set_coupling`` writes in."""
+        if self._pending:
+            self._flush_pending()
+        return self._couplings
+
+    @couplings.setter
+    def couplings(self, value: torch.Tensor) -> None:
+        self._pending.clear()
+        self._couplings = value
+        self._cache_valid = False
+
+    def _flush_pending(self) -> None:
+        """Apply the queued writes to the COO tensor: entries written are replaced (last write
+        wins), zero strengths are dropped (what dense[i, j] = v; to_sparse() leaves)."""
+        n = self.n_spins
+        keys_u = np.fromiter(self._pending.keys(), dtype=np.int64, count=len(self._pending))
+        vals_u = np.fromiter(self._pending.values(), dtype=np.float32, count=len(self._pending))
+        self._pending.clear()
+        old = self._couplings.coalesce()
+        idx = old.indices().cpu().numpy()
+        keys_o = idx[0].astype(np.int64) * n + idx[1]
+        vals_o = old.values().cpu().numpy().astype(np.float32)
+        keep = ~np.isin(keys_o, keys_u)
+        nz = vals_u != 0.0
+        keys = np.concatenate([keys_o[keep], keys_u[nz]])
+        vals = np.concatenate([vals_o[keep], vals_u[nz]])
+        order = np.argsort(keys, kind="stable")
+        keys, vals = keys[order], vals[order]
+        ind = torch.from_numpy(np.stack([keys // n, keys % n]))
+        self._couplings = torch.sparse_coo_tensor(ind, torch.from_numpy(vals), (n, n), device=self.device,
+                                                  check_invariants=False, is_coalesced=True)
+
     def dense_couplings(self) -> torch.Tensor:
         """Couplings as a dense float32 [n, n] tensor (what the engine uploads)."""
         J = self.couplings
@@ -67,11 +111,10 @@ class IsingModel:
     def set_coupling(self, i: int, j: int, strength: float) -> None:
         if not (0 <= i < self.n_spins and 0 <= j < self.n_spins):
             raise ValueError(f"Spin indices out of range: i={i}, j={j}, n_spins={self.n_spins}")
-        if self.config.use_sparse:
-            dense = self.couplings.to_dense()
-            dense[i, j] = strength
-            dense[j, i] = strength
-            self._store_couplings(dense)
+        if self._couplings.is_sparse:
+            self._pending[i * self.n_spins + j] = float(strength)
+            self._pending[j * self.n_spins + i] = float(strength)
+            self._invalidate_cache()
         else:
             self.couplings[i, j] = strength
             self.couplings[j, i] = strength
@@ -80,7 +123,16 @@ class IsingModel:
     def get_coupling(self, i: int, j: int) -> float:
         if not (0 <= i < self.n_spins and 0 <= j < self.n_spins):
             raise ValueError(f"Spin indices out of range: i={i}, j={j}, n_spins={self.n_spins}")
-        return float(self.dense_couplings()[i, j].item())
+        key = i * self.n_spins + j
+        if key in self._pending:
+            return self._pending[key]
+        J = self._couplings
+        if not J.is_sparse:
+            return float(J[i, j].item())
+        J = J.coalesce()
+        idx = J.indices()
+        sel = (idx[0] == i) & (idx[1] == j)
+        return float(J.values()[sel].sum().item())
 
     def set_couplings_from_matrix(self, coupling_matrix: torch.Tensor) -> None:
         self._store_couplings(coupling_matrix.clone().to(self.device))
