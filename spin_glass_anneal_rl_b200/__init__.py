@@ -15,9 +15,10 @@ __version__ = "0.1.0"
 from .annealing import (AnnealingResult, GPUAnnealer, GPUAnnealerConfig, ParallelTempering,
                         ParallelTemperingConfig, ScheduleType, TemperatureScheduler)
 from .core import IsingModel, IsingModelConfig, SpinDynamics, UpdateRule
-from .api import anneal, batch_energies, batch_local_fields, install_as_spin_glass_rl
+from .api import (BatchProcessor, VectorizedOperations, anneal, batch_energies, batch_local_fields,
+                  install_as_spin_glass_rl)
 
-__all__ = ["IsingModel", "IsingModelConfig", "SpinDynamics", "UpdateRule", "GPUAnnealer",
+__all__ = ["BatchProcessor", "VectorizedOperations", "IsingModel", "IsingModelConfig", "SpinDynamics", "UpdateRule", "GPUAnnealer",
            "GPUAnnealerConfig", "ParallelTempering", "ParallelTemperingConfig", "AnnealingResult",
            "ScheduleType", "TemperatureScheduler", "anneal", "batch_energies",
            "batch_local_fields", "install_as_spin_glass_rl"]

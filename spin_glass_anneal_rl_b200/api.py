@@ -7,6 +7,7 @@
 * ``batch_energies`` / ``batch_local_fields`` -- BatchProcessor.process_batch_energies and
   VectorizedOperations.vectorized_local_fields
   (reference optimization/high_performance_computing.py:98-165, 357-372) on the GPU.
+* ``VectorizedOperations`` / ``BatchProcessor`` -- the reference's class names for the same.
 * ``install_as_spin_glass_rl`` -- sys.modules aliases for the reference's import paths.
 """
 from __future__ import annotations
@@ -73,6 +74,48 @@ def batch_local_fields(spin_configurations: torch.Tensor, couplings: torch.Tenso
     _, f = _engine_for_tensors(couplings, external_fields).batch_energies(
         spin_configurations.sign().to(torch.int8), want_fields=True)
     return f
+
+
+class VectorizedOperations:
+    """Reference optimization/high_performance_computing.py:338-386, same static methods.
+    The field GEMM runs on the int8 tensor-core kernel (K2-TC); the two index operations are
+    element-wise gathers on the caller's tensors."""
+
+    @staticmethod
+    def vectorized_spin_flips(spin_configurations: torch.Tensor, flip_indices: torch.Tensor) -> torch.Tensor:
+        """Copy of ``spin_configurations`` [B, n] with the spins at ``flip_indices`` [B, k] negated
+        (an index listed twice is flipped once, as with the reference's indexed ``*=``)."""
+        result = spin_configurations.clone()
+        rows = torch.arange(result.shape[0], device=result.device).unsqueeze(1)
+        result[rows, flip_indices.to(result.device)] *= -1
+        return result
+
+    @staticmethod
+    def vectorized_local_fields(spin_configurations: torch.Tensor, couplings: torch.Tensor,
+                                external_fields: torch.Tensor) -> torch.Tensor:
+        """F[b, i] = sum_j J_ij s_bj + h_i for every configuration of the batch."""
+        return batch_local_fields(spin_configurations, couplings, external_fields).to(spin_configurations.dtype)
+
+    @staticmethod
+    def vectorized_energy_differences(spin_configurations: torch.Tensor, local_fields: torch.Tensor,
+                                      flip_indices: torch.Tensor) -> torch.Tensor:
+        """dE[b, k] = 2 s_{b, i} F_{b, i} with i = flip_indices[b, k]."""
+        idx = flip_indices.to(local_fields.device)
+        s = torch.gather(spin_configurations.to(local_fields.device), 1, idx)
+        return 2.0 * s * torch.gather(local_fields, 1, idx)
+
+
+class BatchProcessor:
+    """Energy half of the reference's BatchProcessor
+    (optimization/high_performance_computing.py:86-165): ``process_batch_energies``."""
+
+    def __init__(self, config=None):
+        self.config = config
+        self.batch_size = getattr(config, "batch_size", None)
+
+    def process_batch_energies(self, spin_configurations: torch.Tensor, couplings: torch.Tensor,
+                               external_fields: torch.Tensor) -> torch.Tensor:
+        return batch_energies(spin_configurations, couplings, external_fields)
 
 
 def install_as_spin_glass_rl(force: bool = False) -> None:

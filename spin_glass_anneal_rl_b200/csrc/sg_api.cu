@@ -82,6 +82,14 @@ struct sg_engine {
     int g_n = 0;
     int* g_group_of = nullptr;
     float* g_coupling = nullptr;
+    // partitions of the groups (P x W grid of the partitioned group kernel)
+    int gp_P = 0, gp_max_sites = 0, gp_max_groups = 0;
+    int* gp_tables = nullptr;   // part_of_group, part_off, part_sites, local_site, part_goff,
+                                // part_groups, local_group, goff, gsites (one allocation)
+    short* gp_sums = nullptr;
+    size_t gp_sums_cap = 0;
+    void* gp_scratch = nullptr;
+    size_t gp_scratch_cap = 0;
     uint32_t *l_lat = nullptr, *l_best = nullptr;
     uint8_t* l_bond = nullptr;
     // sparse (CSR) mode: replica-minor state, see sg_sweep_csr.cu
@@ -172,8 +180,32 @@ void free_lat_model(sg_engine* e) {
     cudaFree(e->l_bond); e->l_bond = nullptr;
     cudaFree(e->g_group_of); e->g_group_of = nullptr;
     cudaFree(e->g_coupling); e->g_coupling = nullptr;
+    cudaFree(e->gp_tables); e->gp_tables = nullptr;
+    cudaFree(e->gp_sums); e->gp_sums = nullptr; e->gp_sums_cap = 0;
+    cudaFree(e->gp_scratch); e->gp_scratch = nullptr; e->gp_scratch_cap = 0;
+    e->gp_P = 0;
     e->lat = false;
     e->grp = false;
+}
+
+sg::GrpPartDev grp_part_dev(const sg_engine* e) {
+    sg::GrpPartDev q{};
+    const int n = e->n, G = e->g_n, P = e->gp_P;
+    const int* t = e->gp_tables;
+    q.P = P;
+    q.part_of_group = t;            t += G;
+    q.part_off = t;                 t += P + 1;
+    q.part_sites = t;               t += n;
+    q.local_site = t;               t += n;
+    q.part_goff = t;                t += P + 1;
+    q.part_groups = t;              t += G;
+    q.local_group = t;              t += G;
+    q.goff = t;                     t += G + 1;
+    q.gsites = t;
+    q.sums = e->gp_sums;
+    q.max_sites = e->gp_max_sites;
+    q.max_groups = e->gp_max_groups;
+    return q;
 }
 
 sg::GrpDev grp_dev(const sg_engine* e) {
@@ -555,11 +587,45 @@ int lat_sweep(sg_engine* e, const sg_sweep_params* p, sg::SweepDev a, cudaStream
             e->c_sites_cap = need;
         }
         SG_CUDA(sg::launch_sites_table(a, static_cast<int*>(e->c_sites), st));
+        e->launches += 1;
+        // the groups are spread over P partitions (P x W one-warp CTAs, several resident per SM)
+        // instead of one warp per 32 replicas holding the whole model (one warp per SM):
+        // 14x faster at 1024 replicas, 6x at 4096 (tools/grp_perf.py); SG_GRP_PART=0 forces the
+        // one-warp-per-word kernel
+        const int W = (e->R + 31) / 32;
+        bool part = e->gp_P >= 2;
+        if (const char* env = getenv("SG_GRP_PART")) part = e->gp_P >= 2 && atoi(env) != 0;
+        if (part) {
+            const size_t need_sums = (size_t)W * e->g_n * 32 * sizeof(short);
+            const size_t need_scr = sg::groups_part_scratch_bytes(e->n, p->n_sweeps, e->R, e->gp_P);
+            if (need_sums > e->gp_sums_cap || need_scr > e->gp_scratch_cap) {
+                SG_CUDA(cudaStreamSynchronize(st));
+                if (need_sums > e->gp_sums_cap) {
+                    cudaFree(e->gp_sums); e->gp_sums = nullptr; e->gp_sums_cap = 0;
+                    cudaError_t ce = cudaMalloc(&e->gp_sums, need_sums);
+                    if (ce != cudaSuccess) return fail(SG_ERR_NOMEM, "cudaMalloc(group sums)", ce);
+                    e->gp_sums_cap = need_sums;
+                }
+                if (need_scr > e->gp_scratch_cap) {
+                    cudaFree(e->gp_scratch); e->gp_scratch = nullptr; e->gp_scratch_cap = 0;
+                    cudaError_t ce = cudaMalloc(&e->gp_scratch, need_scr);
+                    if (ce != cudaSuccess) return fail(SG_ERR_NOMEM, "cudaMalloc(attempt lists)", ce);
+                    e->gp_scratch_cap = need_scr;
+                }
+            }
+            if (e->profiling) e->timer.begin(0, st);
+            SG_CUDA(sg::launch_sweep_groups_part(grp_dev(e), grp_part_dev(e), a,
+                                                 p->rng_mode == SG_RNG_INJECTED,
+                                                 static_cast<const int*>(e->c_sites), e->gp_scratch,
+                                                 &e->launches, st));
+            if (e->profiling) e->timer.end(st);
+            return SG_OK;
+        }
         if (e->profiling) e->timer.begin(0, st);
         SG_CUDA(sg::launch_sweep_groups(grp_dev(e), a, p->rng_mode == SG_RNG_INJECTED,
                                         static_cast<const int*>(e->c_sites), st));
         if (e->profiling) e->timer.end(st);
-        e->launches += 2;
+        e->launches += 1;
         return SG_OK;
     }
     SG_REQUIRE(p->site_mode == SG_SITES_CHECKERBOARD,
@@ -684,6 +750,58 @@ extern "C" int sg_set_model_groups(sg_engine* e, int n, int n_groups, const int3
     if ((rc = upload(&e->g_group_of, reinterpret_cast<const int*>(group_of), (size_t)n, st)) != SG_OK) return rc;
     if ((rc = upload(&e->g_coupling, coupling, (size_t)n_groups, st)) != SG_OK) return rc;
     if ((rc = upload(&e->h, h, (size_t)n, st)) != SG_OK) return rc;
+    {
+        // partitions: groups dealt out largest first to the least loaded of P <= 32 partitions
+        const int G = n_groups, P = G < 32 ? G : 32;
+        std::vector<int> gsize(G, 0), order(G), part_of(G), load(P, 0), cnt_g(P, 0);
+        for (int i = 0; i < n; ++i) gsize[group_of[i]]++;
+        for (int g = 0; g < G; ++g) order[g] = g;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return gsize[x] > gsize[y]; });
+        for (int g : order) {
+            int best = 0;
+            for (int q = 1; q < P; ++q)
+                if (load[q] < load[best]) best = q;
+            part_of[g] = best;
+            load[best] += gsize[g];
+            cnt_g[best]++;
+        }
+        std::vector<int> tab((size_t)3 * G + 2 * (P + 1) + 3 * (size_t)n + G + 1);
+        int* t = tab.data();
+        int* part_of_group = t;  t += G;
+        int* part_off = t;       t += P + 1;
+        int* part_sites = t;     t += n;
+        int* local_site = t;     t += n;
+        int* part_goff = t;      t += P + 1;
+        int* part_groups = t;    t += G;
+        int* local_group = t;    t += G;
+        int* goff = t;           t += G + 1;
+        int* gsites = t;
+        part_off[0] = part_goff[0] = 0;
+        for (int q = 0; q < P; ++q) {
+            part_off[q + 1] = part_off[q] + load[q];
+            part_goff[q + 1] = part_goff[q] + cnt_g[q];
+        }
+        std::vector<int> fill_s(part_off, part_off + P), fill_g(part_goff, part_goff + P);
+        for (int g = 0; g < G; ++g) {
+            part_of_group[g] = part_of[g];
+            local_group[g] = fill_g[part_of[g]] - part_goff[part_of[g]];
+            part_groups[fill_g[part_of[g]]++] = g;
+        }
+        for (int i = 0; i < n; ++i) {
+            const int q = part_of[group_of[i]];
+            local_site[i] = fill_s[q] - part_off[q];
+            part_sites[fill_s[q]++] = i;
+        }
+        goff[0] = 0;
+        for (int g = 0; g < G; ++g) goff[g + 1] = goff[g] + gsize[g];
+        std::vector<int> fill(goff, goff + G);
+        for (int i = 0; i < n; ++i) gsites[fill[group_of[i]]++] = i;
+        e->gp_P = P;
+        e->gp_max_sites = *std::max_element(load.begin(), load.end());
+        e->gp_max_groups = *std::max_element(cnt_g.begin(), cnt_g.end());
+        if ((rc = upload(&e->gp_tables, tab.data(), tab.size(), st)) != SG_OK) return rc;
+        SG_CUDA(cudaStreamSynchronize(st));   // tab goes out of scope
+    }
     SG_CUDA(cudaStreamSynchronize(st));
     e->n = n;
     e->n_pad = n;

@@ -169,6 +169,25 @@ struct GrpDev {
     uint32_t* best_words;     // [W][n]
     int n_groups;
 };
+// groups dealt out to P partitions (static per model) for the P x W grid of the partitioned kernel
+struct GrpPartDev {
+    int P;
+    const int* part_of_group;  // [n_groups]
+    const int* part_off;       // [P+1] offsets into part_sites
+    const int* part_sites;     // [n]   sites ordered by partition
+    const int* local_site;     // [n]   index of a site inside its partition
+    const int* part_goff;      // [P+1] offsets into part_groups
+    const int* part_groups;    // [n_groups] groups ordered by partition
+    const int* local_group;    // [n_groups] index of a group inside its partition
+    const int* goff;           // [n_groups+1] offsets into gsites
+    const int* gsites;         // [n] sites ordered by group
+    short* sums;               // [W][n_groups][32] group sums per replica word (scratch)
+    int max_sites, max_groups; // largest partition
+};
+size_t groups_part_scratch_bytes(int n, int n_sweeps, int R, int P);
+cudaError_t launch_sweep_groups_part(const GrpDev& m, const GrpPartDev& q, const SweepDev& a, bool inject,
+                                     const int* sites, void* scratch, uint64_t* launches,
+                                     cudaStream_t st);
 size_t groups_smem_bytes(int n, int n_groups);
 cudaError_t launch_sweep_groups(const GrpDev& m, const SweepDev& a, bool inject, const int* sites,
                                 cudaStream_t st);

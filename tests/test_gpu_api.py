@@ -233,6 +233,30 @@ def test_readme_shaped_anneal_and_batch_api(oracle):
         assert np.allclose(E, k["E"], rtol=1e-5, atol=1e-4) and np.allclose(F, k["F"], rtol=1e-5, atol=1e-5)
 
 
+def test_vectorized_operations_mirror(oracle):
+    """VectorizedOperations / BatchProcessor (reference optimization/high_performance_computing.py
+    :98-165, 338-386): batched fields on the tensor-core GEMM, dE = 2 s f for chosen sites equals
+    the energy difference of actually flipping them one at a time."""
+    k = load_golden("kat_energy_int_n64")
+    J, h = torch.from_numpy(k["J"]), torch.from_numpy(k["h"])
+    S = torch.from_numpy(k["S"].astype(np.float32))
+    B, n = S.shape
+    F = sg.VectorizedOperations.vectorized_local_fields(S, J, h)
+    assert np.array_equal(F.cpu().numpy().astype(np.float64), k["F"])
+    E = sg.BatchProcessor().process_batch_energies(S, J, h)
+    assert np.array_equal(E.cpu().numpy().astype(np.float64), k["E"])
+    e1 = sg.BatchProcessor().process_batch_energies(S[0], J, h)
+    assert e1.dim() == 0 and float(e1) == k["E"][0]
+    idx = torch.from_numpy(np.random.default_rng(2).integers(0, n, size=(B, 3)))
+    dE = sg.VectorizedOperations.vectorized_energy_differences(S.to(F.device), F, idx).cpu().numpy()
+    for j in range(3):
+        one = sg.VectorizedOperations.vectorized_spin_flips(S, idx[:, j:j + 1])
+        assert int((one != S).sum()) == B
+        e_after = np.array([oracle.energy(k["J"], k["h"], one[b].numpy()) for b in range(B)])
+        # the diagonal of this instance is zero, so dE(flip i) = E_after - E_before exactly
+        assert np.array_equal(dE[:, j], e_after - k["E"])
+
+
 def test_spin_dynamics_facade(oracle):
     g = load_golden("sa_pm1_n48")
     m = _model(g["J"], g["h"], g["spins0"])

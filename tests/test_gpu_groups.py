@@ -22,6 +22,14 @@ def engine():
     return Engine(0)
 
 
+@pytest.fixture(params=["0", "1"], ids=["one-warp-per-word", "partitioned"])
+def part(request, monkeypatch):
+    """Both group kernels: one warp per 32 replicas with the whole model in shared memory, and
+    the P x W grid over partitions of the groups (SG_GRP_PART forces either)."""
+    monkeypatch.setenv("SG_GRP_PART", request.param)
+    return request.param
+
+
 def _sched(T, A, integer_h=True, seed=None):
     rowptr, colidx, val, h = inst.scheduling_ising(*inst.random_scheduling(T, A, seed=seed or T * A))
     if integer_h:
@@ -33,7 +41,7 @@ def _sched(T, A, integer_h=True, seed=None):
 
 @pytest.mark.parametrize("T,A,rule", [(6, 5, "metropolis"), (12, 8, "metropolis"), (9, 7, "glauber"),
                                       (5, 33, "heat_bath")])
-def test_groups_replay_is_bit_exact(engine, oracle, T, A, rule):
+def test_groups_replay_is_bit_exact(engine, oracle, part, T, A, rule):
     rowptr, colidx, val, h, group_of, coupling = _sched(T, A)
     n = T * A
     J = inst.csr_to_dense(rowptr, colidx, val, n)
@@ -65,7 +73,7 @@ def test_groups_replay_is_bit_exact(engine, oracle, T, A, rule):
     assert np.array_equal(engine.batch_energies(best_s).cpu().numpy(), best_e.cpu().numpy())
 
 
-def test_groups_equal_sparse_kernel_in_philox_mode(engine):
+def test_groups_equal_sparse_kernel_in_philox_mode(engine, part):
     rowptr, colidx, val, h, group_of, coupling = _sched(40, 25)
     n, R, ns = 1000, 70, 5
     rng = np.random.default_rng(4)
@@ -88,7 +96,38 @@ def test_groups_equal_sparse_kernel_in_philox_mode(engine):
     assert outs[0][2].sum() > 0
 
 
-def test_groups_full_size_cfg5(engine):
+def test_partitioned_and_plain_group_kernels_agree(engine, monkeypatch):
+    """Uneven group sizes (so partitions are unbalanced), ragged replica count, several launches:
+    identical spins, per-sweep energies, acceptance counts and best-so-far records."""
+    rng = np.random.default_rng(12)
+    sizes = rng.integers(3, 40, size=57)
+    group_of = np.repeat(np.arange(57), sizes).astype(np.int32)
+    rng.shuffle(group_of)                          # groups are not contiguous in site order
+    n = group_of.shape[0]
+    coupling = rng.integers(1, 6, size=57).astype(np.float32) * 10.0
+    h = rng.integers(-30, 31, size=n).astype(np.float32)
+    R = 77
+    S0 = (rng.integers(0, 2, size=(R, n)) * 2 - 1).astype(np.int8)
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("SG_GRP_PART", flag)
+        engine.set_model_groups(group_of, coupling, h)
+        engine.alloc_replicas(R)
+        engine.set_spins(S0)
+        engine.init_fields()
+        traces = []
+        for k, T in enumerate((30.0, 12.0, 4.0)):
+            traces.append(engine.sweep(3, np.array([T]), seed=21, sweep_base=3 * k, site_order="random",
+                                       energy_trace=True).cpu().numpy())
+        outs.append((engine.spins().cpu().numpy(), np.concatenate(traces), engine.accepted().cpu().numpy(),
+                     engine.energies().cpu().numpy(), engine.best()[0].cpu().numpy(),
+                     engine.best()[1].cpu().numpy()))
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+    assert outs[0][2].sum() > 0
+
+
+def test_groups_full_size_cfg5(engine, part):
     """500 tasks x 100 agents, float fields: no field array exists, so nothing drifts; the carried
     energy stays within 1e-5 relative of an exact recomputation."""
     import torch
