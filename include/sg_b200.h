@@ -59,9 +59,12 @@ typedef enum {
                                        then all odd ones -- each site once per sweep          */
 
 /* which sweep kernel runs (sg_sweep_params.kernel) */
-#define SG_KERNEL_AUTO 0 /* tensor-core kernel when the model/launch shape allows it, else SIMT   */
+#define SG_KERNEL_AUTO 0 /* n <= 224: SMALL; else the tensor-core kernel when the model/launch
+                            shape allows it; else SIMT                                          */
 #define SG_KERNEL_SIMT 1 /* register-resident fields, sequential fp32 FMAs (sg_sweep.cu)          */
 #define SG_KERNEL_TC 2   /* TMEM-resident fields, tcgen05 rank-16 block updates (sg_sweep_tc.cu)  */
+#define SG_KERNEL_SMALL 3 /* n <= 224: J in shared memory, one warp per replica, fields in
+                             registers (sg_sweep_small.cu)                                      */
 
 typedef struct sg_engine sg_engine;
 

@@ -19,7 +19,7 @@ CSRC = os.path.join(_PKG, "csrc")
 SG_RULE = {"metropolis": 0, "glauber": 1, "heat_bath": 2}
 SG_RNG_PHILOX, SG_RNG_INJECTED = 0, 1
 SG_SITES = {"sequential": 0, "random": 1, "explicit": 2, "random_per_block": 3, "checkerboard": 4}
-SG_KERNEL = {"auto": 0, "simt": 1, "tc": 2}
+SG_KERNEL = {"auto": 0, "simt": 1, "tc": 2, "small": 3}
 
 
 class SweepParams(Structure):

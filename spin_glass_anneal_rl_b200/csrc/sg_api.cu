@@ -1215,12 +1215,40 @@ int sg_sweep(sg_engine* e, const sg_sweep_params* p, void* stream) {
     a.dbg = e->dbg;
     a.site_de = p->site_energy_changes;
     SG_REQUIRE(!a.site_de || (!e->csr && !e->lat && p->kernel != SG_KERNEL_TC &&
-                              (p->kernel == SG_KERNEL_SIMT || p->rng_mode == SG_RNG_INJECTED)),
-               "sg_sweep: site_energy_changes needs a dense model on the sequential-FMA kernel");
+                              (p->kernel == SG_KERNEL_SIMT || p->kernel == SG_KERNEL_SMALL ||
+                               p->rng_mode == SG_RNG_INJECTED || sg::sweep_small_supported(e->n))),
+               "sg_sweep: site_energy_changes needs a dense model on a sequential-FMA kernel");
     if (e->csr) return csr_sweep(e, p, a, static_cast<cudaStream_t>(stream));
     if (e->lat) return lat_sweep(e, p, a, static_cast<cudaStream_t>(stream));
     const bool inject = (p->rng_mode == SG_RNG_INJECTED);
-    SG_REQUIRE(p->kernel >= SG_KERNEL_AUTO && p->kernel <= SG_KERNEL_TC, "sg_sweep: unknown kernel");
+    SG_REQUIRE(p->kernel >= SG_KERNEL_AUTO && p->kernel <= SG_KERNEL_SMALL, "sg_sweep: unknown kernel");
+    const bool shared_order = p->site_mode != SG_SITES_RANDOM_PER_BLOCK &&
+                              !(p->site_mode == SG_SITES_EXPLICIT && p->sites_block_stride != 0) &&
+                              p->replicas_per_block == 0;
+    const bool small_ok = e->Jt && sg::sweep_small_supported(e->n) && shared_order;
+    if (p->kernel == SG_KERNEL_SMALL)
+        SG_REQUIRE(small_ok, "sg_sweep: the small-model kernel needs a dense model with n <= 224, one "
+                             "site order for the grid and replicas_per_block = 0");
+    if (p->kernel == SG_KERNEL_SMALL || (p->kernel == SG_KERNEL_AUTO && small_ok)) {
+        const size_t need = sg::csr_sites_bytes(e->n, p->n_sweeps);
+        if (need > e->c_sites_cap) {
+            SG_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+            cudaFree(e->c_sites);
+            e->c_sites = nullptr;
+            e->c_sites_cap = 0;
+            cudaError_t ce = cudaMalloc(&e->c_sites, need);
+            if (ce != cudaSuccess) return fail(SG_ERR_NOMEM, "cudaMalloc(site tables)", ce);
+            e->c_sites_cap = need;
+        }
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        SG_CUDA(sg::launch_sites_table(a, static_cast<int*>(e->c_sites), st));
+        if (e->profiling) e->timer.begin(0, st);
+        SG_CUDA(sg::launch_sweep_small(a, p->rng_mode == SG_RNG_INJECTED,
+                                       static_cast<const int*>(e->c_sites), st));
+        if (e->profiling) e->timer.end(st);
+        e->launches += 2;
+        return SG_OK;
+    }
     SG_REQUIRE(p->coupling_planes >= 0 && p->coupling_planes <= 3,
                "sg_sweep: coupling_planes must be 0..3");
     const bool tc_ok = e->Jp && sg::sweep_tc_supported(e->n, e->n_tc) &&

@@ -40,6 +40,11 @@ size_t sweep_smem_bytes(int n_pad, int g_template, int D);
 // Picks D, sets the smem attribute, launches.  Returns cudaError_t.
 cudaError_t launch_sweep(SweepDev a, bool inject, int grid, cudaStream_t st);
 
+// K1-SMALL (sg_sweep_small.cu): n <= 224, J in shared memory, one warp per replica.
+// sites: int32 table [n_sweeps][n] from launch_sites_table.
+bool sweep_small_supported(int n);
+cudaError_t launch_sweep_small(const SweepDev& a, bool inject, const int* sites, cudaStream_t st);
+
 // K2 + helpers (sg_fields.cu)
 cudaError_t launch_pad_transpose(const float* J, int64_t ldJ, int n, float* Jt, int n_pad,
                                  cudaStream_t st);
