@@ -108,6 +108,11 @@ def cpu_reference(n_threads, budget_s, sweeps=1):
     return att / dt, threads, f"{R} replicas x {sweeps} sweep(s) of SK N={N_SPINS} at T={TEMPERATURE} ({dt:.1f} s)"
 
 
+def workload_name(replicas, sweeps):
+    return (f"SK dense N={N_SPINS} Gaussian J (cfg3), Metropolis sweep, T={TEMPERATURE}, "
+            f"{replicas} replicas/GPU x {sweeps} sweeps per step, shared random site order")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -128,8 +133,10 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"SK dense N={N_SPINS} Gaussian J (cfg3), Metropolis sweep, T={TEMPERATURE}",
-                   "replicas_per_gpu": REPLICAS_PER_GPU, "note": "bounded CPU sample of the same workload"},
+        "config": {"workload": workload_name(args.replicas, args.sweeps),
+                   "replicas_per_gpu": args.replicas, "sweeps_per_step": args.sweeps,
+                   "note": "the reference's algorithm (CPU port, all host threads) on a bounded sample "
+                           "of the same workload: replicas x 1 sweep per step, see cpu_baseline.sample"},
         "cpu_baseline": {"value": value, "unit": "attempts/s", "cores": threads, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "attempts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -358,8 +365,7 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"SK dense N={N_SPINS} Gaussian J (cfg3), Metropolis sweep, T={TEMPERATURE}, "
-                                   f"{R} replicas/GPU x {sweeps} sweeps per step, shared random site order",
+            "config": {"workload": workload_name(R, sweeps),
                        "kernel": "tensor-core (tcgen05, TMEM-resident fields)" if use_tc else "simt",
                        "coupling_planes": planes if use_tc else None,
                        "replicas_per_gpu": R, "sweeps_per_step": sweeps, "replicas_per_block": gmax,
