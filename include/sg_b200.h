@@ -113,6 +113,17 @@ int sg_lattice_sequence_index(int L, int x, int y);
 int sg_set_model_groups(sg_engine *e, int n, int n_groups, const int32_t *group_of,
                         const float *coupling, const float *h, void *stream);
 
+/* Several small dense models in one engine (n <= 224 each, same n): J is [n_models][n][n]
+ * float32 contiguous, h is [n_models][n].  The replicas allocated afterwards are model-major
+ * (n_replicas / n_models each; replica r anneals model r / (n_replicas / n_models)), every
+ * launch covers all models at once on the small-model kernel (sg_sweep_small.cu).  This is what
+ * BatchProcessor.process_models_batch (annealing/batch_processor.py:231-288, 423-454: one
+ * GPUAnnealer.anneal per model on a 4-thread pool) and the RL environment's many short anneals
+ * (rl_integration/environment.py:318-336) become.  sg_batch_energies then takes a model-major
+ * batch (a multiple of n_models configurations). */
+int sg_set_model_dense_batch(sg_engine *e, int n_models, int n, const float *J, const float *h,
+                             int on_device, void *stream);
+
 /* Allocate R replicas (spins, local fields, energies, best-so-far, counters). */
 int sg_alloc_replicas(sg_engine *e, int n_replicas, void *stream);
 

@@ -49,6 +49,7 @@ PROTOTYPES = {
     "sg_create": (c_int, [c_int, POINTER(c_void_p)]),
     "sg_destroy": (None, [c_void_p]),
     "sg_set_model_dense": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
+    "sg_set_model_dense_batch": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "sg_set_model_csr": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p]),
     "sg_set_model_lattice2d": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),

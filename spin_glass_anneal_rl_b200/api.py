@@ -121,7 +121,8 @@ class BatchProcessor:
 def install_as_spin_glass_rl(force: bool = False) -> None:
     """Alias this package's modules to the reference's import paths for the hot path."""
     from . import annealing, core
-    from .annealing import cuda_kernels, gpu_annealer, parallel_tempering, result, temperature_scheduler
+    from .annealing import (batch_processor, cuda_kernels, gpu_annealer, parallel_tempering, result,
+                            temperature_scheduler)
     from .core import ising_model, spin_dynamics
     from .utils import exceptions
     if "spin_glass_rl" in sys.modules and not force:
@@ -137,6 +138,7 @@ def install_as_spin_glass_rl(force: bool = False) -> None:
         "spin_glass_rl.core.spin_dynamics": spin_dynamics,
         "spin_glass_rl.annealing.gpu_annealer": gpu_annealer,
         "spin_glass_rl.annealing.cuda_kernels": cuda_kernels,
+        "spin_glass_rl.annealing.batch_processor": batch_processor,
         "spin_glass_rl.annealing.parallel_tempering": parallel_tempering,
         "spin_glass_rl.annealing.temperature_scheduler": temperature_scheduler,
         "spin_glass_rl.annealing.result": result,

@@ -59,6 +59,10 @@ struct sg_engine {
     int device = 0;
     int sm_count = 0;
     int n = 0, n_pad = 0, R = 0;
+    int n_models = 1;     // stacked small dense models (sg_set_model_dense_batch), K1-SMALL only
+    bool stacked = false;
+    void* stage = nullptr;   // device staging for host-side model stacks and batch evaluations
+    size_t stage_cap = 0;
     float* Jt = nullptr;  // [n][n_pad]
     float* h = nullptr;   // [n_pad]
     void* Jp = nullptr;   // bf16 planes [3][n][n_tc] of Jt for the tensor-core sweep (n <= 4096)
@@ -485,6 +489,8 @@ extern "C" int sg_set_model_csr(sg_engine* e, int n, int64_t nnz, const int64_t*
     e->n_pad = n;
     e->n_tc = 0;
     e->csr = true;
+    e->n_models = 1;
+    e->stacked = false;
     e->fields_valid = false;
     return SG_OK;
 }
@@ -721,6 +727,8 @@ extern "C" int sg_set_model_lattice2d(sg_engine* e, int L, const int8_t* Jx, con
     e->l_L = L;
     e->l_bonds = n_bonds;
     e->lat = true;
+    e->n_models = 1;
+    e->stacked = false;
     e->fields_valid = false;
     return SG_OK;
 }
@@ -807,6 +815,8 @@ extern "C" int sg_set_model_groups(sg_engine* e, int n, int n_groups, const int3
     e->n_pad = n;
     e->n_tc = 0;
     e->g_n = n_groups;
+    e->n_models = 1;
+    e->stacked = false;
     e->lat = true;
     e->grp = true;
     e->fields_valid = false;
@@ -856,6 +866,7 @@ void sg_destroy(sg_engine* e) {
     cudaFree(e->Jp);
     cudaFree(e->tc_sites);
     cudaFree(e->tc_stream);
+    cudaFree(e->stage);
     cudaFree(e->dig);
     cudaFree(e->scale);
     cudaFree(e->info);
@@ -882,6 +893,12 @@ int sg_set_model_dense(sg_engine* e, int n, const float* J, int64_t ldJ, const f
     }
     free_csr_model(e);
     free_lat_model(e);
+    if (e->stacked) {
+        free_replicas(e);
+        free_ladder(e);
+    }
+    e->n_models = 1;
+    e->stacked = false;
     e->n = n;
     e->n_pad = n_pad;
     int rc;
@@ -932,17 +949,84 @@ int sg_set_model_dense(sg_engine* e, int n, const float* J, int64_t ldJ, const f
     return SG_OK;
 }
 
+int sg_set_model_dense_batch(sg_engine* e, int n_models, int n, const float* J, const float* h,
+                             int on_device, void* stream) {
+    SG_REQUIRE(e && J && h, "sg_set_model_dense_batch: NULL argument");
+    SG_REQUIRE(n_models >= 1 && n >= 2, "sg_set_model_dense_batch: need n_models >= 1 and n >= 2");
+    if (!sg::sweep_small_supported(n))
+        return fail(SG_ERR_UNSUPPORTED, "sg_set_model_dense_batch: stacked models need n <= 224");
+    int n_pad = sg::kColQuantum;
+    while (n_pad < n) n_pad += sg::kColQuantum;
+    DeviceGuard g(e->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t M = (size_t)n_models;
+    int rc;
+    // a stack of the same shape as the current one (the RL loop: new couplings, same sizes)
+    // reuses every buffer, replicas included; cudaMalloc / cudaFree cost milliseconds each
+    const bool same = e->stacked && e->n_models == n_models && e->n == n && e->Jt && e->h && !e->csr && !e->lat;
+    if (!same) {
+        free_replicas(e);
+        free_csr_replicas(e);
+        free_lat_replicas(e);
+        free_ladder(e);
+        free_csr_model(e);
+        free_lat_model(e);
+        cudaFree(e->dig); e->dig = nullptr;
+        cudaFree(e->Jp); e->Jp = nullptr;
+        e->n = n;
+        e->n_pad = n_pad;
+        e->n_tc = 0;
+        e->n_models = n_models;
+        e->stacked = true;
+        if ((rc = dev_alloc(&e->Jt, M * n * n_pad)) != SG_OK) return rc;
+        if ((rc = dev_alloc(&e->h, M * n_pad)) != SG_OK) return rc;
+    }
+    const float *Jdev = J, *hdev = h;
+    if (!on_device) {
+        const size_t need = (M * n * n + M * n) * sizeof(float);
+        if (need > e->stage_cap) {
+            SG_CUDA(cudaStreamSynchronize(st));
+            cudaFree(e->stage); e->stage = nullptr; e->stage_cap = 0;
+            cudaError_t ce = cudaMalloc(&e->stage, need);
+            if (ce != cudaSuccess) return fail(SG_ERR_NOMEM, "cudaMalloc(model staging)", ce);
+            e->stage_cap = need;
+        }
+        float* tmp = static_cast<float*>(e->stage);
+        SG_CUDA(cudaMemcpyAsync(tmp, J, M * n * n * sizeof(float), cudaMemcpyHostToDevice, st));
+        SG_CUDA(cudaMemcpyAsync(tmp + M * n * n, h, M * n * sizeof(float), cudaMemcpyHostToDevice, st));
+        Jdev = tmp;
+        hdev = tmp + M * n * n;
+    }
+    SG_CUDA(sg::launch_stack_models(Jdev, hdev, n_models, n, n_pad, e->Jt, e->h, st));
+    e->launches += 1;
+    if (!on_device) SG_CUDA(cudaStreamSynchronize(st));   // the host arrays may be reused by the caller
+    e->fields_valid = false;
+    return SG_OK;
+}
+
 int sg_alloc_replicas(sg_engine* e, int n_replicas, void* stream) {
     SG_REQUIRE(e && e->n > 0, "sg_alloc_replicas: set the model first");
     SG_REQUIRE(n_replicas >= 1, "sg_alloc_replicas: need n_replicas >= 1");
+    SG_REQUIRE(!e->stacked || e->csr || e->lat || n_replicas % e->n_models == 0,
+               "sg_alloc_replicas: stacked models need the same number of replicas each");
     DeviceGuard g(e->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (e->csr) return csr_alloc_replicas(e, n_replicas, st);
     if (e->lat) return lat_alloc_replicas(e, n_replicas, st);
-    free_replicas(e);
-    free_ladder(e);
     const size_t R = (size_t)n_replicas, np = (size_t)e->n_pad;
     int rc;
+    if (e->R == n_replicas && e->spins && e->fields && e->accepted) {
+        // same shape as before (repeated anneals of same-sized models): keep the buffers
+        free_ladder(e);
+        SG_CUDA(cudaMemsetAsync(e->fields, 0, R * np * sizeof(float), st));
+        SG_CUDA(cudaMemsetAsync(e->spins, 1, R * np, st));
+        SG_CUDA(cudaMemsetAsync(e->best_spins, 1, R * np, st));
+        SG_CUDA(cudaMemsetAsync(e->accepted, 0, R * sizeof(unsigned long long), st));
+        e->fields_valid = false;
+        return SG_OK;
+    }
+    free_replicas(e);
+    free_ladder(e);
     if ((rc = dev_alloc(&e->spins, R * np)) != SG_OK) return rc;
     if ((rc = dev_alloc(&e->fields, R * np)) != SG_OK) return rc;
     if ((rc = dev_alloc(&e->energy, R)) != SG_OK) return rc;
@@ -1033,6 +1117,12 @@ int sg_reset_best(sg_engine* e, void* stream) {
 static int compute_fields(sg_engine* e, cudaStream_t st) {
     if (e->csr) return csr_compute_fields(e, st);
     if (e->lat) return lat_compute_energy(e, st);
+    if (e->stacked) {
+        SG_CUDA(sg::launch_fields_small(e->Jt, e->h, e->spins, e->fields, e->energy, e->n, e->n_pad,
+                                        e->R, e->R / e->n_models, st));
+        e->launches += 1;
+        return SG_OK;
+    }
     if (e->dig && !getenv("SG_K2_SIMT")) {
         const size_t need = sg::fields_tc_spin_tiles_bytes(e->n, e->R);
         if (need > e->spin_tiles_cap) {
@@ -1214,6 +1304,7 @@ int sg_sweep(sg_engine* e, const sg_sweep_params* p, void* stream) {
     a.track_best = p->track_best ? 1 : 0;
     a.dbg = e->dbg;
     a.site_de = p->site_energy_changes;
+    a.rpm = (e->stacked && !e->csr && !e->lat) ? e->R / e->n_models : 0;
     SG_REQUIRE(!a.site_de || (!e->csr && !e->lat && p->kernel != SG_KERNEL_TC &&
                               (p->kernel == SG_KERNEL_SIMT || p->kernel == SG_KERNEL_SMALL ||
                                p->rng_mode == SG_RNG_INJECTED || sg::sweep_small_supported(e->n))),
@@ -1226,6 +1317,10 @@ int sg_sweep(sg_engine* e, const sg_sweep_params* p, void* stream) {
                               !(p->site_mode == SG_SITES_EXPLICIT && p->sites_block_stride != 0) &&
                               p->replicas_per_block == 0;
     const bool small_ok = e->Jt && sg::sweep_small_supported(e->n) && shared_order;
+    if (e->stacked)
+        SG_REQUIRE(small_ok && (p->kernel == SG_KERNEL_AUTO || p->kernel == SG_KERNEL_SMALL),
+                   "sg_sweep: stacked models run on the small-model kernel (one site order for the "
+                   "grid, replicas_per_block = 0)");
     if (p->kernel == SG_KERNEL_SMALL)
         SG_REQUIRE(small_ok, "sg_sweep: the small-model kernel needs a dense model with n <= 224, one "
                              "site order for the grid and replicas_per_block = 0");
@@ -1411,6 +1506,47 @@ int sg_batch_energies(sg_engine* e, int batch, const int8_t* spins, float* energ
     if (e->csr) return csr_batch_energies(e, batch, spins, energies, fields, on_device, st);
     if (e->lat) return lat_batch_energies(e, batch, spins, energies, fields, on_device, st);
     const size_t B = (size_t)batch, n = (size_t)e->n, np = (size_t)e->n_pad;
+    if (e->stacked) {
+        // stacked models: configuration b belongs to model b / (batch / n_models)
+        SG_REQUIRE(batch % e->n_models == 0, "sg_batch_energies: stacked models need a multiple of "
+                                             "n_models configurations (model-major)");
+        auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+        const size_t o_sp = 0, o_fp = o_sp + up16(B * np), o_ed = o_fp + up16(B * np * 4),
+                     o_in = o_ed + up16(B * 4), o_fo = o_in + up16(B * n), need = o_fo + up16(B * n * 4);
+        if (need > e->stage_cap) {
+            SG_CUDA(cudaStreamSynchronize(st));
+            cudaFree(e->stage); e->stage = nullptr; e->stage_cap = 0;
+            cudaError_t ce0 = cudaMalloc(&e->stage, need);
+            if (ce0 != cudaSuccess) return fail(SG_ERR_NOMEM, "cudaMalloc(batch staging)", ce0);
+            e->stage_cap = need;
+        }
+        unsigned char* base = static_cast<unsigned char*>(e->stage);
+        int8_t* sp = reinterpret_cast<int8_t*>(base + o_sp);
+        float* fp = reinterpret_cast<float*>(base + o_fp);
+        float* ed = reinterpret_cast<float*>(base + o_ed);
+        int8_t* sin = reinterpret_cast<int8_t*>(base + o_in);
+        float* fo = reinterpret_cast<float*>(base + o_fo);
+        const int8_t* src = spins;
+        if (!on_device) {
+            SG_CUDA(cudaMemcpyAsync(sin, spins, B * n, cudaMemcpyHostToDevice, st));
+            src = sin;
+        }
+        SG_CUDA(sg::launch_pad_spins(src, e->n, sp, e->n_pad, batch, st));
+        SG_CUDA(sg::launch_fields_small(e->Jt, e->h, sp, fp, ed, e->n, e->n_pad, batch,
+                                        batch / e->n_models, st));
+        e->launches += 2;
+        if (energies)
+            SG_CUDA(cudaMemcpyAsync(energies, ed, B * sizeof(float),
+                                    on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        if (fields) {
+            float* dstf = on_device ? fields : fo;
+            SG_CUDA(sg::launch_unpad_f32(fp, e->n_pad, dstf, e->n, batch, st));
+            if (!on_device)
+                SG_CUDA(cudaMemcpyAsync(fields, fo, B * n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        }
+        if (!on_device) SG_CUDA(cudaStreamSynchronize(st));
+        return SG_OK;
+    }
     int8_t *s_in = nullptr, *s_pad = nullptr;
     unsigned char* tiles = nullptr;
     float *f_pad = nullptr, *e_dev = nullptr, *f_out = nullptr;

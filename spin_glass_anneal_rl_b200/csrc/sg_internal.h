@@ -31,6 +31,7 @@ struct SweepDev {
     int n, n_pad, R, G, n_sweeps, rule, site_mode, track_best, D;
     long long* dbg;           // optional timeline buffer (development aid), block 0 only
     float* site_de;           // optional [R][n]: sum of the accepted energy changes per site
+    int rpm;                  // stacked models (K1-SMALL): replicas per model, 0 = one model
 };
 
 // Largest number of replicas one block can hold for this padded size (0 = unsupported).
@@ -44,6 +45,12 @@ cudaError_t launch_sweep(SweepDev a, bool inject, int grid, cudaStream_t st);
 // sites: int32 table [n_sweeps][n] from launch_sites_table.
 bool sweep_small_supported(int n);
 cudaError_t launch_sweep_small(const SweepDev& a, bool inject, const int* sites, cudaStream_t st);
+// J [M][n][n], h [M][n] (device) -> padded column-major stacks Jt [M][n][n_pad], h_pad [M][n_pad]
+cudaError_t launch_stack_models(const float* J, const float* h, int M, int n, int n_pad, float* Jt,
+                                float* h_pad, cudaStream_t st);
+// fields / energies of B configurations of stacked models (configuration b uses model b / rpm)
+cudaError_t launch_fields_small(const float* Jt, const float* h, const int8_t* spins, float* fields,
+                                float* energy, int n, int n_pad, int B, int rpm, cudaStream_t st);
 
 // K2 + helpers (sg_fields.cu)
 cudaError_t launch_pad_transpose(const float* J, int64_t ldJ, int n, float* Jt, int n_pad,

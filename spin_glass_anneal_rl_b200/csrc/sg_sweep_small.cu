@@ -29,13 +29,21 @@ sweep_small_kernel(const SweepDev a, const int* __restrict__ sites_g) {
     constexpr int ROW = NR * 32;
     const int n = a.n, n_pad = a.n_pad;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // several models in one launch (a.rpm replicas each, couplings and fields stacked): a CTA
+    // serves 8 replicas of ONE model
+    const int rpm = a.rpm > 0 ? a.rpm : a.R;
+    const int cpm = (rpm + kSmallWarps - 1) / kSmallWarps;
+    const int model = blockIdx.x / cpm;
+    const int rim = (blockIdx.x - model * cpm) * kSmallWarps + warp;
+    const float* Jm = a.Jt + (size_t)model * n * n_pad;
+    const float* hm = a.h + (size_t)model * n_pad;
     for (int idx = tid; idx < n * ROW; idx += kSmallWarps * 32) {
         const int i = idx / ROW, c = idx - i * ROW;
-        Js[idx] = (c < n) ? a.Jt[(size_t)i * n_pad + c] : 0.0f;
+        Js[idx] = (c < n) ? Jm[(size_t)i * n_pad + c] : 0.0f;
     }
     __syncthreads();
-    const int rep = blockIdx.x * kSmallWarps + warp;
-    if (rep >= a.R) return;
+    if (rim >= rpm) return;
+    const int rep = model * rpm + rim;
 
     // this replica's state: column c = k * 32 + lane lives in f[k] / bit k of sb
     float f[NR], hv[NR];
@@ -44,7 +52,7 @@ sweep_small_kernel(const SweepDev a, const int* __restrict__ sites_g) {
     for (int k = 0; k < NR; ++k) {
         const int c = k * 32 + lane;
         f[k] = (c < n) ? a.fields[(size_t)rep * n_pad + c] : 0.0f;
-        hv[k] = (c < n) ? a.h[c] : 0.0f;
+        hv[k] = (c < n) ? hm[c] : 0.0f;
         if (c < n && a.spins[(size_t)rep * n_pad + c] >= 0) sb |= 1u << k;
     }
     float cur_e = a.energy[rep];
@@ -165,10 +173,53 @@ sweep_small_kernel(const SweepDev a, const int* __restrict__ sites_g) {
     }
 }
 
+// F = S J^T + h and E = -1/2 sum s (F + h) for stacked models, one warp per configuration
+// (fp32, one FMA per coupling in column order: exact for integer couplings)
+__global__ void __launch_bounds__(kSmallWarps * 32)
+fields_small_kernel(const float* __restrict__ Jt, const float* __restrict__ h,
+                    const int8_t* __restrict__ spins, float* __restrict__ fields,
+                    float* __restrict__ energy, int n, int n_pad, int B, int rpm) {
+    const int lane = threadIdx.x & 31;
+    const int rep = blockIdx.x * kSmallWarps + (threadIdx.x >> 5);
+    if (rep >= B) return;
+    const int model = rep / rpm;
+    const float* Jm = Jt + (size_t)model * n * n_pad;
+    const float* hm = h + (size_t)model * n_pad;
+    const int8_t* sp = spins + (size_t)rep * n_pad;
+    float part = 0.0f;
+    for (int c = lane; c < n; c += 32) {
+        float acc = 0.0f;
+        for (int j = 0; j < n; ++j) acc = fmaf(Jm[(size_t)j * n_pad + c], (float)sp[j], acc);
+        const float f = acc + hm[c];
+        if (fields) fields[(size_t)rep * n_pad + c] = f;
+        const float t = f + hm[c];
+        part += (sp[c] >= 0) ? t : -t;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
+    if (lane == 0 && energy) energy[rep] = -0.5f * part;
+}
+
+// stacked models: Jt[m][i][c] = J[m][c][i] (c < n, else 0), h_pad[m][c] = h[m][c] (else 0)
+__global__ void __launch_bounds__(256)
+stack_models_kernel(const float* __restrict__ J, const float* __restrict__ h, int M, int n, int n_pad,
+                    float* __restrict__ Jt, float* __restrict__ h_pad) {
+    const size_t total = (size_t)M * n * n_pad;
+    for (size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (size_t)gridDim.x * 256) {
+        const int c = (int)(idx % n_pad);
+        const size_t mi = idx / n_pad;
+        const int i = (int)(mi % n);
+        const size_t m = mi / n;
+        Jt[idx] = (c < n) ? J[(m * n + c) * n + i] : 0.0f;
+        if (i == 0) h_pad[m * n_pad + c] = (c < n) ? h[m * n + c] : 0.0f;
+    }
+}
+
 template <int NR>
 cudaError_t launch_nr(const SweepDev& a, bool inject, const int* sites, cudaStream_t st) {
     const size_t smem = (size_t)a.n * NR * 32 * sizeof(float);
-    const int grid = (a.R + kSmallWarps - 1) / kSmallWarps;
+    const int rpm = a.rpm > 0 ? a.rpm : a.R;
+    const int grid = (a.R / rpm) * ((rpm + kSmallWarps - 1) / kSmallWarps);
     cudaError_t e;
     if (inject) {
         e = cudaFuncSetAttribute(sweep_small_kernel<NR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -185,6 +236,21 @@ cudaError_t launch_nr(const SweepDev& a, bool inject, const int* sites, cudaStre
 }  // namespace
 
 bool sweep_small_supported(int n) { return n >= 1 && n <= 224; }
+
+cudaError_t launch_stack_models(const float* J, const float* h, int M, int n, int n_pad, float* Jt,
+                                float* h_pad, cudaStream_t st) {
+    const size_t total = (size_t)M * n * n_pad;
+    int grid = (int)((total + 255) / 256 < 4736 ? (total + 255) / 256 : 4736);
+    stack_models_kernel<<<grid, 256, 0, st>>>(J, h, M, n, n_pad, Jt, h_pad);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fields_small(const float* Jt, const float* h, const int8_t* spins, float* fields,
+                                float* energy, int n, int n_pad, int B, int rpm, cudaStream_t st) {
+    fields_small_kernel<<<(B + kSmallWarps - 1) / kSmallWarps, kSmallWarps * 32, 0, st>>>(
+        Jt, h, spins, fields, energy, n, n_pad, B, rpm);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_sweep_small(const SweepDev& a, bool inject, const int* sites, cudaStream_t st) {
     if (!sweep_small_supported(a.n)) return cudaErrorInvalidValue;

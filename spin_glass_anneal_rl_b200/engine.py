@@ -87,9 +87,34 @@ class Engine:
             check(self._lib.sg_set_model_dense(self._h, n, Jh.ctypes.data_as(ctypes.c_void_p), n,
                                                hh.ctypes.data_as(ctypes.c_void_p), 0, self.stream),
                   "sg_set_model_dense")
-        if n != self.n or getattr(self, "_csr", False):
+        if n != self.n or getattr(self, "_csr", False) or getattr(self, "_stacked", False):
             self.n_replicas = 0
         self._csr = False
+        self._stacked = False
+        self.n_models = 1
+        self.n = n
+
+    def set_models(self, J: ArrayLike, h: ArrayLike) -> None:
+        """Several small dense models at once: J [M, n, n], h [M, n] (n <= 224).  Replicas are
+        model-major afterwards (``alloc_replicas(M * r)``: replica k anneals model k // r) and
+        every launch covers all models."""
+        M, n = int(J.shape[0]), int(J.shape[1])
+        assert tuple(J.shape) == (M, n, n) and tuple(h.shape) == (M, n)
+        if isinstance(J, torch.Tensor) and J.is_cuda:
+            Jd, hd = self._dev(J, torch.float32), self._dev(h, torch.float32)
+            check(self._lib.sg_set_model_dense_batch(self._h, M, n, self._ptr(Jd), self._ptr(hd), 1,
+                                                     self.stream), "sg_set_model_dense_batch")
+            self._keep += [Jd, hd]
+        else:
+            Jh, hh = _as_host(J, np.float32), _as_host(h, np.float32)
+            check(self._lib.sg_set_model_dense_batch(self._h, M, n, Jh.ctypes.data_as(ctypes.c_void_p),
+                                                     hh.ctypes.data_as(ctypes.c_void_p), 0, self.stream),
+                  "sg_set_model_dense_batch")
+        if not (getattr(self, "n_models", 1) == M and self.n == n and getattr(self, "_stacked", False)):
+            self.n_replicas = 0            # same-shaped stacks keep their replica buffers
+        self._csr = False
+        self._stacked = True
+        self.n_models = M
         self.n = n
 
     def set_model_csr(self, rowptr: ArrayLike, colidx: ArrayLike, val: ArrayLike, h: ArrayLike) -> None:
@@ -106,6 +131,8 @@ class Engine:
         self.n = n
         self.n_replicas = 0
         self._csr = True
+        self._stacked = False
+        self.n_models = 1
 
     def set_model_lattice2d(self, Jx: ArrayLike, Jy: ArrayLike) -> None:
         """2D +-J lattice: Jx[x, y] couples (x, y)-(x+1, y), Jy[x, y] couples (x, y)-(x, y+1);
@@ -119,6 +146,8 @@ class Engine:
         self.n = L * L
         self.n_replicas = 0
         self._csr = True   # not the dense layout
+        self._stacked = False
+        self.n_models = 1
 
     def set_model_groups(self, group_of: ArrayLike, coupling: ArrayLike, h: ArrayLike) -> None:
         """Block-clique couplings: J_ij = coupling[g] for i != j in the same group g."""
@@ -131,6 +160,8 @@ class Engine:
         self.n = int(hh.shape[0])
         self.n_replicas = 0
         self._csr = True   # not the dense layout
+        self._stacked = False
+        self.n_models = 1
 
     def alloc_replicas(self, n_replicas: int) -> None:
         check(self._lib.sg_alloc_replicas(self._h, int(n_replicas), self.stream),
