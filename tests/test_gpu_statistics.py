@@ -73,7 +73,7 @@ def _z(a, b):
     return abs(a.mean() - b.mean()) / np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b))
 
 
-@pytest.mark.parametrize("kernel", ["simt", "tc"])
+@pytest.mark.parametrize("kernel", ["simt", "tc", "small"])
 def test_annealing_statistics_match_the_reference_algorithm(engine, oracle, kernel):
     J, h = cfg1_instance()
     temps = geometric_temps(160)
@@ -96,7 +96,7 @@ def test_annealing_statistics_match_the_reference_algorithm(engine, oracle, kern
     assert abs(pg - pc) < Z * se + 0.02, (pg, pc)
 
 
-@pytest.mark.parametrize("kernel", ["simt", "tc"])
+@pytest.mark.parametrize("kernel", ["simt", "tc", "small"])
 @pytest.mark.parametrize("T", [0.5, 1.0, 2.0, 4.0])
 def test_acceptance_rate_curve(engine, oracle, kernel, T):
     """Equilibrium acceptance rate at fixed T within 1 % absolute."""
