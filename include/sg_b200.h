@@ -218,6 +218,20 @@ typedef struct {
  * (annealing/cuda_kernels.py:326-369).  Temperatures move, configurations stay. */
 int sg_exchange(sg_engine *e, const sg_exchange_params *p, void *stream);
 
+/* One step of the ADAPTIVE temperature schedule on the device (AdaptiveSchedule.update,
+ * annealing/temperature_scheduler.py:206-249; GPUAnnealer feeds it the cumulative acceptance rate
+ * of its replica, annealing/gpu_annealer.py:140-147): reads replica `replica`'s acceptance
+ * counter, appends rate = (accepted - accepted_base) / (sweep * n) to the ring in `state`
+ * (device, window + 1 doubles, zero-initialised by the caller), and writes the temperature of
+ * sweep `sweep` to temps_out[sweep]: base_temps[sweep] (device, the geometric base schedule),
+ * times (1 - adaptation_rate) / (1 + adaptation_rate) once `window` rates have been seen and
+ * their mean is above / below target_acceptance, never below final_temp.  Asynchronous on
+ * `stream`: launch it between two sg_sweep calls that take temps_out + sweep as their
+ * temperature, and the schedule needs no device -> host read per sweep. */
+int sg_adaptive_temperature(sg_engine *e, int replica, uint64_t accepted_base, int sweep, int window,
+                            double target_acceptance, double adaptation_rate, double final_temp,
+                            const double *base_temps, double *state, double *temps_out, void *stream);
+
 /* The exchange in the shape of the reference's operator,
  * CUDAKernelManager.parallel_tempering_exchange_optimized(spins_arrays, energies, temperatures)
  * (annealing/cuda_kernels.py:326-369; the loop that runs upstream is

@@ -55,6 +55,8 @@ PROTOTYPES = {
     "sg_set_model_lattice2d": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "sg_lattice_sequence_index": (c_int, [c_int, c_int, c_int]),
     "sg_set_model_groups": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sg_adaptive_temperature": (c_int, [c_void_p, c_int, c_uint64, c_int, c_int, c_double, c_double, c_double,
+                                        c_void_p, c_void_p, c_void_p, c_void_p]),
     "sg_exchange_chain": (c_int, [c_int, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p,
                                   c_uint64, c_uint64, POINTER(c_int32), c_void_p]),
     "sg_alloc_replicas": (c_int, [c_void_p, c_int, c_void_p]),

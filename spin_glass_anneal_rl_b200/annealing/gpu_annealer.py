@@ -20,6 +20,7 @@ sweeps between two record points fused into one launch.
 """
 from __future__ import annotations
 
+import os
 import time
 from dataclasses import dataclass
 from typing import Dict, List, Optional
@@ -125,6 +126,40 @@ class GPUAnnealer:
         sweep = 0
         done = 0  # sweeps executed
         stopped = False
+        if temps_all is None and not os.environ.get("SG_ADAPTIVE_HOST"):
+            # ADAPTIVE on the device: the geometric base schedule is precomputed, the feedback
+            # step (running acceptance rate of replica 0 -> temperature of the next sweep) is a
+            # one-thread kernel between two sweep launches, so the host only synchronises at the
+            # record points, like for every other schedule
+            sc = schedule.config
+            base = torch.tensor([float(schedule.base_schedule.get_temperature(s)) for s in range(cfg.n_sweeps)],
+                                dtype=torch.float64, device=eng.device)
+            temps_dev = torch.zeros(cfg.n_sweeps, dtype=torch.float64, device=eng.device)
+            state = torch.zeros(int(sc.adaptation_window) + 1, dtype=torch.float64, device=eng.device)
+            while done < cfg.n_sweeps and not stopped:
+                eng.adaptive_temperature(done, base, state, temps_dev, accepted_base=int(acc_base),
+                                         window=int(sc.adaptation_window),
+                                         target_acceptance=float(sc.target_acceptance),
+                                         adaptation_rate=float(sc.adaptation_rate),
+                                         final_temp=float(sc.final_temp))
+                trace = eng.sweep(1, temps_dev[done:done + 1], temps_sweep_stride=1, rule=rule,
+                                  site_order=site_order_for(eng, cfg.site_order), seed=philox_seed,
+                                  sweep_base=done, energy_trace=True, track_best=True,
+                                  replicas_per_block=cfg.replicas_per_block)
+                eng.refresh_fields()
+                sweep = done
+                done += 1
+                if sweep % interval == 0:
+                    cur_e = float(trace[-1, 0].item())
+                    acc = eng.accepted()[0].item() - acc_base
+                    energy_history.append(cur_e)
+                    temperature_history.append(float(temps_dev[sweep].item()))
+                    acceptance_rate_history.append(acc / (done * n))
+                    if self._check_convergence(energy_history):
+                        print(f"Converged at sweep {sweep}")
+                        stopped = True
+            schedule.temperature_history.extend(temps_dev[:done].cpu().tolist())
+            schedule.current_temp = schedule.temperature_history[-1]
         while done < cfg.n_sweeps and not stopped:
             # run up to and including the next record sweep (sweep % interval == 0)
             if temps_all is not None:

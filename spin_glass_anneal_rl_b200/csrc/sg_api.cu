@@ -1453,6 +1453,21 @@ int sg_exchange(sg_engine* e, const sg_exchange_params* p, void* stream) {
     return SG_OK;
 }
 
+int sg_adaptive_temperature(sg_engine* e, int replica, uint64_t accepted_base, int sweep, int window,
+                            double target_acceptance, double adaptation_rate, double final_temp,
+                            const double* base_temps, double* state, double* temps_out, void* stream) {
+    SG_REQUIRE(e && base_temps && state && temps_out, "sg_adaptive_temperature: NULL argument");
+    SG_REQUIRE(e->R > 0 && replica >= 0 && replica < e->R && e->accepted,
+               "sg_adaptive_temperature: allocate replicas first");
+    SG_REQUIRE(sweep >= 0 && window >= 1, "sg_adaptive_temperature: bad sweep / window");
+    DeviceGuard g(e->device);
+    SG_CUDA(sg::launch_adaptive_temperature(e->accepted + replica, accepted_base, e->n, sweep, window,
+                                            target_acceptance, adaptation_rate, final_temp, base_temps,
+                                            state, temps_out, static_cast<cudaStream_t>(stream)));
+    e->launches++;
+    return SG_OK;
+}
+
 int sg_exchange_chain(int device, void* rows, int64_t row_stride_bytes, int64_t row_bytes,
                       int n_replicas, float* energies, const float* temperatures,
                       const float* uniforms, uint64_t seed, uint64_t round, int32_t* n_accepted,

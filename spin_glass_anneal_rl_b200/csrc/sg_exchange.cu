@@ -130,7 +130,50 @@ __global__ void move_rows_kernel(unsigned char* __restrict__ dst, long long dst_
     }
 }
 
+// ---- ADAPTIVE temperature schedule evaluated on the device (TemperatureScheduler's
+// AdaptiveSchedule.update, reference annealing/temperature_scheduler.py:206-249): geometric base
+// temperature (precomputed by the host), multiplied by (1 -/+ adaptation_rate) once
+// `window` cumulative acceptance rates of the tracked replica have been seen and their mean is
+// above / below the target.  One thread, launched between two sweeps: the host never has to
+// read the acceptance counter back.
+//   state[0 .. window-1] = ring of the last rates, state[window] = number of rates seen
+__global__ void adaptive_temperature_kernel(const unsigned long long* __restrict__ accepted,
+                                            unsigned long long accepted_base, int n, int sweep,
+                                            int window, double target, double rate, double t_final,
+                                            const double* __restrict__ base_temps,
+                                            double* __restrict__ state, double* __restrict__ temps_out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double attempts = (double)sweep * (double)n;
+    const double acc = (double)(accepted[0] - accepted_base);
+    const double r = attempts > 0.0 ? acc / attempts : 0.0;
+    int cnt = (int)state[window];
+    state[cnt % window] = r;
+    ++cnt;
+    state[window] = (double)cnt;
+    const double base = base_temps[sweep];
+    double cur = base;
+    if (cnt >= window) {
+        double sum = 0.0;
+        for (int k = 0; k < window; ++k) sum += state[(cnt + k) % window];   // oldest first
+        const double recent = sum / (double)window;
+        double factor = 1.0;
+        if (recent > target) factor = 1.0 - rate;
+        else if (recent < target) factor = 1.0 + rate;
+        cur = fmax(base * factor, t_final);
+    }
+    temps_out[sweep] = fmax(cur, 1e-10);
+}
+
 }  // namespace
+
+cudaError_t launch_adaptive_temperature(const unsigned long long* accepted, unsigned long long accepted_base,
+                                        int n, int sweep, int window, double target, double rate,
+                                        double t_final, const double* base_temps, double* state,
+                                        double* temps_out, cudaStream_t st) {
+    adaptive_temperature_kernel<<<1, 32, 0, st>>>(accepted, accepted_base, n, sweep, window, target, rate,
+                                                 t_final, base_temps, state, temps_out);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_exchange_chain(void* rows, long long row_stride, long long row_bytes, int R,
                                   float* energies, const float* temps, const float* uniforms,

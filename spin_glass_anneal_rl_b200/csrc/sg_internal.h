@@ -221,6 +221,11 @@ struct ExchangeDev {
     int L, K, parity, inject;
 };
 cudaError_t launch_exchange(ExchangeDev a, cudaStream_t st);
+// ADAPTIVE schedule step on the device (see sg_exchange.cu)
+cudaError_t launch_adaptive_temperature(const unsigned long long* accepted, unsigned long long accepted_base,
+                                        int n, int sweep, int window, double target, double rate,
+                                        double t_final, const double* base_temps, double* state,
+                                        double* temps_out, cudaStream_t st);
 // operator-form exchange (one ordered pass over adjacent pairs, rows swapped in place)
 size_t exchange_chain_header_bytes(int R);
 cudaError_t launch_exchange_chain(void* rows, long long row_stride, long long row_bytes, int R,

@@ -297,6 +297,22 @@ class Engine:
             self.synchronize()
         return trace
 
+    def adaptive_temperature(self, sweep: int, base_temps: torch.Tensor, state: torch.Tensor,
+                             temps_out: torch.Tensor, *, accepted_base: int = 0, replica: int = 0,
+                             window: int = 100, target_acceptance: float = 0.44,
+                             adaptation_rate: float = 0.1, final_temp: float = 0.0) -> None:
+        """One ADAPTIVE-schedule step on the device: temps_out[sweep] from the geometric base
+        temperature and the running acceptance rate of ``replica`` (no host read-back).
+        ``base_temps`` / ``temps_out``: device float64 [n_sweeps]; ``state``: device float64
+        [window + 1], zeroed before the first step."""
+        for t in (base_temps, state, temps_out):
+            if t.device != self.device or t.dtype != torch.float64 or not t.is_contiguous():
+                raise ValueError("adaptive_temperature needs contiguous device float64 tensors")
+        check(self._lib.sg_adaptive_temperature(
+            self._h, int(replica), int(accepted_base), int(sweep), int(window), float(target_acceptance),
+            float(adaptation_rate), float(final_temp), self._ptr(base_temps), self._ptr(state),
+            self._ptr(temps_out), self.stream), "sg_adaptive_temperature")
+
     # ------------------------------------------------------------------ parallel tempering
     def set_ladder(self, ladder_temps: Sequence[float]) -> None:
         arr = (ctypes.c_double * len(ladder_temps))(*[float(t) for t in ladder_temps])

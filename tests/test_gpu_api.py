@@ -114,6 +114,36 @@ def test_every_schedule_type_runs(sched, params):
     assert res.best_energy == int(res.best_energy)  # integer couplings -> exact integer energies
 
 
+@pytest.mark.parametrize("window,target", [(5, 0.3), (12, 0.6), (100, 0.44)])
+def test_adaptive_schedule_on_device_equals_host_evaluation(monkeypatch, window, target):
+    """ADAPTIVE (reference annealing/temperature_scheduler.py:206-249): the feedback step runs as a
+    device kernel between sweeps; the same run with the schedule evaluated on the host after a
+    read-back of the acceptance counter per sweep (SG_ADAPTIVE_HOST=1) must give the same
+    temperatures, energies and best configuration."""
+    g = load_golden("sa_sched_linear_n24")
+    out = []
+    for host in ("1", ""):
+        if host:
+            monkeypatch.setenv("SG_ADAPTIVE_HOST", host)
+        else:
+            monkeypatch.delenv("SG_ADAPTIVE_HOST", raising=False)
+        m = _model(g["J"], g["h"], g["spins0"])
+        cfg = sg.GPUAnnealerConfig(n_sweeps=150, initial_temp=4.0, final_temp=0.2,
+                                   schedule_type=ScheduleType.ADAPTIVE,
+                                   schedule_params={"alpha": 0.97, "adaptation_window": window,
+                                                    "target_acceptance": target, "adaptation_rate": 0.2},
+                                   record_interval=1, random_seed=3, energy_tolerance=0.0)
+        out.append((sg.GPUAnnealer(cfg).anneal(m), m.spins.clone()))
+    (a, sa), (b, sb) = out
+    assert len(a.temperature_history) == len(b.temperature_history) == 151
+    assert np.allclose(a.temperature_history, b.temperature_history, rtol=1e-14, atol=0)
+    assert len(set(np.round(a.temperature_history, 12))) > 20         # the feedback really acts
+    assert a.energy_history == b.energy_history
+    assert a.acceptance_rate_history == b.acceptance_rate_history
+    assert a.best_energy == b.best_energy and torch.equal(a.best_configuration, b.best_configuration)
+    assert torch.equal(sa, sb)
+
+
 @pytest.mark.parametrize("rule", [UpdateRule.GLAUBER, UpdateRule.HEAT_BATH])
 def test_other_update_rules(rule, oracle):
     g = load_golden("sa_glauber_int_n32")
