@@ -350,11 +350,13 @@ def run_ours(args):
                     "frac_of_hbm_peak": achieved / hbm,
                     "kernel": kname, "bytes_per_launch": bytes_per_launch,
                     "ms_per_launch": ms_launch, "launches_timed": n_klaunch,
-                    # what actually bounds the tensor-core kernel: every operand byte is written to
-                    # shared memory by TMA and read from it by tcgen05.mma (128 B/clk/SM)
-                    "smem_traffic_gbs": 2.0 * achieved if use_tc else None,
+                    # what actually bounds the tensor-core kernel: every J byte is written to shared
+                    # memory by TMA and read from it by tcgen05.mma, which also reads the 512-byte
+                    # B operand (the block's decisions) once per 4 KB A tile: 2.125 x the J stream
+                    # through a 128 B/clk/SM port
+                    "smem_traffic_gbs": 2.125 * achieved if use_tc else None,
                     "smem_peak_gbs": q["sm_count"] * 128 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9,
-                    "smem_frac": (2.0 * achieved) / (q["sm_count"] * 128 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9) if use_tc else None,
+                    "smem_frac": (2.125 * achieved) / (q["sm_count"] * 128 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9) if use_tc else None,
                     "gather_ms_per_launch": prof["gather_ms"] / max(1, int(prof["gather_launches"]))}
         cpu = None
         if world == 1 or True:

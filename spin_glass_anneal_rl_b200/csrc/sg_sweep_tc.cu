@@ -1195,6 +1195,48 @@ tc_mma_bench_kernel(int variant_in, int n_dim, int iters, long long* out) {
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tbase = tptr;
+    if (commit_every == 15) {
+        // probe: how long does a tcgen05.ld of an untouched TMEM column take while `iters` x 32
+        // MMAs (to other columns) are queued?  warp 1 issues the MMAs, sets a flag after the
+        // first 32, warp 0 then issues one tcgen05.ld (+ wait) and times it.
+        __shared__ volatile int go;
+        __shared__ long long t_mma_done;
+        if (tid == 0) go = 0;
+        __syncthreads();
+        if (warp == 1) {
+            const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 150 * 1024);
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(16 >> 3) << 17) | (8u << 24);
+            const uint64_t bdesc = tc::make_smem_desc(b0, 16 * 16, 128);
+            const uint64_t adesc0 = tc::make_smem_desc(a0, 2048, 128);
+            const long long t0 = clock64();
+            for (int it = 0; it < iters; ++it) {
+#pragma unroll
+                for (int t = 0; t < 32; ++t) {
+                    if (tc::elect_one())
+                        tc::mma_bf16_ss(tbase + (t & 15) * 16, adesc0 + (uint64_t)((t * 4608) >> 4), bdesc, idesc, 1u);
+                }
+                if (it == 0 && tid == 32) go = 1;
+            }
+            if (tc::elect_one()) tc::mma_commit(&bar);
+            mbar_wait(&bar, 0);
+            if (tid == 32) t_mma_done = clock64() - t0;
+        } else if (warp == 0) {
+            while (go == 0) {
+            }
+            float v[16];
+            const long long t0 = clock64();
+            tc::tmem_ld16(tbase + 400, v);
+            tc::wait_ld();
+            const long long t1 = clock64();
+            if (tid == 0) out[0] = (t1 - t0) + (v[0] == 12345.0f ? 1 : 0);
+        }
+        __syncthreads();
+        if (tid == 0) out[1] = t_mma_done;
+        tc::fence_before_sync();
+        __syncthreads();
+        if (warp == 0) tc::tmem_dealloc(tbase, 512);
+        return;
+    }
     if (warp == 1) {
         // the whole warp runs the loop (warp-uniform descriptor math); one elected lane issues
         const uint32_t a0 = smem_u32(smem);            // 32 A tiles, 4608 B apart (128 KB + pad)

@@ -18,3 +18,8 @@ for ce, label in ((0, "32 per elect, no commit"), (13, "12 per elect, no commit"
     f(eng._h, ce * 16, 16, 8, out)
     f(eng._h, ce * 16, 16, 8, out)
     print(f"MN nosw N=16, {label}: issue {out[0] / 256:.1f} clk/MMA, complete {out[1] / 256:.1f} clk/MMA")
+for iters in (1, 2, 4, 8, 16):
+    out = (ctypes.c_longlong * 2)()
+    f(eng._h, 15 * 16, 16, iters, out)
+    f(eng._h, 15 * 16, 16, iters, out)
+    print(f"tcgen05.ld of an untouched column while {iters * 32} MMAs are issued: ld+wait {out[0]} clk, all MMAs done after {out[1]} clk")
