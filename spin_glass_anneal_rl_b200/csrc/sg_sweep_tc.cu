@@ -717,42 +717,55 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 // block kg-LAG is not issued before the read is done.  (LAG = 2 in the cluster
                 // variant gives the cross-CTA exchange and the decision a whole block of slack.)
                 float* rawb = raw_s + slot * kBlk * NG;
-#pragma unroll
+                // lane b keeps site b; the loops below stay rolled (this is hot code shared with six
+                // other warps' loops in one instruction cache: unrolled 16 x 2 it made the cluster
+                // variant's working set spill out of it)
+                // lane b (< 16) owns site b of the block and decides, before any waiting, whether
+                // this warp reads it (its column is in this CTA and in this warp's TMEM lane
+                // quarter) and in which column half: two ballots replace a 16-step scan per half
+                // in what is, in the cluster variant, the critical path between two blocks' MMAs
+                const int my_site = (int)stab[i0 + (lane & 15)];
+                const int my_lc = my_site - col0;          // column inside this CTA
+                const bool my_take = lane < nbk && ((C == 1) || (my_lc >= 0 && my_lc < cols_cta)) &&
+                                     ((my_lc >> 5) & 3) == q && !(dbg & 4);
+                const uint32_t take0 = __ballot_sync(0xFFFFFFFFu, my_take && my_lc < half_cols);
+                const uint32_t take1 = __ballot_sync(0xFFFFFFFFu, my_take && my_lc >= half_cols);
+#pragma unroll 1
                 for (int h = 0; h < 2; ++h) {
                     if (kg >= LAG + 1)
                         mbar_wait(&hdone[2 * ((kg - LAG - 1) & (kSlots - 1)) + h],
                                   (uint32_t)((kg - LAG - 1) >> 2) & 1u);
                     tc::fence_after_sync();
                     if (warp == 0) SG_STAMP(2 + h);
+                    uint32_t todo = h ? take1 : take0;
+#pragma unroll 1
+                    while (todo) {
+                        const int b = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const int lc = __shfl_sync(0xFFFFFFFFu, my_lc, b);
+                        float* dl = rawb + b * NG;
 #pragma unroll
-                    for (int b = 0; b < kBlk; ++b) {
-                        const int site = (int)((swq[b >> 1] >> (16 * (b & 1))) & 0xFFFFu);
-                        const int lc = site - col0;          // column inside this CTA
-                        const bool mine = (C == 1) || (lc >= 0 && lc < cols_cta);
-                        const bool in_h = (lc < half_cols) == (h == 0);
-                        if (b < nbk && mine && in_h && ((lc >> 5) & 3) == q && !(dbg & 4)) {
-#pragma unroll
-                            for (int gi = 0; gi < NGRP; ++gi) {
-                                float v[16];
-                                tc::tmem_ld16(tq + (lc >> 7) * NG + gi * 16, v);
-                                tc::wait_ld();
-                                if (lane == (lc & 31)) {
-                                    float* dl = rawb + b * NG + gi * 16;
-                                    float4* d4 = reinterpret_cast<float4*>(dl);
-                                    d4[0] = make_float4(v[0], v[1], v[2], v[3]);
-                                    d4[1] = make_float4(v[4], v[5], v[6], v[7]);
-                                    d4[2] = make_float4(v[8], v[9], v[10], v[11]);
-                                    d4[3] = make_float4(v[12], v[13], v[14], v[15]);
-                                    if (C == 2) {
-                                        // the 64 bytes just written go to the same place in the
-                                        // peer's shared memory (one DSMEM bulk copy, bytes counted
-                                        // on the peer's rall[slot])
-                                        fence_proxy_async();
-                                        bulk_s2peer(map_to_rank(dl, peer), dl, 64u,
-                                                    map_to_rank(&rall[slot], peer));
-                                    }
+                        for (int gi = 0; gi < NGRP; ++gi) {
+                            float v[16];
+                            tc::tmem_ld16(tq + (lc >> 7) * NG + gi * 16, v);
+                            tc::wait_ld();
+                            if (lane == (lc & 31)) {
+                                float4* d4 = reinterpret_cast<float4*>(dl + gi * 16);
+                                d4[0] = make_float4(v[0], v[1], v[2], v[3]);
+                                d4[1] = make_float4(v[4], v[5], v[6], v[7]);
+                                d4[2] = make_float4(v[8], v[9], v[10], v[11]);
+                                d4[3] = make_float4(v[12], v[13], v[14], v[15]);
+                                if (C == 2) {
+                                    // the same 64 bytes straight from the registers into the peer's
+                                    // shared memory (asynchronous remote stores that count their
+                                    // bytes on the peer's rall[slot])
+                                    const uint32_t ra = map_to_rank(dl + gi * 16, peer);
+                                    const uint32_t rb = map_to_rank(&rall[slot], peer);
+                                    st_async_f4(ra, make_float4(v[0], v[1], v[2], v[3]), rb);
+                                    st_async_f4(ra + 16, make_float4(v[4], v[5], v[6], v[7]), rb);
+                                    st_async_f4(ra + 32, make_float4(v[8], v[9], v[10], v[11]), rb);
+                                    st_async_f4(ra + 48, make_float4(v[12], v[13], v[14], v[15]), rb);
                                 }
-
                             }
                         }
                     }
