@@ -474,8 +474,8 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_gpu(int* p, int v) {
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // C = 1: one CTA holds all field columns of 16 replicas.  C = 2: a cluster pair holds 32
@@ -594,8 +594,8 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
         const int g_act = min(NG, a.R - rep0);
         // ---- item prologue: the group's previous chunk is complete, then state HBM -> SM
         SG_ISTAMP(0);
-        if (item.ch > 0 && tid == 0) {
-            while (ld_acquire_gpu(done_g + item.g) < item.ch) __nanosleep(256);
+        if (item.ch > 0 && tid == 0) {   // every CTA of the group's previous chunk has published
+            while (ld_acquire_gpu(done_g + item.g) < C * item.ch) __nanosleep(256);
         }
         named_sync(2);
         SG_ISTAMP(1);
@@ -861,7 +861,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
         SG_ISTAMP(6);
         named_sync(2);   // every store of the item (quarter warps and decision warp) is fenced
         SG_ISTAMP(7);
-        if (tid == 0 && n_chunks > 1) st_release_gpu(done_g + item.g, item.ch + 1);
+        if (tid == 0 && n_chunks > 1) red_release_gpu_add(done_g + item.g, 1);
         }  // items
     } else if (warp == 4) {
         // ======================================================== PRODUCER (TMA)
@@ -1460,6 +1460,29 @@ static cudaError_t launch_tc_variant(const SweepDev& a, const __nv_bfloat16* J, 
                               tabs, s0, s1, spi, done, dbg);
 }
 
+// cluster pairs that can be resident at the same time (the persistent work-item schedule must
+// not launch more: a waiting pair would otherwise hold the SMs a pair it depends on needs)
+static int tc_max_cluster_pairs(size_t smem) {
+    cudaFuncSetAttribute(sweep_tc_kernel<3, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2, 1, 1);
+    cfg.blockDim = dim3(kTcThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int ncl = 0;
+    if (cudaOccupancyMaxActiveClusters(&ncl, sweep_tc_kernel<3, false, 2>, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return ncl;
+}
+
 cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int planes, bool inject,
                             void* sites_buf, void* stream_buf, size_t stream_cap,
                             uint64_t* launches, KernelTimer* timer, cudaStream_t st) {
@@ -1483,9 +1506,9 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
     // the TMEM-read round trips are then on the critical path and cluster speed varies with
     // placement; profiles/r1_notes.md).
     const int T = n_tc / kTileM;
-    int C = 1;
+    int C = (T % (2 * kChunkTiles) == 0 && a.R > kG) ? 2 : 1;
     if (const char* c_env = getenv("SG_TC_CLUSTER")) {
-        if (atoi(c_env) == 2 && T % (2 * kChunkTiles) == 0 && a.R > kG) C = 2;
+        if (atoi(c_env) == 1) C = 1;
     }
     int NS = kMaxStagesTc;
     while (NS > 2 && tc_layout(n_tc, planes, NS, C).total > 227 * 1024) --NS;
@@ -1513,9 +1536,13 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
     int dev = 0, n_sm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    bool sm_env_set = false;
     if (const char* sm_env = getenv("SG_TC_SM")) {   // tests: pretend the GPU has fewer SMs
         const int v = atoi(sm_env);
-        if (v >= 1 && v < n_sm) n_sm = v;
+        if (v >= 1 && v < n_sm) {
+            n_sm = v;
+            sm_env_set = true;
+        }
     }
     // per-group progress counters live behind the site tables
     int* done = reinterpret_cast<int*>(static_cast<unsigned char*>(sites_buf) +
@@ -1528,14 +1555,22 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
         // SMs: no partial last wave (SG_TC_SPI=0 forces one CTA per group for all sweeps)
         const int groups = (a.R + kG * C - 1) / (kG * C);
         int spi = s1 - s0, grid_groups = groups;
-        if (C == 1 && groups > n_sm) {
-            spi = tc_pick_spi(groups, s1 - s0, n_sm);
+        // CTAs (C = 1) or cluster pairs (C = 2) resident at once
+        int n_slots = n_sm;
+        if (C == 2) {
+            n_slots = tc_max_cluster_pairs(smem);
+            if (n_slots > n_sm / 2) n_slots = n_sm / 2;
+            if (sm_env_set && n_sm / 2 < n_slots) n_slots = n_sm / 2 > 0 ? n_sm / 2 : 1;
+            if (n_slots < 1) n_slots = 1;
+        }
+        if (groups > n_slots) {
+            spi = tc_pick_spi(groups, s1 - s0, n_slots);
             if (spi_env > 0) spi = spi_env < s1 - s0 ? spi_env : s1 - s0;
             if (spi_env == 0) spi = s1 - s0;
             const int chunks = (s1 - s0 + spi - 1) / spi;
             if (chunks > 1) {
                 const long long n_items = (long long)groups * chunks;
-                grid_groups = (int)(n_items < n_sm ? n_items : n_sm);
+                grid_groups = (int)(n_items < n_slots ? n_items : n_slots);
                 err = cudaMemsetAsync(done, 0, (size_t)groups * sizeof(int), st);
                 if (err != cudaSuccess) return err;
             }
