@@ -181,9 +181,11 @@ def run_ours(args):
                   track_best=True, kernel=kernel, coupling_planes=planes)
 
     use_tc = kernel in ("auto", "tc")
+    cluster = 1
     if use_tc:
         gmax = 16
         blocks = (R + gmax - 1) // gmax
+        cluster = max(1, eng.tc_cluster_size())
 
     def barrier():
         if world > 1:
@@ -315,7 +317,10 @@ def run_ours(args):
         # one block per SM) measured on this box
         if use_tc:
             n_tc = (n + 127) // 128 * 128
-            bytes_per_sweep_block = float(n) * n_tc * 2 * planes
+            # per group of 16 replicas and sweep: every one of the n rows (n_tc couplings, 2 bytes
+            # per plane) enters an SM once; a cluster pair takes each row in once for 32 replicas
+            # (half of it per SM), i.e. half as many bytes per replica
+            bytes_per_sweep_block = float(n) * n_tc * 2 * planes / cluster
             kname = "sg::sweep_tc_kernel"
             stream_desc = f"{planes} bf16 planes of J in UMMA operand layout ({planes * 2 * n * n_tc / 1e6:.0f} MB per sweep)"
         else:
@@ -340,6 +345,8 @@ def run_ours(args):
                 "dram_bytes_per_launch"]
         except Exception:
             pass
+        # B operand per MMA: 16 attempts x (16 x cluster) replicas x 2 bytes against a 4 KB A tile
+        smem_factor = 2.0 + 0.125 * cluster
         roofline = {"bound": "hbm", "achieved": achieved, "peak": l2_peak, "unit": "GB/s",
                     "frac": achieved / l2_peak, "traffic": traffic,
                     "peak_source": "measured on this box (sg_measure_tma_stream): TMA bulk-copy stream of "
@@ -354,9 +361,9 @@ def run_ours(args):
                     # memory by TMA and read from it by tcgen05.mma, which also reads the 512-byte
                     # B operand (the block's decisions) once per 4 KB A tile: 2.125 x the J stream
                     # through a 128 B/clk/SM port
-                    "smem_traffic_gbs": 2.125 * achieved if use_tc else None,
+                    "smem_traffic_gbs": smem_factor * achieved if use_tc else None,
                     "smem_peak_gbs": q["sm_count"] * 128 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9,
-                    "smem_frac": (2.125 * achieved) / (q["sm_count"] * 128 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9) if use_tc else None,
+                    "smem_frac": (smem_factor * achieved) / (q["sm_count"] * 128 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9) if use_tc else None,
                     "gather_ms_per_launch": prof["gather_ms"] / max(1, int(prof["gather_launches"]))}
         cpu = None
         if world == 1 or True:
@@ -368,13 +375,17 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": workload_name(R, sweeps),
-                       "kernel": "tensor-core (tcgen05, TMEM-resident fields)" if use_tc else "simt",
+                       "kernel": ("tensor-core (tcgen05, TMEM-resident fields"
+                                  + (", cluster pairs: 32 replicas per 2 SMs, half of the field columns each)"
+                                     if cluster == 2 else ")")) if use_tc else "simt",
                        "coupling_planes": planes if use_tc else None,
-                       "replicas_per_gpu": R, "sweeps_per_step": sweeps, "replicas_per_block": gmax,
-                       "replica_groups": blocks,
-                       "schedule": ("one persistent CTA per SM walks (sweep chunk, replica group) work "
+                       "replicas_per_gpu": R, "sweeps_per_step": sweeps,
+                       "replicas_per_group": gmax * cluster, "ctas_per_group": cluster,
+                       "replica_groups": (R + gmax * cluster - 1) // (gmax * cluster),
+                       "schedule": ("persistent CTAs (cluster pairs) walk (sweep chunk, replica group) work "
                                     "items; a group's fields/spins move through HBM between its items")
-                                   if use_tc and blocks > q["sm_count"] else "one CTA per replica group",
+                                   if use_tc and (R + gmax * cluster - 1) // (gmax * cluster) > q["sm_count"] // cluster
+                                   else "one CTA (cluster pair) per replica group",
                        "n_pad": q["n_pad"], "acceptance_rate": acc_rate,
                        "l2_policy": f"inputs (J planes 100 MB + operand stream {sweeps * 100} MB per step + "
                                     "170 MB replica state) exceed the 126 MB L2; no flush between steps",

@@ -283,6 +283,11 @@ int sg_tc_selftest(sg_engine *e, int planes, const int32_t *sites16, const float
                    const float *fields_in, float *fields_out);
 
 /* Layout facts the host side needs (padded row length, resident replicas per block...). */
+/* CTAs per replica group of the tensor-core sweep for the current model and replica count:
+ * 2 = a thread-block cluster pair per 32 replicas, each CTA owning half of the field columns;
+ * 1 = one CTA per 16 replicas; 0 = the tensor-core kernel does not take this model. */
+int sg_tc_cluster_size(sg_engine *e);
+
 int sg_query(sg_engine *e, int32_t *n, int32_t *n_pad, int32_t *n_replicas,
              int32_t *max_replicas_per_block, int32_t *sm_count);
 

@@ -1777,6 +1777,11 @@ int sg_debug_mma_bench(sg_engine* e, int variant, int n_dim, int iters, long lon
     return SG_OK;
 }
 
+int sg_tc_cluster_size(sg_engine* e) {
+    if (!e || !e->Jp || e->R <= 0 || !sg::sweep_tc_supported(e->n, e->n_tc)) return 0;
+    return sg::sweep_tc_cluster_size(e->n_tc, e->R);
+}
+
 int sg_query(sg_engine* e, int32_t* n, int32_t* n_pad, int32_t* n_replicas,
              int32_t* max_replicas_per_block, int32_t* sm_count) {
     SG_REQUIRE(e, "sg_query: NULL engine");

@@ -113,6 +113,7 @@ cudaError_t launch_tc_selftest(const void* Jp, int n, int n_tc, int planes, cons
 cudaError_t launch_tc_mma_bench(int variant, int n_dim, int iters, long long* out, cudaStream_t st);
 bool sweep_tc_supported(int n, int n_tc);
 size_t sweep_tc_sites_bytes(int n, int n_sweeps, int R);
+int sweep_tc_cluster_size(int n_tc, int R);
 size_t sweep_tc_stream_bytes_per_sweep(int n, int n_tc, int planes);
 // sites_buf: device scratch of sweep_tc_sites_bytes(); stream_buf: device scratch for the operand
 // stream, at least one sweep's worth (the launch is cut into sub-launches of as many sweeps as

@@ -1460,6 +1460,18 @@ static cudaError_t launch_tc_variant(const SweepDev& a, const __nv_bfloat16* J, 
                               tabs, s0, s1, spi, done, dbg);
 }
 
+// CTAs per replica group the launcher uses for this shape: 2 = a cluster pair holds 32 replicas
+// and each CTA owns half of the field columns (needs n_tc / 128 tiles divisible by 8 and more
+// than 16 replicas; SG_TC_CLUSTER=1 switches it off), else 1
+int sweep_tc_cluster_size(int n_tc, int R) {
+    const int T = n_tc / kTileM;
+    int C = (T % (2 * kChunkTiles) == 0 && R > kG) ? 2 : 1;
+    if (const char* c_env = getenv("SG_TC_CLUSTER")) {
+        if (atoi(c_env) == 1) C = 1;
+    }
+    return C;
+}
+
 // cluster pairs that can be resident at the same time (the persistent work-item schedule must
 // not launch more: a waiting pair would otherwise hold the SMs a pair it depends on needs)
 static int tc_max_cluster_pairs(size_t smem) {
@@ -1506,10 +1518,7 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
     // the TMEM-read round trips are then on the critical path and cluster speed varies with
     // placement; profiles/r1_notes.md).
     const int T = n_tc / kTileM;
-    int C = (T % (2 * kChunkTiles) == 0 && a.R > kG) ? 2 : 1;
-    if (const char* c_env = getenv("SG_TC_CLUSTER")) {
-        if (atoi(c_env) == 1) C = 1;
-    }
+    const int C = sweep_tc_cluster_size(n_tc, a.R);
     int NS = kMaxStagesTc;
     while (NS > 2 && tc_layout(n_tc, planes, NS, C).total > 227 * 1024) --NS;
     if (const char* ns_env = getenv("SG_TC_STAGES")) {

@@ -367,6 +367,10 @@ class Engine:
         return dict(n=v[0].value, n_pad=v[1].value, n_replicas=v[2].value,
                     max_replicas_per_block=v[3].value, sm_count=v[4].value)
 
+    def tc_cluster_size(self) -> int:
+        """CTAs per replica group of the tensor-core sweep (2 = cluster pairs, 1, or 0 = n/a)."""
+        return int(self._lib.sg_tc_cluster_size(self._h))
+
     def set_profiling(self, enable: bool) -> None:
         check(self._lib.sg_set_profiling(self._h, 1 if enable else 0), "sg_set_profiling")
 
