@@ -218,6 +218,37 @@ def test_tc_full_size_many_waves_matches_one_cta_per_group(engine, monkeypatch):
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("n,R", [(1024, 16 * 7 + 5), (2048, 70)])
+def test_tc_cluster_pairs_equal_single_cta_groups(engine, monkeypatch, n, R):
+    """The default for n_tc divisible by 1024: a thread-block cluster pair holds 32 replicas, each
+    CTA owns half of the field columns, raw field values and energy partial sums cross the pair
+    through distributed shared memory.  Same decisions, so nothing may differ from one CTA per
+    16 replicas (SG_TC_CLUSTER=1) -- also when few SMs force the persistent work-item schedule
+    (cluster pairs handing replica groups to each other through HBM)."""
+    rng = np.random.default_rng(n + R)
+    J, h = _int_instance(rng, n)
+    S0 = (rng.integers(0, 2, size=(R, n)) * 2 - 1).astype(np.int8)
+    ns = 5
+    temps = np.linspace(2.5, 0.6, ns)
+    outs = []
+    for env in ({"SG_TC_CLUSTER": "1"}, {}, {"SG_TC_SM": "2"}, {"SG_TC_SM": "4", "SG_TC_SPI": "2"}):
+        for k in ("SG_TC_CLUSTER", "SG_TC_SM", "SG_TC_SPI"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        _setup(engine, J, h, S0)
+        assert engine.tc_cluster_size() == (1 if env.get("SG_TC_CLUSTER") == "1" else 2)
+        tr = engine.sweep(ns, temps, temps_sweep_stride=1, seed=5, sweep_base=3, site_order="random",
+                          energy_trace=True, kernel="tc", coupling_planes=1).cpu().numpy()
+        outs.append((engine.spins().cpu().numpy(), tr, engine.accepted().cpu().numpy(),
+                     engine.best()[0].cpu().numpy(), engine.best()[1].cpu().numpy(),
+                     engine.fields().cpu().numpy()))
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert np.array_equal(a, b)
+    assert outs[0][2].sum() > 0
+
+
 def test_tc_launch_chunking_is_invisible(engine):
     rng = np.random.default_rng(11)
     n, R = 300, 50
