@@ -490,7 +490,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 const int tmem_cols, const unsigned char* __restrict__ Q,
                 const unsigned char* __restrict__ tabs_g, const int s_begin, const int s_end,
                 const int spi, int* __restrict__ done_g, const int dbg) {
-    constexpr int LAG = C;                   // raw field values are read LAG+1 blocks before use
+    constexpr int LAG = 1;                   // raw field values are read LAG+1 blocks before use
     constexpr int NG = kG * C;               // replicas per group = MMA N
     constexpr int NGRP = NG / 16;            // 16-column TMEM load/store groups per tile
     constexpr uint32_t IDESC = tc::make_idesc_bf16(kTileM, NG);
