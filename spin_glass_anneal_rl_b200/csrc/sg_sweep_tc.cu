@@ -44,6 +44,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 
 #include "sg_common.cuh"
 #include "sg_internal.h"
@@ -1472,6 +1473,16 @@ int sweep_tc_cluster_size(int n_tc, int R) {
     return C;
 }
 
+// Launches with the persistent work-item schedule spin-wait on each other's CTAs, so two of them
+// must never share the GPU (each could hold the SMs the other's missing CTAs need).  Launches of
+// one process are chained with an event per device, whatever streams they are on.
+struct TcItemGate {
+    std::mutex mu;
+    cudaEvent_t ev[64] = {};
+    bool have[64] = {};
+};
+static TcItemGate g_item_gate;
+
 // cluster pairs that can be resident at the same time (the persistent work-item schedule must
 // not launch more: a waiting pair would otherwise hold the SMs a pair it depends on needs)
 static int tc_max_cluster_pairs(size_t smem) {
@@ -1564,6 +1575,7 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
         // SMs: no partial last wave (SG_TC_SPI=0 forces one CTA per group for all sweeps)
         const int groups = (a.R + kG * C - 1) / (kG * C);
         int spi = s1 - s0, grid_groups = groups;
+        bool item_mode = false;
         // CTAs (C = 1) or cluster pairs (C = 2) resident at once
         int n_slots = n_sm;
         if (C == 2) {
@@ -1581,6 +1593,15 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
                 const long long n_items = (long long)groups * chunks;
                 grid_groups = (int)(n_items < n_slots ? n_items : n_slots);
                 err = cudaMemsetAsync(done, 0, (size_t)groups * sizeof(int), st);
+                if (err != cudaSuccess) return err;
+                item_mode = true;
+            }
+        }
+        std::unique_lock<std::mutex> gate(g_item_gate.mu, std::defer_lock);
+        if (item_mode && dev >= 0 && dev < 64) {
+            gate.lock();
+            if (g_item_gate.have[dev]) {
+                err = cudaStreamWaitEvent(st, g_item_gate.ev[dev], 0);
                 if (err != cudaSuccess) return err;
             }
         }
@@ -1613,6 +1634,15 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
 #undef SG_TC
         err = cudaGetLastError();
         if (err != cudaSuccess) return err;
+        if (gate.owns_lock()) {
+            if (!g_item_gate.have[dev]) {
+                err = cudaEventCreateWithFlags(&g_item_gate.ev[dev], cudaEventDisableTiming);
+                if (err != cudaSuccess) return err;
+                g_item_gate.have[dev] = true;
+            }
+            err = cudaEventRecord(g_item_gate.ev[dev], st);
+            if (err != cudaSuccess) return err;
+        }
         *launches += 3;
     }
     return err;

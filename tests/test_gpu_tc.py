@@ -249,6 +249,43 @@ def test_tc_cluster_pairs_equal_single_cta_groups(engine, monkeypatch, n, R):
     assert outs[0][2].sum() > 0
 
 
+def test_tc_work_item_launches_on_two_streams_do_not_deadlock(monkeypatch):
+    """Two engines, two CUDA streams, both launches in the persistent work-item mode (their CTAs
+    spin-wait on each other's progress flags): the library chains such launches per device, so
+    the two kernels never share the GPU half-resident.  Results equal the serial runs."""
+    if not has_cuda():
+        pytest.skip("needs a CUDA device")
+    import torch
+    from spin_glass_anneal_rl_b200.engine import Engine
+    monkeypatch.setenv("SG_TC_SM", "4")
+    rng = np.random.default_rng(99)
+    n, R, ns = 1024, 32 * 6, 6
+    models = [_int_instance(rng, n) for _ in range(2)]
+    S0 = (rng.integers(0, 2, size=(R, n)) * 2 - 1).astype(np.int8)
+    ref = []
+    for J, h in models:
+        e = Engine(0)
+        _setup(e, J, h, S0)
+        e.sweep(ns, np.array([1.3]), seed=4, site_order="random", kernel="tc", coupling_planes=1)
+        ref.append(e.spins().cpu().numpy())
+    engines, streams = [], [torch.cuda.Stream(), torch.cuda.Stream()]
+    for (J, h), st in zip(models, streams):
+        with torch.cuda.stream(st):
+            e = Engine(0)
+            _setup(e, J, h, S0)
+            engines.append(e)
+    torch.cuda.synchronize()
+    for rep in range(3):           # interleaved launches, nothing synchronises in between
+        for e, st in zip(engines, streams):
+            with torch.cuda.stream(st):
+                e.sweep(2, np.array([1.3]), seed=4, sweep_base=2 * rep, site_order="random", kernel="tc",
+                        coupling_planes=1)
+    torch.cuda.synchronize()
+    for e, st, r in zip(engines, streams, ref):
+        with torch.cuda.stream(st):
+            assert np.array_equal(e.spins().cpu().numpy(), r)
+
+
 def test_tc_launch_chunking_is_invisible(engine):
     rng = np.random.default_rng(11)
     n, R = 300, 50
