@@ -14,7 +14,7 @@ def run(seed0=0, cases=40, verbose=True):
   bad = 0
   for c in range(cases):
       rng = np.random.default_rng(seed0 * 1000 + c)
-      n = int(rng.choice([16, 17, 31, 32, 33, 100, 127, 128, 129, 255, 300, 511, 513, 777, 1024, 1100]))
+      n = int(rng.choice([16, 17, 31, 32, 33, 100, 127, 128, 129, 255, 300, 511, 513, 777, 1000, 1024, 1024, 1100, 2048]))
       R = int(rng.integers(1, 70))
       ns = int(rng.integers(1, 4))
       rule = str(rng.choice(["metropolis", "glauber", "heat_bath"]))
