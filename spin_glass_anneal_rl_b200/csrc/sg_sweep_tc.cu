@@ -1523,11 +1523,9 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
         if (e != cudaSuccess) return e;
         ++*launches;
     }
-    // C = 1: one CTA per 16 replicas (default).  C = 2 (SG_TC_CLUSTER=2, experimental): a cluster
-    // pair per 32 replicas, each CTA owning half of the field columns -- half the operand bytes
-    // per SM, bit-identical results, but in round 1 still slower end to end (the decision warp and
-    // the TMEM-read round trips are then on the critical path and cluster speed varies with
-    // placement; profiles/r1_notes.md).
+    // C = 2 (default where the shape allows it): a cluster pair per 32 replicas, each CTA owning
+    // half of the field columns -- half the operand bytes per SM and attempt, bit-identical
+    // results, 1.6x the throughput of C = 1 (one CTA per 16 replicas; SG_TC_CLUSTER=1).
     const int T = n_tc / kTileM;
     const int C = sweep_tc_cluster_size(n_tc, a.R);
     int NS = kMaxStagesTc;
