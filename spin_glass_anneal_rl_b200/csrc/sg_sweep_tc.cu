@@ -375,15 +375,6 @@ __device__ __forceinline__ uint32_t map_to_rank(const void* p, uint32_t rank) {
 }
 // asynchronous remote store that counts its bytes on an mbarrier of the target CTA (both
 // addresses are shared::cluster addresses of the same CTA): no fence, no remote arrive
-// bulk copy from this CTA's shared memory into a peer CTA's, bytes counted on the peer's mbarrier
-__device__ __forceinline__ void bulk_s2peer(uint32_t dst_cluster_addr, const void* src, uint32_t bytes,
-                                            uint32_t bar_cluster_addr) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            dst_cluster_addr),
-        "r"(smem_u32(src)), "r"(bytes), "r"(bar_cluster_addr)
-        : "memory");
-}
 __device__ __forceinline__ void st_async_f4(uint32_t addr, float4 v, uint32_t bar) {
     asm volatile(
         "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr),
