@@ -956,23 +956,23 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 const uint32_t* dup_p = reinterpret_cast<const uint32_t*>(tab_s + slot * kTabBytes) + 3 * kBlk * kBlk;
                 // correction for the flips of the previous LAG blocks (not yet in the raw values),
                 // oldest block first
-                float v[kBlk];
+                // (pairs of fields per register pair: one FFMA2 = two independent fp32 FMAs, same
+                // results as scalar fmaf, half the instructions of this warp's serial budget)
+                float2 v2[kBlk / 2];
 #pragma unroll
-                for (int b = 0; b < kBlk; ++b) v[b] = 0.0f;
+                for (int b = 0; b < kBlk / 2; ++b) v2[b] = make_float2(0.0f, 0.0f);
 #pragma unroll
                 for (int l = LAG; l >= 1; --l) {
                     if (k >= l) {
                         const float4* ccr4 = cin4 + l * (kBlk * kBlk / 4);
 #pragma unroll
                         for (int aa = 0; aa < kBlk; ++aa) {
-                            const float da = pdec[l - 1][aa];
+                            const float2 da2 = make_float2(pdec[l - 1][aa], pdec[l - 1][aa]);
 #pragma unroll
                             for (int b4 = 0; b4 < kBlk / 4; ++b4) {
                                 const float4 c4 = ccr4[aa * 4 + b4];
-                                v[4 * b4 + 0] = fmaf(da, c4.x, v[4 * b4 + 0]);
-                                v[4 * b4 + 1] = fmaf(da, c4.y, v[4 * b4 + 1]);
-                                v[4 * b4 + 2] = fmaf(da, c4.z, v[4 * b4 + 2]);
-                                v[4 * b4 + 3] = fmaf(da, c4.w, v[4 * b4 + 3]);
+                                v2[2 * b4 + 0] = __ffma2_rn(da2, make_float2(c4.x, c4.y), v2[2 * b4 + 0]);
+                                v2[2 * b4 + 1] = __ffma2_rn(da2, make_float2(c4.z, c4.w), v2[2 * b4 + 1]);
                             }
                         }
                     }
@@ -989,7 +989,10 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 mbar_wait(&rall[slot], par);
                 SG_STAMP(6);
 #pragma unroll
-                for (int b = 0; b < kBlk; ++b) v[b] += rawp[b * NG];
+                for (int b = 0; b < kBlk / 2; ++b) {
+                    v2[b].x += rawp[(2 * b) * NG];
+                    v2[b].y += rawp[(2 * b + 1) * NG];
+                }
                 // the 16 attempts of the block, strictly in order, registers only
                 uint32_t myflips = 0;
                 float d[kBlk];
@@ -997,7 +1000,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 for (int aa = 0; aa < kBlk; ++aa) {
                     const bool up = (((w0[aa] >> (site[aa] & 31)) ^ (uint32_t)__popc(myflips & dup[aa])) & 1u) != 0u;
                     bool flip = false;
-                    const float fv = v[aa];
+                    const float fv = (aa & 1) ? v2[aa >> 1].y : v2[aa >> 1].x;
                     if (!INJECT) {
                         if (a.rule == 0) {
                             const float x = up ? 2.0f * fv : -2.0f * fv;  // dE = 2 s f
@@ -1022,12 +1025,13 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                     myflips |= flip ? (1u << aa) : 0u;
                     // bring the later sites of the block up to date (row aa of the in-block table)
 #pragma unroll
-                    for (int b4 = (aa + 1) / 4; b4 < kBlk / 4; ++b4) {
-                        const float4 c4 = cin4[aa * 4 + b4];
-                        if (4 * b4 + 0 > aa) v[4 * b4 + 0] = fmaf(da, c4.x, v[4 * b4 + 0]);
-                        if (4 * b4 + 1 > aa) v[4 * b4 + 1] = fmaf(da, c4.y, v[4 * b4 + 1]);
-                        if (4 * b4 + 2 > aa) v[4 * b4 + 2] = fmaf(da, c4.z, v[4 * b4 + 2]);
-                        if (4 * b4 + 3 > aa) v[4 * b4 + 3] = fmaf(da, c4.w, v[4 * b4 + 3]);
+                    // (values of sites already decided are dead, so whole pairs are updated)
+                    const float2 da2 = make_float2(da, da);
+#pragma unroll
+                    for (int p2 = (aa + 1) / 2; p2 < kBlk / 2; ++p2) {
+                        const float2 c2 = *reinterpret_cast<const float2*>(
+                            reinterpret_cast<const float*>(cin4) + aa * kBlk + 2 * p2);
+                        v2[p2] = __ffma2_rn(da2, c2, v2[p2]);
                     }
                 }
                 n_acc += (unsigned int)__popc(myflips);
