@@ -996,6 +996,37 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 // the 16 attempts of the block, strictly in order, registers only
                 uint32_t myflips = 0;
                 float d[kBlk];
+                uint32_t anydup = 0u;
+#pragma unroll
+                for (int b = 0; b < kBlk; ++b) anydup |= dup[b];
+                if (!INJECT && a.rule == 0 && anydup == 0u) {
+                    // Fast path (Metropolis, production RNG, no site twice in the block -- 97 % of
+                    // the blocks at N = 4096): the spin of every attempt is known up front and
+                    // inactive attempts get a threshold of -inf, so the chain from one decision to
+                    // the next is FFMA2 -> FMUL -> FSETP -> FSEL instead of running through the
+                    // flip mask, a population count and three predicate combinations as well.
+                    float sg2[kBlk], the[kBlk];
+#pragma unroll
+                    for (int aa = 0; aa < kBlk; ++aa) {
+                        sg2[aa] = ((w0[aa] >> (site[aa] & 31)) & 1u) ? 2.0f : -2.0f;   // 2 s
+                        the[aa] = (active && aa < nbk) ? th[aa] : -INFINITY;
+                    }
+#pragma unroll
+                    for (int aa = 0; aa < kBlk; ++aa) {
+                        const float fv = (aa & 1) ? v2[aa >> 1].y : v2[aa >> 1].x;
+                        const bool flip = sg2[aa] * fv < the[aa];       // dE = 2 s f < -T ln u
+                        const float da = flip ? -sg2[aa] : 0.0f;
+                        d[aa] = da;
+                        myflips |= flip ? (1u << aa) : 0u;
+                        const float2 da2 = make_float2(da, da);
+#pragma unroll
+                        for (int p2 = (aa + 1) / 2; p2 < kBlk / 2; ++p2) {
+                            const float2 c2 = *reinterpret_cast<const float2*>(
+                                reinterpret_cast<const float*>(cin4) + aa * kBlk + 2 * p2);
+                            v2[p2] = __ffma2_rn(da2, c2, v2[p2]);
+                        }
+                    }
+                } else {
 #pragma unroll
                 for (int aa = 0; aa < kBlk; ++aa) {
                     const bool up = (((w0[aa] >> (site[aa] & 31)) ^ (uint32_t)__popc(myflips & dup[aa])) & 1u) != 0u;
@@ -1033,6 +1064,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                             reinterpret_cast<const float*>(cin4) + aa * kBlk + 2 * p2);
                         v2[p2] = __ffma2_rn(da2, c2, v2[p2]);
                     }
+                }
                 }
                 n_acc += (unsigned int)__popc(myflips);
                 SG_STAMP(7);
