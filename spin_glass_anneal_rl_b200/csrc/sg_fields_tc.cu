@@ -240,7 +240,8 @@ fields_tc_kernel(const unsigned char* __restrict__ dig, const unsigned char* __r
         tc::fence_after_sync();
         const uint32_t tq = tbase + ((uint32_t)(warp * 32) << 16);
         const int j = jt * kFM + warp * 32 + lane;
-        const float hv = h[j];
+        const bool j_ok = j < ldF;          // the row length n_tc may exceed the padded row of F / h
+        const float hv = j_ok ? h[j] : 0.0f;
         const double inv = scale[1];
 #pragma unroll 1
         for (int c = 0; c < kFN / 16; ++c) {
@@ -255,7 +256,7 @@ fields_tc_kernel(const unsigned char* __restrict__ dig, const unsigned char* __r
                 const int r = rt * kFN + c * 16 + e;
                 const long long q = (long long)(int)d0[e] + ((long long)(int)d1[e] << 8) +
                                     ((long long)(int)d2[e] << 16) + ((long long)(int)d3[e] << 24);
-                if (r < R) F[(size_t)r * ldF + j] = (float)((double)q * inv + (double)hv);
+                if (r < R && j_ok) F[(size_t)r * ldF + j] = (float)((double)q * inv + (double)hv);
             }
         }
     }

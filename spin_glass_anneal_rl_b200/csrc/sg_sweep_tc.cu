@@ -600,7 +600,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 const int w = w0 + u * 128;
                 const int r = w / W, word = w - r * W;
                 lo[u] = hi[u] = make_uint4(0u, 0u, 0u, 0u);
-                if (w < NG * W && r < g_act) {
+                if (w < NG * W && r < g_act && word * 32 < n_pad) {   // n_tc may exceed n_pad
                     const uint4* src =
                         reinterpret_cast<const uint4*>(a.spins + (size_t)(rep0 + r) * n_pad + word * 32);
                     lo[u] = __ldcg(src);
@@ -613,7 +613,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 const int r = w / W, word = w - r * W;
                 if (w >= NG * W) break;
                 uint32_t bits = 0xFFFFFFFFu;
-                if (r < g_act) {
+                if (r < g_act && word * 32 < n_pad) {
                     const uint32_t x[8] = {lo[u].x, lo[u].y, lo[u].z, lo[u].w, hi[u].x, hi[u].y, hi[u].z, hi[u].w};
                     bits = 0;
 #pragma unroll
@@ -638,7 +638,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 for (int gi = 0; gi < NGRP; ++gi)
 #pragma unroll
                     for (int r = 0; r < 16; ++r)
-                        v[u][gi][r] = (t + u < Tl && gi * 16 + r < g_act)
+                        v[u][gi][r] = (t + u < Tl && gi * 16 + r < g_act && col < n_pad)
                                           ? __ldcg(a.fields + (size_t)(rep0 + gi * 16 + r) * n_pad + col) : 0.0f;
             }
 #pragma unroll
@@ -780,7 +780,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 for (int r = 0; r < NG; ++r) part[r] = 0.0f;
                 for (int t = 0; t < Tl; ++t) {
                     const int colb = col0 + t * kTileM + q * 32;   // first column of this lane group
-                    const float hv = a.h[colb + lane];
+                    const float hv = (colb + lane < n_pad) ? a.h[colb + lane] : 0.0f;
 #pragma unroll
                     for (int gi = 0; gi < NGRP; ++gi) {
                         float f[16];
@@ -821,7 +821,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
             if (im != 0u && crank == 0) {
                 for (int w = tid; w < NG * W; w += 128) {
                     const int r = w / W, word = w - r * W;
-                    if ((im >> r) & 1u)
+                    if (((im >> r) & 1u) && word * 32 < n_pad)
                         store_spin_word(a.best_spins + (size_t)(rep0 + r) * n_pad + word * 32, sbits[r * Wp + word]);
                 }
             }
@@ -838,14 +838,15 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 tc::wait_ld();
 #pragma unroll
                 for (int r = 0; r < 16; ++r)
-                    if (gi * 16 + r < g_act)
+                    if (gi * 16 + r < g_act && col < n_pad)
                         __stcg(a.fields + (size_t)(rep0 + gi * 16 + r) * n_pad + col, v[r]);
             }
         }
         if (crank == 0) {
             for (int w = tid; w < NG * W; w += 128) {
                 const int r = w / W, word = w - r * W;
-                if (r < g_act) store_spin_word(a.spins + (size_t)(rep0 + r) * n_pad + word * 32, sbits[r * Wp + word]);
+                if (r < g_act && word * 32 < n_pad)
+                    store_spin_word(a.spins + (size_t)(rep0 + r) * n_pad + word * 32, sbits[r * Wp + word]);
             }
         }
         SG_ISTAMP(5);

@@ -286,6 +286,36 @@ def test_tc_work_item_launches_on_two_streams_do_not_deadlock(monkeypatch):
             assert np.array_equal(e.spins().cpu().numpy(), r)
 
 
+@pytest.mark.parametrize("n,pairs", [(777, True), (1500, True), (3000, True), (1100, False), (600, False)])
+def test_tc_row_length_padding_enables_cluster_pairs(engine, oracle, n, pairs):
+    """The plane row length is rounded up to a multiple of 1024 when that costs at most 40 % more
+    (zero) columns, so that these sizes run on cluster pairs too; it then exceeds the padded row of
+    the replica arrays (n rounded to 896) and every access beyond it is guarded.  Replay against
+    the oracle, bit for bit, fields included."""
+    rng = np.random.default_rng(n)
+    J, h = _int_instance(rng, n)
+    R, ns = 37, 2
+    S0 = (rng.integers(0, 2, size=(R, n)) * 2 - 1).astype(np.int8)
+    sites = rng.integers(0, n, size=(ns, n)).astype(np.int32)
+    uni = rng.random((R, ns, n), dtype=np.float32)
+    temps = np.array([2.0, 0.8])
+    _setup(engine, J, h, S0)
+    assert engine.tc_cluster_size() == (2 if pairs else 1)
+    trace = engine.sweep(ns, temps, temps_sweep_stride=1, sites=sites, uniforms=uni, energy_trace=True,
+                         kernel="tc", coupling_planes=1).cpu().numpy()
+    final = engine.spins().cpu().numpy()
+    best_e, best_s = engine.best()
+    for r in range(R):
+        s = S0[r].astype(np.float32).copy()
+        es, _ = oracle.sweeps_scheduled(J, h, s, temps, "metropolis", sites, uni[r])
+        assert np.array_equal(final[r], s.astype(np.int8)), f"replica {r} trajectory differs"
+        assert np.array_equal(trace[:, r].astype(np.float64), es)
+    Fo, Eo = oracle.batch_fields_energies(J, h, final.astype(np.float32))
+    assert np.array_equal(engine.fields().cpu().numpy().astype(np.float64), Fo)
+    assert np.array_equal(engine.energies().cpu().numpy().astype(np.float64), Eo)
+    assert np.array_equal(engine.batch_energies(best_s).cpu().numpy(), best_e.cpu().numpy())
+
+
 def test_tc_launch_chunking_is_invisible(engine):
     rng = np.random.default_rng(11)
     n, R = 300, 50
