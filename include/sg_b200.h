@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 3
+#define SG_ABI_VERSION 4
 
 typedef enum {
     SG_OK = 0,
@@ -182,7 +182,10 @@ typedef struct {
      * exactly (default, 0 means 3), 2 = 16 significant bits, 1 = plain bf16.  Integer couplings
      * |J| <= 256 are exact with 1 plane. */
     int32_t coupling_planes;
-    int32_t reserved;
+    /* global id of this engine's replica 0: the Philox key of replica r is replica_base + r, so a
+     * replica set sharded over several engines / GPUs draws exactly the numbers the same replicas
+     * would draw in one engine (0 for a single engine; a multiple of 32 for lattice models) */
+    int32_t replica_base;
     /* optional dev out [R][n] (float32, caller-zeroed): every accepted flip adds its energy change
      * 2 s_i f_i to entry (replica, site) -- the third return value of
      * CUDAKernelManager.metropolis_update_optimized (annealing/cuda_kernels.py:228-282, 371-397).
@@ -202,15 +205,36 @@ int sg_sweep(sg_engine *e, const sg_sweep_params *p, void *stream);
  * ladder_temps is a host array [n_rungs]. */
 int sg_set_ladder(sg_engine *e, int n_rungs, const double *ladder_temps, void *stream);
 
+/* The same for ladders that span several engines / GPUs: the replica set is
+ * n_global_replicas = n_ladders x n_rungs replicas with global ids, this engine holds the ids
+ * [replica_offset, replica_offset + R).  Every engine keeps the whole rung -> replica map (it
+ * evolves identically everywhere because every rank takes the same decisions from the same
+ * all-gathered energies and the same counter RNG) and the temperatures of its own replicas.
+ * Replaces MultiGPUAnnealer.anneal_replica_exchange (annealing/multi_gpu.py:234-307). */
+int sg_set_ladder_sharded(sg_engine *e, int n_rungs, const double *ladder_temps,
+                          int n_global_replicas, int replica_offset, void *stream);
+
 typedef struct {
     uint32_t struct_size;
     int32_t parity;          /* first rung of the first pair: 0 or 1 (np.random.randint(0,2)) */
     int32_t rng_mode;        /* SG_RNG_PHILOX or SG_RNG_INJECTED                               */
-    int32_t reserved;
+    int32_t method;          /* SG_EXCHANGE_*                                                  */
     uint64_t seed;
     uint64_t round;          /* Philox counter                                                 */
-    const double *uniforms;  /* SG_RNG_INJECTED: dev float64 [n_ladders][n_rungs/2] per pair   */
+    /* SG_RNG_INJECTED: dev float64; NEAREST: [n_ladders][n_rungs/2], one per pair;
+     * ALL_PAIRS: [n_ladders][n_rungs*(n_rungs-1)], consumed in the order the reference draws
+     * them (selection draw of every pair, acceptance draw of the selected ones) */
+    const double *uniforms;
+    /* sharded ladders: dev float32 [n_global_replicas], energy of every replica by GLOBAL id
+     * (the all-gather of sg_get_energies over the ranks); NULL = this engine's own energies */
+    const float *energies_all;
 } sg_exchange_params;
+
+/* exchange move sets (ParallelTemperingConfig.exchange_method) */
+#define SG_EXCHANGE_NEAREST 0   /* even/odd adjacent rungs  annealing/parallel_tempering.py:214-220 */
+#define SG_EXCHANGE_ALL_PAIRS 1 /* every pair i<j with probability 0.1, in order (CPU branch of
+                                   _all_pairs_exchange, annealing/parallel_tempering.py:228-232);
+                                   `parity` is ignored                                            */
 
 /* Replica exchange between adjacent rungs, p = min(1, exp((b_j-b_i)(E_j-E_i))): replaces
  * ParallelTempering._nearest_neighbor_exchange/_attempt_single_exchange
@@ -249,7 +273,15 @@ int sg_exchange_chain(int device, void *rows, int64_t row_stride_bytes, int64_t 
                       const float *uniforms, uint64_t seed, uint64_t round, int32_t *n_accepted,
                       void *stream);
 
-/* rung -> replica map [R], per-replica temperature [R], per-pair statistics
+/* Early-stop test on the device (time-to-target runs; GPUAnnealer's convergence check reads
+ * energies at every record point, annealing/gpu_annealer.py:156-164): if the smallest current
+ * (which = 0) or best-so-far (which = 1) energy of this engine's replicas is <= target and
+ * hit[0] is still negative, writes hit[1] = that replica's global id, then hit[0] = round.
+ * `hit` is an int32[2] the device can write: device memory or pinned host memory (the host can
+ * then poll it without synchronising the stream).  Asynchronous. */
+int sg_check_target(sg_engine *e, int which, float target, int32_t round, int32_t *hit, void *stream);
+
+/* rung -> replica map [n_global_replicas] (= R unless sharded), per-replica temperature [R], per-pair statistics
  * [n_ladders][n_rungs-1] (ParallelTempering.exchange_attempts/accepts). */
 int sg_get_ladder_state(sg_engine *e, int32_t *replica_at_rung, double *replica_temps,
                         uint32_t *attempts, uint32_t *accepts, int on_device, void *stream);

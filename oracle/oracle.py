@@ -412,12 +412,19 @@ def temperature_ladder(n: int, tmin: float, tmax: float, dist: str = "geometric"
 def parallel_tempering(J, h, *, n_replicas: int, n_sweeps: int, temp_min: float, temp_max: float,
                        temp_distribution: str = "geometric", exchange_interval: int = 10,
                        record_interval: int = 10, rule: str = "metropolis", stream: RawStream,
-                       np_rng: np.random.RandomState) -> OracleResult:
-    """ParallelTempering.run with n_threads=1 and nearest-neighbour exchange.
+                       np_rng: np.random.RandomState, exchange_method: str = "nearest_neighbor",
+                       trace: bool = False) -> OracleResult:
+    """ParallelTempering.run with n_threads=1 on device='cpu'.
 
     parallel_tempering.py:82-144 (loop), :175-189 (replica init: model.copy()
     draws n randints that are discarded, reset_to_random() draws n more),
-    :214-258 (exchange), :295-313 (statistics / best)."""
+    :214-220 (nearest-neighbour exchange), :222-232 (all_pairs, CPU branch: every pair i < j
+    is attempted with probability 0.1, statistics filed under min(i, j)), :234-258 (one
+    exchange), :295-313 (statistics / best).
+
+    ``trace=True`` also records what a replay needs: the initial spins per temperature slot,
+    the (site, uniform) of every attempt per (sweep, slot) and the numpy draws of every
+    exchange round (res.extra["spins0" / "sites" / "uniforms" / "exchange_draws"])."""
     J, h = _f32(J), _f32(h)
     n = J.shape[0]
     temps = temperature_ladder(n_replicas, temp_min, temp_max, temp_distribution)
@@ -426,28 +433,52 @@ def parallel_tempering(J, h, *, n_replicas: int, n_sweeps: int, temp_min: float,
     for _ in range(n_replicas):  # :180-189
         stream.take(n)  # IsingModel(config) inside copy(): spins overwritten
         reps.append(raw_to_spins(stream.take(n)).copy())  # reset_to_random()
+    spins0 = np.stack(reps).copy()
     n_acc = [0] * n_replicas
     n_tot = [0] * n_replicas
     attempts = np.zeros(n_replicas - 1)
     accepts = np.zeros(n_replicas - 1)
     e_hists: List[List[float]] = [[] for _ in range(n_replicas)]
     best_e, best_cfg = float("inf"), None
+    tr_sites = np.zeros((n_sweeps, n_replicas, n), np.int32) if trace else None
+    tr_uni = np.zeros((n_sweeps, n_replicas, n), np.float32) if trace else None
+    draws: List[List[float]] = []
+
+    def attempt(i, j, log):  # :234-258
+        bi, bj = 1.0 / temps[i], 1.0 / temps[j]
+        ei, ej = energy(J, h, reps[i]), energy(J, h, reps[j])
+        prob = min(1.0, np.exp((bj - bi) * (ej - ei)))  # :244-246
+        attempts[min(i, j)] += 1
+        u = np_rng.rand()  # :252 (always drawn)
+        log.append(float(u))
+        if u < prob:
+            reps[i], reps[j] = reps[j], reps[i]  # :254-256 swap configurations
+            accepts[min(i, j)] += 1
+
     for sweep in range(n_sweeps):  # :108
         for r in range(n_replicas):  # :193-196 (sequential, shared global stream)
-            _, acc, _, _ = sweeps(J, h, reps[r], [max(temps[r], 1e-10)], rule, stream)
+            _, acc, ts, tu = sweeps(J, h, reps[r], [max(temps[r], 1e-10)], rule, stream, trace=trace)
+            if trace:
+                tr_sites[sweep, r], tr_uni[sweep, r] = ts, tu
             n_acc[r] += int(acc[0])
             n_tot[r] += n
         if sweep % exchange_interval == 0 and sweep > 0:  # :113-114
-            start = np_rng.randint(0, 2)  # :217
-            for i in range(start, n_replicas - 1, 2):  # :219-220
-                j = i + 1
-                bi, bj = 1.0 / temps[i], 1.0 / temps[j]
-                ei, ej = energy(J, h, reps[i]), energy(J, h, reps[j])
-                prob = min(1.0, np.exp((bj - bi) * (ej - ei)))  # :244-246
-                attempts[i] += 1
-                if np_rng.rand() < prob:  # :252 (always drawn)
-                    reps[i], reps[j] = reps[j], reps[i]  # :254-256 swap configurations
-                    accepts[i] += 1
+            log: List[float] = []
+            if exchange_method == "nearest_neighbor":
+                start = int(np_rng.randint(0, 2))  # :217
+                log.append(float(start))
+                for i in range(start, n_replicas - 1, 2):  # :219-220
+                    attempt(i, i + 1, log)
+            elif exchange_method == "all_pairs":  # :228-232
+                for i in range(n_replicas - 1):
+                    for j in range(i + 1, n_replicas):
+                        pick = np_rng.rand()
+                        log.append(float(pick))
+                        if pick < 0.1:
+                            attempt(i, j, log)
+            else:
+                raise ValueError(exchange_method)
+            draws.append(log)
         if sweep % record_interval == 0:  # :117-125
             es = [energy(J, h, s) for s in reps]
             for r in range(n_replicas):
@@ -459,7 +490,8 @@ def parallel_tempering(J, h, *, n_replicas: int, n_sweeps: int, temp_min: float,
                        [n_acc[r] / n_tot[r] if n_tot[r] else 0.0 for r in range(n_replicas)],
                        n_sweeps, np.stack(reps), [], stream.pos - start_pos)
     res.extra = {"temperatures": temps, "exchange_attempts": attempts, "exchange_accepts": accepts,
-                 "energy_histories": e_hists}
+                 "energy_histories": e_hists, "spins0": spins0, "sites": tr_sites,
+                 "uniforms": tr_uni, "exchange_draws": draws}
     return res
 
 

@@ -20,6 +20,8 @@ SG_RULE = {"metropolis": 0, "glauber": 1, "heat_bath": 2}
 SG_RNG_PHILOX, SG_RNG_INJECTED = 0, 1
 SG_SITES = {"sequential": 0, "random": 1, "explicit": 2, "random_per_block": 3, "checkerboard": 4}
 SG_KERNEL = {"auto": 0, "simt": 1, "tc": 2, "small": 3}
+SG_EXCHANGE = {"nearest_neighbor": 0, "all_pairs": 1}
+SG_ABI_VERSION = 4
 
 
 class SweepParams(Structure):
@@ -31,14 +33,15 @@ class SweepParams(Structure):
         ("sites", c_void_p), ("sites_block_stride", c_int64), ("sites_sweep_stride", c_int64),
         ("uniforms", c_void_p), ("energy_trace", c_void_p),
         ("track_best", c_int32), ("kernel", c_int32), ("coupling_planes", c_int32),
-        ("reserved", c_int32), ("site_energy_changes", c_void_p),
+        ("replica_base", c_int32), ("site_energy_changes", c_void_p),
     ]
 
 
 class ExchangeParams(Structure):
     _fields_ = [
         ("struct_size", c_uint32), ("parity", c_int32), ("rng_mode", c_int32),
-        ("reserved", c_int32), ("seed", c_uint64), ("round", c_uint64), ("uniforms", c_void_p),
+        ("method", c_int32), ("seed", c_uint64), ("round", c_uint64), ("uniforms", c_void_p),
+        ("energies_all", c_void_p),
     ]
 
 
@@ -71,7 +74,9 @@ PROTOTYPES = {
     "sg_get_best": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "sg_sweep": (c_int, [c_void_p, POINTER(SweepParams), c_void_p]),
     "sg_set_ladder": (c_int, [c_void_p, c_int, POINTER(c_double), c_void_p]),
+    "sg_set_ladder_sharded": (c_int, [c_void_p, c_int, POINTER(c_double), c_int, c_int, c_void_p]),
     "sg_exchange": (c_int, [c_void_p, POINTER(ExchangeParams), c_void_p]),
+    "sg_check_target": (c_int, [c_void_p, c_int, c_float, c_int32, c_void_p, c_void_p]),
     "sg_get_ladder_state": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                     c_void_p]),
     "sg_batch_energies": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
@@ -125,7 +130,7 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.sg_abi_version() != 3:
+    if lib.sg_abi_version() != SG_ABI_VERSION:
         raise RuntimeError("libsg_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -28,9 +28,18 @@ def rule_name(update_rule) -> str:
     return name
 
 
-def _signature(model):
-    J, h = model.couplings, model.external_fields
-    return (id(J), J._version, tuple(J.shape), bool(J.is_sparse), id(h), h._version)
+class _Signature:
+    """Identity of the (J, h) an engine was built from.  It HOLDS the two tensors: ids (and data
+    pointers) of freed tensors are reused, so only `is` on live objects plus the version counter
+    identifies a model."""
+
+    def __init__(self, model):
+        self.J, self.h = model.couplings, model.external_fields
+        self.vJ, self.vh = self.J._version, self.h._version
+
+    def matches(self, model) -> bool:
+        J, h = model.couplings, model.external_fields
+        return J is self.J and h is self.h and J._version == self.vJ and h._version == self.vh
 
 
 def _lattice_bonds(rows, cols, vals, h, n):
@@ -108,9 +117,9 @@ def engine_for(model, device_index: int = 0) -> Engine:
         raise AttributeError("anneal() needs an IsingModel (couplings / external_fields / spins)")
     try:
         cached = getattr(model, "_sg_engine", None)
-        sig = _signature(model)
-        if cached is not None and cached[0] == sig and cached[1].device_index == device_index:
+        if cached is not None and cached[0].matches(model) and cached[1].device_index == device_index:
             return cached[1]
+        sig = _Signature(model)
         eng = cached[1] if cached is not None and cached[1].device_index == device_index \
             else Engine(device_index)
         J = model.couplings
@@ -146,6 +155,19 @@ def engine_for(model, device_index: int = 0) -> Engine:
         if isinstance(exc, DeviceError):
             raise
         raise DeviceError(f"B200 annealing engine unavailable: {exc}") from exc
+
+
+def mix_seed(*parts: int) -> int:
+    """64-bit Philox key from (seed, rank, launch, ...): splitmix64 over the parts, so that large
+    seeds do not alias and neighbouring (seed, launch) pairs give unrelated streams."""
+    x = 0x9E3779B97F4A7C15
+    for p in parts:
+        x = (x ^ (int(p) & 0xFFFFFFFFFFFFFFFF)) & 0xFFFFFFFFFFFFFFFF
+        x = (x + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+        x ^= x >> 31
+    return x
 
 
 def random_spins(n_replicas: int, n: int, device, generator: torch.Generator) -> torch.Tensor:

@@ -67,13 +67,14 @@ class CUDAKernelManager:
         return self.device.index if self.device.index is not None else torch.cuda.current_device()
 
     def _engine(self, couplings: torch.Tensor, external_fields: torch.Tensor, zero_diagonal: bool):
-        """Engine holding (J, h); cached on the identity and version of the caller's tensors."""
-        key = (couplings.data_ptr() if not couplings.is_sparse else id(couplings), couplings._version,
-               tuple(couplings.shape), external_fields.data_ptr(), external_fields._version, zero_diagonal)
-        eng = self._engines.get(key)
-        if eng is not None:
-            self._engines.move_to_end(key)
-            return eng
+        """Engine holding (J, h).  A cache entry KEEPS the caller's tensors and matches only the
+        very same objects at the same version: addresses and ids of freed tensors are handed out
+        again by the allocators, so they cannot identify a model."""
+        for key, (Jc, hc, vJ, vh, zd, eng) in list(self._engines.items()):
+            if (Jc is couplings and hc is external_fields and vJ == couplings._version
+                    and vh == external_fields._version and zd == zero_diagonal):
+                self._engines.move_to_end(key)
+                return eng
         from ..engine import Engine
         J = couplings.to_dense() if couplings.is_sparse else couplings
         J = J.to(device=self.device, dtype=torch.float32)
@@ -83,9 +84,11 @@ class CUDAKernelManager:
         eng = Engine(self._device_index())
         eng.set_model(J, external_fields.to(device=self.device, dtype=torch.float32))
         eng.alloc_replicas(1)
-        self._engines[key] = eng
+        self._cache_serial = getattr(self, "_cache_serial", 0) + 1
+        self._engines[self._cache_serial] = (couplings, external_fields, couplings._version,
+                                             external_fields._version, zero_diagonal, eng)
         while len(self._engines) > self._MAX_CACHED_MODELS:
-            self._engines.popitem(last=False)[1].close()
+            self._engines.popitem(last=False)[1][-1].close()
         return eng
 
     # ------------------------------------------------------------------ the three operators

@@ -4,7 +4,8 @@ Drop-in for the reference's ``GPUAnnealer(GPUAnnealerConfig).anneal(model, updat
 -> AnnealingResult`` (reference annealing/gpu_annealer.py:30-183):
 
 * the config keeps every reference field with the same defaults (:30-59) and appends
-  ``n_replicas``, ``site_order``, ``replicas_per_block``, ``device_index``;
+  ``n_replicas``, ``site_order``, ``replicas_per_block``, ``device_index``, ``rng_mode`` /
+  ``replay`` (injected reference stream), ``kernel``, ``coupling_dtype``;
 * the loop keeps the reference's bookkeeping: temperature from the schedule per sweep
   (:141-142, clamp of SpinDynamics.set_temperature), best energy / configuration compared
   after EVERY sweep (:151-153, done inside the kernel), histories appended when
@@ -29,7 +30,7 @@ import numpy as np
 import torch
 
 from ..core.spin_dynamics import UpdateRule
-from ._backend import as_pm1_float, engine_for, random_spins, rule_name, site_order_for
+from ._backend import as_pm1_float, engine_for, mix_seed, random_spins, rule_name, site_order_for
 from .result import AnnealingResult
 from .temperature_scheduler import ScheduleType, TemperatureScheduler
 
@@ -56,6 +57,17 @@ class GPUAnnealerConfig:
     site_order: str = "random"       # "random" | "sequential" | "random_per_block"
     replicas_per_block: int = 0      # 0 = let the engine choose
     device_index: int = 0
+    # "philox": in-kernel counter RNG (production).  "replay": the (site, uniform) of every attempt
+    # is injected from a recorded stream of the reference -- ``replay`` = {"sites": int [n_sweeps,
+    # n], "uniforms": float32 [n_sweeps, n] (or [n_replicas, n_sweeps, n])}; anneal() then follows
+    # the reference's trajectory (bit for bit on integer couplings)
+    rng_mode: str = "philox"
+    replay: Optional[Dict] = None
+    kernel: str = "auto"             # "auto" | "simt" | "tc" | "small" (SG_KERNEL_*)
+    # how the dense couplings are held for the tensor-core sweep: "auto"/"fp32" = three bf16
+    # planes (every fp32 coupling exactly), "bf16" = one plane, "int8" = one plane, integer
+    # couplings required (exact)
+    coupling_dtype: str = "auto"
 
     def __post_init__(self):
         if self.schedule_params is None:
@@ -67,7 +79,7 @@ class GPUAnnealer:
         self.config = config
         if config.random_seed is not None:
             torch.manual_seed(config.random_seed)
-            np.random.seed(config.random_seed)
+            np.random.seed(int(config.random_seed) & 0xFFFFFFFF)
         self.use_cuda = torch.cuda.is_available()
         self.device = torch.device("cuda", config.device_index) if self.use_cuda else torch.device("cpu")
         if self.use_cuda:
@@ -96,7 +108,40 @@ class GPUAnnealer:
         n, R = model.n_spins, max(1, int(cfg.n_replicas))
         seed = cfg.random_seed if cfg.random_seed is not None else int(torch.initial_seed() & 0x7FFFFFFF)
         self._launch_seed += 1
-        philox_seed = (int(seed) << 20) ^ self._launch_seed
+        philox_seed = mix_seed(seed, self._launch_seed)
+
+        if cfg.rng_mode not in ("philox", "replay"):
+            raise ValueError(f"Unknown rng_mode: {cfg.rng_mode}")
+        planes = {"auto": 0, "fp32": 3, "bf16": 1, "int8": 1}.get(cfg.coupling_dtype)
+        if planes is None:
+            raise ValueError(f"Unknown coupling_dtype: {cfg.coupling_dtype}")
+        if cfg.coupling_dtype == "int8":
+            Jm = model.couplings.to_dense() if model.couplings.is_sparse else model.couplings
+            if not bool(torch.all(Jm == Jm.round())) or float(Jm.abs().max()) > 256:
+                raise ValueError("coupling_dtype='int8' needs integer couplings with |J| <= 256")
+        replay_sites = replay_uni = None
+        if cfg.rng_mode == "replay":
+            if not cfg.replay or "sites" not in cfg.replay or "uniforms" not in cfg.replay:
+                raise ValueError("rng_mode='replay' needs replay={'sites': ..., 'uniforms': ...}")
+            replay_sites = torch.as_tensor(np.asarray(cfg.replay["sites"]), dtype=torch.int32,
+                                           device=eng.device).reshape(-1, n)
+            replay_uni = torch.as_tensor(np.nan_to_num(np.asarray(cfg.replay["uniforms"], np.float32), nan=0.5),
+                                         dtype=torch.float32, device=eng.device)
+            replay_uni = replay_uni.reshape(-1, replay_sites.shape[0], n)
+            if replay_uni.shape[0] == 1 and R > 1:
+                replay_uni = replay_uni.expand(R, -1, -1)
+            if replay_uni.shape[0] != R:   # (a recorded run that stopped early holds fewer sweeps)
+                raise ValueError("replay stream: need sites [n_sweeps, n] and uniforms [(R,) n_sweeps, n]")
+
+        def launch(k, temps, first):
+            """k sweeps starting at absolute sweep `first`."""
+            common = dict(temps_sweep_stride=1, rule=rule, sweep_base=first, energy_trace=True,
+                          track_best=True, kernel=cfg.kernel, coupling_planes=planes)
+            if replay_sites is not None:
+                return eng.sweep(k, temps, sites=replay_sites[first:first + k].contiguous(),
+                                 uniforms=replay_uni[:, first:first + k, :].contiguous(), **common)
+            return eng.sweep(k, temps, site_order=site_order_for(eng, cfg.site_order), seed=philox_seed,
+                             replicas_per_block=cfg.replicas_per_block, **common)
 
         gen = torch.Generator(device=eng.device)
         gen.manual_seed(int(seed) + 7919 * self._launch_seed)
@@ -142,15 +187,12 @@ class GPUAnnealer:
                                          target_acceptance=float(sc.target_acceptance),
                                          adaptation_rate=float(sc.adaptation_rate),
                                          final_temp=float(sc.final_temp))
-                trace = eng.sweep(1, temps_dev[done:done + 1], temps_sweep_stride=1, rule=rule,
-                                  site_order=site_order_for(eng, cfg.site_order), seed=philox_seed,
-                                  sweep_base=done, energy_trace=True, track_best=True,
-                                  replicas_per_block=cfg.replicas_per_block)
+                trace = launch(1, temps_dev[done:done + 1], done)
                 eng.refresh_fields()
                 sweep = done
                 done += 1
                 if sweep % interval == 0:
-                    cur_e = float(trace[-1, 0].item())
+                    cur_e = float(eng.energies()[0].item())   # exact: fields were just refreshed
                     acc = eng.accepted()[0].item() - acc_base
                     energy_history.append(cur_e)
                     temperature_history.append(float(temps_dev[sweep].item()))
@@ -171,16 +213,14 @@ class GPUAnnealer:
                 chunk_t = np.array([max(schedule.update(done, acceptance_rate=rate), 1e-10)])
                 last = done
             k = len(chunk_t)
-            trace = eng.sweep(k, chunk_t, temps_sweep_stride=1, rule=rule, site_order=site_order_for(eng, cfg.site_order),
-                              seed=philox_seed, sweep_base=done, energy_trace=True, track_best=True,
-                              replicas_per_block=cfg.replicas_per_block)
+            trace = launch(k, chunk_t, done)
             # incremental field updates drift for non-integer couplings; the reference recomputes
             # every field from scratch, so refresh them exactly between launches (one K2 pass)
             eng.refresh_fields()
             done += k
             sweep = last
             if sweep % interval == 0:
-                cur_e = float(trace[-1, 0].item())
+                cur_e = float(eng.energies()[0].item())   # exact: fields were just refreshed
                 acc = eng.accepted()[0].item() - acc_base
                 energy_history.append(cur_e)
                 temperature_history.append(float(chunk_t[-1]))

@@ -3,10 +3,14 @@
 Replaces the reference's ``annealing/multi_gpu.py`` (thread pool over Python objects,
 :110-307; its "communication_backend" string is never used, :26,41).  Replicas are
 independent between exchanges and an exchange touches only (E, beta) scalars of one
-ladder, so whole ladders are placed on one GPU and the sweep path needs NO data-path
-collective.  The only collective is the final argmin: an all_gather of
+ladder, so whole ladders are placed on one GPU where possible and the sweep path needs NO
+data-path collective.  Collectives: C2, the final argmin -- an all_gather of
 (best energy, rank, local replica) followed by a broadcast of the winning configuration
-from its owner (N bytes).  Works with the nccl backend on GPUs and with gloo on CPU
+from its owner (N bytes) -- and C1, for ladders that span GPUs
+(``shard_replicas_split``): one all-gather of the per-replica energies per exchange round
+(``gather_energies``), after which every rank applies the same decisions from the same
+counter RNG (``sg_exchange`` with ``energies_all``; temperatures move, configurations stay;
+replaces ``anneal_replica_exchange``, reference annealing/multi_gpu.py:234-307).  Works with the nccl backend on GPUs and with gloo on CPU
 tensors (used by the CPU tests of the host logic).
 """
 from __future__ import annotations
@@ -82,9 +86,50 @@ def global_argmin(best_energy: torch.Tensor, best_spins: torch.Tensor,
     return energy, winner, gid
 
 
-def rank_seed(seed: Optional[int], rank: int) -> Optional[int]:
-    """Independent Philox keys per rank (replica ids are local to a rank)."""
-    return None if seed is None else int(seed) * 1_000_003 + rank
+def rank_seed(seed: Optional[int], rank: int) -> int:
+    """Independent Philox keys per rank (replica ids are local to a rank).  With ``seed=None`` the
+    base is torch's initial seed -- which the usual ``torch.manual_seed(k)`` on every rank makes
+    identical across ranks -- so the rank is always mixed in (splitmix64)."""
+    from ._backend import mix_seed
+    base = int(torch.initial_seed()) if seed is None else int(seed)
+    return int(mix_seed(base, 0x52414E4B, rank) & 0x7FFFFFFFFFFFFFFF)
+
+
+def shard_replicas_split(n_replicas: int, world: int, rank: int, n_rungs: int = 1) -> ReplicaShard:
+    """Equal contiguous blocks that MAY cut a ladder (fewer ladders than GPUs, or one long
+    ladder): exchanges then need the all-gathered energy table (``gather_energies``)."""
+    if n_rungs < 1 or n_replicas % n_rungs != 0:
+        raise ValueError("n_replicas must be a multiple of the ladder length")
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    if n_replicas % world != 0:
+        raise ValueError("split ladders need n_replicas divisible by the number of ranks")
+    per = n_replicas // world
+    return ReplicaShard(rank, world, rank * per, per, n_rungs)
+
+
+def gather_energies(local_energy: torch.Tensor, n_global: int, group=None) -> torch.Tensor:
+    """Collective C1: all-gather of the per-replica energies (4 B per replica; the rung of every
+    replica is already known to every rank, since all ranks apply the same exchange decisions).
+    local_energy [R_local] float32 on this rank's device -> [n_global] by global replica id.
+    NCCL on GPUs (NVLink), gloo on CPU tensors.  Without a process group: the input itself."""
+    if not (dist.is_available() and dist.is_initialized()):
+        if local_energy.numel() != n_global:
+            raise ValueError("no process group: the local energies must be the whole table")
+        return local_energy
+    world = dist.get_world_size(group)
+    if local_energy.numel() * world != n_global:
+        raise ValueError("gather_energies needs equal shards (n_global = world x R_local)")
+    out = torch.empty(n_global, dtype=local_energy.dtype, device=local_energy.device)
+    dist.all_gather_into_tensor(out, local_energy.contiguous(), group=group)
+    return out
+
+
+def sum_over_ranks(t: torch.Tensor, group=None) -> torch.Tensor:
+    if dist.is_available() and dist.is_initialized():
+        t = t.clone()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
 
 
 @dataclass
@@ -121,6 +166,8 @@ class MultiGPUAnnealer:
 
     def shard(self) -> ReplicaShard:
         rungs = self.config.n_rungs if self.config.strategy == "replica_exchange" else 1
+        if rungs > 1 and self.world > 1 and (self.config.n_replicas // rungs) % self.world != 0:
+            return shard_replicas_split(self.config.n_replicas, self.world, self.rank, rungs)
         return shard_replicas(self.config.n_replicas, self.world, self.rank, rungs)
 
     def anneal(self, model, update_rule=None):
@@ -134,9 +181,23 @@ class MultiGPUAnnealer:
         local_device = torch.cuda.current_device() if torch.cuda.is_available() else 0
         if self.config.strategy == "replica_exchange":
             cfg = copy.copy(self.annealer_config) if self.annealer_config else ParallelTemperingConfig()
+            ladders = self.config.n_replicas // self.config.n_rungs
+            cfg.device_index = local_device
+            if self.world > 1 and ladders % self.world != 0:
+                # ladders span GPUs: one global replica set, same seed everywhere, energies
+                # all-gathered at every exchange round (C1); the result is already global
+                cfg.n_replicas, cfg.n_ladders = self.config.n_rungs, ladders
+                cfg.shard = shard_replicas_split(self.config.n_replicas, self.world, self.rank,
+                                                 self.config.n_rungs)
+                if cfg.random_seed is None:
+                    t = torch.tensor([torch.initial_seed() & 0x7FFFFFFF], dtype=torch.int64,
+                                     device=torch.device("cuda", local_device)
+                                     if torch.cuda.is_available() else "cpu")
+                    dist.broadcast(t, src=0)
+                    cfg.random_seed = int(t.item())
+                return ParallelTempering(cfg).run(model, rule)
             cfg.n_replicas, cfg.n_ladders = self.config.n_rungs, max(1, sh.n_ladders)
             cfg.random_seed = rank_seed(cfg.random_seed, self.rank)
-            cfg.device_index = local_device
             res = ParallelTempering(cfg).run(model, rule)
         else:
             cfg = copy.copy(self.annealer_config) if self.annealer_config else GPUAnnealerConfig()

@@ -4,7 +4,14 @@ Drop-in for the reference's ``ParallelTempering(ParallelTemperingConfig).run(mod
 update_rule) -> AnnealingResult`` (reference annealing/parallel_tempering.py:16-144):
 
 * same config fields and defaults (:16-36) plus ``n_ladders`` (independent ladders run
-  side by side; R = n_ladders x n_replicas replicas) and ``device_index``;
+  side by side; R = n_ladders x n_replicas replicas), ``device_index``, ``rng_mode`` /
+  ``replay`` (the reference's recorded random stream, injected) and ``shard`` (ladders that
+  span GPUs);
+* ``exchange_method``: "nearest_neighbor" (:214-220) and "all_pairs" as the reference's CPU branch
+  runs it (:228-232: every pair i < j attempted with probability 0.1, in order);
+* ``acceptance_rate_history`` is per TEMPERATURE as in the reference (:137), although the
+  configurations do not move: every launch credits a replica's accepted flips to the rung it sat
+  on;
 * the ladder is generated exactly as in the reference (:146-173); rung 0 is the HOTTEST;
 * every outer iteration sweeps all replicas once (:191-203 -> one kernel launch for all
   sweeps up to the next exchange / record point), exchanges are attempted when
@@ -27,7 +34,7 @@ import numpy as np
 import torch
 
 from ..core.spin_dynamics import UpdateRule
-from ._backend import as_pm1_float, engine_for, random_spins, rule_name, site_order_for
+from ._backend import as_pm1_float, engine_for, mix_seed, random_spins, rule_name, site_order_for
 from .result import AnnealingResult
 
 
@@ -47,6 +54,22 @@ class ParallelTemperingConfig:
     n_ladders: int = 1
     site_order: str = "random"
     device_index: int = 0
+    kernel: str = "auto"
+    # "replay": every random number comes from a recorded run of the reference, by TEMPERATURE
+    # SLOT (the reference keeps slot k at temperature k and moves configurations):
+    #   replay = {"spins0": [K, n], "sites": int [n_sweeps, K, n], "uniforms": f32 [n_sweeps, K, n],
+    #             "exchange_draws": one list of numpy draws per exchange round, in the order the
+    #             reference made them (nearest_neighbor: the start parity, then one uniform per
+    #             pair; all_pairs: selection draw per pair + acceptance draw per selected pair)}
+    # One ladder; the best configuration is then taken at the record points over the slots, as
+    # the reference does (:117-125), instead of after every sweep.
+    rng_mode: str = "philox"
+    replay: Optional[dict] = None
+    # ladders that span GPUs (one process per GPU): this rank holds the global replicas
+    # [shard.start, shard.start + shard.count) of n_ladders x n_replicas; every exchange round
+    # all-gathers the energies (multi_gpu.gather_energies) and every rank applies the same
+    # decisions.  None = all replicas on this GPU.
+    shard: Optional[object] = None
 
 
 class ParallelTempering:
@@ -54,7 +77,7 @@ class ParallelTempering:
         self.config = config
         if config.random_seed is not None:
             torch.manual_seed(config.random_seed)
-            np.random.seed(config.random_seed)
+            np.random.seed(int(config.random_seed) & 0xFFFFFFFF)
         self.temperatures = self._generate_temperature_ladder()
         self.replicas: List = []   # reference attribute (list of models); state lives on the GPU
         self.dynamics: List = []
@@ -89,24 +112,62 @@ class ParallelTempering:
         start = time.time()
         if c.exchange_method not in ("nearest_neighbor", "all_pairs"):
             raise ValueError(f"Unknown exchange method: {c.exchange_method}")
+        if c.rng_mode not in ("philox", "replay"):
+            raise ValueError(f"Unknown rng_mode: {c.rng_mode}")
         rule = rule_name(update_rule)
         eng = engine_for(model, c.device_index)
         n, K, L = model.n_spins, c.n_replicas, max(1, int(c.n_ladders))
-        R = K * L
+        Rg = K * L                               # replicas over all ranks
+        sh = c.shard
+        lo, R = (int(sh.start), int(sh.count)) if sh is not None else (0, Rg)
+        replay = c.replay if c.rng_mode == "replay" else None
+        if c.rng_mode == "replay":
+            if replay is None or L != 1 or sh is not None:
+                raise ValueError("rng_mode='replay' needs the replay streams, one ladder and no sharding")
         seed = c.random_seed if c.random_seed is not None else int(torch.initial_seed() & 0x7FFFFFFF)
-        host_rng = np.random.RandomState(seed & 0xFFFFFFFF)
-        gen = torch.Generator(device=eng.device)
-        gen.manual_seed(int(seed) + 104729)
+        host_rng = np.random.RandomState(seed & 0xFFFFFFFF)   # same draws on every rank
+        key = mix_seed(seed, 0x50540001)
+        xkey = mix_seed(seed, 0x50540002)
 
         if eng.n_replicas != R:
             eng.alloc_replicas(R)
-        eng.set_spins(random_spins(R, n, eng.device, gen))  # replicas start random (:175-189)
+        if replay is not None:
+            spins0 = torch.as_tensor(np.asarray(replay["spins0"]), device=eng.device).to(torch.int8)
+            r_sites = torch.as_tensor(np.asarray(replay["sites"]), dtype=torch.int32, device=eng.device)
+            r_uni = torch.as_tensor(np.nan_to_num(np.asarray(replay["uniforms"], np.float32), nan=0.5),
+                                    dtype=torch.float32, device=eng.device)
+            draws = [list(d) for d in replay["exchange_draws"]]
+        else:
+            gen = torch.Generator(device=eng.device)
+            gen.manual_seed(int(mix_seed(seed, 0x50540003) & 0x7FFFFFFFFFFFFFFF))
+            # replicas start random (:175-189); a shard takes its rows of the global draw, so a
+            # sharded run starts from the configurations the single-GPU run would
+            spins0 = random_spins(Rg, n, eng.device, gen)[lo:lo + R]
+        eng.set_spins(spins0.contiguous())
         eng.init_fields()
-        eng.set_ladder([max(float(t), 1e-10) for t in self.temperatures])
+        eng.set_ladder([max(float(t), 1e-10) for t in self.temperatures], n_global=Rg, replica_offset=lo)
+
+        def all_energies():
+            """Energies of every replica by global id (the collective C1 when sharded)."""
+            e = eng.energies()
+            if sh is None:
+                return e
+            from .multi_gpu import gather_energies
+            return gather_energies(e, Rg)
+
+        def rung_of_local():
+            rep_at = eng.ladder_state()[0].long()
+            rung = torch.empty(Rg, dtype=torch.long, device=eng.device)
+            rung[rep_at] = torch.arange(Rg, device=eng.device) % K
+            return rep_at, rung[lo:lo + R]
 
         self.energy_histories = [[] for _ in range(K)]
         self.temp_histories = [[] for _ in range(K)]
         recorded = []  # device tensors [K] of rung energies (ladder 0), fetched once at the end
+        rung_acc = torch.zeros(K, dtype=torch.long, device=eng.device)   # accepted flips per rung
+        acc_prev = eng.accepted().clone()
+        rp_best_e = torch.full((), float("inf"), dtype=torch.float32, device=eng.device)
+        rp_best_s = torch.zeros(n, dtype=torch.int8, device=eng.device)
         sweep = 0
         xround = 0
         ex_iv, rec_iv = max(1, c.exchange_interval), max(1, c.record_interval)
@@ -118,16 +179,49 @@ class ParallelTempering:
                     break
                 nxt += 1
             k = nxt - sweep + 1
-            eng.sweep(k, None, rule=rule, site_order=site_order_for(eng, c.site_order), seed=int(seed),
-                      sweep_base=sweep, track_best=True)
+            rep_at, rung_loc = rung_of_local()
+            if replay is not None:
+                # slot (= rung) streams -> the replica that sits on the rung in this segment
+                sl = r_sites[sweep:sweep + k]                       # [k, K, n]
+                ul = r_uni[sweep:sweep + k]
+                sites_rep = sl[:, rung_loc, :].permute(1, 0, 2).contiguous()   # [R, k, n]
+                uni_rep = ul[:, rung_loc, :].permute(1, 0, 2).contiguous()
+                eng.sweep(k, None, rule=rule, sites=sites_rep, sites_block_stride=k * n,
+                          sites_sweep_stride=n, uniforms=uni_rep, replicas_per_block=1,
+                          track_best=True, kernel="simt" if c.kernel == "auto" else c.kernel)
+            else:
+                eng.sweep(k, None, rule=rule, site_order=site_order_for(eng, c.site_order), seed=key,
+                          sweep_base=sweep, track_best=True, kernel=c.kernel, replica_base=lo)
             eng.refresh_fields()  # exact fields / energies before they feed an exchange decision
+            acc_now = eng.accepted()
+            rung_acc.index_add_(0, rung_loc, (acc_now - acc_prev))
+            acc_prev = acc_now.clone()
             sweep = nxt
             if sweep % ex_iv == 0 and sweep > 0:
-                eng.exchange(int(host_rng.randint(0, 2)), seed=int(seed) ^ 0x5DEECE66D, round=xround)
+                e_all = all_energies() if sh is not None else None
+                if replay is not None:
+                    d = draws[xround]
+                    if c.exchange_method == "nearest_neighbor":
+                        eng.exchange(int(d[0]), uniforms=np.asarray(d[1:] + [0.0] * (K // 2), np.float64)[:max(K // 2, 1)])
+                    else:
+                        u = np.zeros(K * (K - 1), np.float64)
+                        u[:len(d)] = d
+                        eng.exchange(0, uniforms=u, method="all_pairs")
+                elif c.exchange_method == "nearest_neighbor":
+                    eng.exchange(int(host_rng.randint(0, 2)), seed=xkey, round=xround, energies_all=e_all)
+                else:
+                    eng.exchange(0, seed=xkey, round=xround, method="all_pairs", energies_all=e_all)
                 xround += 1
             if sweep % rec_iv == 0:
                 rep_at = eng.ladder_state()[0][:K].long()
-                recorded.append(eng.energies()[rep_at])
+                e_now = all_energies()
+                rung_e = e_now[rep_at]
+                recorded.append(rung_e)
+                if replay is not None:      # the reference's best tracking (:121-125)
+                    idx = torch.argmin(rung_e)          # first minimum, like min() over the slots
+                    better = rung_e[idx] < rp_best_e
+                    rp_best_e = torch.where(better, rung_e[idx], rp_best_e)
+                    rp_best_s = torch.where(better, eng.spins()[rep_at[idx]], rp_best_s)
             sweep += 1
 
         rep_at, rep_T, att, acc = eng.ladder_state()
@@ -138,16 +232,26 @@ class ParallelTempering:
             for r in range(K):
                 self.energy_histories[r] = hist[:, r].tolist()
                 self.temp_histories[r] = [self.temperatures[r]] * hist.shape[0]
-        _, best_s = eng.best()
-        best_e = eng.batch_energies(best_s)   # exact energies of the best configurations
-        r_best = int(torch.argmin(best_e).item())
-        accepted = eng.accepted().double()
-        rates = (accepted[rep_at[:K].long()] / float(c.n_sweeps * n)).cpu().tolist()
+        if sh is not None:
+            from .multi_gpu import sum_over_ranks
+            rung_acc = sum_over_ranks(rung_acc)
+        # acceptance rate per TEMPERATURE (the reference's dynamics[k] stays with slot k, :137)
+        rates = (rung_acc.double() / float(c.n_sweeps * n * L)).cpu().tolist()
         self._final_spins = eng.spins()
         self._rung_replica = rep_at.cpu().numpy()
+        if replay is not None:
+            best_cfg, best_val = rp_best_s, float(rp_best_e.item())
+        else:
+            _, best_s = eng.best()
+            best_e = eng.batch_energies(best_s)   # exact energies of the best configurations
+            r_best = int(torch.argmin(best_e).item())
+            best_cfg, best_val = best_s[r_best], float(best_e[r_best].item())
+            if sh is not None:
+                from .multi_gpu import global_argmin
+                best_val, best_cfg, _ = global_argmin(best_e, best_s, sh)
         total_time = time.time() - start
         return AnnealingResult(
-            best_configuration=as_pm1_float(best_s[r_best]), best_energy=float(best_e[r_best].item()),
+            best_configuration=as_pm1_float(best_cfg), best_energy=best_val,
             energy_history=list(self.energy_histories[0]), temperature_history=list(self.temp_histories[0]),
             acceptance_rate_history=rates, total_time=total_time, n_sweeps=c.n_sweeps,
             algorithm="parallel_tempering", device=str(self.device), random_seed=c.random_seed)

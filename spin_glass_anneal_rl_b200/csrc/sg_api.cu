@@ -116,6 +116,7 @@ struct sg_engine {
     bool fields_valid = false;
     // ladder
     int K = 0, L = 0;
+    int n_global = 0, rep_lo = 0;   // sharded ladders: global replica count, id of local replica 0
     int* rep_at = nullptr;
     double* rep_temp = nullptr;
     double* ladder = nullptr;
@@ -255,6 +256,7 @@ void free_ladder(sg_engine* e) {
     cudaFree(e->attempts); e->attempts = nullptr;
     cudaFree(e->accepts); e->accepts = nullptr;
     e->K = e->L = 0;
+    e->n_global = e->rep_lo = 0;
 }
 
 }  // namespace
@@ -1315,6 +1317,9 @@ int sg_sweep(sg_engine* e, const sg_sweep_params* p, void* stream) {
     a.dbg = e->dbg;
     a.site_de = p->site_energy_changes;
     a.rpm = (e->stacked && !e->csr && !e->lat) ? e->R / e->n_models : 0;
+    SG_REQUIRE(p->replica_base >= 0 && (!e->lat || p->replica_base % 32 == 0),
+               "sg_sweep: replica_base must be >= 0 (a multiple of 32 for lattice models)");
+    a.rep_base = p->replica_base;
     SG_REQUIRE(!a.site_de || (!e->csr && !e->lat && p->kernel != SG_KERNEL_TC &&
                               (p->kernel == SG_KERNEL_SIMT || p->kernel == SG_KERNEL_SMALL ||
                                p->rng_mode == SG_RNG_INJECTED || sg::sweep_small_supported(e->n))),
@@ -1411,15 +1416,23 @@ int sg_sweep(sg_engine* e, const sg_sweep_params* p, void* stream) {
 }
 
 int sg_set_ladder(sg_engine* e, int n_rungs, const double* ladder_temps, void* stream) {
+    SG_REQUIRE(e && e->R > 0, "sg_set_ladder: allocate replicas first");
+    return sg_set_ladder_sharded(e, n_rungs, ladder_temps, e->R, 0, stream);
+}
+
+int sg_set_ladder_sharded(sg_engine* e, int n_rungs, const double* ladder_temps, int n_global_replicas,
+                          int replica_offset, void* stream) {
     SG_REQUIRE(e && ladder_temps && e->R > 0, "sg_set_ladder: allocate replicas first");
-    SG_REQUIRE(n_rungs >= 1 && e->R % n_rungs == 0,
-               "sg_set_ladder: n_replicas must be a multiple of n_rungs");
+    SG_REQUIRE(n_rungs >= 1 && n_global_replicas >= e->R && n_global_replicas % n_rungs == 0,
+               "sg_set_ladder: the (global) replica count must be a multiple of n_rungs");
+    SG_REQUIRE(replica_offset >= 0 && replica_offset + e->R <= n_global_replicas,
+               "sg_set_ladder_sharded: local replicas must lie inside the global range");
     DeviceGuard g(e->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     free_ladder(e);
-    const int K = n_rungs, L = e->R / n_rungs;
+    const int K = n_rungs, L = n_global_replicas / n_rungs;
     int rc;
-    if ((rc = dev_alloc(&e->rep_at, (size_t)e->R)) != SG_OK) return rc;
+    if ((rc = dev_alloc(&e->rep_at, (size_t)n_global_replicas)) != SG_OK) return rc;
     if ((rc = dev_alloc(&e->rep_temp, (size_t)e->R)) != SG_OK) return rc;
     if ((rc = dev_alloc(&e->ladder, (size_t)K)) != SG_OK) return rc;
     const size_t nstat = (size_t)L * (K > 1 ? K - 1 : 1);
@@ -1429,11 +1442,14 @@ int sg_set_ladder(sg_engine* e, int n_rungs, const double* ladder_temps, void* s
                             cudaMemcpyHostToDevice, st));
     SG_CUDA(cudaMemsetAsync(e->attempts, 0, nstat * sizeof(unsigned int), st));
     SG_CUDA(cudaMemsetAsync(e->accepts, 0, nstat * sizeof(unsigned int), st));
-    SG_CUDA(sg::launch_ladder_init(e->rep_at, e->rep_temp, e->ladder, L, K, st));
+    SG_CUDA(sg::launch_ladder_init(e->rep_at, e->rep_temp, e->ladder, n_global_replicas, K,
+                                   replica_offset, e->R, st));
     e->launches++;
     SG_CUDA(cudaStreamSynchronize(st));  // ladder_temps is a host buffer
     e->K = K;
     e->L = L;
+    e->n_global = n_global_replicas;
+    e->rep_lo = replica_offset;
     return SG_OK;
 }
 
@@ -1442,13 +1458,17 @@ int sg_exchange(sg_engine* e, const sg_exchange_params* p, void* stream) {
     SG_REQUIRE(p->struct_size == sizeof(sg_exchange_params), "sg_exchange: struct_size mismatch");
     SG_REQUIRE(e->K > 0, "sg_exchange: call sg_set_ladder first");
     SG_REQUIRE(p->parity == 0 || p->parity == 1, "sg_exchange: parity must be 0 or 1");
+    SG_REQUIRE(p->method == SG_EXCHANGE_NEAREST || p->method == SG_EXCHANGE_ALL_PAIRS,
+               "sg_exchange: unknown method");
     SG_REQUIRE(p->rng_mode != SG_RNG_INJECTED || p->uniforms, "sg_exchange: uniforms missing");
+    SG_REQUIRE(p->energies_all || e->n_global == e->R,
+               "sg_exchange: a sharded ladder needs the all-gathered energy table (energies_all)");
     DeviceGuard g(e->device);
     sg::ExchangeDev a{};
     a.rep_at = e->rep_at;
     a.rep_temp = e->rep_temp;
     a.ladder = e->ladder;
-    a.energy = e->energy;
+    a.energy = p->energies_all ? p->energies_all : e->energy;
     a.attempts = e->attempts;
     a.accepts = e->accepts;
     a.uniforms = p->uniforms;
@@ -1458,7 +1478,20 @@ int sg_exchange(sg_engine* e, const sg_exchange_params* p, void* stream) {
     a.K = e->K;
     a.parity = p->parity;
     a.inject = (p->rng_mode == SG_RNG_INJECTED);
+    a.method = p->method;
+    a.rep_lo = e->rep_lo;
+    a.rep_n = e->R;
     SG_CUDA(sg::launch_exchange(a, static_cast<cudaStream_t>(stream)));
+    e->launches++;
+    return SG_OK;
+}
+
+int sg_check_target(sg_engine* e, int which, float target, int32_t round, int32_t* hit, void* stream) {
+    SG_REQUIRE(e && hit && e->R > 0 && e->fields_valid, "sg_check_target: call sg_init_fields first");
+    SG_REQUIRE(which == 0 || which == 1, "sg_check_target: which must be 0 (current) or 1 (best so far)");
+    DeviceGuard g(e->device);
+    SG_CUDA(sg::launch_check_target(which ? e->best_energy : e->energy, e->R, e->rep_lo, target, round,
+                                    hit, static_cast<cudaStream_t>(stream)));
     e->launches++;
     return SG_OK;
 }
@@ -1512,7 +1545,7 @@ int sg_get_ladder_state(sg_engine* e, int32_t* replica_at_rung, double* replica_
     const size_t nstat = (size_t)e->L * (e->K > 1 ? e->K - 1 : 1);
     int rc = SG_OK;
     if (replica_at_rung)
-        rc = copy_out(replica_at_rung, e->rep_at, (size_t)e->R * sizeof(int), on_device, st);
+        rc = copy_out(replica_at_rung, e->rep_at, (size_t)e->n_global * sizeof(int), on_device, st);
     if (rc == SG_OK && replica_temps)
         rc = copy_out(replica_temps, e->rep_temp, (size_t)e->R * sizeof(double), on_device, st);
     if (rc == SG_OK && attempts)

@@ -8,7 +8,10 @@
 // i+1; here the configurations stay where they are and the TEMPERATURES move: the
 // map rung -> replica (rep_at) and the per-replica temperature are swapped instead,
 // which is the same Markov chain with O(1) traffic per accepted exchange.
-// One thread per (ladder, pair); pairs of one parity are disjoint.
+// One warp per ladder, partner energies by warp shuffle; pairs of one parity are disjoint.
+// Sharded ladders (one ladder over several GPUs): `energy` is the all-gathered table indexed by
+// GLOBAL replica id, every rank takes the same decisions from the same counter RNG and keeps the
+// same rung -> replica map; only the temperatures of its own replicas are stored locally.
 #include "sg_common.cuh"
 #include "sg_internal.h"
 
@@ -16,46 +19,150 @@ namespace sg {
 
 namespace {
 
+// 53-bit uniform in [0, 1) from two Philox words
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
+    return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+// The temperature of a replica is stored only by the rank that holds it (sharded ladders: the
+// rung -> replica map is global and kept identically by every rank, rep_temp is local).
+__device__ __forceinline__ void set_temp(const ExchangeDev& a, int rep, double T) {
+    const int loc = rep - a.rep_lo;
+    if (loc >= 0 && loc < a.rep_n) a.rep_temp[loc] = T;
+}
+
+// One WARP per ladder: lane j owns rungs j, j + 32, ... and keeps (replica, energy) of its rung
+// in registers; the upper partner of a pair comes from the next lane with a shuffle, so every
+// energy is read once.  Pairs of one parity are disjoint, so all lanes decide at once.
 __global__ void exchange_kernel(const ExchangeDev a) {
+    const int lane = threadIdx.x & 31;
+    const int l = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (l >= a.L) return;
     const int npairs = (a.K - a.parity) / 2;  // pairs (k, k+1), k = parity, parity+2, ... < K-1
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.L * npairs) return;
-    const int l = t / npairs, m = t - l * npairs;
-    const int k = a.parity + 2 * m;
-    if (k + 1 >= a.K) return;
     int* slot = a.rep_at + (size_t)l * a.K;
-    const int ra = slot[k], rb = slot[k + 1];
-    const double Ti = a.ladder[k], Tj = a.ladder[k + 1];
-    const double bi = 1.0 / Ti, bj = 1.0 / Tj;
-    const double Ei = (double)a.energy[ra], Ej = (double)a.energy[rb];
-    const double arg = (bj - bi) * (Ej - Ei);
-    const double prob = fmin(1.0, exp(arg));
-    double u;
-    if (a.inject) {
-        u = a.uniforms[(size_t)l * (a.K / 2) + m];
-    } else {
-        const uint4 x = philox4x32_10(
-            make_uint4(0xE8C4A46Eu, (uint32_t)a.round, (uint32_t)(a.round >> 32), (uint32_t)t),
-            make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
-        u = ((double)(x.x >> 5) * 67108864.0 + (double)(x.y >> 6)) * (1.0 / 9007199254740992.0);
-    }
-    const size_t st = (size_t)l * (a.K - 1) + k;
-    a.attempts[st] += 1u;
-    if (u < prob) {
-        slot[k] = rb;
-        slot[k + 1] = ra;
-        a.rep_temp[ra] = Tj;
-        a.rep_temp[rb] = Ti;
-        a.accepts[st] += 1u;
+    for (int k0 = 0; k0 < a.K; k0 += 32) {
+        const int k = k0 + lane;
+        const int rep = (k < a.K) ? slot[k] : 0;
+        const double E = (k < a.K) ? (double)a.energy[rep] : 0.0;
+        // partner on rung k + 1: the next lane's values; the last lane reaches into the next chunk
+        int rep_up = __shfl_down_sync(0xFFFFFFFFu, rep, 1);
+        double E_up = __shfl_down_sync(0xFFFFFFFFu, E, 1);
+        if (lane == 31 && k + 1 < a.K) {
+            rep_up = slot[k + 1];
+            E_up = (double)a.energy[rep_up];
+        }
+        const bool mine = k + 1 < a.K && k >= a.parity && ((k - a.parity) & 1) == 0;
+        // (all loads and shuffles of the chunk are done before any lane rewrites the map)
+        __syncwarp();
+        if (mine) {
+            const int m = (k - a.parity) >> 1;
+            const double Ti = a.ladder[k], Tj = a.ladder[k + 1];
+            const double arg = (1.0 / Tj - 1.0 / Ti) * (E_up - E);
+            const double prob = fmin(1.0, exp(arg));
+            double u;
+            if (a.inject) {
+                u = a.uniforms[(size_t)l * (a.K / 2) + m];
+            } else {
+                const int t = l * npairs + m;
+                const uint4 x = philox4x32_10(
+                    make_uint4(0xE8C4A46Eu, (uint32_t)a.round, (uint32_t)(a.round >> 32), (uint32_t)t),
+                    make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+                u = u53(x.x, x.y);
+            }
+            const size_t st = (size_t)l * (a.K - 1) + k;
+            a.attempts[st] += 1u;
+            if (u < prob) {
+                slot[k] = rep_up;
+                slot[k + 1] = rep;
+                set_temp(a, rep, Tj);
+                set_temp(a, rep_up, Ti);
+                a.accepts[st] += 1u;
+            }
+        }
+        __syncwarp();
     }
 }
 
-__global__ void ladder_init_kernel(int* rep_at, double* rep_temp, const double* ladder, int L,
-                                   int K) {
+// ParallelTempering._all_pairs_exchange, CPU branch (reference annealing/parallel_tempering.py:
+// 228-232): every pair i < j is attempted with probability 0.1, in order, each attempt seeing the
+// swaps before it; statistics are filed under min(i, j).  A dependency chain over K (K-1) / 2
+// scalars per ladder: one thread per ladder.  Draw c of ladder l is uniforms[l * K (K-1) + c]
+// (injected: the caller's stream in consumption order) or Philox word pair c.
+__global__ void exchange_all_pairs_kernel(const ExchangeDev a) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= a.L) return;
+    int* slot = a.rep_at + (size_t)l * a.K;
+    const double* inj = a.inject ? a.uniforms + (size_t)l * a.K * (a.K - 1) : nullptr;
+    unsigned int c = 0;
+    auto draw = [&]() -> double {
+        double u;
+        if (inj) {
+            u = inj[c];
+        } else {
+            const uint4 x = philox4x32_10(
+                make_uint4(0xA11FA125u ^ (uint32_t)l, (uint32_t)a.round, (uint32_t)(a.round >> 32), c),
+                make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+            u = u53(x.x, x.y);
+        }
+        ++c;
+        return u;
+    };
+    for (int i = 0; i + 1 < a.K; ++i)
+        for (int j = i + 1; j < a.K; ++j) {
+            if (!(draw() < 0.1)) continue;
+            const int ra = slot[i], rb = slot[j];
+            const double Ti = a.ladder[i], Tj = a.ladder[j];
+            const double arg = (1.0 / Tj - 1.0 / Ti) * ((double)a.energy[rb] - (double)a.energy[ra]);
+            const double prob = fmin(1.0, exp(arg));
+            const size_t st = (size_t)l * (a.K - 1) + i;
+            a.attempts[st] += 1u;
+            if (draw() < prob) {
+                slot[i] = rb;
+                slot[j] = ra;
+                set_temp(a, ra, Tj);
+                set_temp(a, rb, Ti);
+                a.accepts[st] += 1u;
+            }
+        }
+}
+
+// hit[0] = first `round` at which min_r energy[r] <= target (-1 until then), hit[1] = that replica
+// (global id).  hit may live in pinned host memory: the host polls it without synchronising.
+__global__ void check_target_kernel(const float* __restrict__ energy, int R, int rep_lo, float target,
+                                    int round, volatile int* hit) {
+    __shared__ float s_e[32];
+    __shared__ int s_r[32];
+    float best = 3.0e38f;
+    int arg = 0x7FFFFFFF;
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        const float v = energy[r];
+        if (v < best) { best = v; arg = r; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const float v = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+        const int w = __shfl_xor_sync(0xFFFFFFFFu, arg, o);
+        if (v < best || (v == best && w < arg)) { best = v; arg = w; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_e[threadIdx.x >> 5] = best; s_r[threadIdx.x >> 5] = arg; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+            if (s_e[w] < best || (s_e[w] == best && s_r[w] < arg)) { best = s_e[w]; arg = s_r[w]; }
+        if (arg != 0x7FFFFFFF && best <= target && hit[0] < 0) {
+            hit[1] = rep_lo + arg;
+            __threadfence_system();
+            hit[0] = round;
+        }
+    }
+}
+
+__global__ void ladder_init_kernel(int* rep_at, double* rep_temp, const double* ladder, int n_global,
+                                   int K, int rep_lo, int rep_n) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= L * K) return;
+    if (t >= n_global) return;
     rep_at[t] = t;  // replica l*K + k starts on rung k of ladder l
-    rep_temp[t] = ladder[t % K];
+    const int loc = t - rep_lo;
+    if (loc >= 0 && loc < rep_n) rep_temp[loc] = ladder[t % K];
 }
 
 // ---- the reference's operator form of the exchange (annealing/cuda_kernels.py:326-369 with the
@@ -203,16 +310,26 @@ cudaError_t launch_exchange_chain(void* rows, long long row_stride, long long ro
 size_t exchange_chain_header_bytes(int R) { return (((size_t)R + 1) * sizeof(int) + 15) & ~(size_t)15; }
 
 cudaError_t launch_exchange(ExchangeDev a, cudaStream_t st) {
-    const int npairs = (a.K - a.parity) / 2;
-    const int total = a.L * npairs;
-    if (total <= 0) return cudaSuccess;
-    exchange_kernel<<<(total + 127) / 128, 128, 0, st>>>(a);
+    if (a.L <= 0 || a.K < 2) return cudaSuccess;
+    if (a.method == 1) {
+        exchange_all_pairs_kernel<<<(a.L + 63) / 64, 64, 0, st>>>(a);
+    } else {
+        if ((a.K - a.parity) / 2 <= 0) return cudaSuccess;
+        exchange_kernel<<<(a.L + 3) / 4, 128, 0, st>>>(a);   // one warp per ladder
+    }
     return cudaGetLastError();
 }
 
-cudaError_t launch_ladder_init(int* rep_at, double* rep_temp, const double* ladder, int L, int K,
-                               cudaStream_t st) {
-    ladder_init_kernel<<<(L * K + 127) / 128, 128, 0, st>>>(rep_at, rep_temp, ladder, L, K);
+cudaError_t launch_check_target(const float* energy, int R, int rep_lo, float target, int round, int* hit,
+                                cudaStream_t st) {
+    check_target_kernel<<<1, 1024, 0, st>>>(energy, R, rep_lo, target, round, hit);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ladder_init(int* rep_at, double* rep_temp, const double* ladder, int n_global, int K,
+                               int rep_lo, int rep_n, cudaStream_t st) {
+    ladder_init_kernel<<<(n_global + 127) / 128, 128, 0, st>>>(rep_at, rep_temp, ladder, n_global, K,
+                                                                rep_lo, rep_n);
     return cudaGetLastError();
 }
 

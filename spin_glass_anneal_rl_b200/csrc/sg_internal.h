@@ -32,6 +32,7 @@ struct SweepDev {
     long long* dbg;           // optional timeline buffer (development aid), block 0 only
     float* site_de;           // optional [R][n]: sum of the accepted energy changes per site
     int rpm;                  // stacked models (K1-SMALL): replicas per model, 0 = one model
+    int rep_base;             // global id of replica 0 (Philox key of replica r = rep_base + r; sharded runs)
 };
 
 // Largest number of replicas one block can hold for this padded size (0 = unsupported).
@@ -211,15 +212,17 @@ cudaError_t launch_sites_table(const SweepDev& a, int* out, cudaStream_t st);
 
 // K3 (sg_exchange.cu)
 struct ExchangeDev {
-    int* rep_at;              // [L][K] replica currently at rung k of ladder l
-    double* rep_temp;         // [R]
+    int* rep_at;              // [L][K] (global) replica currently at rung k of ladder l
+    double* rep_temp;         // [rep_n] temperatures of the local replicas
     const double* ladder;     // [K]
-    const float* energy;      // [R]
+    const float* energy;      // indexed by global replica id ([rep_n] when unsharded)
     unsigned int* attempts;   // [L][K-1]
     unsigned int* accepts;    // [L][K-1]
-    const double* uniforms;   // injected [L][K/2] or null
+    const double* uniforms;   // injected [L][K/2] (nearest) / [L][K(K-1)] (all pairs) or null
     unsigned long long seed, round;
     int L, K, parity, inject;
+    int method;               // 0 = nearest neighbour (even/odd), 1 = all pairs
+    int rep_lo, rep_n;        // local replicas are the global ids [rep_lo, rep_lo + rep_n)
 };
 cudaError_t launch_exchange(ExchangeDev a, cudaStream_t st);
 // ADAPTIVE schedule step on the device (see sg_exchange.cu)
@@ -233,7 +236,9 @@ cudaError_t launch_exchange_chain(void* rows, long long row_stride, long long ro
                                   float* energies, const float* temps, const float* uniforms,
                                   unsigned long long seed, unsigned long long round, void* scratch,
                                   cudaStream_t st);
-cudaError_t launch_ladder_init(int* rep_at, double* rep_temp, const double* ladder, int L, int K,
-                               cudaStream_t st);
+cudaError_t launch_ladder_init(int* rep_at, double* rep_temp, const double* ladder, int n_global, int K,
+                               int rep_lo, int rep_n, cudaStream_t st);
+cudaError_t launch_check_target(const float* energy, int R, int rep_lo, float target, int round, int* hit,
+                                cudaStream_t st);
 
 }  // namespace sg

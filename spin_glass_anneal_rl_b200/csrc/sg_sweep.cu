@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_kernel(const SweepDev 
         const unsigned long long sa = a.sweep_base + (unsigned long long)s;
         const float T = (float)a.temps[(long long)s * a.t_ss + (long long)rep * a.t_rs];
         const uint4 x = philox4x32_10(
-            make_uint4((uint32_t)rep, (uint32_t)sa, (uint32_t)(sa >> 32), (uint32_t)(i0 >> 2)), key);
+            make_uint4((uint32_t)(rep + a.rep_base), (uint32_t)sa, (uint32_t)(sa >> 32), (uint32_t)(i0 >> 2)), key);
         const uint32_t v[4] = {x.x, x.y, x.z, x.w};
         float* dst = theta + (size_t)buf * (kSB * 32) + (q * 4) * 32 + r;
 #pragma unroll

@@ -93,7 +93,7 @@ sweep_csr_kernel(const CsrDev m, const SweepDev a, const int* __restrict__ sites
             }
             if (!INJECT && (i & 3) == 0) {
                 const uint4 x = philox4x32_10(
-                    make_uint4((uint32_t)rep, (uint32_t)sa, (uint32_t)(sa >> 32), (uint32_t)(i >> 2)), key);
+                    make_uint4((uint32_t)(rep + a.rep_base), (uint32_t)sa, (uint32_t)(sa >> 32), (uint32_t)(i >> 2)), key);
                 const uint32_t vv[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {

@@ -89,7 +89,7 @@ sweep_groups_kernel(const GrpDev m, const SweepDev a, const int* __restrict__ si
             const float cg = __shfl_sync(0xFFFFFFFFu, b_c, i & 31);
             if (!INJECT && (i & 3) == 0) {
                 const uint4 x = philox4x32_10(
-                    make_uint4((uint32_t)rep, (uint32_t)sa, (uint32_t)(sa >> 32), (uint32_t)(i >> 2)), key);
+                    make_uint4((uint32_t)(rep + a.rep_base), (uint32_t)sa, (uint32_t)(sa >> 32), (uint32_t)(i >> 2)), key);
                 const uint32_t vv[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -307,7 +307,7 @@ sweep_groups_part_kernel(const GrpDev m, const GrpPartDev q, const SweepDev a, c
     };
     auto threshold = [&](int i) -> float {
         const uint4 x = philox4x32_10(
-            make_uint4((uint32_t)rep, (uint32_t)sa, (uint32_t)(sa >> 32), (uint32_t)(i >> 2)), key);
+            make_uint4((uint32_t)(rep + a.rep_base), (uint32_t)sa, (uint32_t)(sa >> 32), (uint32_t)(i >> 2)), key);
         const uint32_t sel = (i & 2) ? ((i & 1) ? x.w : x.z) : ((i & 1) ? x.y : x.x);
         const float u = u01(sel);
         return (a.rule == 0) ? -__logf(u) * Tm : 0.5f * Tm * (__logf(u) - __logf(1.0f - u));

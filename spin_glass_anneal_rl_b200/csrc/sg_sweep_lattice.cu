@@ -97,7 +97,7 @@ lat_update_kernel(const LatDev m, const SweepDev a, int s, int color) {
             uint32_t rr[4] = {0u, 0u, 0u, 0u};
             if (!INJECT) {
                 const uint4 r4 = philox4x32_10(
-                    make_uint4(kLatStreamTag - (uint32_t)q, (uint32_t)sa, (uint32_t)(sa >> 32) ^ ((uint32_t)w << 8),
+                    make_uint4(kLatStreamTag - (uint32_t)q, (uint32_t)sa, (uint32_t)(sa >> 32) ^ ((uint32_t)(w + (a.rep_base >> 5)) << 8),
                                (uint32_t)(iseq)), key);
                 rr[0] = r4.x; rr[1] = r4.y; rr[2] = r4.z; rr[3] = r4.w;
             }

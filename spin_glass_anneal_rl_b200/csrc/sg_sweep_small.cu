@@ -82,7 +82,7 @@ sweep_small_kernel(const SweepDev a, const int* __restrict__ sites_g) {
             }
             if (!INJECT && i0 + 4 * lane < n) {
                 const uint4 x = philox4x32_10(
-                    make_uint4((uint32_t)rep, (uint32_t)sa, (uint32_t)(sa >> 32), (uint32_t)((i0 >> 2) + lane)), key);
+                    make_uint4((uint32_t)(rep + a.rep_base), (uint32_t)sa, (uint32_t)(sa >> 32), (uint32_t)((i0 >> 2) + lane)), key);
                 const uint32_t vv[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {

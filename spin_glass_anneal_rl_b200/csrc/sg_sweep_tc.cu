@@ -674,7 +674,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                         const int rep = rep0 + r;
                         const float Tm = (float)a.temps[(long long)s * a.t_ss + (long long)rep * a.t_rs];
                         const uint4 x = philox4x32_10(
-                            make_uint4((uint32_t)rep, (uint32_t)sa, (uint32_t)(sa >> 32),
+                            make_uint4((uint32_t)(rep + a.rep_base), (uint32_t)sa, (uint32_t)(sa >> 32),
                                        (uint32_t)(ia >> 2)), key);
                         const uint32_t vv[4] = {x.x, x.y, x.z, x.w};
                         float* dst = theta_s + slot * kBlk * NG + (qq * 4) * NG + r;

@@ -234,7 +234,7 @@ class Engine:
               sites_block_stride: int = 0, sites_sweep_stride: Optional[int] = None,
               uniforms: Optional[ArrayLike] = None, energy_trace: bool = False,
               track_best: bool = True, replicas_per_block: int = 0, kernel: str = "auto",
-              coupling_planes: int = 0,
+              coupling_planes: int = 0, replica_base: int = 0,
               site_energy_changes: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
         """Run ``n_sweeps`` sweeps on every replica (one kernel launch).
 
@@ -255,6 +255,7 @@ class Engine:
         p.track_best = 1 if track_best else 0
         p.kernel = _lib.SG_KERNEL[kernel]
         p.coupling_planes = int(coupling_planes)
+        p.replica_base = int(replica_base)
         keep = []
         if temps is not None:
             t = self._dev(temps, torch.float64)
@@ -314,17 +315,27 @@ class Engine:
             self._ptr(temps_out), self.stream), "sg_adaptive_temperature")
 
     # ------------------------------------------------------------------ parallel tempering
-    def set_ladder(self, ladder_temps: Sequence[float]) -> None:
+    def set_ladder(self, ladder_temps: Sequence[float], *, n_global: Optional[int] = None,
+                   replica_offset: int = 0) -> None:
+        """Temperature ladder (rung 0 = hottest).  ``n_global`` / ``replica_offset``: the ladders
+        span several engines; this one holds the global replicas [offset, offset + R)."""
         arr = (ctypes.c_double * len(ladder_temps))(*[float(t) for t in ladder_temps])
-        check(self._lib.sg_set_ladder(self._h, len(ladder_temps), arr, self.stream),
-              "sg_set_ladder")
+        ng = self.n_replicas if n_global is None else int(n_global)
+        check(self._lib.sg_set_ladder_sharded(self._h, len(ladder_temps), arr, ng, int(replica_offset),
+                                              self.stream), "sg_set_ladder")
         self.n_rungs = len(ladder_temps)
+        self.n_global = ng
+        self.replica_offset = int(replica_offset)
 
-    def exchange(self, parity: int, *, seed: int = 0, round: int = 0,
-                 uniforms: Optional[ArrayLike] = None) -> None:
+    def exchange(self, parity: int = 0, *, seed: int = 0, round: int = 0,
+                 uniforms: Optional[ArrayLike] = None, method: str = "nearest_neighbor",
+                 energies_all: Optional[torch.Tensor] = None) -> None:
+        """One exchange round.  ``energies_all``: device float32 [n_global] table of every replica's
+        energy by global id (sharded ladders: the all-gather of ``energies()`` over the ranks)."""
         p = ExchangeParams()
         p.struct_size = ctypes.sizeof(ExchangeParams)
         p.parity = int(parity)
+        p.method = _lib.SG_EXCHANGE[method]
         p.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         p.round = int(round)
         if uniforms is not None:
@@ -334,13 +345,28 @@ class Engine:
             p.rng_mode = _lib.SG_RNG_INJECTED
         else:
             p.rng_mode = _lib.SG_RNG_PHILOX
+        if energies_all is not None:
+            ea = energies_all
+            if (ea.device != self.device or ea.dtype != torch.float32 or not ea.is_contiguous()
+                    or ea.numel() != self.n_global):
+                raise ValueError("energies_all must be a contiguous device float32 [n_global] tensor")
+            self._keep.append(ea)
+            p.energies_all = ea.data_ptr()
         check(self._lib.sg_exchange(self._h, ctypes.byref(p), self.stream), "sg_exchange")
+
+    def check_target(self, target: float, round: int, hit: torch.Tensor, *, best: bool = False) -> None:
+        """Asynchronous early-stop test: hit (int32[2], device or PINNED host tensor, hit[0] = -1
+        initially) receives (round, replica) the first time min energy <= target."""
+        assert hit.dtype == torch.int32 and hit.numel() >= 2 and (hit.is_cuda or hit.is_pinned())
+        check(self._lib.sg_check_target(self._h, 1 if best else 0, float(target), int(round),
+                                        ctypes.c_void_p(hit.data_ptr()), self.stream), "sg_check_target")
 
     def ladder_state(self):
         """(replica_at_rung[R], replica_temps[R], attempts[L, K-1], accepts[L, K-1]) on device."""
         R, K = self.n_replicas, self.n_rungs
-        L = R // K
-        rep_at = torch.empty(R, dtype=torch.int32, device=self.device)
+        Rg = getattr(self, "n_global", R)
+        L = Rg // K
+        rep_at = torch.empty(Rg, dtype=torch.int32, device=self.device)
         temps = torch.empty(R, dtype=torch.float64, device=self.device)
         att = torch.empty((L, max(K - 1, 1)), dtype=torch.int32, device=self.device)
         acc = torch.empty((L, max(K - 1, 1)), dtype=torch.int32, device=self.device)

@@ -160,12 +160,14 @@ def run_sa(name, J, h, spins0, *, seed, n_sweeps, T0, Tf, schedule="geometric", 
 
 
 def run_pt(name, J, h, *, seed, n_replicas, n_sweeps, tmin, tmax, dist="geometric",
-           exchange_interval=5, record_interval=5, rule="metropolis"):
+           exchange_interval=5, record_interval=5, rule="metropolis",
+           method="nearest_neighbor"):
     n = J.shape[0]
     model = make_model(J, h, np.ones(n, np.float32))
     cfg = ParallelTemperingConfig(n_replicas=n_replicas, n_sweeps=n_sweeps, temp_min=tmin,
                                   temp_max=tmax, temp_distribution=dist,
                                   exchange_interval=exchange_interval, n_threads=1,
+                                  exchange_method=method,
                                   record_interval=record_interval, random_seed=seed)
     pt = ParallelTempering(cfg)
     with Recorder() as rec:
@@ -173,6 +175,8 @@ def run_pt(name, J, h, *, seed, n_replicas, n_sweeps, tmin, tmax, dist="geometri
     cfgd = dict(kind="pt", seed=seed, n_replicas=n_replicas, n_sweeps=n_sweeps, tmin=tmin,
                 tmax=tmax, dist=dist, exchange_interval=exchange_interval,
                 record_interval=record_interval, rule=rule)
+    if method != "nearest_neighbor":
+        cfgd["method"] = method
     np.savez_compressed(
         os.path.join(OUT, name + ".npz"), config=json.dumps(cfgd), J=J, h=h,
         best_energy=np.float64(res.best_energy),
@@ -280,6 +284,11 @@ def main():
            dist="linear", exchange_interval=3, record_interval=2)
     run_pt("pt_int_n40_r5_exp", J, np.zeros(40, np.float32), seed=23, n_replicas=5, n_sweeps=40,
            tmin=0.4, tmax=5.0, dist="exponential", exchange_interval=4, record_interval=4)
+
+    # --- the all_pairs exchange (CPU branch of _all_pairs_exchange, parallel_tempering.py:228-232)
+    run_pt("pt_int_n40_r6_allpairs", J, np.zeros(40, np.float32), seed=24, n_replicas=6,
+           n_sweeps=60, tmin=0.5, tmax=6.0, exchange_interval=3, record_interval=3,
+           method="all_pairs")
 
     # --- known-answer energies / local fields
     run_kat("kat_energy_int_n64", sym_pm1(64, rng), rng.integers(-1, 2, size=64).astype(np.float32),

@@ -1,0 +1,219 @@
+"""Replay at the Python API: GPUAnnealer.anneal / ParallelTempering.run fed with the random stream
+the UNMODIFIED reference consumed (tests/golden/*.npz, recorded by tests/golden/make_golden.py)
+must reproduce the reference's own outputs -- best configuration, final spins, histories,
+exchange statistics: bit for bit on integer couplings, within 1e-5 relative on float couplings
+(north_star).  Also the same replays through the tensor-core kernel (the benchmarked one), and a
+cluster-sized float case (N = 4096 Gaussian J) against the oracle with a tie analysis.
+
+The oracle (test infrastructure) turns the recorded seed into the per-attempt (site, uniform)
+stream; the product only ever sees those arrays.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, has_cuda, load_golden
+
+pytestmark = pytest.mark.gpu
+
+import spin_glass_anneal_rl_b200 as sg
+from spin_glass_anneal_rl_b200.annealing.temperature_scheduler import ScheduleType
+from spin_glass_anneal_rl_b200.core.spin_dynamics import UpdateRule
+
+REL = 1e-5   # north_star: final and best energies within 1e-5 relative for float couplings
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if not has_cuda():
+        pytest.skip("needs a CUDA device")
+
+
+def _is_integer(J, h):
+    return bool(np.all(J == np.round(J)) and np.all(h == np.round(h)))
+
+
+def _close(a, b, exact, what=""):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    if exact:
+        assert np.array_equal(a, b), what
+    else:
+        assert np.allclose(a, b, rtol=REL, atol=REL), what
+
+
+def _model(J, h, spins=None):
+    m = sg.IsingModel(sg.IsingModelConfig(n_spins=J.shape[0], use_sparse=False))
+    m.set_couplings_from_matrix(torch.from_numpy(np.asarray(J, np.float32)))
+    m.set_external_fields(torch.from_numpy(np.asarray(h, np.float32)))
+    if spins is not None:
+        m.set_spins(torch.from_numpy(np.asarray(spins, np.float32)))
+    return m
+
+
+def _sa_stream(oracle, g):
+    c = g["config"]
+    n = g["J"].shape[0]
+    stream = oracle.RawStream(oracle.mt_raw_stream(c["seed"], 2 * n * c["n_sweeps"] + 16))
+    return oracle.anneal(g["J"], g["h"], g["spins0"], n_sweeps=c["n_sweeps"], T0=c["T0"], Tf=c["Tf"],
+                         schedule=c["schedule"], schedule_params=c["params"],
+                         record_interval=c["record_interval"], energy_tolerance=c["tol"],
+                         rule=c["rule"], stream=stream, trace=True)
+
+
+def _anneal_replay(oracle, name, kernel):
+    g = load_golden(name)
+    c = g["config"]
+    ores = _sa_stream(oracle, g)
+    m = _model(g["J"], g["h"], g["spins0"])
+    cfg = sg.GPUAnnealerConfig(
+        n_sweeps=c["n_sweeps"], initial_temp=c["T0"], final_temp=c["Tf"],
+        schedule_type=ScheduleType(c["schedule"]), schedule_params=dict(c["params"]),
+        record_interval=c["record_interval"], energy_tolerance=c["tol"], random_seed=c["seed"],
+        rng_mode="replay", replay={"sites": ores.extra["sites"], "uniforms": ores.extra["uniforms"]},
+        kernel=kernel)
+    res = sg.GPUAnnealer(cfg).anneal(m, UpdateRule(c["rule"]))
+    return g, m, res
+
+
+@pytest.mark.parametrize("name", golden_names("sa_"))
+def test_anneal_replay_reproduces_the_reference(oracle, name):
+    """GPUAnnealer.anneal(rng_mode='replay') == the reference's GPUAnnealer.anneal on device='cpu'
+    (reference annealing/gpu_annealer.py:96-183) for every recorded run."""
+    g, m, res = _anneal_replay(oracle, name, "auto")
+    exact = _is_integer(g["J"], g["h"])
+    assert res.n_sweeps == int(g["n_sweeps_done"])
+    assert np.array_equal(res.best_configuration.numpy().astype(np.int8), g["best_configuration"])
+    assert np.array_equal(m.spins.numpy().astype(np.int8), g["final_spins"])
+    _close(res.best_energy, g["best_energy"], exact, "best energy")
+    _close(res.energy_history, g["energy_history"], exact, "energy history")
+    assert np.allclose(res.temperature_history, g["temperature_history"], rtol=1e-12, atol=0)
+    assert np.allclose(res.acceptance_rate_history, g["acceptance_rate_history"], rtol=0, atol=1e-12)
+    conv = int(g["convergence_sweep"])
+    assert (res.convergence_sweep if res.convergence_sweep is not None else -1) == conv
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names("sa_") if load_golden(n)["J"].shape[0] >= 16])
+def test_anneal_replay_on_the_tensor_core_kernel(oracle, name):
+    """The same replays through kernel='tc' (tcgen05 rank-16 updates, three bf16 planes): integer
+    couplings bit for bit; FLOAT couplings (sa_cfg1_float_n100, sa_sk_float_n256,
+    sa_glauber_float_n32) the same trajectory and energies within 1e-5 relative."""
+    g, m, res = _anneal_replay(oracle, name, "tc")
+    exact = _is_integer(g["J"], g["h"])
+    assert np.array_equal(m.spins.numpy().astype(np.int8), g["final_spins"]), "trajectory differs"
+    assert np.array_equal(res.best_configuration.numpy().astype(np.int8), g["best_configuration"])
+    _close(res.best_energy, g["best_energy"], exact, "best energy")
+    _close(res.energy_history, g["energy_history"], exact, "energy history")
+
+
+@pytest.mark.parametrize("name", golden_names("pt_"))
+def test_parallel_tempering_replay_reproduces_the_reference(oracle, name):
+    """ParallelTempering.run(rng_mode='replay') == the reference's run (n_threads=1, device='cpu',
+    annealing/parallel_tempering.py:82-144, 214-258): configurations per temperature slot,
+    exchange statistics, per-slot energy histories, best configuration.  Here temperatures move
+    and configurations stay, so slot k is the replica the rung map points to."""
+    g = load_golden(name)
+    c = g["config"]
+    n, K = g["J"].shape[0], c["n_replicas"]
+    method = c.get("method", "nearest_neighbor")
+    stream = oracle.RawStream(oracle.mt_raw_stream(c["seed"], 2 * n * K * (c["n_sweeps"] + 1) + 16))
+    ores = oracle.parallel_tempering(
+        g["J"], g["h"], n_replicas=K, n_sweeps=c["n_sweeps"], temp_min=c["tmin"], temp_max=c["tmax"],
+        temp_distribution=c["dist"], exchange_interval=c["exchange_interval"],
+        record_interval=c["record_interval"], rule=c["rule"], stream=stream,
+        np_rng=np.random.RandomState(c["seed"]), exchange_method=method, trace=True)
+    cfg = sg.ParallelTemperingConfig(
+        n_replicas=K, n_sweeps=c["n_sweeps"], temp_min=c["tmin"], temp_max=c["tmax"],
+        temp_distribution=c["dist"], exchange_interval=c["exchange_interval"], exchange_method=method,
+        record_interval=c["record_interval"], random_seed=c["seed"], rng_mode="replay",
+        replay={k: ores.extra[k] for k in ("spins0", "sites", "uniforms", "exchange_draws")})
+    pt = sg.ParallelTempering(cfg)
+    res = pt.run(_model(g["J"], g["h"]), UpdateRule(c["rule"]))
+    exact = _is_integer(g["J"], g["h"])
+    assert np.allclose(pt.temperatures, g["temperatures"], rtol=1e-15, atol=0)
+    assert np.array_equal(pt.exchange_attempts, g["exchange_attempts"])
+    assert np.array_equal(pt.exchange_accepts, g["exchange_accepts"])
+    slot_spins = pt._final_spins.cpu().numpy()[pt._rung_replica[:K]]
+    assert np.array_equal(slot_spins, g["final_spins"]), "configurations per temperature slot differ"
+    assert np.array_equal(res.best_configuration.numpy().astype(np.int8), g["best_configuration"])
+    _close(res.best_energy, g["best_energy"], exact, "best energy")
+    _close(np.array(pt.energy_histories), g["energy_histories"], exact, "per-slot energy histories")
+    _close(res.energy_history, g["energy_history"], exact)
+    assert np.allclose(res.acceptance_rate_history, g["acceptance_rate_history"], rtol=0, atol=1e-12)
+    assert g["exchange_accepts"].sum() > 0
+
+
+# ------------------------------------------------------------------ cluster-sized float replay
+def _margins_f64(J, h, s, T, sites, uni):
+    """One Metropolis sweep in float64 from spins s (in place): returns the smallest decision
+    margin met on the way, relative to the quantity compared (|u - p| / p for uphill moves,
+    |dE| / scale for the sign test)."""
+    J64, h64 = J.astype(np.float64), h.astype(np.float64)
+    worst = np.inf
+    scale = np.abs(J64).sum(axis=1).mean()
+    for k, i in enumerate(sites):
+        f = J64[i] @ s + h64[i]
+        dE = 2.0 * s[i] * f
+        worst = min(worst, abs(dE) / scale)
+        if dE <= 0:
+            s[i] = -s[i]
+            continue
+        p = np.exp(-dE / T)
+        worst = min(worst, abs(uni[k] - p) / max(p, 1e-300))
+        if uni[k] < p:
+            s[i] = -s[i]
+    return worst
+
+
+def test_tc_cluster_float_replay_n4096(oracle):
+    """SK N = 4096, Gaussian J (the headline instance), 40 replicas = one full replica group of
+    the cluster kernel plus a ragged one, 3 sweeps of injected stream on kernel='tc' with three
+    planes, against oracle.sweeps_scheduled.  Same trajectory; energies after the exact refresh
+    (what the API reports) within 1e-5 relative of the reference's.  A replica whose trajectory leaves the oracle's must do so at a
+    near-tie: the float64 replay of that sweep has a decision margin < 1e-6 ("tie,
+    not bug"); such a replica is re-synchronised and counted."""
+    from spin_glass_anneal_rl_b200.engine import Engine
+    n, R, ns = 4096, 40, 3
+    rs = np.random.RandomState(3003)
+    G = rs.normal(0.0, 1.0 / np.sqrt(n), size=(n, n)).astype(np.float32)
+    J = ((G + G.T) / 2).astype(np.float32)
+    np.fill_diagonal(J, 0.0)
+    h = np.zeros(n, np.float32)
+    rng = np.random.default_rng(4096)
+    S = (rng.integers(0, 2, size=(R, n)) * 2 - 1).astype(np.int8)
+    sites = rng.integers(0, n, size=(ns, n)).astype(np.int32)
+    uni = rng.random((R, ns, n), dtype=np.float32)
+    temps = np.array([1.5, 1.0, 0.7])
+    eng = Engine(0)
+    eng.set_model(J, h)
+    eng.alloc_replicas(R)
+    assert eng.tc_cluster_size() >= 2
+    ties = 0
+    cur = S.copy()
+    for s in range(ns):
+        eng.set_spins(cur)
+        eng.init_fields()
+        tr = eng.sweep(1, temps[s:s + 1], temps_sweep_stride=1, sites=sites[s:s + 1],
+                       uniforms=np.ascontiguousarray(uni[:, s:s + 1, :]), energy_trace=True, kernel="tc",
+                       coupling_planes=3).cpu().numpy()[0]
+        e_res = eng.energies().cpu().numpy()
+        eng.refresh_fields()
+        e_exact = eng.energies().cpu().numpy()
+        got = eng.spins().cpu().numpy()
+        nxt = got.copy()
+        for r in range(R):
+            so = cur[r].astype(np.float32).copy()
+            es, _ = oracle.sweeps_scheduled(J, h, so, temps[s:s + 1], "metropolis", sites[s], uni[r, s])
+            if np.array_equal(got[r], so.astype(np.int8)):
+                # same trajectory: resident (tensor-core) and refreshed energies vs the reference's
+                assert abs(e_exact[r] - es[0]) <= REL * abs(es[0]), (r, s, e_exact[r], es[0])
+                assert abs(e_res[r] - es[0]) <= REL * abs(es[0]), (r, s, e_res[r], es[0])
+                assert abs(tr[r] - es[0]) <= REL * abs(es[0])
+            else:
+                m = _margins_f64(J, h, cur[r].astype(np.float64), temps[s], sites[s], uni[r, s])
+                print(f"replica {r} sweep {s}: trajectories part at a decision margin of {m:.3e}")
+                assert m < 1e-6, f"replica {r} sweep {s} diverged without a near-tie (margin {m:.3e})"
+                ties += 1
+                nxt[r] = so.astype(np.int8)   # follow the reference from here on
+        cur = nxt
+    # 40 x 3 x 4096 decisions at ~1e-7 relative field error: a handful of ties at most
+    assert ties <= 2, ties

@@ -122,15 +122,17 @@ def test_tc_replay_is_bit_exact_for_integer_couplings(engine, oracle, n, R, ns, 
     assert np.array_equal(engine.batch_energies(best_s).cpu().numpy(), best_e.cpu().numpy())
 
 
-@pytest.mark.parametrize("name", [g for g in golden_names("sa_") if "int" in g or "pm1" in g])
-def test_tc_replays_integer_reference_traces(engine, oracle, name):
-    """The golden traces recorded from the reference (integer couplings) through the TC kernel."""
+@pytest.mark.parametrize("name", [g for g in golden_names("sa_") if load_golden(g)["J"].shape[0] >= 16])
+def test_tc_replays_reference_traces(engine, oracle, name):
+    """Every golden trace recorded from the reference with n >= 16 (the tensor-core path's lower
+    limit) through the TC kernel with three planes: integer couplings bit for bit, FLOAT couplings
+    (sa_cfg1_float_n100, sa_sk_float_n256, sa_glauber_float_n32) the same trajectory and per-sweep /
+    best energies within 1e-5 relative (north_star's tolerance)."""
     g = load_golden(name)
     c = g["config"]
     J, h = g["J"], g["h"]
     n = J.shape[0]
-    if n < 16 or not (np.all(J == np.round(J)) and np.all(h == np.round(h))):
-        pytest.skip("tensor-core path: integer couplings, n >= 16")
+    exact = bool(np.all(J == np.round(J)) and np.all(h == np.round(h)))
     stream = oracle.RawStream(oracle.mt_raw_stream(c["seed"], 2 * n * c["n_sweeps"] + 16))
     ores = oracle.anneal(J, h, g["spins0"], n_sweeps=c["n_sweeps"], T0=c["T0"], Tf=c["Tf"],
                          schedule=c["schedule"], schedule_params=c["params"],
@@ -145,8 +147,12 @@ def test_tc_replays_integer_reference_traces(engine, oracle, name):
     best_e, best_s = engine.best()
     assert np.array_equal(engine.spins().cpu().numpy()[0], g["final_spins"])
     assert np.array_equal(best_s.cpu().numpy()[0], g["best_configuration"])
-    assert float(best_e[0]) == float(g["best_energy"])
-    assert np.array_equal(trace.astype(np.float64), ores.sweep_energies)
+    if exact:
+        assert float(best_e[0]) == float(g["best_energy"])
+        assert np.array_equal(trace.astype(np.float64), ores.sweep_energies)
+    else:
+        assert abs(float(best_e[0]) - float(g["best_energy"])) <= 1e-5 * abs(float(g["best_energy"]))
+        assert np.allclose(trace, ores.sweep_energies, rtol=1e-5, atol=1e-5)
 
 
 # ------------------------------------------------------------------ Philox mode: TC == SIMT
@@ -354,12 +360,16 @@ def test_tc_sequential_site_order(engine, oracle):
 
 
 # ------------------------------------------------------------------ float couplings
-@pytest.mark.parametrize("planes,f_tol,e_tol", [(3, 2e-3, 3e-4), (2, 2e-3, 3e-4)])
+@pytest.mark.parametrize("planes,f_tol,e_tol", [(3, 6e-4, 1e-4), (2, 2e-3, 3e-4)])
 def test_tc_float_couplings_field_drift(engine, planes, f_tol, e_tol):
     """SK N=4096, Gaussian J: after 10 sweeps (~20k rank-16 updates per field) the TMEM-resident
     fields stay within f_tol (absolute, |f| ~ 1) of an exact recomputation from the spins and the
-    energies derived from them within e_tol relative.  The engine's best/final energies can be
-    refreshed exactly at any time with sg_init_fields / sg_batch_energies."""
+    energies derived from them within e_tol relative (three planes, measured with
+    tools/drift_probe.py: |df| <= 3.5e-4, energy 7.5e-5 -- a truncation BIAS of the tensor core's
+    fp32 accumulate, every field shrinks by ~6e-6 per sweep).  The host API refreshes fields and
+    energies exactly after every launch (sg_refresh_fields) and re-evaluates best configurations,
+    so what it reports is exact: tests/test_gpu_replay_api.py holds those to 1e-5 against the
+    reference."""
     import torch
     n, R = 4096, 32
     J, h = _sk(n)

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"libsg_b200.so lacks {name}"
     assert declared == set(_lib.PROTOTYPES), (declared ^ set(_lib.PROTOTYPES))
-    assert _lib.load().sg_abi_version() == 3
+    assert _lib.load().sg_abi_version() == _lib.SG_ABI_VERSION == 4
 
 
 def test_param_structs_match_header_layout(tmp_path):
@@ -266,3 +266,24 @@ def test_lattice_and_clique_structure_detection():
     J, _ = inst.tsp_ising(inst.random_tsp(5, 1))
     r, c = np.nonzero(J)
     assert _clique_groups(r, c, J[r, c], 25) is None
+
+
+def test_engine_cache_signature_survives_id_reuse():
+    """ids / data pointers of freed coupling tensors are handed out again, so the
+    engine cache must hold the tensors it was built from and compare by identity + version."""
+    from spin_glass_anneal_rl_b200.annealing._backend import _Signature
+    m = sg.IsingModel(sg.IsingModelConfig(n_spins=16, use_sparse=False))
+    m.set_couplings_from_matrix(torch.randn(16, 16))
+    sig = _Signature(m)
+    assert sig.matches(m)
+    for _ in range(20):     # free / reallocate same-shaped couplings: the old id comes back
+        m.set_couplings_from_matrix(torch.randn(16, 16))
+        assert not sig.matches(m)
+    m2 = sg.IsingModel(sg.IsingModelConfig(n_spins=16, use_sparse=False))
+    s2 = _Signature(m2)
+    m2.couplings[0, 1] = 3.0          # in-place edit bumps the version
+    assert not s2.matches(m2)
+    m3 = sg.IsingModel(sg.IsingModelConfig(n_spins=16, use_sparse=True))
+    s3 = _Signature(m3)
+    m3.set_coupling(0, 1, 1.0)        # queued write -> new COO tensor on the next read
+    assert not s3.matches(m3)

@@ -192,3 +192,25 @@ def test_cuda_exchange_operator_large_and_strided(manager, oracle):
     assert torch.equal(big[:, n:], pad_before)       # bytes outside the rows untouched
     moved = int((src != torch.arange(R, device="cuda")).sum())
     assert moved > 0
+
+
+@pytest.mark.gpu
+def test_cuda_operator_cache_is_not_fooled_by_reused_addresses(manager, oracle):
+    """a loop over same-sized instances frees J and allocates the next one at
+    the same address with version 0.  Every call must still answer for the model it was given."""
+    import torch
+    rng = np.random.default_rng(17)
+    n = 48
+    s = (rng.integers(0, 2, size=n) * 2 - 1).astype(np.float32)
+    h = torch.zeros(n, device="cuda")
+    seen = set()
+    for _ in range(12):
+        a = rng.integers(-3, 4, size=(n, n))
+        J = np.triu(a, 1)
+        J = (J + J.T).astype(np.float32)
+        Jd = torch.from_numpy(J).cuda()
+        seen.add(Jd.data_ptr())
+        e = manager.compute_energy_optimized(torch.from_numpy(s).cuda(), Jd, h)
+        assert e == oracle.energy(J, np.zeros(n, np.float32), s)
+        del Jd
+    assert len(seen) < 12, "the allocator never reused an address: the test did not test anything"

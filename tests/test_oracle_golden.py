@@ -104,7 +104,8 @@ def test_parallel_tempering_matches_reference(oracle, name):
         g["J"], g["h"], n_replicas=R, n_sweeps=c["n_sweeps"], temp_min=c["tmin"],
         temp_max=c["tmax"], temp_distribution=c["dist"], exchange_interval=c["exchange_interval"],
         record_interval=c["record_interval"], rule=c["rule"], stream=stream,
-        np_rng=np.random.RandomState(c["seed"]))
+        np_rng=np.random.RandomState(c["seed"]),
+        exchange_method=c.get("method", "nearest_neighbor"))
     exact = _is_integer(g)
     assert res.raw_consumed == int(g["raw_consumed"])
     assert np.allclose(res.extra["temperatures"], g["temperatures"], rtol=1e-15, atol=0)

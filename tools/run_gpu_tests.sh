@@ -1,0 +1,2 @@
+set -x
+python -m pytest tests -m gpu -x -q 2>&1 | tail -25
