@@ -326,13 +326,26 @@ tc_tables_kernel(const __nv_bfloat16* __restrict__ Jp, int n, int n_tc,
 }
 
 // ---------------------------------------------------------------- the sweep
-constexpr int kTcThreads = 224;
 constexpr int kSlots = 4;
+// Column parts of a CTA's tiles: the raw reads of block k+1 in a part chase the MMA wavefront of
+// block k-1 and must be done before block k's MMAs of that part are issued.  Two parts; four were
+// tried (the read of one part would overlap the execution of three others) and were slower on
+// every cluster size (C = 4: 16.6 instead of 19.2 G attempts/s): every part costs the MMA warp a
+// barrier round trip through the quarter warps.
+constexpr int kParts = 2;
 constexpr int kMaxStagesTc = 8;
-constexpr int kSyncThreads = 160;  // quarter warps + decision warp (named barriers 1..3)
+// C = CTAs per replica group: NG = 16 C replicas, decision warps = one per 32 replicas
+__host__ __device__ constexpr int tc_ndw(int C) { return (kG * C + 31) / 32; }
+// threads: 4 quarter warps, producer, decision warp 0, MMA issuer (, decision warps 1..3)
+__host__ __device__ constexpr int tc_threads(int C) { return 224 + 32 * (tc_ndw(C) - 1); }
+// quarter warps + decision warps meet at the named barriers 1..3
+__host__ __device__ constexpr int tc_sync_threads(int C) { return 128 + 32 * tc_ndw(C); }
+// tiles per ring stage: clusters of 4 hold 64 replicas' state in shared memory and have room for
+// 120 KB of ring only -- five 2-tile stages keep more copies in flight than two 4-tile ones
+__host__ __device__ constexpr int tc_chunk_tiles(int C) { return C == 8 ? 1 : C == 4 ? 2 : kChunkTiles; }
 
 struct TcSmem {
-    size_t ring, bop, sbits, theta, raw, tab, red, flags, bars, tptr, total;
+    size_t ring, bop, sbits, theta, raw, tab, ztab, red, flags, bars, tptr, total;
 };
 
 // C = CTAs per replica group (1, or 2 = a cluster pair that splits the field columns)
@@ -340,22 +353,24 @@ __host__ __device__ inline TcSmem tc_layout(int n_tc, int P, int NS, int C) {
     const int NG = kG * C;
     TcSmem L;
     size_t off = 0;
-    L.ring = off;  off += (size_t)NS * kChunkTiles * P * kTileBytes;
+    L.ring = off;  off += (size_t)NS * tc_chunk_tiles(C) * P * kTileBytes;
     L.bop = off;   off += (size_t)kSlots * 32 * NG;
     L.sbits = off; off += (size_t)NG * (n_tc / 32 + 1) * sizeof(uint32_t);   // stride W + 1: no bank conflicts
     L.theta = off; off += (size_t)kSlots * kBlk * NG * sizeof(float);
     L.raw = off;   off += (size_t)kSlots * kBlk * NG * sizeof(float);
     L.tab = off;   off += (size_t)kSlots * kTabBytes;
+    L.ztab = off;  off += (size_t)kBlk * kBlk * sizeof(float);   // a cross table of zeros
     L.red = off;   off += (size_t)C * 4 * NG * sizeof(float);
     L.flags = off; off += 4 * sizeof(uint32_t);
     off = (off + 15) & ~(size_t)15;
-    L.bars = off;  off += (size_t)(2 * kMaxStagesTc + 7 * kSlots + 2) * sizeof(uint64_t);
+    L.bars = off;  off += (size_t)(2 * kMaxStagesTc + (5 + 2 * kParts) * kSlots + 2) * sizeof(uint64_t);
     L.tptr = off;  off += 16;
     L.total = off;
     return L;
 }
 
-__device__ __forceinline__ void named_sync(int id) { named_bar_sync(id, kSyncThreads); }
+template <int C>
+__device__ __forceinline__ void named_sync_c(int id) { named_bar_sync(id, tc_sync_threads(C)); }
 
 // ---- thread-block-cluster helpers (C = 2)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -379,6 +394,13 @@ __device__ __forceinline__ void st_async_f4(uint32_t addr, float4 v, uint32_t ba
     asm volatile(
         "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr),
         "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(bar)
+        : "memory");
+}
+
+__device__ __forceinline__ void st_async_f2(uint32_t addr, float2 v, uint32_t bar) {
+    asm volatile(
+        "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(addr),
+        "f"(v.x), "f"(v.y), "r"(bar)
         : "memory");
 }
 
@@ -470,13 +492,14 @@ __device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
     asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// C = 1: one CTA holds all field columns of 16 replicas.  C = 2: a cluster pair holds 32
-// replicas, CTA `crank` owns the columns [crank * n_tc/2, (crank+1) * n_tc/2) (so each SM streams
-// and multiplies only half of every J row: half the shared-memory traffic per attempt); both
-// CTAs run the same decision warp on identical inputs (raw field values are exchanged through
-// distributed shared memory), so no decision has to cross the cluster.
+// C = 1: one CTA holds all field columns of 16 replicas.  C = 2 / 4: a thread-block cluster holds
+// 16 C replicas, CTA `crank` owns the columns [crank * n_tc/C, (crank+1) * n_tc/C) (so each SM
+// streams and multiplies only 1/C of every J row for C times the replicas: 1/C of the
+// shared-memory traffic per attempt); all CTAs run the same decision warps (one per 32 replicas)
+// on identical inputs (raw field values are exchanged through distributed shared memory), so no
+// decision has to cross the cluster.
 template <int P, bool INJECT, int C>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(tc_threads(C), 1)
 sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const int n_tc,
                 const uint16_t* __restrict__ sites_g, const int n_s, const int NS,
                 const int tmem_cols, const unsigned char* __restrict__ Q,
@@ -486,6 +509,10 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
     constexpr int NG = kG * C;               // replicas per group = MMA N
     constexpr int NGRP = NG / 16;            // 16-column TMEM load/store groups per tile
     constexpr uint32_t IDESC = tc::make_idesc_bf16(kTileM, NG);
+    constexpr int CT = tc_chunk_tiles(C);    // tiles per ring stage
+    constexpr int NDW = tc_ndw(C);           // decision warps
+    constexpr int kThWarps = (NG / 8 < 4) ? NG / 8 : 4;   // quarter warps that draw thresholds
+    auto named_sync = [](int id) { named_sync_c<C>(id); };
     constexpr int BOP = 32 * NG;             // B operand bytes per slot
     constexpr uint32_t BLBO = 16 * NG;       // B: k-group stride ((NG/8) n-groups of 128 B)
     extern __shared__ __align__(128) unsigned char smem[];
@@ -495,13 +522,14 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                                              // word x of 32 planes: odd stride = 32 distinct banks)
     const int T = n_tc / kTileM;             // tiles of the whole model
     const int Tl = T / C;                    // tiles of this CTA
-    const int nchunk = (T + kChunkTiles - 1) / kChunkTiles;       // chunks per block in Q
-    const int nchunk_l = (Tl + kChunkTiles - 1) / kChunkTiles;    // ... consumed by this CTA
-    const int hc = (nchunk_l + 1) >> 1;                 // local chunks [0, hc) = half 0
-    const int half_cols = hc * kChunkTiles * kTileM;    // local columns below this are in half 0
+    // Q holds every block as (T rounded up to kChunkTiles) tiles x P planes, tile-major; this CTA
+    // consumes its Tl tiles in stages of CT tiles
+    const int tiles_q = (T + kChunkTiles - 1) / kChunkTiles * kChunkTiles;
+    const int nchunk_l = (Tl + CT - 1) / CT;            // stages per block consumed by this CTA
+    // part h = local chunks [pb(h), pb(h+1)) (some parts are empty when there are fewer chunks)
+    auto pb = [nchunk_l](int h) { return (nchunk_l * h + kParts - 1) / kParts; };
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t crank = (C == 2) ? cluster_ctarank() : 0u;
-    const uint32_t peer = crank ^ 1u;
+    const uint32_t crank = (C > 1) ? cluster_ctarank() : 0u;
     const int cols_cta = Tl * kTileM;        // field columns per CTA
     const int col0 = (int)crank * cols_cta;
 
@@ -512,6 +540,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
     float* theta_s = reinterpret_cast<float*>(smem + L.theta);  // [slot][b][r]
     float* raw_s = reinterpret_cast<float*>(smem + L.raw);      // [slot][b][r]
     unsigned char* tab_s = smem + L.tab;  // [slot]{cin[16][16], ccr[16][16], dup[16]} (TMA)
+    float* ztab_s = reinterpret_cast<float*>(smem + L.ztab);
     float* red = reinterpret_cast<float*>(smem + L.red);        // [rank][quarter][r]
     uint32_t* flags = reinterpret_cast<uint32_t*>(smem + L.flags);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);
@@ -519,12 +548,12 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
     uint64_t* tabbar = empty + kMaxStagesTc;   // [slot]     decision tables of a block landed (TMA)
     uint64_t* thbar = tabbar + kSlots;         // [slot]     thresholds of a block published
     uint64_t* rloc = thbar + kSlots;           // [slot][2]  this CTA's raw reads of a half done
-    uint64_t* rall = rloc + 2 * kSlots;        // [slot]     all raw values of a block published
+    uint64_t* rall = rloc + kParts * kSlots;   // [slot]     all raw values of a block published
     uint64_t* decbar = rall + kSlots;          // [slot]     block decided, B operand written
     uint64_t* hdone = decbar + kSlots;         // [slot][2]  MMAs of a half of a block completed
-    uint64_t* ebar = hdone + 2 * kSlots;       // energy partial sums of a sweep published
+    uint64_t* ebar = hdone + kParts * kSlots;  // energy partial sums of a sweep published
     uint32_t* tptr = reinterpret_cast<uint32_t*>(smem + L.tptr);
-    constexpr int kStageBytes = kChunkTiles * P * kTileBytes;
+    constexpr int kStageBytes = CT * P * kTileBytes;
 
     const int n_sweeps = a.n_sweeps;
     const int nblk = (n + kBlk - 1) / kBlk;
@@ -552,25 +581,27 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
         }
         for (int d = 0; d < kSlots; ++d) {
             mbar_init(&tabbar[d], 1);
-            mbar_init(&thbar[d], NG / 8);
-            mbar_init(&rloc[2 * d], 4);
-            mbar_init(&rloc[2 * d + 1], 4);
-            mbar_init(&rall[d], 8 + (C - 1));   // 4 warps x 2 halves (+ the expect_tx arrival)
-            mbar_init(&decbar[d], 1);
-            mbar_init(&hdone[2 * d], 1);
-            mbar_init(&hdone[2 * d + 1], 1);
+            mbar_init(&thbar[d], kThWarps);
+            for (int h = 0; h < kParts; ++h) {
+                mbar_init(&rloc[kParts * d + h], 4);
+                mbar_init(&hdone[kParts * d + h], 1);
+            }
+            mbar_init(&rall[d], 4 * kParts + (C > 1 ? 1 : 0));   // 4 warps x parts (+ the expect_tx arrival)
+            mbar_init(&decbar[d], NDW);
         }
-        mbar_init(ebar, 4 + (C - 1));
+        mbar_init(ebar, 4 + (C > 1 ? 1 : 0));
+        flags[0] = flags[1] = flags[2] = flags[3] = 0u;
         fence_mbar_init();
         fence_proxy_async();
     }
+    for (int i = tid; i < kBlk * kBlk; i += tc_threads(C)) ztab_s[i] = 0.0f;
     if (warp == 0) {
         tc::tmem_alloc(tptr, (uint32_t)tmem_cols);
         tc::tmem_relinquish();
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (C == 2) cluster_sync_all();   // the peer's barriers exist before anything remote arrives
+    if (C > 1) cluster_sync_all();   // the peers' barriers exist before anything remote arrives
     tc::fence_after_sync();
     const uint32_t tbase = *tptr;
 
@@ -628,24 +659,28 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
             }
         }
         SG_ISTAMP(2);
-        // resident fields -> TMEM, two tiles (32 loads per thread) in flight
-        for (int t = 0; t < Tl; t += 2) {
-            float v[2][NGRP][16];
+        // resident fields -> TMEM, 32+ loads per thread in flight
+        constexpr int GS = (NGRP < 4) ? NGRP : 4;      // 16-replica groups per pass (<= 64 registers)
+        constexpr int TU = (GS >= 4) ? 1 : 2;
+        for (int t = 0; t < Tl; t += TU)
+#pragma unroll 1
+        for (int g0 = 0; g0 < NGRP; g0 += GS) {
+            float v[TU][GS][16];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < TU; ++u) {
                 const int col = col0 + (t + u) * kTileM + q * 32 + lane;
 #pragma unroll
-                for (int gi = 0; gi < NGRP; ++gi)
+                for (int gi = 0; gi < GS; ++gi)
 #pragma unroll
                     for (int r = 0; r < 16; ++r)
-                        v[u][gi][r] = (t + u < Tl && gi * 16 + r < g_act && col < n_pad)
-                                          ? __ldcg(a.fields + (size_t)(rep0 + gi * 16 + r) * n_pad + col) : 0.0f;
+                        v[u][gi][r] = (t + u < Tl && (g0 + gi) * 16 + r < g_act && col < n_pad)
+                                          ? __ldcg(a.fields + (size_t)(rep0 + (g0 + gi) * 16 + r) * n_pad + col) : 0.0f;
             }
 #pragma unroll
-            for (int u = 0; u < 2; ++u)
+            for (int u = 0; u < TU; ++u)
                 if (t + u < Tl) {
 #pragma unroll
-                    for (int gi = 0; gi < NGRP; ++gi) tc::tmem_st16(tq + (t + u) * NG + gi * 16, v[u][gi]);
+                    for (int gi = 0; gi < GS; ++gi) tc::tmem_st16(tq + (t + u) * NG + (g0 + gi) * 16, v[u][gi]);
                 }
         }
         tc::wait_st();
@@ -653,31 +688,25 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
         named_sync(2);   // bit planes complete (decision warp reads them)
         tc::fence_after_sync();
         SG_ISTAMP(3);
+        // thresholds of block (s, kb) -> theta_s[slot]: thread (qq, r) covers attempts 4qq..4qq+3.
+        // They depend on nothing but the counters, so they are drawn ONE BLOCK AHEAD, after the raw
+        // reads of the current block (which sit on the critical path between two blocks' MMAs).
+        auto draw_thresholds = [&](int s_t, int kb_t, int slot_t) {
+            if (!INJECT) {
+                const unsigned long long sa_t = a.sweep_base + (unsigned long long)s_t;
+                const int i0_t = kb_t * kBlk;
 #pragma unroll 1
-        for (int s = item.s_lo; s < item.s_hi; ++s) {
-            const uint16_t* stab = sites_g + (size_t)s * n_s;
-            const unsigned long long sa = a.sweep_base + (unsigned long long)s;
-#pragma unroll 1
-            for (int kb = 0; kb < nblk; ++kb, ++kg) {
-                const int slot = kg & (kSlots - 1);
-                const int i0 = kb * kBlk;
-                const int nbk = min(kBlk, n - i0);
-                if (warp == 0) SG_STAMP(0);
-                const uint4 sq0 = *reinterpret_cast<const uint4*>(stab + i0);
-                const uint4 sq1 = *reinterpret_cast<const uint4*>(stab + i0 + 8);
-                const uint32_t swq[8] = {sq0.x, sq0.y, sq0.z, sq0.w, sq1.x, sq1.y, sq1.z, sq1.w};
-                // --- thresholds: thread (qq, r) covers attempts 4qq..4qq+3 of the block
-                if (!INJECT && tid < 4 * NG) {
-                    const int qq = tid / NG, r = tid - qq * NG;
-                    const int ia = i0 + qq * 4;
+                for (int tt = tid; tt < 4 * NG; tt += 128) {
+                    const int qq = tt / NG, r = tt - qq * NG;
+                    const int ia = i0_t + qq * 4;
                     if (r < g_act && ia < n) {
                         const int rep = rep0 + r;
-                        const float Tm = (float)a.temps[(long long)s * a.t_ss + (long long)rep * a.t_rs];
+                        const float Tm = (float)a.temps[(long long)s_t * a.t_ss + (long long)rep * a.t_rs];
                         const uint4 x = philox4x32_10(
-                            make_uint4((uint32_t)(rep + a.rep_base), (uint32_t)sa, (uint32_t)(sa >> 32),
+                            make_uint4((uint32_t)(rep + a.rep_base), (uint32_t)sa_t, (uint32_t)(sa_t >> 32),
                                        (uint32_t)(ia >> 2)), key);
                         const uint32_t vv[4] = {x.x, x.y, x.z, x.w};
-                        float* dst = theta_s + slot * kBlk * NG + (qq * 4) * NG + r;
+                        float* dst = theta_s + slot_t * kBlk * NG + (qq * 4) * NG + r;
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const float u = u01(vv[e]);
@@ -688,10 +717,39 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                         }
                     }
                 }
-                __syncwarp();
-                if (warp < NG / 8 && lane == 0) mbar_arrive(&thbar[slot]);
-                if (C == 2 && warp == 0 && lane == 0) {
-                    // the peer will store the raw values of the sites it owns straight into this
+            }
+            __syncwarp();
+            if (warp < kThWarps && lane == 0) mbar_arrive(&thbar[slot_t]);
+        };
+        draw_thresholds(item.s_lo, 0, kg & (kSlots - 1));
+        // the 16 sites of a block come from global memory (L2: ~500 clocks): they are fetched one
+        // block ahead, like the thresholds
+        uint4 nsq0, nsq1;
+        int n_my_site;
+        auto fetch_sites = [&](int s_t, int kb_t) {
+            const uint16_t* st_t = sites_g + (size_t)s_t * n_s + kb_t * kBlk;
+            nsq0 = *reinterpret_cast<const uint4*>(st_t);
+            nsq1 = *reinterpret_cast<const uint4*>(st_t + 8);
+            n_my_site = (int)st_t[lane & 15];
+        };
+        fetch_sites(item.s_lo, 0);
+#pragma unroll 1
+        for (int s = item.s_lo; s < item.s_hi; ++s) {
+#pragma unroll 1
+            for (int kb = 0; kb < nblk; ++kb, ++kg) {
+                const int slot = kg & (kSlots - 1);
+                const int i0 = kb * kBlk;
+                const int nbk = min(kBlk, n - i0);
+                if (warp == 0) SG_STAMP(0);
+                const uint4 sq0 = nsq0, sq1 = nsq1;
+                const int my_site = n_my_site;
+                const uint32_t swq[8] = {sq0.x, sq0.y, sq0.z, sq0.w, sq1.x, sq1.y, sq1.z, sq1.w};
+                {   // next block of this item (its data are consumed in the next iteration)
+                    const bool more = kb + 1 < nblk;
+                    if (more || s + 1 < item.s_hi) fetch_sites(more ? s : s + 1, more ? kb + 1 : 0);
+                }
+                if (C > 1 && warp == 0 && lane == 0) {
+                    // the peers will store the raw values of the sites they own straight into this
                     // CTA's raw_s[slot], counting bytes on rall[slot]
                     int n_remote = 0;
 #pragma unroll
@@ -709,6 +767,15 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 // block kg-LAG is not issued before the read is done.  (LAG = 2 in the cluster
                 // variant gives the cross-CTA exchange and the decision a whole block of slack.)
                 float* rawb = raw_s + slot * kBlk * NG;
+                uint32_t raw_peer[C > 1 ? C - 1 : 1], bar_peer[C > 1 ? C - 1 : 1];
+                if (NGRP >= 4) {
+#pragma unroll
+                    for (int pp = 1; pp < C; ++pp) {
+                        const uint32_t peer = (crank + (uint32_t)pp) & (uint32_t)(C - 1);
+                        raw_peer[pp - 1] = map_to_rank(rawb, peer);
+                        bar_peer[pp - 1] = map_to_rank(&rall[slot], peer);
+                    }
+                }
                 // lane b keeps site b; the loops below stay rolled (this is hot code shared with six
                 // other warps' loops in one instruction cache: unrolled 16 x 2 it made the cluster
                 // variant's working set spill out of it)
@@ -716,26 +783,67 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 // this warp reads it (its column is in this CTA and in this warp's TMEM lane
                 // quarter) and in which column half: two ballots replace a 16-step scan per half
                 // in what is, in the cluster variant, the critical path between two blocks' MMAs
-                const int my_site = (int)stab[i0 + (lane & 15)];
                 const int my_lc = my_site - col0;          // column inside this CTA
                 const bool my_take = lane < nbk && ((C == 1) || (my_lc >= 0 && my_lc < cols_cta)) &&
                                      ((my_lc >> 5) & 3) == q && !(dbg & 4);
-                const uint32_t take0 = __ballot_sync(0xFFFFFFFFu, my_take && my_lc < half_cols);
-                const uint32_t take1 = __ballot_sync(0xFFFFFFFFu, my_take && my_lc >= half_cols);
+                int my_part = 0;
+                {
+                    const int my_chunk = my_lc / (CT * kTileM);
+#pragma unroll
+                    for (int h = 1; h < kParts; ++h) my_part = (my_chunk >= pb(h)) ? h : my_part;
+                }
+                // (rolled: this is hot code shared with the other warps' loops in one instruction cache)
 #pragma unroll 1
-                for (int h = 0; h < 2; ++h) {
+                for (int h = 0; h < kParts; ++h) {
+                    uint32_t todo = __ballot_sync(0xFFFFFFFFu, my_take && my_part == h);
                     if (kg >= LAG + 1)
-                        mbar_wait(&hdone[2 * ((kg - LAG - 1) & (kSlots - 1)) + h],
+                        mbar_wait(&hdone[kParts * ((kg - LAG - 1) & (kSlots - 1)) + h],
                                   (uint32_t)((kg - LAG - 1) >> 2) & 1u);
                     tc::fence_after_sync();
-                    if (warp == 0) SG_STAMP(2 + h);
-                    uint32_t todo = h ? take1 : take0;
+                    if (warp == 0 && (h == 0 || h == kParts - 1)) SG_STAMP(h == 0 ? 2 : 3);
+
 #pragma unroll 1
                     while (todo) {
                         const int b = __ffs(todo) - 1;
                         todo &= todo - 1;
                         const int lc = __shfl_sync(0xFFFFFFFFu, my_lc, b);
                         float* dl = rawb + b * NG;
+                        if (NGRP >= 4) {
+                            // 64 / 128 replicas: four loads in flight per wait; the owning lane puts
+                            // the row into this CTA's table, then EVERY lane forwards its 8 (16)
+                            // bytes of it to each peer (asynchronous remote stores that count their
+                            // bytes on the peer's rall[slot]) -- C-1 stores per lane instead of
+                            // 16 (C-1) from one lane, in the critical path between two blocks' MMAs
+#pragma unroll 1
+                            for (int g0 = 0; g0 < NGRP; g0 += 4) {
+                                float v[4][16];
+#pragma unroll
+                                for (int gi = 0; gi < 4; ++gi) tc::tmem_ld16(tq + (lc >> 7) * NG + (g0 + gi) * 16, v[gi]);
+                                tc::wait_ld();
+                                if (lane == (lc & 31)) {
+#pragma unroll
+                                    for (int gi = 0; gi < 4; ++gi) {
+                                        float4* d4 = reinterpret_cast<float4*>(dl + (g0 + gi) * 16);
+                                        d4[0] = make_float4(v[gi][0], v[gi][1], v[gi][2], v[gi][3]);
+                                        d4[1] = make_float4(v[gi][4], v[gi][5], v[gi][6], v[gi][7]);
+                                        d4[2] = make_float4(v[gi][8], v[gi][9], v[gi][10], v[gi][11]);
+                                        d4[3] = make_float4(v[gi][12], v[gi][13], v[gi][14], v[gi][15]);
+                                    }
+                                }
+                            }
+                            __syncwarp();
+                            constexpr int FW = NG / 32;   // floats of the row each lane forwards
+                            const uint32_t off = (uint32_t)((b * NG + FW * lane) * 4);
+                            if (FW == 2) {
+                                const float2 mine = *reinterpret_cast<const float2*>(dl + 2 * lane);
+#pragma unroll
+                                for (int pp = 1; pp < C; ++pp) st_async_f2(raw_peer[pp - 1] + off, mine, bar_peer[pp - 1]);
+                            } else {
+                                const float4 mine = *reinterpret_cast<const float4*>(dl + 4 * lane);
+#pragma unroll
+                                for (int pp = 1; pp < C; ++pp) st_async_f4(raw_peer[pp - 1] + off, mine, bar_peer[pp - 1]);
+                            }
+                        } else
 #pragma unroll
                         for (int gi = 0; gi < NGRP; ++gi) {
                             float v[16];
@@ -747,16 +855,20 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                                 d4[1] = make_float4(v[4], v[5], v[6], v[7]);
                                 d4[2] = make_float4(v[8], v[9], v[10], v[11]);
                                 d4[3] = make_float4(v[12], v[13], v[14], v[15]);
-                                if (C == 2) {
-                                    // the same 64 bytes straight from the registers into the peer's
-                                    // shared memory (asynchronous remote stores that count their
-                                    // bytes on the peer's rall[slot])
-                                    const uint32_t ra = map_to_rank(dl + gi * 16, peer);
-                                    const uint32_t rb = map_to_rank(&rall[slot], peer);
-                                    st_async_f4(ra, make_float4(v[0], v[1], v[2], v[3]), rb);
-                                    st_async_f4(ra + 16, make_float4(v[4], v[5], v[6], v[7]), rb);
-                                    st_async_f4(ra + 32, make_float4(v[8], v[9], v[10], v[11]), rb);
-                                    st_async_f4(ra + 48, make_float4(v[12], v[13], v[14], v[15]), rb);
+                                if (C > 1) {
+                                    // the same 64 bytes straight from the registers into every
+                                    // peer's shared memory (asynchronous remote stores that count
+                                    // their bytes on the peer's rall[slot])
+#pragma unroll
+                                    for (int pp = 1; pp < C; ++pp) {
+                                        const uint32_t peer = (crank + (uint32_t)pp) & (uint32_t)(C - 1);
+                                        const uint32_t ra = map_to_rank(dl + gi * 16, peer);
+                                        const uint32_t rb = map_to_rank(&rall[slot], peer);
+                                        st_async_f4(ra, make_float4(v[0], v[1], v[2], v[3]), rb);
+                                        st_async_f4(ra + 16, make_float4(v[4], v[5], v[6], v[7]), rb);
+                                        st_async_f4(ra + 32, make_float4(v[8], v[9], v[10], v[11]), rb);
+                                        st_async_f4(ra + 48, make_float4(v[12], v[13], v[14], v[15]), rb);
+                                    }
                                 }
                             }
                         }
@@ -764,64 +876,74 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                     tc::fence_before_sync();
                     __syncwarp();
                     if (lane == 0) {
-                        mbar_arrive(&rloc[2 * slot + h]);
+                        mbar_arrive(&rloc[kParts * slot + h]);
                         mbar_arrive(&rall[slot]);
                     }
                 }
                 if (warp == 0) SG_STAMP(15);
+                // thresholds of the next block of this item
+                if (kb + 1 < nblk) draw_thresholds(s, kb + 1, (kg + 1) & (kSlots - 1));
+                else if (s + 1 < item.s_hi) draw_thresholds(s + 1, 0, (kg + 1) & (kSlots - 1));
             }
             // ---- end of sweep: energy partial sums over this CTA's columns
-            mbar_wait(&hdone[2 * ((kg - 1) & (kSlots - 1)) + 1], (uint32_t)((kg - 1) >> 2) & 1u);
+            mbar_wait(&hdone[kParts * ((kg - 1) & (kSlots - 1)) + kParts - 1], (uint32_t)((kg - 1) >> 2) & 1u);
             tc::fence_after_sync();
             named_sync(1);  // decision warp has flipped the last spins of the sweep
             {
-                float part[NG];
+                constexpr int PG = (NGRP < 4) ? NGRP : 4;   // 16-replica groups per pass
+                if (C > 1 && q == 0 && lane == 0) mbar_arrive_expect_tx(ebar, (uint32_t)((C - 1) * 4 * NG * 4));
+#pragma unroll 1
+                for (int g0 = 0; g0 < NGRP; g0 += PG) {
+                    float part[PG * 16];
 #pragma unroll
-                for (int r = 0; r < NG; ++r) part[r] = 0.0f;
-                for (int t = 0; t < Tl; ++t) {
-                    const int colb = col0 + t * kTileM + q * 32;   // first column of this lane group
-                    const float hv = (colb + lane < n_pad) ? a.h[colb + lane] : 0.0f;
+                    for (int r = 0; r < PG * 16; ++r) part[r] = 0.0f;
+                    for (int t = 0; t < Tl; ++t) {
+                        const int colb = col0 + t * kTileM + q * 32;   // first column of this lane group
+                        const float hv = (colb + lane < n_pad) ? a.h[colb + lane] : 0.0f;
 #pragma unroll
-                    for (int gi = 0; gi < NGRP; ++gi) {
-                        float f[16];
-                        tc::tmem_ld16(tq + t * NG + gi * 16, f);
-                        tc::wait_ld();
+                        for (int gi = 0; gi < PG; ++gi) {
+                            float f[16];
+                            tc::tmem_ld16(tq + t * NG + (g0 + gi) * 16, f);
+                            tc::wait_ld();
 #pragma unroll
-                        for (int r = 0; r < 16; ++r) {
-                            const uint32_t w = sbits[(gi * 16 + r) * Wp + (colb >> 5)];
-                            const float tt = f[r] + hv;
-                            part[gi * 16 + r] += ((w >> lane) & 1u) ? tt : -tt;
+                            for (int r = 0; r < 16; ++r) {
+                                const uint32_t w = sbits[((g0 + gi) * 16 + r) * Wp + (colb >> 5)];
+                                const float tt = f[r] + hv;
+                                part[gi * 16 + r] += ((w >> lane) & 1u) ? tt : -tt;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < PG * 16; ++r) {
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) part[r] += __shfl_xor_sync(0xFFFFFFFFu, part[r], o);
+                    }
+                    if (lane == 0) {
+                        float* dst = red + ((int)crank * 4 + q) * NG + g0 * 16;
+#pragma unroll
+                        for (int r = 0; r < PG * 16; ++r) dst[r] = part[r];
+                        if (C > 1) {
+#pragma unroll 1
+                            for (int pp = 1; pp < C; ++pp) {
+                                const uint32_t peer = (crank + (uint32_t)pp) & (uint32_t)(C - 1);
+                                const uint32_t ra = map_to_rank(dst, peer);
+                                const uint32_t rb = map_to_rank(ebar, peer);
+#pragma unroll
+                                for (int r4 = 0; r4 < PG * 4; ++r4)
+                                    st_async_f4(ra + 16 * r4, make_float4(part[4 * r4], part[4 * r4 + 1],
+                                                                         part[4 * r4 + 2], part[4 * r4 + 3]), rb);
+                            }
                         }
                     }
                 }
-#pragma unroll
-                for (int r = 0; r < NG; ++r) {
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) part[r] += __shfl_xor_sync(0xFFFFFFFFu, part[r], o);
-                }
-                if (lane == 0) {
-                    float* dst = red + ((int)crank * 4 + q) * NG;
-#pragma unroll
-                    for (int r = 0; r < NG; ++r) dst[r] = part[r];
-                    if (C == 2) {
-                        if (q == 0) mbar_arrive_expect_tx(ebar, (uint32_t)(4 * NG * 4));
-                        const uint32_t ra = map_to_rank(dst, peer);
-                        const uint32_t rb = map_to_rank(ebar, peer);
-#pragma unroll
-                        for (int r4 = 0; r4 < NG / 4; ++r4)
-                            st_async_f4(ra + 16 * r4, make_float4(part[4 * r4], part[4 * r4 + 1],
-                                                                 part[4 * r4 + 2], part[4 * r4 + 3]), rb);
-                    }
-                    mbar_arrive(ebar);
-                }
+                if (lane == 0) mbar_arrive(ebar);
             }
             tc::fence_before_sync();
-            named_sync(3);  // flags[0] = mask of replicas that improved
-            const uint32_t im = flags[0];
-            if (im != 0u && crank == 0) {
+            named_sync(3);  // flags[dw] = mask of the replicas of decision warp dw that improved
+            if ((flags[0] | flags[1] | flags[2] | flags[3]) != 0u && crank == 0) {
                 for (int w = tid; w < NG * W; w += 128) {
                     const int r = w / W, word = w - r * W;
-                    if (((im >> r) & 1u) && word * 32 < n_pad)
+                    if (((flags[r >> 5] >> (r & 31)) & 1u) && word * 32 < n_pad)
                         store_spin_word(a.best_spins + (size_t)(rep0 + r) * n_pad + word * 32, sbits[r * Wp + word]);
                 }
             }
@@ -885,7 +1007,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 SG_STAMP(13);
                 issue_tables();
                 const unsigned char* src =
-                    Q + (wq.stream_block(items, nblk) * nchunk + (size_t)crank * nchunk_l) * kStageBytes;
+                    Q + (wq.stream_block(items, nblk) * tiles_q + (size_t)crank * Tl) * (size_t)(P * kTileBytes);
 #pragma unroll 1
                 for (int c = 0; c < nchunk_l; ++c) {
                     mbar_wait(&empty[stage], epar);
@@ -897,14 +1019,20 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 SG_STAMP(14);
             }
         }
-    } else if (warp == 5) {
-        // ======================================================== DECISION WARP
-        const int r = lane & (NG - 1);
-        float pdec[LAG][kBlk];   // deltas of the previous LAG blocks ([0] = most recent)
-#pragma unroll
-        for (int l = 0; l < LAG; ++l)
-#pragma unroll
-            for (int b = 0; b < kBlk; ++b) pdec[l][b] = 0.0f;
+    } else if (warp == 5 || warp >= 7) {
+        // ======================================================== DECISION WARPS
+        // (one per 32 replicas of the group: warp 5, and warps 7.. for the replicas beyond 32)
+        const int dw = (warp == 5) ? 0 : warp - 6;
+        const int rl = dw * 32 + lane;           // replica of the group this lane decides
+        const int r = rl & (NG - 1);
+        static_assert(LAG == 1, "the decision warps carry one block of corrections");
+        // cn[b] = correction of site b of the NEXT block for the flips of the current block (they
+        // are not in the raw values the next block reads): accumulated while the current block's
+        // attempts are decided -- row a of the next block's table as soon as attempt a is known,
+        // independent work that fills the latency gaps of the sequential decision chain (it used
+        // to be a separate 16 x 16 pass at the start of every block, ~900 clocks of this warp's
+        // serial budget).  Same FMAs in the same order as before.
+        float2 cn[kBlk / 2];
         int kg = 0;
         uint32_t epar = 0;
 #pragma unroll 1
@@ -912,21 +1040,30 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
         const TcItem item = tc_item(items, it);
         const int rep0 = item.g * NG;
         const int g_act = min(NG, a.R - rep0);
-        const bool active = lane < g_act;
+        const bool active = rl < g_act;
         named_sync(2);   // the group's previous chunk is complete
         float best_e = 3.0e38f, cur_e = 0.0f;
         unsigned int n_acc = 0;
         if (active) {
-            cur_e = __ldcg(a.energy + rep0 + lane);
-            best_e = a.track_best ? __ldcg(a.best_energy + rep0 + lane) : 3.0e38f;
+            cur_e = __ldcg(a.energy + rep0 + rl);
+            best_e = a.track_best ? __ldcg(a.best_energy + rep0 + rl) : 3.0e38f;
         }
         named_sync(2);   // bit planes loaded
+#pragma unroll
+        for (int b = 0; b < kBlk / 2; ++b) cn[b] = make_float2(0.0f, 0.0f);
+        // the block's 16 sites come from global memory (L2, ~500 clocks): fetched one block ahead
+        uint4 ns0, ns1;
+        auto fetch_sites = [&](int s_t, int k_t) {
+            const uint16_t* st_t = sites_g + (size_t)s_t * n_s + k_t * kBlk;
+            ns0 = *reinterpret_cast<const uint4*>(st_t);
+            ns1 = *reinterpret_cast<const uint4*>(st_t + 8);
+        };
+        fetch_sites(item.s_lo, 0);
 #pragma unroll 1
         for (int s = item.s_lo; s < item.s_hi; ++s) {
-            const uint16_t* stab = sites_g + (size_t)s * n_s;
             double dT = 1.0;
             if (INJECT && active)
-                dT = a.temps[(long long)s * a.t_ss + (long long)(rep0 + lane) * a.t_rs];
+                dT = a.temps[(long long)s * a.t_ss + (long long)(rep0 + rl) * a.t_rs];
 #pragma unroll 1
             for (int k = 0; k < nblk; ++k, ++kg) {
                 const int slot = kg & (kSlots - 1);
@@ -934,9 +1071,12 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 const int i0 = k * kBlk;
                 const int nbk = min(kBlk, n - i0);
                 // the 16 sites of the block (uniform)
-                const uint4 s0 = *reinterpret_cast<const uint4*>(stab + i0);
-                const uint4 s1 = *reinterpret_cast<const uint4*>(stab + i0 + 8);
+                const uint4 s0 = ns0, s1 = ns1;
                 const uint32_t sw[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                {
+                    const bool more = k + 1 < nblk;
+                    if (more || s + 1 < item.s_hi) fetch_sites(more ? s : s + 1, more ? k + 1 : 0);
+                }
                 int site[kBlk];
 #pragma unroll
                 for (int b = 0; b < kBlk; ++b) site[b] = (int)((sw[b >> 1] >> (16 * (b & 1))) & 0xFFFFu);
@@ -945,7 +1085,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
 #pragma unroll
                     for (int b = 0; b < kBlk; ++b)
                         uu[b] = (active && b < nbk)
-                                    ? a.uniforms[((size_t)(rep0 + lane) * n_sweeps + s) * n + i0 + b]
+                                    ? a.uniforms[((size_t)(rep0 + rl) * n_sweeps + s) * n + i0 + b]
                                     : 0.0f;
                 }
                 SG_STAMP(4);
@@ -955,28 +1095,23 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 const float* thp = theta_s + slot * kBlk * NG + r;
                 const float4* cin4 = reinterpret_cast<const float4*>(tab_s + slot * kTabBytes);
                 const uint32_t* dup_p = reinterpret_cast<const uint32_t*>(tab_s + slot * kTabBytes) + 3 * kBlk * kBlk;
-                // correction for the flips of the previous LAG blocks (not yet in the raw values),
-                // oldest block first
+                // the next block's cross table (couplings from this block's sites into the next
+                // block's; none across a sweep boundary: the first block of a sweep reads its raw
+                // values after everything before it has landed)
+                const bool has_next = k + 1 < nblk;
+                if (has_next) mbar_wait(&tabbar[(kg + 1) & (kSlots - 1)], (uint32_t)((kg + 1) >> 2) & 1u);
+                // (no next block: a table of zeros, so that the loads below are unconditional and
+                // can be scheduled across the whole unrolled attempt chain)
+                const float4* nx4 = has_next
+                    ? reinterpret_cast<const float4*>(tab_s + ((kg + 1) & (kSlots - 1)) * kTabBytes) + (kBlk * kBlk / 4)
+                    : reinterpret_cast<const float4*>(ztab_s);
                 // (pairs of fields per register pair: one FFMA2 = two independent fp32 FMAs, same
                 // results as scalar fmaf, half the instructions of this warp's serial budget)
                 float2 v2[kBlk / 2];
 #pragma unroll
-                for (int b = 0; b < kBlk / 2; ++b) v2[b] = make_float2(0.0f, 0.0f);
-#pragma unroll
-                for (int l = LAG; l >= 1; --l) {
-                    if (k >= l) {
-                        const float4* ccr4 = cin4 + l * (kBlk * kBlk / 4);
-#pragma unroll
-                        for (int aa = 0; aa < kBlk; ++aa) {
-                            const float2 da2 = make_float2(pdec[l - 1][aa], pdec[l - 1][aa]);
-#pragma unroll
-                            for (int b4 = 0; b4 < kBlk / 4; ++b4) {
-                                const float4 c4 = ccr4[aa * 4 + b4];
-                                v2[2 * b4 + 0] = __ffma2_rn(da2, make_float2(c4.x, c4.y), v2[2 * b4 + 0]);
-                                v2[2 * b4 + 1] = __ffma2_rn(da2, make_float2(c4.z, c4.w), v2[2 * b4 + 1]);
-                            }
-                        }
-                    }
+                for (int b = 0; b < kBlk / 2; ++b) {
+                    v2[b] = cn[b];
+                    cn[b] = make_float2(0.0f, 0.0f);
                 }
                 float th[kBlk];
                 uint32_t w0[kBlk], dup[kBlk];
@@ -1026,6 +1161,12 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                                 reinterpret_cast<const float*>(cin4) + aa * kBlk + 2 * p2);
                             v2[p2] = __ffma2_rn(da2, c2, v2[p2]);
                         }
+#pragma unroll
+                        for (int b4 = 0; b4 < kBlk / 4; ++b4) {
+                            const float4 c4 = nx4[aa * 4 + b4];
+                            cn[2 * b4 + 0] = __ffma2_rn(da2, make_float2(c4.x, c4.y), cn[2 * b4 + 0]);
+                            cn[2 * b4 + 1] = __ffma2_rn(da2, make_float2(c4.z, c4.w), cn[2 * b4 + 1]);
+                        }
                     }
                 } else {
 #pragma unroll
@@ -1065,13 +1206,19 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                             reinterpret_cast<const float*>(cin4) + aa * kBlk + 2 * p2);
                         v2[p2] = __ffma2_rn(da2, c2, v2[p2]);
                     }
+#pragma unroll
+                    for (int b4 = 0; b4 < kBlk / 4; ++b4) {
+                        const float4 c4 = nx4[aa * 4 + b4];
+                        cn[2 * b4 + 0] = __ffma2_rn(da2, make_float2(c4.x, c4.y), cn[2 * b4 + 0]);
+                        cn[2 * b4 + 1] = __ffma2_rn(da2, make_float2(c4.z, c4.w), cn[2 * b4 + 1]);
+                    }
                 }
                 }
                 n_acc += (unsigned int)__popc(myflips);
                 SG_STAMP(7);
                 // B operand (K-major bf16): byte(n, k) = (n/8)*128 + (k/8)*BLBO + (n%8)*16 + (k%8)*2
-                if (lane < NG) {
-                    unsigned char* bo = bop_s + slot * BOP + (lane & 7) * 16 + (lane >> 3) * kBSbo;
+                if (rl < NG) {
+                    unsigned char* bo = bop_s + slot * BOP + (rl & 7) * 16 + (rl >> 3) * kBSbo;
                     *reinterpret_cast<uint4*>(bo) =
                         make_uint4(pack_bf16x2(d[0], d[1]), pack_bf16x2(d[2], d[3]),
                                    pack_bf16x2(d[4], d[5]), pack_bf16x2(d[6], d[7]));
@@ -1083,18 +1230,12 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&decbar[slot]);
                 // spin bit planes (lane r owns plane r; XOR commutes, so order is irrelevant)
-                if (lane < NG) {
+                if (rl < NG) {
 #pragma unroll
                     for (int aa = 0; aa < kBlk; ++aa)
                         atomicXor(&sbits[r * Wp + (site[aa] >> 5)],
                                   ((myflips >> aa) & 1u) << (site[aa] & 31));
                 }
-#pragma unroll
-                for (int l = LAG - 1; l >= 1; --l)
-#pragma unroll
-                    for (int b = 0; b < kBlk; ++b) pdec[l][b] = pdec[l - 1][b];
-#pragma unroll
-                for (int b = 0; b < kBlk; ++b) pdec[0][b] = d[b];
                 SG_STAMP(8);
             }
             // ---- end of sweep: energy, best tracking
@@ -1106,25 +1247,25 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 float acc = 0.0f;
 #pragma unroll
                 for (int rk = 0; rk < C; ++rk) {
-                    const float* pr = red + rk * 4 * NG + lane;
+                    const float* pr = red + rk * 4 * NG + r;
                     acc += (pr[0] + pr[NG]) + (pr[2 * NG] + pr[3 * NG]);
                 }
                 cur_e = -0.5f * acc;
-                if (a.energy_trace && crank == 0) a.energy_trace[(size_t)s * a.R + rep0 + lane] = cur_e;
+                if (a.energy_trace && crank == 0) a.energy_trace[(size_t)s * a.R + rep0 + rl] = cur_e;
                 if (a.track_best && cur_e < best_e) {
                     best_e = cur_e;
                     improved = true;
                 }
             }
             const uint32_t im = __ballot_sync(0xFFFFFFFFu, improved);
-            if (lane == 0) flags[0] = im;
+            if (lane == 0) flags[dw] = im;
             named_sync(3);
             named_sync(1);
         }
         if (active && crank == 0) {
-            __stcg(a.energy + rep0 + lane, cur_e);
-            if (a.track_best) __stcg(a.best_energy + rep0 + lane, best_e);
-            __stcg(a.accepted + rep0 + lane, __ldcg(a.accepted + rep0 + lane) + (unsigned long long)n_acc);
+            __stcg(a.energy + rep0 + rl, cur_e);
+            if (a.track_best) __stcg(a.best_energy + rep0 + rl, best_e);
+            __stcg(a.accepted + rep0 + rl, __ldcg(a.accepted + rep0 + rl) + (unsigned long long)n_acc);
         }
         __threadfence();
         named_sync(2);   // item complete (tid 0 publishes the group's progress)
@@ -1151,28 +1292,28 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 SG_STAMP(10);
                 const uint64_t bdesc = tc::make_smem_desc(smem_u32(bop_s + slot * BOP), BLBO, kBSbo);
 #pragma unroll 1
-                for (int h = 0; h < 2; ++h) {
-                    // this CTA's raw reads of block k+LAG in this column half must be done before
-                    // this block's update of the half is issued
+                for (int h = 0; h < kParts; ++h) {
+                    // this CTA's raw reads of block k+LAG in this column part must be done before
+                    // this block's update of the part is issued
                     if (k + LAG < nblk)
-                        mbar_wait(&rloc[2 * ((kg + LAG) & (kSlots - 1)) + h],
+                        mbar_wait(&rloc[kParts * ((kg + LAG) & (kSlots - 1)) + h],
                                   (uint32_t)((kg + LAG) >> 2) & 1u);
                     if (h == 0) SG_STAMP(11);
-                    const int c_end = h ? nchunk_l : hc;
+                    const int c_end = pb(h + 1);
 #pragma unroll 1
-                    for (int c = h ? hc : 0; c < c_end; ++c) {
+                    for (int c = pb(h); c < c_end; ++c) {
                         mbar_wait(&full[stage], fpar);
                         tc::fence_after_sync();
-                        const int nt = (dbg & 2) ? 0 : min(kChunkTiles, Tl - c * kChunkTiles);
+                        const int nt = (dbg & 2) ? 0 : min(CT, Tl - c * CT);
                         const uint64_t adesc0 = tc::make_smem_desc(
                             smem_u32(ring + (size_t)stage * kStageBytes), kALbo, kASbo);
-                        const uint32_t d0 = tbase + (uint32_t)(c * kChunkTiles * NG);
+                        const uint32_t d0 = tbase + (uint32_t)(c * CT * NG);
                         // (the issue pattern is not the limit here: a branch-free block of 12 MMAs
                         // issues at 48 clocks per MMA in isolation, tools/mma_bench.py, but the phase
                         // is bound by shared-memory bandwidth -- TMA writes plus operand reads)
                         if (tc::elect_one()) {
 #pragma unroll
-                            for (int tt = 0; tt < kChunkTiles; ++tt) {
+                            for (int tt = 0; tt < CT; ++tt) {
                                 if (tt < nt) {
 #pragma unroll
                                     for (int p = 0; p < P; ++p)
@@ -1186,7 +1327,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                         __syncwarp();
                         if (++stage == NS) { stage = 0; fpar ^= 1u; }
                     }
-                    if (tc::elect_one()) tc::mma_commit(&hdone[2 * slot + h]);
+                    if (tc::elect_one()) tc::mma_commit(&hdone[kParts * slot + h]);
                     __syncwarp();
                 }
                 SG_STAMP(12);
@@ -1203,7 +1344,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
         a.dbg[8192 + blockIdx.x * 4 + 1] = (long long)gt;
         a.dbg[8192 + blockIdx.x * 4 + 3] = (long long)clock64();
     }
-    if (C == 2) cluster_sync_all();   // no CTA exits while its peer may still write into it
+    if (C > 1) cluster_sync_all();   // no CTA exits while a peer may still write into it
     if (warp == 0) tc::tmem_dealloc(tbase, (uint32_t)tmem_cols);
 }
 
@@ -1469,7 +1610,7 @@ static cudaError_t launch_tc_variant(const SweepDev& a, const __nv_bfloat16* J, 
     if (err != cudaSuccess) return err;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(grid_groups * C), 1, 1);
-    cfg.blockDim = dim3(kTcThreads, 1, 1);
+    cfg.blockDim = dim3(tc_threads(C), 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -1489,14 +1630,21 @@ static cudaError_t launch_tc_variant(const SweepDev& a, const __nv_bfloat16* J, 
                               tabs, s0, s1, spi, done, dbg);
 }
 
-// CTAs per replica group the launcher uses for this shape: 2 = a cluster pair holds 32 replicas
-// and each CTA owns half of the field columns (needs n_tc / 128 tiles divisible by 8 and more
-// than 16 replicas; SG_TC_CLUSTER=1 switches it off), else 1
+// CTAs per replica group the launcher uses for this shape: 4 = a thread-block cluster holds 64
+// replicas and each CTA owns a quarter of the field columns (needs n_tc / 128 tiles divisible by 8
+// and more than 32 replicas), 2 = a pair holds 32 replicas (same shapes, more than 16 replicas),
+// else 1.  SG_TC_CLUSTER=1 / 2 caps it (tests, A/B timing).
 int sweep_tc_cluster_size(int n_tc, int R) {
     const int T = n_tc / kTileM;
-    int C = (T % (2 * kChunkTiles) == 0 && R > kG) ? 2 : 1;
+    int C = 1;
+    if (T % (2 * kChunkTiles) == 0) C = (R > 2 * kG) ? 4 : (R > kG) ? 2 : 1;
     if (const char* c_env = getenv("SG_TC_CLUSTER")) {
-        if (atoi(c_env) == 1) C = 1;
+        const int cap = atoi(c_env);
+        if (cap == 1 || cap == 2) C = (C < cap) ? C : cap;
+        // clusters of 8 (128 replicas, an eighth of the columns, four decision warps) are built and
+        // bit-identical, but slower: 15 clusters fit the GPU (120 SMs) and four decision warps per
+        // SM slow each other down (11 G attempts/s at the headline shape against 19 for C = 4)
+        if (cap == 8 && C == 4 && R > 4 * kG) C = 8;
     }
     return C;
 }
@@ -1511,23 +1659,24 @@ struct TcItemGate {
 };
 static TcItemGate g_item_gate;
 
-// cluster pairs that can be resident at the same time (the persistent work-item schedule must
-// not launch more: a waiting pair would otherwise hold the SMs a pair it depends on needs)
-static int tc_max_cluster_pairs(size_t smem) {
-    cudaFuncSetAttribute(sweep_tc_kernel<3, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+// clusters of C CTAs that can be resident at the same time (the persistent work-item schedule must
+// not launch more: a waiting cluster would otherwise hold the SMs a cluster it depends on needs)
+template <int C>
+static int tc_max_clusters(size_t smem) {
+    cudaFuncSetAttribute(sweep_tc_kernel<3, false, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2, 1, 1);
-    cfg.blockDim = dim3(kTcThreads, 1, 1);
+    cfg.gridDim = dim3(C, 1, 1);
+    cfg.blockDim = dim3(tc_threads(C), 1, 1);
     cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.x = C;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int ncl = 0;
-    if (cudaOccupancyMaxActiveClusters(&ncl, sweep_tc_kernel<3, false, 2>, &cfg) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveClusters(&ncl, sweep_tc_kernel<3, false, C>, &cfg) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
@@ -1551,9 +1700,9 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
         if (e != cudaSuccess) return e;
         ++*launches;
     }
-    // C = 2 (default where the shape allows it): a cluster pair per 32 replicas, each CTA owning
-    // half of the field columns -- half the operand bytes per SM and attempt, bit-identical
-    // results, 1.6x the throughput of C = 1 (one CTA per 16 replicas; SG_TC_CLUSTER=1).
+    // C = 4 / 2 (default where the shape allows it): a cluster per 64 / 32 replicas, each CTA
+    // owning 1/C of the field columns -- 1/C of the operand bytes per SM and attempt, bit-identical
+    // results (C = 1: one CTA per 16 replicas; SG_TC_CLUSTER=1 / 2 caps C).
     const int T = n_tc / kTileM;
     const int C = sweep_tc_cluster_size(n_tc, a.R);
     int NS = kMaxStagesTc;
@@ -1602,12 +1751,12 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
         const int groups = (a.R + kG * C - 1) / (kG * C);
         int spi = s1 - s0, grid_groups = groups;
         bool item_mode = false;
-        // CTAs (C = 1) or cluster pairs (C = 2) resident at once
+        // CTAs (C = 1) or clusters (C = 2, 4) resident at once
         int n_slots = n_sm;
-        if (C == 2) {
-            n_slots = tc_max_cluster_pairs(smem);
-            if (n_slots > n_sm / 2) n_slots = n_sm / 2;
-            if (sm_env_set && n_sm / 2 < n_slots) n_slots = n_sm / 2 > 0 ? n_sm / 2 : 1;
+        if (C > 1) {
+            n_slots = (C == 8) ? tc_max_clusters<8>(smem) : (C == 4) ? tc_max_clusters<4>(smem) : tc_max_clusters<2>(smem);
+            if (n_slots > n_sm / C) n_slots = n_sm / C;
+            if (sm_env_set && n_sm / C < n_slots) n_slots = n_sm / C > 0 ? n_sm / C : 1;
             if (n_slots < 1) n_slots = 1;
         }
         if (groups > n_slots) {
@@ -1645,7 +1794,11 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
         err = cudaGetLastError();                                                              \
         if (err != cudaSuccess) return err;                                                    \
         if (timer) timer->begin(0, st);                                                        \
-        err = (C == 2) ? launch_tc_variant<P, INJ, 2>(a, J, n_tc, sites, n_s, NS, cols, Qc, tabs,\
+        err = (C == 8) ? launch_tc_variant<P, INJ, 8>(a, J, n_tc, sites, n_s, NS, cols, Qc, tabs,\
+                                                      s0, s1, spi, grid_groups, done, dbg, smem, st) \
+            : (C == 4) ? launch_tc_variant<P, INJ, 4>(a, J, n_tc, sites, n_s, NS, cols, Qc, tabs,\
+                                                      s0, s1, spi, grid_groups, done, dbg, smem, st) \
+            : (C == 2) ? launch_tc_variant<P, INJ, 2>(a, J, n_tc, sites, n_s, NS, cols, Qc, tabs,\
                                                       s0, s1, spi, grid_groups, done, dbg, smem, st) \
                        : launch_tc_variant<P, INJ, 1>(a, J, n_tc, sites, n_s, NS, cols, Qc, tabs,\
                                                       s0, s1, spi, grid_groups, done, dbg, smem, st); \

@@ -224,26 +224,31 @@ def test_tc_full_size_many_waves_matches_one_cta_per_group(engine, monkeypatch):
         assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("n,R", [(1024, 16 * 7 + 5), (2048, 70)])
-def test_tc_cluster_pairs_equal_single_cta_groups(engine, monkeypatch, n, R):
-    """The default for n_tc divisible by 1024: a thread-block cluster pair holds 32 replicas, each
-    CTA owns half of the field columns, raw field values and energy partial sums cross the pair
-    through distributed shared memory.  Same decisions, so nothing may differ from one CTA per
-    16 replicas (SG_TC_CLUSTER=1) -- also when few SMs force the persistent work-item schedule
-    (cluster pairs handing replica groups to each other through HBM)."""
+@pytest.mark.parametrize("n,R", [(1024, 16 * 7 + 5), (2048, 70), (4096, 64 * 3 + 40)])
+def test_tc_clusters_equal_single_cta_groups(engine, monkeypatch, n, R):
+    """The default for n_tc divisible by 1024 and more than 32 replicas: a thread-block cluster of
+    4 holds 64 replicas, each CTA owns a quarter of the field columns, raw field values and energy
+    partial sums cross the cluster through distributed shared memory, two decision warps of 32
+    replicas each (SG_TC_CLUSTER=2: pairs, 32 replicas, half of the columns; =8: 128 replicas, an
+    eighth of the columns, four decision warps -- built, identical, slower).  Same decisions, so
+    nothing may differ from one CTA per 16 replicas (SG_TC_CLUSTER=1) -- also when few SMs force
+    the persistent work-item schedule (clusters handing replica groups to each other through
+    HBM)."""
     rng = np.random.default_rng(n + R)
     J, h = _int_instance(rng, n)
     S0 = (rng.integers(0, 2, size=(R, n)) * 2 - 1).astype(np.int8)
     ns = 5
     temps = np.linspace(2.5, 0.6, ns)
     outs = []
-    for env in ({"SG_TC_CLUSTER": "1"}, {}, {"SG_TC_SM": "2"}, {"SG_TC_SM": "4", "SG_TC_SPI": "2"}):
+    for env in ({"SG_TC_CLUSTER": "1"}, {"SG_TC_CLUSTER": "2"}, {"SG_TC_CLUSTER": "8"}, {}, {"SG_TC_SM": "2"},
+                {"SG_TC_SM": "8", "SG_TC_SPI": "2"}, {"SG_TC_CLUSTER": "8", "SG_TC_SM": "16", "SG_TC_SPI": "2"},
+                {"SG_TC_CLUSTER": "2", "SG_TC_SM": "4", "SG_TC_SPI": "2"}):
         for k in ("SG_TC_CLUSTER", "SG_TC_SM", "SG_TC_SPI"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         _setup(engine, J, h, S0)
-        assert engine.tc_cluster_size() == (1 if env.get("SG_TC_CLUSTER") == "1" else 2)
+        assert engine.tc_cluster_size() == int(env.get("SG_TC_CLUSTER", "4"))
         tr = engine.sweep(ns, temps, temps_sweep_stride=1, seed=5, sweep_base=3, site_order="random",
                           energy_trace=True, kernel="tc", coupling_planes=1).cpu().numpy()
         outs.append((engine.spins().cpu().numpy(), tr, engine.accepted().cpu().numpy(),
@@ -306,7 +311,7 @@ def test_tc_row_length_padding_enables_cluster_pairs(engine, oracle, n, pairs):
     uni = rng.random((R, ns, n), dtype=np.float32)
     temps = np.array([2.0, 0.8])
     _setup(engine, J, h, S0)
-    assert engine.tc_cluster_size() == (2 if pairs else 1)
+    assert engine.tc_cluster_size() == (4 if pairs else 1)
     trace = engine.sweep(ns, temps, temps_sweep_stride=1, sites=sites, uniforms=uni, energy_trace=True,
                          kernel="tc", coupling_planes=1).cpu().numpy()
     final = engine.spins().cpu().numpy()

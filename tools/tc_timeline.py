@@ -33,7 +33,7 @@ if ist[7] > 0:
 t0 = t[0, 0]
 names = ["q_start", "q_tabs", "q_h0ok", "q_h1ok", "d_start", "d_pre", "d_rawok", "d_dec", "d_done", "m_wait", "m_decok", "m_r0ok", "m_done", "p_start", "p_end", "q_done"]
 print("blk " + " ".join(f"{x:>8s}" for x in names))
-for k in list(range(0, 6)) + list(range(100, 106)) + list(range(254, 260)):
+for k in list(range(0, 4)) + list(range(100, 112)) + list(range(254, 258)):
     print(f"{k:3d} " + " ".join(f"{int(t[k, i] - t0):8d}" for i in range(16)))
 d = t[40:240].astype(np.int64)
 def m(a, b): return float((d[:, a] - d[:, b]).mean())
