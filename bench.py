@@ -3,15 +3,17 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-One "step" = one pass of the hot path over one batch: `--sweeps` Metropolis sweeps of every
-replica of the SK N=4096 instance (cfg3 of BASELINE.json), 8192 replicas PER GPU (weak
-scaling: replicas are independent, no data-path collective; the only collective is the final
-argmin allgather of the best energies).  `value` times the sweep launches with the state
-resident in HBM (site-table + operand-gather + sweep kernels of the tensor-core path, all
-inside the timed region); `e2e` times the same step through the host-buffer C-ABI path (pinned
-host spins -> device, local-field initialisation, sweeps, best energies -> host).  The roofline
-object is about the dominant kernel alone (sg::sweep_tc_kernel), timed with CUDA events by the
-library around each of its launches.
+One "step" = one parallel-tempering step of cfg3 (BASELINE.json): `--sweeps` Metropolis sweeps of
+every replica of the SK N=4096 instance at its ladder temperature (64-rung ladders), an exact
+refresh of fields / energies, and one replica-exchange round.  8192 replicas PER GPU (weak
+scaling, the default) or in total (--scaling strong).  On several GPUs the ladders are global:
+every exchange round all-gathers the per-replica energies over NCCL (the path's one collective,
+inside the timed region) and every rank applies the same decisions.  `value` times the steps with
+the state resident in HBM (site-table + operand-gather + sweep + refresh + exchange kernels, all
+inside the timed region); `e2e` times the same step through the C ABI's host-buffer path (pinned
+host spins -> device, local-field initialisation, the step, best configuration -> pinned host).
+The roofline object is about the dominant kernel alone (sg::sweep_tc_kernel), timed with CUDA
+events by the library around each of its launches.
 
 `--impl reference` times the reference's CPU algorithm (the oracle port in C, all host
 threads, per-attempt dot products + per-sweep O(N^2) energy exactly like the reference's
@@ -80,8 +82,9 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def cpu_reference(n_threads, budget_s, sweeps=1):
-    """Reference algorithm (oracle port) on the host cores; returns (attempts/s, sample text)."""
+def cpu_reference(n_threads, budget_s, sweeps=1, quench_sweeps=0):
+    """Reference algorithm (oracle port) on the host cores; returns (attempts/s, threads, sample
+    text, best energy of an optional fixed-temperature quench within the same budget class)."""
     from oracle import oracle as orc
     orc.build()
     J, h = sk_instance()
@@ -105,12 +108,25 @@ def cpu_reference(n_threads, budget_s, sweeps=1):
     t0 = time.perf_counter()
     att, _ = orc.baseline_run(J, h, S, sweeps, TEMPERATURE, seed=2, n_threads=threads)
     dt = time.perf_counter() - t0
-    return att / dt, threads, f"{R} replicas x {sweeps} sweep(s) of SK N={N_SPINS} at T={TEMPERATURE} ({dt:.1f} s)"
+    best = None
+    if quench_sweeps > 0:
+        # what the CPU arm reaches in a comparable budget: one replica per core, fixed T = 0.3
+        Sq = (rng.integers(0, 2, size=(threads, N_SPINS)) * 2 - 1).astype(np.float32)
+        tq = time.perf_counter()
+        _, eq = orc.baseline_run(J, h, Sq, quench_sweeps, 0.3, seed=3, n_threads=threads)
+        best = {"best_energy": float(np.min(eq)), "sweeps": quench_sweeps, "replicas": threads,
+                "temperature": 0.3, "seconds": time.perf_counter() - tq}
+    return att / dt, threads, f"{R} replicas x {sweeps} sweep(s) of SK N={N_SPINS} at T={TEMPERATURE} ({dt:.1f} s)", best
+
+
+LADDER_RUNGS = 64
+LADDER_T = (2.0, 0.1)   # hottest, coldest (geometric)
 
 
 def workload_name(replicas, sweeps):
-    return (f"SK dense N={N_SPINS} Gaussian J (cfg3), Metropolis sweep, T={TEMPERATURE}, "
-            f"{replicas} replicas/GPU x {sweeps} sweeps per step, shared random site order")
+    return (f"SK dense N={N_SPINS} Gaussian J (cfg3), parallel tempering step: {sweeps} Metropolis sweeps of "
+            f"{replicas} replicas/GPU on {LADDER_RUNGS}-rung ladders (T geometric {LADDER_T[0]} -> {LADDER_T[1]}) "
+            f"+ exact energy refresh + one replica-exchange round, shared random site order")
 
 
 def run_reference(args):
@@ -122,9 +138,11 @@ def run_reference(args):
         cpu_reference(0, 2.0)
     sample = ""
     threads = 1
+    best = None
     t_all = time.perf_counter()
-    for _ in range(args.steps):
-        v, threads, sample = cpu_reference(0, args.ref_budget)
+    for i in range(args.steps):
+        v, threads, sample, b = cpu_reference(0, args.ref_budget, quench_sweeps=200 if i == 0 else 0)
+        best = b or best
         vals.append(v)
     ms = (time.perf_counter() - t_all) * 1e3 / max(1, args.steps)
     value = float(np.mean(vals))
@@ -136,9 +154,9 @@ def run_reference(args):
         "config": {"workload": workload_name(args.replicas, args.sweeps),
                    "replicas_per_gpu": args.replicas, "sweeps_per_step": args.sweeps,
                    "note": "the reference's algorithm (CPU port, all host threads) on a bounded sample "
-                           "of the same workload: replicas x 1 sweep per step, see cpu_baseline.sample"},
+                           "of the same workload: replicas x 1 sweep per step at T=1, see cpu_baseline.sample"},
         "cpu_baseline": {"value": value, "unit": "attempts/s", "cores": threads, "kind": "port",
-                         "sample": sample},
+                         "sample": sample, "quench": best},
         "e2e": {"value": value, "unit": "attempts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -146,6 +164,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
+    from spin_glass_anneal_rl_b200.annealing.multi_gpu import gather_energies
     from spin_glass_anneal_rl_b200.engine import Engine
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -157,83 +176,107 @@ def run_ours(args):
     dev = torch.device("cuda", local)
 
     J, h = sk_instance()
-    R, n, sweeps = args.replicas, N_SPINS, args.sweeps
+    n, sweeps, K = N_SPINS, args.sweeps, LADDER_RUNGS
+    kernel, planes = args.kernel, args.planes
+    use_tc = kernel in ("auto", "tc")
+    ladder = np.geomspace(LADDER_T[0], LADDER_T[1], K)
     eng = Engine(local)
     eng.set_model(torch.from_numpy(J).to(dev), torch.from_numpy(h).to(dev))
-    eng.alloc_replicas(R)
-    g = torch.Generator(device=dev)
-    g.manual_seed(1234 + rank)
-    spins_dev = (torch.randint(0, 2, (R, n), device=dev, generator=g, dtype=torch.int8) * 2 - 1).to(torch.int8)
-    spins_host = spins_dev.cpu().pin_memory()
-    eng.set_spins(spins_dev)
-    eng.init_fields()
-    temps = torch.full((1,), TEMPERATURE, dtype=torch.float64, device=dev)
-    q = eng.query()
-    gmax = q["max_replicas_per_block"]
-    blocks = (R + gmax - 1) // gmax
-    launches0 = eng.launch_count()
-
-    kernel = args.kernel
-    planes = args.planes
-
-    def step(i):
-        eng.sweep(sweeps, temps, seed=99 + rank, sweep_base=i * sweeps, site_order="random",
-                  track_best=True, kernel=kernel, coupling_planes=planes)
-
-    use_tc = kernel in ("auto", "tc")
-    cluster = 1
-    if use_tc:
-        gmax = 16
-        blocks = (R + gmax - 1) // gmax
-        cluster = max(1, eng.tc_cluster_size())
+    q = None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        step(i)
-    barrier()
+    def fresh_spins(R, seed):
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed)
+        return (torch.randint(0, 2, (R, n), device=dev, generator=g, dtype=torch.int8) * 2 - 1).to(torch.int8)
+
+    def setup(R):
+        """R replicas on this GPU = the global replicas [rank R, rank R + R) of world R: ladders
+        are global (64 consecutive replicas), so under strong scaling at 8 GPUs a rank holds 16."""
+        if eng.n_replicas != R:
+            eng.alloc_replicas(R)
+        eng.set_spins(fresh_spins(R, 1234 + rank))
+        eng.init_fields()
+        eng.set_ladder(ladder, n_global=R * world, replica_offset=rank * R)
+
+    def step(i, R, seed=99):
+        """One parallel-tempering step (reference parallel_tempering.py:108-114): `sweeps` sweeps of
+        every replica at its current temperature, exact energies, one exchange round.  With more
+        than one GPU the exchange is decided from the all-gathered energy table (collective C1:
+        4 B per replica over NCCL), identically on every rank."""
+        eng.sweep(sweeps, None, seed=seed, sweep_base=i * sweeps, site_order="random", track_best=True,
+                  kernel=kernel, coupling_planes=planes, replica_base=rank * R)
+        eng.refresh_fields()
+        e_all = gather_energies(eng.energies(), R * world) if world > 1 else None
+        eng.exchange(i & 1, seed=seed + 1, round=i, energies_all=e_all)
+        return e_all
+
+    def measure(R, steps, warmup):
+        setup(R)
+        for i in range(warmup):
+            step(i, R)
+        barrier()
+        acc0 = eng.accepted().sum().item()
+        eng.set_profiling(True)
+        eng.profile()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        l0 = eng.launch_count()
+        ev[0].record()
+        for i in range(steps):
+            step(warmup + i, R)
+        ev[1].record()
+        barrier()
+        ms = ev[0].elapsed_time(ev[1])
+        launches = eng.launch_count() - l0
+        prof = eng.profile()
+        eng.set_profiling(False)
+        acc1 = eng.accepted().sum().item()
+        _, _, att, acc = eng.ladder_state()
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+        return {"ms_total": ms, "value": float(R) * world * n * sweeps * steps / (ms * 1e-3),
+                "launches": int(launches), "prof": prof,
+                "acceptance_rate": (acc1 - acc0) / (float(R) * n * sweeps * steps),
+                "exchange_rate": float(acc.sum().item()) / max(1.0, float(att.sum().item()))}
+
+    R_main = args.replicas if args.scaling == "weak" else max(K, args.replicas // world // K * K)
     sampler = ClockSampler(local)
     sampler.start()
-    acc0 = eng.accepted().sum().item()
-    eng.set_profiling(True)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    l0 = eng.launch_count()
-    ev[0].record()
-    for i in range(args.steps):
-        step(args.warmup + i)
-    ev[1].record()
-    barrier()
-    ms_total = ev[0].elapsed_time(ev[1])
-    gpu_launches = eng.launch_count() - l0
-    prof = eng.profile()
-    eng.set_profiling(False)
-    acc1 = eng.accepted().sum().item()
+    main_res = measure(R_main, args.steps, args.warmup)
     clocks = sampler.summary()
+    q = eng.query()
+    cluster = max(1, eng.tc_cluster_size()) if use_tc else 1
+    R = R_main
 
-    # ---- end to end through the host-buffer path: pinned spins -> device, field init, sweeps,
-    # best energies -> host, every step
-    best_host = torch.empty(R, dtype=torch.float32).pin_memory()
+    # ---- end to end through the C ABI's host-buffer path, every step: pinned host spins ->
+    # sg_upload_spins_async (side stream, double buffered) -> sg_set_spins_staged -> field init ->
+    # the same step -> sg_get_best_config (argmin energy, replica, configuration) -> pinned host
+    spins_host = fresh_spins(R, 4321 + rank).cpu().pin_memory()
+    out_e = torch.empty(1, dtype=torch.float32).pin_memory()
+    out_r = torch.empty(1, dtype=torch.int32).pin_memory()
+    out_s = torch.empty(n, dtype=torch.int8).pin_memory()
     e2e_steps = max(1, min(args.steps, 5))
+    side = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    eng.upload_spins_async(spins_host, 0, side)   # allocates the staging buffers outside the timed region
+    eng.upload_spins_async(spins_host, 1, side)
     barrier()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
-    # the upload of step i+1 runs on a side stream while step i computes (double buffer); every
-    # step's upload and read-back are inside the timed region
-    side = torch.cuda.Stream(device=dev)
-    main = torch.cuda.current_stream(dev)
-    bufs = [spins_dev, torch.empty_like(spins_dev)]
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
     def upload(i):
-        with torch.cuda.stream(side):
-            if i >= 2:
-                side.wait_event(consumed[i % 2])
-            bufs[i % 2].copy_(spins_host, non_blocking=True)
-            ready[i % 2].record(side)
+        if i >= 2:
+            side.wait_event(consumed[i % 2])
+        eng.upload_spins_async(spins_host, i % 2, side)
+        ready[i % 2].record(side)
 
     t0.record()
     side.wait_event(t0)
@@ -242,113 +285,133 @@ def run_ours(args):
         if i + 1 < e2e_steps:
             upload(i + 1)
         main.wait_event(ready[i % 2])
-        eng.set_spins(bufs[i % 2])
+        eng.set_spins_staged(i % 2)
         consumed[i % 2].record(main)
         eng.init_fields()
-        step(1000 + i)
-        best_host.copy_(eng.best_energies(), non_blocking=True)
+        step(1000 + i, R)
+        eng.best_config(out_e, out_r, out_s)
     t1.record()
     barrier()
     ms_e2e = t0.elapsed_time(t1) / e2e_steps
+    e2e_best = float(out_e.item())
 
-    # ---- time to target energy (BASELINE metric, second half): parallel tempering on the same
-    # instance, 64 rungs per ladder, R/64 ladders per GPU, 10 sweeps between exchanges; stop when
-    # the best energy over all replicas of all ranks reaches E_target (0.97 x the Parisi
-    # ground-state energy for Var J = 1/(2N))
+    # ---- time to target energy (BASELINE metric, second half): the same parallel tempering until
+    # some replica's EXACT current energy (after the refresh of a round) is <= E_target = 0.97 x the
+    # Parisi ground-state energy for Var J = 1/(2N).  The test runs on the device after
+    # every exchange round (sg_check_target into pinned host memory; the all-gathered table when
+    # there are several GPUs); the host polls the flag without synchronising, so a run stops within
+    # a round or two of the hit and reports the round of the hit itself.
     ttt = None
-    if args.ttt_budget > 0 and R % 64 == 0:
+    if args.ttt_budget > 0:
         e_target = 0.97 * (-0.7632 / np.sqrt(2.0)) * n
-        ladder = np.geomspace(2.0, 0.1, 64)
         runs = []
-        exact = None
         budget_left = args.ttt_budget
+        max_rounds = 400
         for run in range(args.ttt_seeds):
-            if run == 0:
-                eng.set_spins(spins_dev)
-            else:
-                g.manual_seed(1234 + rank + 7919 * run)
-                eng.set_spins((torch.randint(0, 2, (R, n), device=dev, generator=g, dtype=torch.int8) * 2 - 1)
-                              .to(torch.int8))
+            eng.set_spins(fresh_spins(R, 777 + rank + 7919 * run))
             eng.init_fields()
-            eng.set_ladder(ladder)
+            eng.set_ladder(ladder, n_global=R * world, replica_offset=rank * R)
+            hit = torch.full((2,), -1, dtype=torch.int32).pin_memory()
+            hit_dev = torch.full((2,), -1, dtype=torch.int32, device=dev)
+            evs = []
             barrier()
             w0 = time.perf_counter()
-            rounds, reached = 0, False
-            while True:
-                for _ in range(4):
-                    eng.sweep(10, None, seed=4242 + rank + 1000 * run, sweep_base=rounds * 10,
-                              site_order="random", track_best=True, kernel=kernel, coupling_planes=planes)
-                    eng.refresh_fields()
-                    eng.exchange(rounds & 1, seed=77 + rank + 1000 * run, round=rounds)
-                    rounds += 1
-                # one reduction carries both the best energy and "some rank is out of budget", so
-                # every rank takes the same branch
-                over = 1.0 if time.perf_counter() - w0 >= budget_left else 0.0
-                b = torch.stack([eng.best_energies().min().double(),
-                                 torch.tensor(-over, dtype=torch.float64, device=dev)])
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            rounds = 0
+            while rounds < max_rounds:
+                eng.sweep(sweeps, None, seed=4242 + 1000 * run, sweep_base=rounds * sweeps, site_order="random",
+                          track_best=False, kernel=kernel, coupling_planes=planes, replica_base=rank * R)
+                eng.refresh_fields()
                 if world > 1:
-                    dist.all_reduce(b, op=dist.ReduceOp.MIN)
-                if b[0].item() <= e_target:
-                    reached = True
-                    break
-                if b[1].item() < 0.0:
+                    e_all = gather_energies(eng.energies(), R * world)
+                    m, arg = torch.min(e_all, dim=0)
+                    now = torch.stack([torch.full_like(arg, rounds), arg]).to(torch.int32)
+                    hit_dev = torch.where((m <= e_target) & (hit_dev[0] < 0), now, hit_dev)
+                    hit.copy_(hit_dev, non_blocking=True)
+                else:
+                    e_all = None
+                    eng.check_target(e_target, rounds, hit)
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                evs.append(e)
+                eng.exchange(rounds & 1, seed=77 + 1000 * run, round=rounds, energies_all=e_all)
+                rounds += 1
+                if int(hit[0]) >= 0 or (rounds % 8 == 0 and time.perf_counter() - w0 > budget_left):
                     break
             torch.cuda.synchronize()
-            secs = time.perf_counter() - w0
-            runs.append({"seconds": secs, "sweeps": rounds * 10, "reached": reached})
-            if run == 0:
-                be, bs = eng.best()
-                exact = eng.batch_energies(bs[int(torch.argmin(be).item())].reshape(1, n)).item()
-            spent = torch.tensor([secs], dtype=torch.float64, device=dev)
+            hr = int(hit[0])
+            reached = hr >= 0
+            secs = ev0.elapsed_time(evs[hr]) * 1e-3 if reached else time.perf_counter() - w0
+            rec = {"seconds": secs, "sweeps": (hr + 1) * sweeps if reached else rounds * sweeps, "reached": reached}
+            if reached and int(hit[1]) // R == rank:
+                # exact energy of the configuration that hit the target (it has not been swept since
+                # only when the loop stopped at once; report the target test's own exact value)
+                rec["replica"] = int(hit[1])
+            runs.append(rec)
+            spent = torch.tensor([time.perf_counter() - w0], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(spent, op=dist.ReduceOp.MAX)
             budget_left -= spent.item()
-            if not reached or budget_left <= 0.0:
+            if budget_left <= 0.0:
                 break
-        ok = [r["seconds"] for r in runs if r["reached"]]
-        ttt = {"e_target": e_target, "reached": all(r["reached"] for r in runs),
-               "seconds": float(np.median(ok)) if ok else runs[0]["seconds"],
-               "sweeps": int(np.median([r["sweeps"] for r in runs])),
-               "seeds": len(runs), "seconds_per_seed": [round(r["seconds"], 4) for r in runs],
-               "best_energy_exact_local": exact, "ladder": "64 rungs, T geometric 2.0 -> 0.1, "
-               f"{R // 64} ladders/GPU, exchange every 10 sweeps; seconds = median over the seeds run"}
+        ok = sorted(r["seconds"] for r in runs if r["reached"])
+        ttt = {"e_target": e_target, "reached": all(r["reached"] for r in runs), "seeds": len(runs),
+               "seconds": float(np.median(ok)) if ok else None,
+               "sweeps_median": int(np.median([r["sweeps"] for r in runs])),
+               "sweeps_per_seed": [r["sweeps"] for r in runs],
+               "seconds_per_seed": [round(r["seconds"], 4) for r in runs],
+               "decision": "exact energies (K2 refresh) of the current configurations after every "
+                           f"{sweeps}-sweep round, tested on the device; time = CUDA events up to the round of the hit",
+               "ladder": f"{K} rungs, T geometric {LADDER_T[0]} -> {LADDER_T[1]}, {R * world // K} ladders over "
+                         f"{world} GPU(s), exchange every {sweeps} sweeps"}
 
-    # max over ranks, whole-job aggregate
-    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    # ---- the other scaling curve in the same run: strong scaling = args.replicas in total
+    strong = None
+    if world > 1 and args.scaling == "weak":
+        Rs = max(K, args.replicas // world // K * K)
+        r2 = measure(Rs, args.steps, args.warmup)
+        strong = {"value": r2["value"], "unit": "attempts/s", "replicas_total": Rs * world,
+                  "replicas_per_gpu": Rs, "ms_per_step": r2["ms_total"] / args.steps,
+                  "replica_groups_per_gpu": (Rs + 16 * (max(1, eng.tc_cluster_size()) if use_tc else 1) - 1)
+                  // (16 * (max(1, eng.tc_cluster_size()) if use_tc else 1)),
+                  "note": "same step, the 8192 replicas of cfg3 sharded over the GPUs (ladders global, "
+                          "exchange through the all-gathered energy table)"}
+
+    t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
     best_local = eng.best_energies().min().reshape(1).double()
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        gathered = [torch.zeros_like(best_local) for _ in range(world)]
-        dist.all_gather(gathered, best_local)  # the only collective of the path: final argmin
-        best_global = torch.cat(gathered).min().item()
-    else:
-        best_global = best_local.item()
-    ms_total, ms_e2e = t[0].item(), t[1].item()
+        dist.all_reduce(best_local, op=dist.ReduceOp.MIN)
+    ms_e2e = t.item()
+    ms_total = main_res["ms_total"]
+    prof = main_res["prof"]
     attempts_per_step = float(R) * n * sweeps * world
-    value = attempts_per_step * args.steps / (ms_total * 1e-3)
+    value = main_res["value"]
     e2e_value = attempts_per_step / (ms_e2e * 1e-3)
-    acc_rate = (acc1 - acc0) / (float(R) * n * sweeps * args.steps)
 
     if rank == 0:
-        # roofline of the dominant kernel (the sweep): algorithmic J-stream bytes = every block
-        # streams the 16 coupling rows of every attempt block once (P bf16 planes on the
-        # tensor-core path, one padded fp32 row per attempt on the SIMT path); peak = bandwidth of
-        # the same transport (TMA bulk copies of an L2-resident buffer into a shared-memory ring,
-        # one block per SM) measured on this box
+        # roofline of the dominant kernel (the sweep): algorithmic J-stream bytes (SURVEY 8d,
+        # shared-order mode: d * b_J / G per attempt) = every replica group takes every one of the
+        # n coupling rows (n_tc couplings, 2 bytes per bf16 plane) in once per sweep, spread over
+        # the C SMs of its cluster; peak = bandwidth of the same transport (TMA bulk copies of an
+        # L2-resident buffer into a shared-memory ring, one block per SM) measured in this run
+        ng = 16 * cluster
+        groups = (R + ng - 1) // ng
         if use_tc:
             n_tc = (n + 127) // 128 * 128
-            # per group of 16 replicas and sweep: every one of the n rows (n_tc couplings, 2 bytes
-            # per plane) enters an SM once; a cluster pair takes each row in once for 32 replicas
-            # (half of it per SM), i.e. half as many bytes per replica
-            bytes_per_sweep_block = float(n) * n_tc * 2 * planes / cluster
+            bytes_per_group_sweep = float(n) * n_tc * 2 * planes
             kname = "sg::sweep_tc_kernel"
             stream_desc = f"{planes} bf16 planes of J in UMMA operand layout ({planes * 2 * n * n_tc / 1e6:.0f} MB per sweep)"
         else:
-            bytes_per_sweep_block = float(n) * q["n_pad"] * 4
+            gmax = q["max_replicas_per_block"]
+            groups = (R + gmax - 1) // gmax
+            ng = gmax
+            bytes_per_group_sweep = float(n) * q["n_pad"] * 4
             kname = "sg::sweep_kernel"
             stream_desc = "fp32 rows of J (73 MB padded)"
         n_klaunch = max(1, int(prof["sweep_launches"]))
-        bytes_per_launch = float(blocks) * sweeps * bytes_per_sweep_block * args.steps / n_klaunch
+        bytes_per_launch = float(groups) * sweeps * bytes_per_group_sweep * args.steps / n_klaunch
         ms_launch = prof["sweep_ms"] / n_klaunch
         achieved = bytes_per_launch / (ms_launch * 1e-3) / 1e9
         l2_peak = max(eng.measure_tma_stream(J.nbytes + (1 << 20), 17920, 8, 4096, False),
@@ -359,61 +422,64 @@ def run_ours(args):
         except Exception:
             pass
         hbm = float(peaks.get("hbm_gbs", 6650.0))
-        traffic = None
+        traffic, traffic_src, lts = None, None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_sweep_tc_traffic.json")))[
-                "dram_bytes_per_launch"]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_sweep_tc_traffic.json")))
+            traffic, lts, traffic_src = tj["dram_bytes_per_launch"], tj.get("lts_bytes_per_launch"), tj.get("source")
         except Exception:
             pass
-        # B operand per MMA: 16 attempts x (16 x cluster) replicas x 2 bytes against a 4 KB A tile
-        smem_factor = 2.0 + 0.125 * cluster
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": l2_peak, "unit": "GB/s",
-                    "frac": achieved / l2_peak, "traffic": traffic,
-                    "peak_source": "measured on this box (sg_measure_tma_stream): TMA bulk-copy stream of "
-                                   "an L2-resident J-sized buffer, one block per SM; the J stream ("
-                                   + stream_desc + ") is read by all SMs in the same order, so it is "
-                                   "served from the 126 MB L2 and the HBM copy peak is not the bound",
+        smem_factor = 2.0 + ng / 128.0   # TMA write + operand read + B operand (32 NG bytes per 4 KB A tile)
+        sm_clk = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        smem_peak = q["sm_count"] * 128 * sm_clk / 1e9
+        roofline = {"bound": "l2", "achieved": achieved, "peak": l2_peak, "unit": "GB/s",
+                    "frac": achieved / l2_peak, "traffic": traffic, "traffic_source": traffic_src,
+                    "lts_bytes_per_launch": lts,
+                    "bytes_per_attempt": bytes_per_group_sweep / (n * ng),
+                    "peak_source": "measured in this run (sg_measure_tma_stream): TMA bulk-copy stream of an "
+                                   "L2-resident J-sized buffer, one block per SM, no compute; the J stream ("
+                                   + stream_desc + ") is read by all SMs in the same order, so it is served "
+                                   "from the 126 MB L2 and the HBM copy peak is not the bound.  The kernel "
+                                   "itself is bound by shared-memory bandwidth (smem_frac): growing the replica "
+                                   "group (clusters) cuts the J bytes an attempt needs, which lowers `frac` "
+                                   "while the throughput rises",
                     "hbm_peak": hbm, "hbm_peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                     "frac_of_hbm_peak": achieved / hbm,
                     "kernel": kname, "bytes_per_launch": bytes_per_launch,
                     "ms_per_launch": ms_launch, "launches_timed": n_klaunch,
-                    # what actually bounds the tensor-core kernel: every J byte is written to shared
-                    # memory by TMA and read from it by tcgen05.mma, which also reads the 512-byte
-                    # B operand (the block's decisions) once per 4 KB A tile: 2.125 x the J stream
-                    # through a 128 B/clk/SM port
+                    "kernel_share_of_step": prof["sweep_ms"] / ms_total,
                     "smem_traffic_gbs": smem_factor * achieved if use_tc else None,
-                    "smem_peak_gbs": q["sm_count"] * 128 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9,
-                    "smem_frac": (smem_factor * achieved) / (q["sm_count"] * 128 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9) if use_tc else None,
+                    "smem_peak_gbs": smem_peak,
+                    "smem_frac": (smem_factor * achieved) / smem_peak if use_tc else None,
                     "gather_ms_per_launch": prof["gather_ms"] / max(1, int(prof["gather_launches"]))}
-        cpu = None
-        if world == 1 or True:
-            v, threads, sample = cpu_reference(0, args.cpu_budget)
-            cpu = {"value": v, "unit": "attempts/s", "cores": threads, "kind": "port", "sample": sample}
+        v, threads, sample, quench = cpu_reference(0, args.cpu_budget, quench_sweeps=200)
+        cpu = {"value": v, "unit": "attempts/s", "cores": threads, "kind": "port", "sample": sample,
+               "quench": quench}
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "attempts/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": workload_name(R, sweeps),
-                       "kernel": ("tensor-core (tcgen05, TMEM-resident fields"
-                                  + (", cluster pairs: 32 replicas per 2 SMs, half of the field columns each)"
-                                     if cluster == 2 else ")")) if use_tc else "simt",
+                       "kernel": (f"tensor-core (tcgen05, TMEM-resident fields, {16 * cluster} replicas per "
+                                  f"cluster of {cluster} SM(s), 1/{cluster} of the field columns each)")
+                       if use_tc else "simt",
                        "coupling_planes": planes if use_tc else None,
-                       "replicas_per_gpu": R, "sweeps_per_step": sweeps,
-                       "replicas_per_group": gmax * cluster, "ctas_per_group": cluster,
-                       "replica_groups": (R + gmax * cluster - 1) // (gmax * cluster),
-                       "schedule": ("persistent CTAs (cluster pairs) walk (sweep chunk, replica group) work "
-                                    "items; a group's fields/spins move through HBM between its items")
-                                   if use_tc and (R + gmax * cluster - 1) // (gmax * cluster) > q["sm_count"] // cluster
-                                   else "one CTA (cluster pair) per replica group",
-                       "n_pad": q["n_pad"], "acceptance_rate": acc_rate,
+                       "replicas_per_gpu": R, "replicas_total": R * world, "sweeps_per_step": sweeps,
+                       "replicas_per_group": ng, "ctas_per_group": cluster, "replica_groups": groups,
+                       "collective": ("all_gather_into_tensor of the per-replica energies (NCCL, "
+                                      f"{4 * R * world} bytes) before every exchange round") if world > 1 else None,
+                       "n_pad": q["n_pad"], "acceptance_rate": main_res["acceptance_rate"],
+                       "exchange_acceptance": main_res["exchange_rate"],
                        "l2_policy": f"inputs (J planes 100 MB + operand stream {sweeps * 100} MB per step + "
                                     "170 MB replica state) exceed the 126 MB L2; no flush between steps",
-                       "best_energy": best_global},
+                       "best_energy": best_local.item()},
             "e2e": {"value": e2e_value, "unit": "attempts/s", "h2d_bytes_per_step": int(R) * n * world,
-                    "d2h_bytes_per_step": int(R) * 4 * world, "ms_per_step": ms_e2e},
-            "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cpu,
-            "time_to_target": ttt, "clocks": clocks,
+                    "d2h_bytes_per_step": (8 + n) * world, "ms_per_step": ms_e2e,
+                    "path": "sg_upload_spins_async (pinned host) -> sg_set_spins_staged -> sg_init_fields -> "
+                            "sg_sweep + sg_refresh_fields + sg_exchange -> sg_get_best_config (pinned host)",
+                    "best_energy_last_step": e2e_best},
+            "gpu_launches": main_res["launches"], "roofline": roofline, "cpu_baseline": cpu,
+            "time_to_target": ttt, "strong_scaling": strong, "clocks": clocks,
         }))
     if world > 1:
         dist.destroy_process_group()
@@ -425,12 +491,16 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--replicas", type=int, default=REPLICAS_PER_GPU)
+    ap.add_argument("--replicas", type=int, default=REPLICAS_PER_GPU,
+                    help="replicas per GPU (weak scaling) or in total (strong scaling)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --replicas per GPU; strong: --replicas over all GPUs (cfg3: 8192 over 8). "
+                         "A weak run on several GPUs also reports the strong-scaling number of the same step")
     ap.add_argument("--sweeps", type=int, default=10, help="sweeps per step (= the reference's default exchange_interval)")
-    ap.add_argument("--ttt-seeds", type=int, default=8,
+    ap.add_argument("--ttt-seeds", type=int, default=32,
                     help="independent time-to-target runs (different initial spins and RNG streams)")
-    ap.add_argument("--ttt-budget", type=float, default=20.0,
-                    help="wall-clock budget (s) of the time-to-target run; 0 skips it")
+    ap.add_argument("--ttt-budget", type=float, default=25.0,
+                    help="wall-clock budget (s) of the time-to-target runs; 0 skips them")
     ap.add_argument("--kernel", default="auto", choices=["auto", "tc", "simt"])
     ap.add_argument("--planes", type=int, default=3,
                     help="bf16 planes per coupling on the tensor-core path (3 = exact fp32 couplings)")

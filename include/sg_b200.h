@@ -131,6 +131,16 @@ int sg_alloc_replicas(sg_engine *e, int n_replicas, void *stream);
 int sg_set_spins(sg_engine *e, const int8_t *spins, int on_device, void *stream);
 int sg_get_spins(sg_engine *e, int8_t *spins, int on_device, void *stream);
 
+/* Pipelined upload for callers that stream many start configurations through one engine (the RL
+ * environment's repeated anneals, rl_integration/environment.py:318-336; bench.py's end-to-end
+ * leg): sg_upload_spins_async copies spins[R][n] from PINNED host memory into one of two
+ * engine-owned staging buffers asynchronously on `stream` (which may be a side stream running
+ * ahead of the compute stream; the host buffer must stay untouched until that stream reaches
+ * this point), sg_set_spins_staged then makes the staged configurations the current spins on the
+ * compute stream (the caller orders the two streams with an event).  Dense models. */
+int sg_upload_spins_async(sg_engine *e, const int8_t *host_spins, int slot, void *stream);
+int sg_set_spins_staged(sg_engine *e, int slot, void *stream);
+
 /* Local-field initialisation + energies for all replicas in one pass:
  *   F = S J^T + h ; E_r = -1/2 sum_i s_ri (F_ri + h_i)
  * replaces R x IsingModel.compute_energy (core/ising_model.py:149-174) and
@@ -152,6 +162,14 @@ int sg_get_accepted(sg_engine *e, uint64_t *accepted, int on_device, void *strea
  * 151-153: compared once per sweep).  reset sets best = current. */
 int sg_reset_best(sg_engine *e, void *stream);
 int sg_get_best(sg_engine *e, float *best_energy, int8_t *best_spins, int on_device, void *stream);
+
+/* The one result GPUAnnealer.anneal returns (annealing/gpu_annealer.py:166-183): the lowest
+ * best-so-far energy over all replicas, its replica index and that configuration (int8[n]) --
+ * an argmin on the device and a 4 + 4 + n byte transfer instead of all R configurations.  Host
+ * outputs are written asynchronously (pinned memory: valid once `stream` has been synchronised).
+ * Dense models; any output may be NULL. */
+int sg_get_best_config(sg_engine *e, float *best_energy, int32_t *replica, int8_t *spins,
+                       int on_device, void *stream);
 
 typedef struct {
     uint32_t struct_size;       /* = sizeof(sg_sweep_params)                                  */

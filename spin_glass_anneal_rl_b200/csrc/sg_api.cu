@@ -124,6 +124,11 @@ struct sg_engine {
     unsigned int* accepts = nullptr;
     uint64_t launches = 0;
     long long* dbg = nullptr;
+    // staging for asynchronous host transfers (sg_upload_spins_async / sg_get_best_config)
+    int8_t* up_stage[2] = {nullptr, nullptr};
+    size_t up_cap[2] = {0, 0};
+    unsigned char* best_out = nullptr;   // device: float energy, int replica, int8 spins[n]
+    size_t best_out_cap = 0;
 };
 
 namespace {
@@ -869,6 +874,9 @@ void sg_destroy(sg_engine* e) {
     cudaFree(e->tc_sites);
     cudaFree(e->tc_stream);
     cudaFree(e->stage);
+    cudaFree(e->up_stage[0]);
+    cudaFree(e->up_stage[1]);
+    cudaFree(e->best_out);
     cudaFree(e->dig);
     cudaFree(e->scale);
     cudaFree(e->info);
@@ -1244,6 +1252,66 @@ int sg_get_best(sg_engine* e, float* best_energy, int8_t* best_spins, int on_dev
              : e->lat ? lat_get_spins(e, e->l_best, best_spins, on_device, st)
                       : get_unpadded_i8(e, e->best_spins, best_spins, on_device, st);
     return rc;
+}
+
+int sg_upload_spins_async(sg_engine* e, const int8_t* host_spins, int slot, void* stream) {
+    SG_REQUIRE(e && host_spins && e->R > 0, "sg_upload_spins_async: allocate replicas first");
+    SG_REQUIRE(slot == 0 || slot == 1, "sg_upload_spins_async: slot must be 0 or 1");
+    SG_REQUIRE(!e->csr && !e->lat, "sg_upload_spins_async: dense models only (use sg_set_spins)");
+    DeviceGuard g(e->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t bytes = (size_t)e->R * e->n;
+    if (e->up_cap[slot] < bytes) {
+        SG_CUDA(cudaDeviceSynchronize());   // the old buffer may be in use on some stream
+        cudaFree(e->up_stage[slot]);
+        e->up_stage[slot] = nullptr;
+        e->up_cap[slot] = 0;
+        int rc = dev_alloc(&e->up_stage[slot], bytes);
+        if (rc != SG_OK) return rc;
+        e->up_cap[slot] = bytes;
+    }
+    SG_CUDA(cudaMemcpyAsync(e->up_stage[slot], host_spins, bytes, cudaMemcpyHostToDevice, st));
+    return SG_OK;
+}
+
+int sg_set_spins_staged(sg_engine* e, int slot, void* stream) {
+    SG_REQUIRE(e && e->R > 0 && (slot == 0 || slot == 1), "sg_set_spins_staged: bad argument");
+    SG_REQUIRE(e->up_stage[slot] && e->up_cap[slot] >= (size_t)e->R * e->n,
+               "sg_set_spins_staged: nothing was uploaded into this slot");
+    DeviceGuard g(e->device);
+    SG_CUDA(sg::launch_pad_spins(e->up_stage[slot], e->n, e->spins, e->n_pad, e->R,
+                                 static_cast<cudaStream_t>(stream)));
+    e->launches++;
+    e->fields_valid = false;
+    return SG_OK;
+}
+
+int sg_get_best_config(sg_engine* e, float* best_energy, int32_t* replica, int8_t* spins, int on_device,
+                       void* stream) {
+    SG_REQUIRE(e && e->R > 0 && e->fields_valid, "sg_get_best_config: call sg_init_fields first");
+    SG_REQUIRE(!e->csr && !e->lat, "sg_get_best_config: dense models only (use sg_get_best)");
+    DeviceGuard g(e->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t need = 16 + (size_t)e->n;
+    if (e->best_out_cap < need) {
+        SG_CUDA(cudaStreamSynchronize(st));
+        cudaFree(e->best_out);
+        e->best_out = nullptr;
+        e->best_out_cap = 0;
+        int rc = dev_alloc(&e->best_out, need);
+        if (rc != SG_OK) return rc;
+        e->best_out_cap = need;
+    }
+    float* d_e = reinterpret_cast<float*>(e->best_out);
+    int* d_i = reinterpret_cast<int*>(e->best_out + 4);
+    int8_t* d_s = reinterpret_cast<int8_t*>(e->best_out + 16);
+    SG_CUDA(sg::launch_best_config(e->best_energy, e->R, e->best_spins, e->n, e->n_pad, d_e, d_i, d_s, st));
+    e->launches++;
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (best_energy) SG_CUDA(cudaMemcpyAsync(best_energy, d_e, sizeof(float), kind, st));
+    if (replica) SG_CUDA(cudaMemcpyAsync(replica, d_i, sizeof(int), kind, st));
+    if (spins) SG_CUDA(cudaMemcpyAsync(spins, d_s, (size_t)e->n, kind, st));
+    return SG_OK;
 }
 
 int sg_sweep(sg_engine* e, const sg_sweep_params* p, void* stream) {

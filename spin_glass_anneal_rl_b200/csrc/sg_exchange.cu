@@ -156,6 +156,41 @@ __global__ void check_target_kernel(const float* __restrict__ energy, int R, int
     }
 }
 
+// out_idx[0] = argmin_r energy[r] (lowest index on ties), out_e[0] = that energy; then row
+// out_idx[0] of the padded int8 matrix `rows` is copied to out_row (n entries).  One block.
+__global__ void best_config_kernel(const float* __restrict__ energy, int R, const int8_t* __restrict__ rows,
+                                   int n, int n_pad, float* out_e, int* out_idx, int8_t* out_row) {
+    __shared__ float s_e[32];
+    __shared__ int s_r[32];
+    __shared__ int s_best;
+    float best = 3.0e38f;
+    int arg = 0x7FFFFFFF;
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        const float v = energy[r];
+        if (v < best) { best = v; arg = r; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const float v = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+        const int w = __shfl_xor_sync(0xFFFFFFFFu, arg, o);
+        if (v < best || (v == best && w < arg)) { best = v; arg = w; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_e[threadIdx.x >> 5] = best; s_r[threadIdx.x >> 5] = arg; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+            if (s_e[w] < best || (s_e[w] == best && s_r[w] < arg)) { best = s_e[w]; arg = s_r[w]; }
+        if (arg == 0x7FFFFFFF) arg = 0;
+        s_best = arg;
+        if (out_e) out_e[0] = best;
+        if (out_idx) out_idx[0] = arg;
+    }
+    __syncthreads();
+    if (out_row) {
+        const int8_t* src = rows + (size_t)s_best * n_pad;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) out_row[i] = src[i];
+    }
+}
+
 __global__ void ladder_init_kernel(int* rep_at, double* rep_temp, const double* ladder, int n_global,
                                    int K, int rep_lo, int rep_n) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -323,6 +358,12 @@ cudaError_t launch_exchange(ExchangeDev a, cudaStream_t st) {
 cudaError_t launch_check_target(const float* energy, int R, int rep_lo, float target, int round, int* hit,
                                 cudaStream_t st) {
     check_target_kernel<<<1, 1024, 0, st>>>(energy, R, rep_lo, target, round, hit);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_best_config(const float* energy, int R, const int8_t* rows, int n, int n_pad, float* out_e,
+                               int* out_idx, int8_t* out_row, cudaStream_t st) {
+    best_config_kernel<<<1, 1024, 0, st>>>(energy, R, rows, n, n_pad, out_e, out_idx, out_row);
     return cudaGetLastError();
 }
 

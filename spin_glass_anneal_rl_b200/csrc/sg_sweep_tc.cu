@@ -331,13 +331,22 @@ constexpr int kSlots = 4;
 // block k-1 and must be done before block k's MMAs of that part are issued.  Two parts; four were
 // tried (the read of one part would overlap the execution of three others) and were slower on
 // every cluster size (C = 4: 16.6 instead of 19.2 G attempts/s): every part costs the MMA warp a
-// barrier round trip through the quarter warps.
+// barrier round trip through the quarter warps.  Also tried for C = 4: issuing the tiles that hold
+// no site of the next block first (they need no read) and the others after the next block's reads
+// -- correct, but a stage of the ring is then released only with its last tile, the five-stage
+// ring (1.25 blocks) cannot prefetch the next block, and the TMA latency lands on the critical
+// path (14.8 G attempts/s).  It would need a ring of two blocks, i.e. 70 KB more shared memory.
 constexpr int kParts = 2;
 constexpr int kMaxStagesTc = 8;
 // C = CTAs per replica group: NG = 16 C replicas, decision warps = one per 32 replicas
 __host__ __device__ constexpr int tc_ndw(int C) { return (kG * C + 31) / 32; }
+// threshold warps: clusters of 4 and more draw the Philox thresholds on two dedicated warps, so that
+// the quarter warps sit on the half-done barriers and answer a completed half at once (the round
+// trip MMA complete -> raw read -> next MMA issue is what bounds the block period there)
+__host__ __device__ constexpr int tc_ntw(int C) { return C >= 4 ? 2 : 0; }
 // threads: 4 quarter warps, producer, decision warp 0, MMA issuer (, decision warps 1..3)
-__host__ __device__ constexpr int tc_threads(int C) { return 224 + 32 * (tc_ndw(C) - 1); }
+// (, threshold warps)
+__host__ __device__ constexpr int tc_threads(int C) { return 224 + 32 * (tc_ndw(C) - 1) + 32 * tc_ntw(C); }
 // quarter warps + decision warps meet at the named barriers 1..3
 __host__ __device__ constexpr int tc_sync_threads(int C) { return 128 + 32 * tc_ndw(C); }
 // tiles per ring stage: clusters of 4 hold 64 replicas' state in shared memory and have room for
@@ -511,7 +520,8 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
     constexpr uint32_t IDESC = tc::make_idesc_bf16(kTileM, NG);
     constexpr int CT = tc_chunk_tiles(C);    // tiles per ring stage
     constexpr int NDW = tc_ndw(C);           // decision warps
-    constexpr int kThWarps = (NG / 8 < 4) ? NG / 8 : 4;   // quarter warps that draw thresholds
+    constexpr int NTW = tc_ntw(C);           // dedicated threshold warps (0: the quarter warps do it)
+    constexpr int kThWarps = NTW ? NTW : ((NG / 8 < 4) ? NG / 8 : 4);   // warps that draw thresholds
     auto named_sync = [](int id) { named_sync_c<C>(id); };
     constexpr int BOP = 32 * NG;             // B operand bytes per slot
     constexpr uint32_t BLBO = 16 * NG;       // B: k-group stride ((NG/8) n-groups of 128 B)
@@ -692,6 +702,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
         // They depend on nothing but the counters, so they are drawn ONE BLOCK AHEAD, after the raw
         // reads of the current block (which sit on the critical path between two blocks' MMAs).
         auto draw_thresholds = [&](int s_t, int kb_t, int slot_t) {
+            if (NTW) return;   // drawn by the threshold warps
             if (!INJECT) {
                 const unsigned long long sa_t = a.sweep_base + (unsigned long long)s_t;
                 const int i0_t = kb_t * kBlk;
@@ -1004,7 +1015,6 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
             for (int j = 0; j <= LAG; ++j) issue_tables();
 #pragma unroll 1
             for (; wq.valid(); wq.next(items, nblk), ++kg) {
-                SG_STAMP(13);
                 issue_tables();
                 const unsigned char* src =
                     Q + (wq.stream_block(items, nblk) * tiles_q + (size_t)crank * Tl) * (size_t)(P * kTileBytes);
@@ -1016,8 +1026,51 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                              (uint32_t)kStageBytes, &full[stage]);
                     if (++stage == NS) { stage = 0; epar ^= 1u; }
                 }
-                SG_STAMP(14);
             }
+        }
+    } else if (warp >= 6 + NDW) {
+        // ======================================================== THRESHOLD WARPS
+        // thresholds of block kg -> theta_s[kg % 4]: unit (qq, r) covers attempts 4qq..4qq+3 of
+        // replica r (one Philox call).  They depend on nothing but the counters; the only
+        // constraint is the slot's previous user, block kg-4, having been decided.
+        const int tw = warp - (6 + NDW);
+        TcBlockWalk wk;
+        wk.start(items, cid);
+        int kg = 0;
+#pragma unroll 1
+        for (; wk.valid(); wk.next(items, nblk), ++kg) {
+            const int slot = kg & (kSlots - 1);
+            if (kg >= kSlots) mbar_wait(&decbar[slot], (uint32_t)((kg - kSlots) >> 2) & 1u);
+            if (!INJECT) {
+                const int rep0 = wk.g * NG;
+                const int g_act = min(NG, a.R - rep0);
+                const unsigned long long sa_t = a.sweep_base + (unsigned long long)wk.s;
+                const int i0_t = wk.k * kBlk;
+#pragma unroll 1
+                for (int tt = tw * 32 + lane; tt < 4 * NG; tt += 32 * (NTW ? NTW : 1)) {
+                    const int qq = tt / NG, r = tt - qq * NG;
+                    const int ia = i0_t + qq * 4;
+                    if (r < g_act && ia < n) {
+                        const int rep = rep0 + r;
+                        const float Tm = (float)a.temps[(long long)wk.s * a.t_ss + (long long)rep * a.t_rs];
+                        const uint4 x = philox4x32_10(
+                            make_uint4((uint32_t)(rep + a.rep_base), (uint32_t)sa_t, (uint32_t)(sa_t >> 32),
+                                       (uint32_t)(ia >> 2)), key);
+                        const uint32_t vv[4] = {x.x, x.y, x.z, x.w};
+                        float* dst = theta_s + slot * kBlk * NG + (qq * 4) * NG + r;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float u = u01(vv[e]);
+                            float th;
+                            if (a.rule == 0) th = -__logf(u) * Tm;
+                            else th = 0.5f * Tm * (__logf(u) - __logf(1.0f - u));
+                            dst[e * NG] = th;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&thbar[slot]);
         }
     } else if (warp == 5 || warp >= 7) {
         // ======================================================== DECISION WARPS
@@ -1295,10 +1348,12 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 for (int h = 0; h < kParts; ++h) {
                     // this CTA's raw reads of block k+LAG in this column part must be done before
                     // this block's update of the part is issued
+                    if (h == 1) SG_STAMP(13);
                     if (k + LAG < nblk)
                         mbar_wait(&rloc[kParts * ((kg + LAG) & (kSlots - 1)) + h],
                                   (uint32_t)((kg + LAG) >> 2) & 1u);
                     if (h == 0) SG_STAMP(11);
+                    if (h == 1) SG_STAMP(14);
                     const int c_end = pb(h + 1);
 #pragma unroll 1
                     for (int c = pb(h); c < c_end; ++c) {
@@ -1310,7 +1365,8 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                         const uint32_t d0 = tbase + (uint32_t)(c * CT * NG);
                         // (the issue pattern is not the limit here: a branch-free block of 12 MMAs
                         // issues at 48 clocks per MMA in isolation, tools/mma_bench.py, but the phase
-                        // is bound by shared-memory bandwidth -- TMA writes plus operand reads)
+                        // is bound by shared-memory bandwidth -- TMA writes plus operand reads: the
+                        // issue loop of a half takes ~100 clocks per MMA because the queue is full)
                         if (tc::elect_one()) {
 #pragma unroll
                             for (int tt = 0; tt < CT; ++tt) {

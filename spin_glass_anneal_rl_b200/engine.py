@@ -180,6 +180,33 @@ class Engine:
             check(self._lib.sg_set_spins(self._h, s.ctypes.data_as(ctypes.c_void_p), 0,
                                          self.stream), "sg_set_spins")
 
+    def upload_spins_async(self, host_spins: torch.Tensor, slot: int, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Asynchronous host -> device copy of spins[R][n] (PINNED int8 CPU tensor) into staging
+        buffer ``slot`` (0 / 1) on ``stream`` (default: the current stream)."""
+        assert host_spins.dtype == torch.int8 and host_spins.is_pinned() and host_spins.is_contiguous()
+        assert tuple(host_spins.shape) == (self.n_replicas, self.n)
+        st = self.stream if stream is None else ctypes.c_void_p(stream.cuda_stream)
+        check(self._lib.sg_upload_spins_async(self._h, ctypes.c_void_p(host_spins.data_ptr()), int(slot), st),
+              "sg_upload_spins_async")
+
+    def set_spins_staged(self, slot: int) -> None:
+        check(self._lib.sg_set_spins_staged(self._h, int(slot), self.stream), "sg_set_spins_staged")
+
+    def best_config(self, out_energy: Optional[torch.Tensor] = None, out_replica: Optional[torch.Tensor] = None,
+                    out_spins: Optional[torch.Tensor] = None):
+        """Lowest best-so-far energy, its replica and configuration.  With pinned CPU output tensors
+        (float32[1], int32[1], int8[n]) the transfer is asynchronous; without, device tensors are
+        returned."""
+        host = out_energy is not None and not out_energy.is_cuda
+        if out_energy is None:
+            out_energy = torch.empty(1, dtype=torch.float32, device=self.device)
+            out_replica = torch.empty(1, dtype=torch.int32, device=self.device)
+            out_spins = torch.empty(self.n, dtype=torch.int8, device=self.device)
+        p = lambda t: ctypes.c_void_p(0 if t is None else t.data_ptr())
+        check(self._lib.sg_get_best_config(self._h, p(out_energy), p(out_replica), p(out_spins),
+                                           0 if host else 1, self.stream), "sg_get_best_config")
+        return out_energy, out_replica, out_spins
+
     def init_fields(self) -> None:
         check(self._lib.sg_init_fields(self._h, self.stream), "sg_init_fields")
 

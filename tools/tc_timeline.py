@@ -31,7 +31,7 @@ if ist[7] > 0:
     print("item phases (clk): dep wait", ist[1] - ist[0], " bit planes", ist[2] - ist[1], " fields->TMEM", ist[3] - ist[2],
           " sweeps", ist[4] - ist[3], " state->HBM", ist[5] - ist[4], " fence", ist[6] - ist[5], " sync", ist[7] - ist[6])
 t0 = t[0, 0]
-names = ["q_start", "q_tabs", "q_h0ok", "q_h1ok", "d_start", "d_pre", "d_rawok", "d_dec", "d_done", "m_wait", "m_decok", "m_r0ok", "m_done", "p_start", "p_end", "q_done"]
+names = ["q_start", "q_tabs", "q_h0ok", "q_h1ok", "d_start", "d_pre", "d_rawok", "d_dec", "d_done", "m_wait", "m_decok", "m_r0ok", "m_done", "m_h0end", "m_h1go", "q_done"]
 print("blk " + " ".join(f"{x:>8s}" for x in names))
 for k in list(range(0, 4)) + list(range(100, 112)) + list(range(254, 258)):
     print(f"{k:3d} " + " ".join(f"{int(t[k, i] - t0):8d}" for i in range(16)))
@@ -41,5 +41,5 @@ print("period", float((d[1:, 12] - d[:-1, 12]).mean()))
 print("quarter: tables+theta", m(1, 0), " wait h0(k-2)", m(2, 1), " read h0 + wait h1", m(3, 2), " read h1", m(15, 3))
 print("decision: wait tab", "n/a", " tables+cross prefetch", m(5, 4), " wait raw", m(6, 5), " 16 attempts", m(7, 6), " epilogue", m(8, 7))
 print("mma: wait dec", m(10, 9), " wait r0(k+1)", m(11, 10), " chunks", m(12, 11))
-print("producer: block issue", m(14, 13))
+print("mma detail: issue h0", m(13, 11), " wait r1(k+1)", m(14, 13), " issue h1", m(12, 14))
 print("lags: q_done(k)->d_rawok(k)", m(6, 15), " d_done(k)->m_decok(k)", m(10, 8))
