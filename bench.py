@@ -249,7 +249,6 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     main_res = measure(R_main, args.steps, args.warmup)
-    clocks = sampler.summary()
     q = eng.query()
     cluster = max(1, eng.tc_cluster_size()) if use_tc else 1
     R = R_main
@@ -292,6 +291,7 @@ def run_ours(args):
         eng.best_config(out_e, out_r, out_s)
     t1.record()
     barrier()
+    clocks = sampler.summary()   # sampled over the timed steps and the end-to-end steps
     ms_e2e = t0.elapsed_time(t1) / e2e_steps
     e2e_best = float(out_e.item())
 
@@ -320,6 +320,10 @@ def run_ours(args):
             ev0.record()
             rounds = 0
             while rounds < max_rounds:
+                if rounds >= 2:
+                    evs[rounds - 2].synchronize()   # the host runs at most two rounds ahead of the device
+                    if int(hit[0]) >= 0:
+                        break
                 eng.sweep(sweeps, None, seed=4242 + 1000 * run, sweep_base=rounds * sweeps, site_order="random",
                           track_best=False, kernel=kernel, coupling_planes=planes, replica_base=rank * R)
                 eng.refresh_fields()

@@ -13,7 +13,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int, c_in
                     c_int64, c_uint32, c_uint64, c_void_p)
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libsg_b200.so")
+LIB_PATH = os.environ.get("SG_B200_LIB") or os.path.join(_PKG, "libsg_b200.so")   # (override: A/B builds)
 CSRC = os.path.join(_PKG, "csrc")
 
 SG_RULE = {"metropolis": 0, "glauber": 1, "heat_bath": 2}

@@ -331,7 +331,12 @@ constexpr int kSlots = 4;
 // block k-1 and must be done before block k's MMAs of that part are issued.  Two parts; four were
 // tried (the read of one part would overlap the execution of three others) and were slower on
 // every cluster size (C = 4: 16.6 instead of 19.2 G attempts/s): every part costs the MMA warp a
-// barrier round trip through the quarter warps.  Also tried for C = 4: issuing the tiles that hold
+// barrier round trip through the quarter warps.  Also tried for C = 4 (profiles/r2_notes.md):
+// issuing the tiles that hold no site of the next block first (they need no read) and the others
+// after the next block's reads -- correct, but a ring stage is then released only with its last
+// tile, the five-stage ring (1.25 blocks) cannot prefetch the next block and the TMA latency lands
+// on the critical path (14.8 G); releasing the ring stages through the part commits instead of a
+// commit per stage (no gain, and the producer can fall two barrier phases behind).  Also tried for C = 4: issuing the tiles that hold
 // no site of the next block first (they need no read) and the others after the next block's reads
 // -- correct, but a stage of the ring is then released only with its last tile, the five-stage
 // ring (1.25 blocks) cannot prefetch the next block, and the TMA latency lands on the critical
