@@ -131,6 +131,18 @@ int sg_alloc_replicas(sg_engine *e, int n_replicas, void *stream);
 int sg_set_spins(sg_engine *e, const int8_t *spins, int on_device, void *stream);
 int sg_get_spins(sg_engine *e, int8_t *spins, int on_device, void *stream);
 
+/* Checkpoint / resume of a run in progress (the reference only saves finished
+ * results, annealing/result.py:147-188).  Together with sg_set_spins these restore everything a
+ * resumed run depends on: best-so-far records, acceptance counters and the ladder state (the
+ * per-replica temperatures follow from the rung -> replica map).  Fields and energies are
+ * recomputed by sg_init_fields -- call it BEFORE sg_set_best, it resets the best records.  The
+ * Philox streams are counter based (seed, absolute sweep index, global replica id), so a run
+ * resumed at sweep s continues exactly as the uninterrupted one.  Dense models. */
+int sg_set_best(sg_engine *e, const float *best_energy, const int8_t *best_spins, int on_device, void *stream);
+int sg_set_accepted(sg_engine *e, const uint64_t *accepted, int on_device, void *stream);
+int sg_set_ladder_state(sg_engine *e, const int32_t *replica_at_rung, const uint32_t *attempts,
+                        const uint32_t *accepts, int on_device, void *stream);
+
 /* Pipelined upload for callers that stream many start configurations through one engine (the RL
  * environment's repeated anneals, rl_integration/environment.py:318-336; bench.py's end-to-end
  * leg): sg_upload_spins_async copies spins[R][n] from PINNED host memory into one of two

@@ -14,11 +14,12 @@ __version__ = "0.1.0"
 
 from .annealing import (AnnealingResult, GPUAnnealer, GPUAnnealerConfig, ParallelTempering,
                         ParallelTemperingConfig, ScheduleType, TemperatureScheduler)
-from .core import IsingModel, IsingModelConfig, SpinDynamics, UpdateRule
+from .core import (ComputeMode, EnergyComputer, EnergyStats, IsingModel, IsingModelConfig, SpinDynamics,
+                   UpdateRule)
 from .api import (BatchProcessor, VectorizedOperations, anneal, batch_energies, batch_local_fields,
                   install_as_spin_glass_rl)
 
-__all__ = ["BatchProcessor", "VectorizedOperations", "IsingModel", "IsingModelConfig", "SpinDynamics", "UpdateRule", "GPUAnnealer",
+__all__ = ["ComputeMode", "EnergyComputer", "EnergyStats", "BatchProcessor", "VectorizedOperations", "IsingModel", "IsingModelConfig", "SpinDynamics", "UpdateRule", "GPUAnnealer",
            "GPUAnnealerConfig", "ParallelTempering", "ParallelTemperingConfig", "AnnealingResult",
            "ScheduleType", "TemperatureScheduler", "anneal", "batch_energies",
            "batch_local_fields", "install_as_spin_glass_rl"]

@@ -65,6 +65,9 @@ PROTOTYPES = {
     "sg_alloc_replicas": (c_int, [c_void_p, c_int, c_void_p]),
     "sg_set_spins": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "sg_get_spins": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "sg_set_best": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "sg_set_accepted": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "sg_set_ladder_state": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "sg_upload_spins_async": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "sg_set_spins_staged": (c_int, [c_void_p, c_int, c_void_p]),
     "sg_get_best_config": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),

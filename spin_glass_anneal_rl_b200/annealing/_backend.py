@@ -14,7 +14,9 @@ import torch
 from ..engine import Engine
 from ..utils.exceptions import DeviceError
 
-DENSE_LIMIT = 4096   # above this many spins the model goes to the sparse (CSR) sweep kernel
+# Dense models up to this many spins stay dense: <= 4096 on the tensor-core sweep, up to 7168 on the
+# sequential-FMA kernel (register-resident fields); beyond, the model goes to the sparse (CSR) kernel.
+DENSE_LIMIT = 7168
 
 RULE_NAMES = {"metropolis": "metropolis", "glauber": "glauber", "heat_bath": "heat_bath"}
 
@@ -124,7 +126,12 @@ def engine_for(model, device_index: int = 0) -> Engine:
             else Engine(device_index)
         J = model.couplings
         n = int(J.shape[0])
-        if n > DENSE_LIMIT:
+        dense_ok = n <= DENSE_LIMIT
+        if dense_ok and n > 4096 and J.is_sparse:
+            # a sparse model of this size is only worth a dense upload if it is not actually sparse
+            nnz = int(J._nnz()) if not J.is_coalesced() else int(J.indices().shape[1])
+            dense_ok = nnz > 0.25 * n * n
+        if not dense_ok:
             # sparse path (K1-CSR): the 50k-spin scheduling QUBOs and lattices the reference's
             # callers build as COO (problems/base.py:107-116) cannot be held as dense matrices
             coo = (J if J.is_sparse else J.to_sparse()).coalesce().cpu()

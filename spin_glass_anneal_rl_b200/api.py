@@ -123,7 +123,7 @@ def install_as_spin_glass_rl(force: bool = False) -> None:
     from . import annealing, core
     from .annealing import (batch_processor, cuda_kernels, gpu_annealer, parallel_tempering, result,
                             temperature_scheduler)
-    from .core import ising_model, spin_dynamics
+    from .core import energy_computer, ising_model, spin_dynamics
     from .utils import exceptions
     if "spin_glass_rl" in sys.modules and not force:
         raise RuntimeError("spin_glass_rl is already imported; pass force=True to shadow it")
@@ -136,6 +136,7 @@ def install_as_spin_glass_rl(force: bool = False) -> None:
         "spin_glass_rl.utils": utils, "spin_glass_rl.utils.exceptions": exceptions,
         "spin_glass_rl.core.ising_model": ising_model,
         "spin_glass_rl.core.spin_dynamics": spin_dynamics,
+        "spin_glass_rl.core.energy_computer": energy_computer,
         "spin_glass_rl.annealing.gpu_annealer": gpu_annealer,
         "spin_glass_rl.annealing.cuda_kernels": cuda_kernels,
         "spin_glass_rl.annealing.batch_processor": batch_processor,

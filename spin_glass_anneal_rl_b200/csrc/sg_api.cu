@@ -1254,6 +1254,60 @@ int sg_get_best(sg_engine* e, float* best_energy, int8_t* best_spins, int on_dev
     return rc;
 }
 
+// ---- checkpoint restore: the state a resumed run needs besides the spins (sg_set_spins)
+int sg_set_best(sg_engine* e, const float* best_energy, const int8_t* best_spins, int on_device, void* stream) {
+    SG_REQUIRE(e && best_energy && best_spins && e->R > 0, "sg_set_best: allocate replicas first");
+    SG_REQUIRE(!e->csr && !e->lat, "sg_set_best: dense models only");
+    DeviceGuard g(e->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t bytes = (size_t)e->R * e->n;
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    SG_CUDA(cudaMemcpyAsync(e->best_energy, best_energy, (size_t)e->R * sizeof(float), kind, st));
+    const int8_t* src = best_spins;
+    int8_t* tmp = nullptr;
+    if (!on_device) {
+        int rc = dev_alloc(&tmp, bytes);
+        if (rc != SG_OK) return rc;
+        SG_CUDA(cudaMemcpyAsync(tmp, best_spins, bytes, cudaMemcpyHostToDevice, st));
+        src = tmp;
+    }
+    SG_CUDA(sg::launch_pad_spins(src, e->n, e->best_spins, e->n_pad, e->R, st));
+    e->launches++;
+    if (tmp) {
+        SG_CUDA(cudaStreamSynchronize(st));
+        cudaFree(tmp);
+    } else if (!on_device) {
+        SG_CUDA(cudaStreamSynchronize(st));
+    }
+    return SG_OK;
+}
+
+int sg_set_accepted(sg_engine* e, const uint64_t* accepted, int on_device, void* stream) {
+    SG_REQUIRE(e && accepted && e->R > 0 && e->accepted, "sg_set_accepted: allocate replicas first");
+    DeviceGuard g(e->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SG_CUDA(cudaMemcpyAsync(e->accepted, accepted, (size_t)e->R * sizeof(uint64_t),
+                            on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    if (!on_device) SG_CUDA(cudaStreamSynchronize(st));
+    return SG_OK;
+}
+
+int sg_set_ladder_state(sg_engine* e, const int32_t* replica_at_rung, const uint32_t* attempts,
+                        const uint32_t* accepts, int on_device, void* stream) {
+    SG_REQUIRE(e && replica_at_rung && e->K > 0, "sg_set_ladder_state: call sg_set_ladder first");
+    DeviceGuard g(e->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    const size_t nstat = (size_t)e->L * (e->K > 1 ? e->K - 1 : 1);
+    SG_CUDA(cudaMemcpyAsync(e->rep_at, replica_at_rung, (size_t)e->n_global * sizeof(int), kind, st));
+    if (attempts) SG_CUDA(cudaMemcpyAsync(e->attempts, attempts, nstat * sizeof(unsigned int), kind, st));
+    if (accepts) SG_CUDA(cudaMemcpyAsync(e->accepts, accepts, nstat * sizeof(unsigned int), kind, st));
+    SG_CUDA(sg::launch_ladder_temps(e->rep_at, e->ladder, e->rep_temp, e->n_global, e->K, e->rep_lo, e->R, st));
+    e->launches++;
+    if (!on_device) SG_CUDA(cudaStreamSynchronize(st));
+    return SG_OK;
+}
+
 int sg_upload_spins_async(sg_engine* e, const int8_t* host_spins, int slot, void* stream) {
     SG_REQUIRE(e && host_spins && e->R > 0, "sg_upload_spins_async: allocate replicas first");
     SG_REQUIRE(slot == 0 || slot == 1, "sg_upload_spins_async: slot must be 0 or 1");

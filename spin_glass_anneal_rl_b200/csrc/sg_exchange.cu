@@ -156,6 +156,15 @@ __global__ void check_target_kernel(const float* __restrict__ energy, int R, int
     }
 }
 
+// temperatures of the local replicas from the rung -> replica map (checkpoint restore)
+__global__ void ladder_temps_kernel(const int* __restrict__ rep_at, const double* __restrict__ ladder,
+                                    double* __restrict__ rep_temp, int n_global, int K, int rep_lo, int rep_n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_global) return;
+    const int loc = rep_at[t] - rep_lo;
+    if (loc >= 0 && loc < rep_n) rep_temp[loc] = ladder[t % K];
+}
+
 // out_idx[0] = argmin_r energy[r] (lowest index on ties), out_e[0] = that energy; then row
 // out_idx[0] of the padded int8 matrix `rows` is copied to out_row (n entries).  One block.
 __global__ void best_config_kernel(const float* __restrict__ energy, int R, const int8_t* __restrict__ rows,
@@ -358,6 +367,12 @@ cudaError_t launch_exchange(ExchangeDev a, cudaStream_t st) {
 cudaError_t launch_check_target(const float* energy, int R, int rep_lo, float target, int round, int* hit,
                                 cudaStream_t st) {
     check_target_kernel<<<1, 1024, 0, st>>>(energy, R, rep_lo, target, round, hit);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ladder_temps(const int* rep_at, const double* ladder, double* rep_temp, int n_global, int K,
+                                int rep_lo, int rep_n, cudaStream_t st) {
+    ladder_temps_kernel<<<(n_global + 127) / 128, 128, 0, st>>>(rep_at, ladder, rep_temp, n_global, K, rep_lo, rep_n);
     return cudaGetLastError();
 }
 

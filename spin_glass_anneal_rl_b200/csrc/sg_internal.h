@@ -238,6 +238,8 @@ cudaError_t launch_exchange_chain(void* rows, long long row_stride, long long ro
                                   cudaStream_t st);
 cudaError_t launch_ladder_init(int* rep_at, double* rep_temp, const double* ladder, int n_global, int K,
                                int rep_lo, int rep_n, cudaStream_t st);
+cudaError_t launch_ladder_temps(const int* rep_at, const double* ladder, double* rep_temp, int n_global, int K,
+                                int rep_lo, int rep_n, cudaStream_t st);
 cudaError_t launch_best_config(const float* energy, int R, const int8_t* rows, int n, int n_pad, float* out_e,
                                int* out_idx, int8_t* out_row, cudaStream_t st);
 cudaError_t launch_check_target(const float* energy, int R, int rep_lo, float target, int round, int* hit,

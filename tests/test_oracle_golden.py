@@ -148,3 +148,24 @@ def test_scheduled_form_equals_stream_form(oracle):
     e2, acc2 = oracle.sweeps_scheduled(g["J"], g["h"], b, temps, "metropolis", tsite,
                                        np.nan_to_num(tu, nan=0.5))
     assert np.array_equal(a, b) and np.array_equal(e1, e2) and np.array_equal(acc1, acc2)
+
+
+@pytest.mark.parametrize("name", golden_names("ec_"))
+def test_energy_computer_kats(oracle, name):
+    """Known answers recorded from the reference's EnergyComputer (core/energy_computer.py:50-231):
+    the oracle's fields / energies reproduce its total energy (all three modes), flip energy
+    changes, gradient, decomposition and batch energies."""
+    g = load_golden(name)
+    J, h, S = g["J"], g["h"], g["S"].astype(np.float32)
+    exact = _is_integer(g)
+    F, E = oracle.batch_fields_energies(J, h, S)
+    for mode in ("full", "incremental", "vectorized"):
+        _close(E[0], g["total_" + mode], exact)
+    _close(E[1], g["total_other"], exact)
+    _close(E, g["batch"], exact)
+    _close(2.0 * S[0] * F[0], g["dE"], exact)
+    _close(-F[0], g["gradient"], exact)
+    inter = -0.5 * np.sum(S[0] * (F[0] - h))
+    field = -np.sum(h * S[0])
+    _close([inter + field, inter, field], g["stats"], exact)
+    _close(-0.5 * S[0] * F[0] - h * S[0], g["per_spin"], exact)
