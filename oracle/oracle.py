@@ -526,5 +526,24 @@ def baseline_run(J, h, spins: np.ndarray, n_sweeps: int, T: float, seed: int = 1
     return int(att), E
 
 
+def baseline_run_csr(rowptr, colidx, val, h, spins: np.ndarray, n_sweeps: int, T: float, seed: int = 1,
+                     n_threads: int = 0):
+    """The same baseline on CSR rows of J (models that cannot be densified at full size: cfg2,
+    cfg5); timing arm only.  Returns (attempts, energies[R])."""
+    rp = np.ascontiguousarray(rowptr, dtype=np.int64)
+    ci = np.ascontiguousarray(colidx, dtype=np.int32)
+    v, h = _f32(val), _f32(h)
+    assert spins.dtype == np.float32 and spins.flags.c_contiguous
+    R, n = spins.shape
+    E = np.empty(R, dtype=np.float64)
+    fn = lib().sgo_baseline_run_csr
+    fn.restype = ctypes.c_int64
+    att = fn(_p(rp, ctypes.c_int64), _p(ci, ctypes.c_int32), _p(v, ctypes.c_float), _p(h, ctypes.c_float),
+             _p(spins, ctypes.c_float), ctypes.c_int(n), ctypes.c_int(R), ctypes.c_int(int(n_sweeps)),
+             ctypes.c_double(float(T)), ctypes.c_uint64(int(seed)), ctypes.c_int(int(n_threads)),
+             _p(E, ctypes.c_double))
+    return int(att), E
+
+
 def num_threads() -> int:
     return int(lib().sgo_num_threads())

@@ -303,6 +303,60 @@ int64_t sgo_baseline_run(const float *J, int64_t ld, const float *h, float *spin
     return total;
 }
 
+/* The same baseline for models the reference's callers hold as sparse COO and that cannot be
+ * densified at full size (cfg2: 65 536 spins, cfg5: 50 000 spins -- SURVEY 8c: "cfg2/cfg5 are timed
+ * with the restatement and labelled as such"): the reference's algorithm with every dense dot
+ * product replaced by the sum over the row's non-zeros, which is what its sparse branch computes
+ * (core/ising_model.py:160-166, 180-183) without materialising the dense matrix per call.  CSR
+ * rows of J.  Timing arm only; parity is always checked on dense (down-scaled) instances. */
+int64_t sgo_baseline_run_csr(const int64_t *rowptr, const int32_t *colidx, const float *val, const float *h,
+                             float *spins, int n, int n_replicas, int n_sweeps, double T, uint64_t seed,
+                             int n_threads, double *energies_out) {
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+    int64_t total = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : total)
+    for (int r = 0; r < n_replicas; ++r) {
+        float *s = spins + (int64_t)r * n;
+        uint64_t x = seed * 0x9E3779B97F4A7C15ull + (uint64_t)(r + 1) * 0xBF58476D1CE4E5B9ull;
+        for (int sw = 0; sw < n_sweeps; ++sw) {
+            for (int k = 0; k < n; ++k) {
+                uint32_t w[2];
+                for (int q = 0; q < 2; ++q) {
+                    x ^= x << 13;
+                    x ^= x >> 7;
+                    x ^= x << 17;
+                    w[q] = (uint32_t)(x >> 16);
+                }
+                const int site = (int)(w[0] % (uint32_t)n);
+                float cf = 0.0f;
+                for (int64_t e = rowptr[site]; e < rowptr[site + 1]; ++e) cf += val[e] * s[colidx[e]];
+                const double lf = (double)cf + (double)h[site];
+                const double dE = 2.0 * (double)s[site] * lf;
+                int accept = dE <= 0.0;
+                if (!accept) {
+                    const float p = expf((float)(-dE / T));
+                    const float u = (float)(w[1] & 0xFFFFFFu) * (1.0f / 16777216.0f);
+                    accept = ((double)u < (double)p);
+                }
+                if (accept) s[site] = -s[site];
+            }
+            /* compute_energy() after the sweep */
+            double inter = 0.0, field = 0.0;
+            for (int i = 0; i < n; ++i) {
+                float cf = 0.0f;
+                for (int64_t e = rowptr[i]; e < rowptr[i + 1]; ++e) cf += val[e] * s[colidx[e]];
+                inter += (double)s[i] * (double)cf;
+                field += (double)h[i] * (double)s[i];
+            }
+            if (energies_out) energies_out[r] = -0.5 * inter - field;
+            total += n;
+        }
+    }
+    return total;
+}
+
 int sgo_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

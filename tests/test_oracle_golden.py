@@ -169,3 +169,24 @@ def test_energy_computer_kats(oracle, name):
     field = -np.sum(h * S[0])
     _close([inter + field, inter, field], g["stats"], exact)
     _close(-0.5 * S[0] * F[0] - h * S[0], g["per_spin"], exact)
+
+
+def test_csr_baseline_equals_dense_baseline(oracle):
+    """The timing arm for models too big to densify (cfg2 / cfg5) walks the same Markov chain as the
+    dense baseline: same RNG, same decisions, same energies on a small integer instance."""
+    rng = np.random.default_rng(9)
+    n, R = 60, 5
+    a = rng.integers(-2, 3, size=(n, n)) * (rng.random((n, n)) < 0.2)
+    J = np.triu(a, 1)
+    J = (J + J.T).astype(np.float32)
+    h = rng.integers(-1, 2, size=n).astype(np.float32)
+    S = (rng.integers(0, 2, size=(R, n)) * 2 - 1).astype(np.float32)
+    rowptr = np.concatenate([[0], np.cumsum((J != 0).sum(axis=1))]).astype(np.int64)
+    colidx = np.concatenate([np.nonzero(J[i])[0] for i in range(n)]).astype(np.int32)
+    val = np.concatenate([J[i][J[i] != 0] for i in range(n)]).astype(np.float32)
+    Sd, Ss = S.copy(), S.copy()
+    a1, e1 = oracle.baseline_run(J, h, Sd, 7, 1.3, seed=5, n_threads=2)
+    a2, e2 = oracle.baseline_run_csr(rowptr, colidx, val, h, Ss, 7, 1.3, seed=5, n_threads=2)
+    assert a1 == a2 == R * n * 7
+    assert np.array_equal(Sd, Ss) and np.array_equal(e1, e2)
+    assert not np.array_equal(Sd, S)
