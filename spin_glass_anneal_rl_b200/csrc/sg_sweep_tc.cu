@@ -1373,11 +1373,15 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                         // is bound by shared-memory bandwidth -- TMA writes plus operand reads: the
                         // issue loop of a half takes ~100 clocks per MMA because the queue is full)
                         if (tc::elect_one()) {
+                            // plane-major: consecutive MMAs go to DIFFERENT accumulator tiles.  The
+                            // planes of one tile accumulate into the same TMEM columns, and issued
+                            // back to back they wait for each other (MMA latency instead of the
+                            // issue rate).
 #pragma unroll
-                            for (int tt = 0; tt < CT; ++tt) {
-                                if (tt < nt) {
+                            for (int p = 0; p < P; ++p) {
 #pragma unroll
-                                    for (int p = 0; p < P; ++p)
+                                for (int tt = 0; tt < CT; ++tt) {
+                                    if (tt < nt)
                                         tc::mma_bf16_ss(d0 + tt * NG,
                                                         adesc0 + (uint64_t)(((tt * P + p) * kTileBytes) >> 4),
                                                         bdesc, IDESC, 1u);
