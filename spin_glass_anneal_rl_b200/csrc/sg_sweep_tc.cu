@@ -1368,20 +1368,20 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                         const uint64_t adesc0 = tc::make_smem_desc(
                             smem_u32(ring + (size_t)stage * kStageBytes), kALbo, kASbo);
                         const uint32_t d0 = tbase + (uint32_t)(c * CT * NG);
-                        // (the issue pattern is not the limit here: a branch-free block of 12 MMAs
-                        // issues at 48 clocks per MMA in isolation, tools/mma_bench.py, but the phase
-                        // is bound by shared-memory bandwidth -- TMA writes plus operand reads: the
-                        // issue loop of a half takes ~100 clocks per MMA because the queue is full)
+                        // (what bounds this loop is the tensor pipe's rate per INSTRUCTION: an
+                        // M128 x N64 x K16 MMA takes 49 clocks in isolation, 61 with a commit per six
+                        // (tools/mma_dep_bench.py; the floor is ~41 clocks however small N is), i.e.
+                        // 24 MMAs = ~1.5 k of the 2.4 k clocks this warp needs per block; waiting for
+                        // full ring stages costs 65 clocks per stage, the copies themselves nothing)
                         if (tc::elect_one()) {
-                            // plane-major: consecutive MMAs go to DIFFERENT accumulator tiles.  The
-                            // planes of one tile accumulate into the same TMEM columns, and issued
-                            // back to back they wait for each other (MMA latency instead of the
-                            // issue rate).
+                            // (tile-major; plane-major -- consecutive MMAs on different accumulator
+                            // tiles -- was measured slower, and tools/mma_dep_bench.py shows no
+                            // penalty for back-to-back MMAs on one accumulator)
 #pragma unroll
-                            for (int p = 0; p < P; ++p) {
+                            for (int tt = 0; tt < CT; ++tt) {
+                                if (tt < nt) {
 #pragma unroll
-                                for (int tt = 0; tt < CT; ++tt) {
-                                    if (tt < nt)
+                                    for (int p = 0; p < P; ++p)
                                         tc::mma_bf16_ss(d0 + tt * NG,
                                                         adesc0 + (uint64_t)(((tt * P + p) * kTileBytes) >> 4),
                                                         bdesc, IDESC, 1u);
@@ -1527,6 +1527,32 @@ tc_mma_bench_kernel(int variant_in, int n_dim, int iters, long long* out) {
                             tc::mma_bf16_ss(dd0 + (t & 3) * n_dim, ad0 + (uint64_t)((t * 4608) >> 4), bdesc, idesc, 1u);
                     }
                     if (tc::elect_one()) tc::mma_commit(&cbar);
+                    __syncwarp();
+                }
+            }
+        } else if (commit_every >= 8 && commit_every <= 11) {
+            // 8: commits only (96 per iteration, no MMA); 9: the sweep kernel's ring-stage pattern,
+            // plane-major (2 tiles x 3 planes, consecutive MMAs on different accumulators, commit);
+            // 10: every MMA accumulates into the SAME tile; 11: the stage pattern tile-major (the
+            // three planes of a tile back to back on one accumulator, commit)
+            for (int it = 0; it < iters; ++it) {
+#pragma unroll 1
+                for (int c = 0; c < 16; ++c) {
+                    const uint64_t ad0 = adesc_of((c * 6) & 24);
+                    if (tc::elect_one()) {
+                        if (commit_every == 8) {
+#pragma unroll
+                            for (int t = 0; t < 6; ++t) tc::mma_commit(&cbar);
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < 6; ++t) {
+                                const int tile = (commit_every == 10) ? 0 : (commit_every == 9) ? (t & 1) : (t / 3);
+                                tc::mma_bf16_ss(tbase + (uint32_t)(tile * n_dim), ad0 + (uint64_t)((t * 4608) >> 4),
+                                                bdesc, idesc, 1u);
+                            }
+                            tc::mma_commit(&cbar);
+                        }
+                    }
                     __syncwarp();
                 }
             }
