@@ -49,7 +49,7 @@ def to_bytes(v, unit):
     m = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
     return float(v.replace(",", "")) * m[unit]
 with open(os.path.join(out_dir, f"{tag}_sweep_tc_ncu.txt"), "w") as f:
-    f.write(f"# ncu --set full --clock-control none --import-source on -k regex:sweep_tc  python tools/prof_tc.py\n")
+    f.write(f"# ncu --set full --clock-control none --import-source on -k regex:sweep_tc  python tools/prof.py tc\n")
     f.write(f"# (SK N=4096, 8192 replicas, 10 sweeps per launch, 3 planes: the bench launch shape)\n")
     f.write(f"kernel: {d[h.index('Kernel Name')]}\n")
     for w in want:
@@ -68,7 +68,7 @@ for cand in ("lts__t_bytes.sum",):
         lts = to_bytes(*get(cand))
 if lts is None and "lts__t_sectors.sum" in h:
     lts = float(get("lts__t_sectors.sum")[0].replace(",", "")) * 32.0
-json.dump({"kernel": "sg::sweep_tc_kernel", "source": f"profiles/{tag}_sweep_tc_ncu.txt (ncu --set full of tools/prof_tc.py)",
+json.dump({"kernel": "sg::sweep_tc_kernel", "source": f"profiles/{tag}_sweep_tc_ncu.txt (ncu --set full of tools/prof.py tc)",
            "shape": "SK N=4096, 8192 replicas, 10 sweeps per launch, 3 bf16 planes",
            "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr,
            "lts_bytes_per_launch": lts,
@@ -81,7 +81,7 @@ if probe and os.path.exists(probe):
     pr = list(csv.reader(praw.splitlines()))
     ph, pu = pr[0], pr[1]
     with open(os.path.join(out_dir, f"{tag}_tma_probe_ncu.txt"), "w") as f:
-        f.write("# ncu --set full --clock-control none -k regex:tma_probe  python tools/prof_tma.py\n")
+        f.write("# ncu --set full --clock-control none -k regex:tma_probe  python tools/prof.py tma\n")
         f.write("# sg_measure_tma_stream: every SM pulls the same L2-resident 65 MB buffer in the same order through a\n")
         f.write("# shared-memory ring with TMA bulk copies, no compute (launch 1: 17.9 KB copies x 8 stages, 2: 48 KB x 4)\n")
         for row in pr[2:]:
