@@ -306,7 +306,7 @@ def run_ours(args):
         e_target = 0.97 * (-0.7632 / np.sqrt(2.0)) * n
         runs = []
         budget_left = args.ttt_budget
-        max_rounds = 400
+        max_rounds = 400 if world == 1 else 60
         for run in range(args.ttt_seeds):
             eng.set_spins(fresh_spins(R, 777 + rank + 7919 * run))
             eng.init_fields()
@@ -321,8 +321,11 @@ def run_ours(args):
             rounds = 0
             while rounds < max_rounds:
                 if rounds >= 2:
-                    evs[rounds - 2].synchronize()   # the host runs at most two rounds ahead of the device
-                    if int(hit[0]) >= 0:
+                    # the host runs at most two rounds ahead of the device.  Every rank must take the
+                    # same branch (the next round contains a collective): after this wait the flag is
+                    # final for rounds <= rounds-2 on every rank, later hits are ignored until then
+                    evs[rounds - 2].synchronize()
+                    if 0 <= int(hit[0]) <= rounds - 2:
                         break
                 eng.sweep(sweeps, None, seed=4242 + 1000 * run, sweep_base=rounds * sweeps, site_order="random",
                           track_best=False, kernel=kernel, coupling_planes=planes, replica_base=rank * R)
@@ -341,7 +344,9 @@ def run_ours(args):
                 evs.append(e)
                 eng.exchange(rounds & 1, seed=77 + 1000 * run, round=rounds, energies_all=e_all)
                 rounds += 1
-                if int(hit[0]) >= 0 or (rounds % 8 == 0 and time.perf_counter() - w0 > budget_left):
+                # (wall-clock budget: single GPU only -- on several GPUs it would let ranks leave the
+                # loop at different rounds; there max_rounds bounds a run)
+                if world == 1 and rounds % 8 == 0 and time.perf_counter() - w0 > budget_left:
                     break
             torch.cuda.synchronize()
             hr = int(hit[0])
