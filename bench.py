@@ -460,6 +460,25 @@ def run_ours(args):
                     "smem_peak_gbs": smem_peak,
                     "smem_frac": (smem_factor * achieved) / smem_peak if use_tc else None,
                     "gather_ms_per_launch": prof["gather_ms"] / max(1, int(prof["gather_launches"]))}
+        if use_tc:
+            # what the kernel is actually bound by (profiles/r2_notes.md): the tensor core's rate per
+            # INSTRUCTION.  A block of 16 attempts needs (n_tc / 128) tiles x planes MMAs per replica
+            # group, spread over the group's `cluster` SMs; one M128 x N(16 cluster) x K16 MMA takes
+            # `clk_per_mma` clocks in isolation (tools/mma_dep_bench.py: 41 / 41 / 49 / 65 at N = 16 /
+            # 32 / 64 / 128), so the MMA time per SM is a floor for the launch
+            clk_per_mma = {1: 41.0, 2: 41.0, 4: 49.0, 8: 65.0}.get(cluster, 49.0)
+            nblk = (n + 15) // 16
+            mma_per_launch = float(groups) * sweeps * nblk * (n_tc // 128) * planes * args.steps / n_klaunch
+            slots = min(groups, max(1, (q["sm_count"] // cluster) * cluster // cluster)) * cluster
+            if cluster == 4:
+                slots = min(groups, 33) * 4   # cudaOccupancyMaxActiveClusters: 33 clusters of 4 (132 SMs)
+            roofline["tensor_issue"] = {
+                "mma_per_launch": mma_per_launch, "clk_per_mma_isolated": clk_per_mma, "sms_used": slots,
+                "frac": mma_per_launch * clk_per_mma / slots / (ms_launch * 1e-3 * sm_clk),
+                "mma_tflops": mma_per_launch * 2.0 * 128 * (16 * cluster) * 16 / (ms_launch * 1e-3) / 1e12,
+                "note": "share of the kernel's time that the tensor pipe of a used SM needs for its MMA "
+                        "instructions at their isolated rate; the remainder is the two barrier round trips "
+                        "per block between MMA completion, the raw field reads and the next issue"}
         v, threads, sample, quench = cpu_reference(0, args.cpu_budget, quench_sweeps=200)
         cpu = {"value": v, "unit": "attempts/s", "cores": threads, "kind": "port", "sample": sample,
                "quench": quench}
