@@ -1359,21 +1359,66 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                                   (uint32_t)((kg + LAG) >> 2) & 1u);
                     if (h == 0) SG_STAMP(11);
                     if (h == 1) SG_STAMP(14);
-                    const int c_end = pb(h + 1);
+                    const int c_begin = pb(h), c_end = pb(h + 1);
+                    // the ring stages of this part: lane l waits for stage l (the barrier tests of all
+                    // stages run side by side instead of one ~65-clock round trip after the other),
+                    // then ONE elected lane issues the whole part: MMAs, the stage releases and the
+                    // part's commit
+                    // (only when the ring holds more than two parts: with a shallow ring -- pairs and
+                    // single CTAs at N = 4096 -- waiting for a whole part before its first MMA would
+                    // take the overlap of copies and MMAs away; those issue stage by stage)
+                    // (compiled for the cluster forms only: the other instantiations keep their loop small)
+                    const bool whole_part = (C >= 4) && 2 * (c_end - c_begin) < NS;
+                    if (!whole_part) {
 #pragma unroll 1
-                    for (int c = pb(h); c < c_end; ++c) {
-                        mbar_wait(&full[stage], fpar);
-                        tc::fence_after_sync();
-                        const int nt = (dbg & 2) ? 0 : min(CT, Tl - c * CT);
-                        const uint64_t adesc0 = tc::make_smem_desc(
-                            smem_u32(ring + (size_t)stage * kStageBytes), kALbo, kASbo);
-                        const uint32_t d0 = tbase + (uint32_t)(c * CT * NG);
-                        // (what bounds this loop is the tensor pipe's rate per INSTRUCTION: an
-                        // M128 x N64 x K16 MMA takes 49 clocks in isolation, 61 with a commit per six
-                        // (tools/mma_dep_bench.py; the floor is ~41 clocks however small N is), i.e.
-                        // 24 MMAs = ~1.5 k of the 2.4 k clocks this warp needs per block; waiting for
-                        // full ring stages costs 65 clocks per stage, the copies themselves nothing)
-                        if (tc::elect_one()) {
+                        for (int c = c_begin; c < c_end; ++c) {
+                            mbar_wait(&full[stage], fpar);
+                            tc::fence_after_sync();
+                            const int nt = (dbg & 2) ? 0 : min(CT, Tl - c * CT);
+                            const uint64_t adesc0 = tc::make_smem_desc(
+                                smem_u32(ring + (size_t)stage * kStageBytes), kALbo, kASbo);
+                            const uint32_t d0 = tbase + (uint32_t)(c * CT * NG);
+                            if (tc::elect_one()) {
+#pragma unroll
+                                for (int tt = 0; tt < CT; ++tt) {
+                                    if (tt < nt) {
+#pragma unroll
+                                        for (int p = 0; p < P; ++p)
+                                            tc::mma_bf16_ss(d0 + tt * NG,
+                                                            adesc0 + (uint64_t)(((tt * P + p) * kTileBytes) >> 4),
+                                                            bdesc, IDESC, 1u);
+                                    }
+                                }
+                                tc::mma_commit(&empty[stage]);
+                            }
+                            __syncwarp();
+                            if (++stage == NS) { stage = 0; fpar ^= 1u; }
+                        }
+                        if (tc::elect_one()) tc::mma_commit(&hdone[kParts * slot + h]);
+                        __syncwarp();
+                        continue;
+                    }
+                    if (lane < c_end - c_begin) {
+                        int st_l = stage + lane;
+                        uint32_t par_l = fpar;
+                        if (st_l >= NS) { st_l -= NS; par_l ^= 1u; }
+                        mbar_wait(&full[st_l], par_l);
+                    }
+                    __syncwarp();
+                    tc::fence_after_sync();
+                    // (what bounds this loop is the tensor pipe's rate per INSTRUCTION: an
+                    // M128 x N64 x K16 MMA takes 49 clocks in isolation, 61 with a commit per six
+                    // (tools/mma_dep_bench.py; the floor is ~41 clocks however small N is), i.e.
+                    // 24 MMAs = ~1.5 k of the clocks this warp needs per block; the copies themselves
+                    // cost nothing)
+                    if (tc::elect_one()) {
+                        int st_c = stage;
+#pragma unroll 1
+                        for (int c = c_begin; c < c_end; ++c) {
+                            const int nt = (dbg & 2) ? 0 : min(CT, Tl - c * CT);
+                            const uint64_t adesc0 = tc::make_smem_desc(
+                                smem_u32(ring + (size_t)st_c * kStageBytes), kALbo, kASbo);
+                            const uint32_t d0 = tbase + (uint32_t)(c * CT * NG);
                             // (tile-major; plane-major -- consecutive MMAs on different accumulator
                             // tiles -- was measured slower, and tools/mma_dep_bench.py shows no
                             // penalty for back-to-back MMAs on one accumulator)
@@ -1387,13 +1432,14 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                                                         bdesc, IDESC, 1u);
                                 }
                             }
-                            tc::mma_commit(&empty[stage]);
+                            tc::mma_commit(&empty[st_c]);
+                            if (++st_c == NS) st_c = 0;
                         }
-                        __syncwarp();
-                        if (++stage == NS) { stage = 0; fpar ^= 1u; }
+                        tc::mma_commit(&hdone[kParts * slot + h]);
                     }
-                    if (tc::elect_one()) tc::mma_commit(&hdone[kParts * slot + h]);
                     __syncwarp();
+                    stage += c_end - c_begin;
+                    if (stage >= NS) { stage -= NS; fpar ^= 1u; }
                 }
                 SG_STAMP(12);
             }
