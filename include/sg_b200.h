@@ -209,8 +209,9 @@ typedef struct {
     int32_t track_best;  /* compare-and-keep best energy/configuration after every sweep       */
     int32_t kernel;      /* SG_KERNEL_*                                                        */
     /* SG_KERNEL_TC: number of bf16 planes the couplings are summed from: 3 = every fp32 coupling
-     * exactly (default, 0 means 3), 2 = 16 significant bits, 1 = plain bf16.  Integer couplings
-     * |J| <= 256 are exact with 1 plane. */
+     * exactly, 2 = 16 significant bits, 1 = plain bf16.  0 (default) = as many as THIS model needs
+     * to be exact: 3 for arbitrary fp32 couplings, 1 when every coupling is a bf16 value (integer
+     * couplings |J| <= 256) -- a third of the tensor-core work, same results. */
     int32_t coupling_planes;
     /* global id of this engine's replica 0: the Philox key of replica r is replica_base + r, so a
      * replica set sharded over several engines / GPUs draws exactly the numbers the same replicas

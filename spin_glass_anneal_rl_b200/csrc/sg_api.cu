@@ -127,6 +127,8 @@ struct sg_engine {
     // staging for asynchronous host transfers (sg_upload_spins_async / sg_get_best_config)
     int8_t* up_stage[2] = {nullptr, nullptr};
     size_t up_cap[2] = {0, 0};
+    int* plane_flags = nullptr;          // device [2]: plane 2 / plane 3 of the couplings non-zero
+    int planes_needed = 0;               // 0 = not read back yet
     unsigned char* best_out = nullptr;   // device: float energy, int replica, int8 spins[n]
     size_t best_out_cap = 0;
 };
@@ -877,6 +879,7 @@ void sg_destroy(sg_engine* e) {
     cudaFree(e->up_stage[0]);
     cudaFree(e->up_stage[1]);
     cudaFree(e->best_out);
+    cudaFree(e->plane_flags);
     cudaFree(e->dig);
     cudaFree(e->scale);
     cudaFree(e->info);
@@ -958,7 +961,13 @@ int sg_set_model_dense(sg_engine* e, int n, const float* J, int64_t ldJ, const f
         cudaError_t ce = cudaMalloc(&jp, (size_t)3 * n * n_tc * 2);
         if (ce != cudaSuccess) return fail(SG_ERR_NOMEM, "cudaMalloc(planes)", ce);
         e->Jp = jp;
-        SG_CUDA(sg::launch_split_planes(e->Jt, n, n_pad, e->Jp, n_tc, st));
+        if (!e->plane_flags) {
+            int rc2 = dev_alloc(&e->plane_flags, (size_t)2);
+            if (rc2 != SG_OK) return rc2;
+        }
+        SG_CUDA(cudaMemsetAsync(e->plane_flags, 0, 2 * sizeof(int), st));
+        SG_CUDA(sg::launch_split_planes(e->Jt, n, n_pad, e->Jp, n_tc, e->plane_flags, st));
+        e->planes_needed = 0;   // read back on the first sweep that leaves the choice to the engine
         e->launches++;
     }
     if (tmp) {
@@ -1508,7 +1517,19 @@ int sg_sweep(sg_engine* e, const sg_sweep_params* p, void* stream) {
             if (ce != cudaSuccess) return fail(SG_ERR_NOMEM, "cudaMalloc(site tables)", ce);
             e->tc_sites_cap = need;
         }
-        const int planes = p->coupling_planes ? p->coupling_planes : 3;
+        // coupling_planes = 0: as many planes as the couplings need to be exact -- three for
+        // arbitrary fp32 values, one when every coupling is a bf16 value (integer couplings up to
+        // 256): a third of the tensor-core instructions and of the operand stream
+        if (p->coupling_planes == 0 && e->planes_needed == 0) {
+            int used[2] = {1, 1};
+            if (e->plane_flags) {
+                SG_CUDA(cudaMemcpyAsync(used, e->plane_flags, sizeof(used), cudaMemcpyDeviceToHost,
+                                        static_cast<cudaStream_t>(stream)));
+                SG_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+            }
+            e->planes_needed = used[1] ? 3 : used[0] ? 2 : 1;
+        }
+        const int planes = p->coupling_planes ? p->coupling_planes : e->planes_needed;
         const size_t per_sweep = sg::sweep_tc_stream_bytes_per_sweep(e->n, e->n_tc, planes);
         size_t want = per_sweep * (size_t)p->n_sweeps;
         const size_t cap_max = (size_t)1 << 30;

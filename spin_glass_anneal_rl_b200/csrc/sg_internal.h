@@ -105,7 +105,7 @@ struct KernelTimer {
 };
 
 // K1-TC (sg_sweep_tc.cu): bf16 coupling planes and the tensor-core sweep
-cudaError_t launch_split_planes(const float* Jt, int n, int n_pad, void* Jp, int n_tc,
+cudaError_t launch_split_planes(const float* Jt, int n, int n_pad, void* Jp, int n_tc, int* used,
                                 cudaStream_t st);
 cudaError_t launch_tc_selftest(const void* Jp, int n, int n_tc, int planes, const int* sites,
                                const float* deltas, const float* fields_in, float* fields_out,

@@ -69,8 +69,10 @@ constexpr int kBopBytes = 512;
 
 // ---------------------------------------------------------------- model planes
 // Jp[p][i][j] (bf16): Jt[i][j] = sum_p Jp[p][i][j] (+ residual below 2^-24 relative for p = 3)
+// used[0] / used[1] are set when the second / third plane holds a non-zero entry: models whose
+// couplings fit fewer planes exactly (integer couplings: one) need fewer MMAs per block
 __global__ void split_planes_kernel(const float* __restrict__ Jt, int n, int n_pad,
-                                    __nv_bfloat16* __restrict__ Jp, int n_tc) {
+                                    __nv_bfloat16* __restrict__ Jp, int n_tc, int* __restrict__ used) {
     const size_t total = (size_t)n * n_tc;
     const size_t plane = total;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -85,6 +87,10 @@ __global__ void split_planes_kernel(const float* __restrict__ Jt, int n, int n_p
         Jp[idx] = hi;
         Jp[plane + idx] = mid;
         Jp[2 * plane + idx] = lo;
+        if (used) {
+            if (r1 != 0.0f) used[0] = 1;
+            if (r2 != 0.0f) used[1] = 1;
+        }
     }
 }
 
@@ -1147,6 +1153,9 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                                     : 0.0f;
                 }
                 SG_STAMP(4);
+                // (these three barrier tests on three lanes instead of one after the other: slower, 19.3
+                // instead of 20.1 G attempts/s -- the thresholds are not always there yet, and a lone
+                // polling lane notices late)
                 mbar_wait(&tabbar[slot], par);
                 mbar_wait(&thbar[slot], par);
                 const float* rawp = raw_s + slot * kBlk * NG + r;
@@ -1657,9 +1666,9 @@ tc_mma_bench_kernel(int variant_in, int n_dim, int iters, long long* out) {
 
 }  // namespace
 
-cudaError_t launch_split_planes(const float* Jt, int n, int n_pad, void* Jp, int n_tc,
+cudaError_t launch_split_planes(const float* Jt, int n, int n_pad, void* Jp, int n_tc, int* used,
                                 cudaStream_t st) {
-    split_planes_kernel<<<1184, 256, 0, st>>>(Jt, n, n_pad, static_cast<__nv_bfloat16*>(Jp), n_tc);
+    split_planes_kernel<<<1184, 256, 0, st>>>(Jt, n, n_pad, static_cast<__nv_bfloat16*>(Jp), n_tc, used);
     return cudaGetLastError();
 }
 

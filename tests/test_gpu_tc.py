@@ -409,3 +409,23 @@ def test_tc_auto_dispatch_and_errors(engine):
     engine.sweep(2, np.array([1.0]), kernel="auto")
     with pytest.raises(SGError):
         engine.sweep(2, np.array([1.0]), kernel="tc")
+
+
+def test_tc_default_plane_count_is_what_the_model_needs(engine):
+    """coupling_planes = 0 (the default): the engine uses as many bf16 planes as the couplings need
+    to be exact -- one for integer couplings (a third of the tensor-core work), three for arbitrary
+    fp32 values -- and the results equal the explicit three-plane run bit for bit."""
+    rng = np.random.default_rng(2)
+    n, R, ns = 1024, 70, 3
+    S0 = (rng.integers(0, 2, size=(R, n)) * 2 - 1).astype(np.int8)
+    Ji, hi = _int_instance(rng, n)
+    Jf, hf = _sk(n, seed=5)
+    for J, h in ((Ji, hi), (Jf, hf), (Ji * 0.5, hi)):      # integers, Gaussian floats, half-integers
+        outs = []
+        for planes in (3, 0):
+            _setup(engine, J.astype(np.float32), h, S0)
+            tr = engine.sweep(ns, np.array([1.3]), seed=8, site_order="random", energy_trace=True, kernel="tc",
+                              coupling_planes=planes).cpu().numpy()
+            outs.append((engine.spins().cpu().numpy(), tr, engine.fields().cpu().numpy()))
+        for a, b in zip(*outs):
+            assert np.array_equal(a, b)
