@@ -1156,7 +1156,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 // (these three barrier tests on three lanes instead of one after the other: slower, 19.3
                 // instead of 20.1 G attempts/s -- the thresholds are not always there yet, and a lone
                 // polling lane notices late)
-                mbar_wait(&tabbar[slot], par);
+                if (k == 0) mbar_wait(&tabbar[slot], par);   // (k > 0: waited for as the previous block's "next" table)
                 mbar_wait(&thbar[slot], par);
                 const float* rawp = raw_s + slot * kBlk * NG + r;
                 const float* thp = theta_s + slot * kBlk * NG + r;
