@@ -357,7 +357,16 @@ __host__ __device__ constexpr int tc_ndw(int C) { return (kG * C + 31) / 32; }
 __host__ __device__ constexpr int tc_ntw(int C) { return C >= 4 ? 2 : 0; }
 // threads: 4 quarter warps, producer, decision warp 0, MMA issuer (, decision warps 1..3)
 // (, threshold warps)
-__host__ __device__ constexpr int tc_threads(int C) { return 224 + 32 * (tc_ndw(C) - 1) + 32 * tc_ntw(C); }
+// Warp slots (warps are dealt to the four SM sub-partitions round robin, slot % 4): the two
+// Philox-heavy threshold warps take slots 4 and 6 + ndw (8 for clusters of 4), both on sub-partition 0,
+// and the TMA producer -- one lane, next to no instructions -- moves to the slot after them (9,
+// sub-partition 1, next to decision warp 0).  Measured alternatives: threshold warps on slots 8 and 9
+// slow decision warp 0, whose instruction stream is the critical path (16 attempts in 1.44 k clocks
+// against 1.15 k undisturbed); on slots 8 and 10 the second one slows the MMA issuer; a single
+// threshold warp cannot keep up (14.8 G attempts/s).
+__host__ __device__ constexpr int tc_threads(int C) {
+    return tc_ntw(C) ? 32 * (6 + tc_ndw(C) + 2) : 224 + 32 * (tc_ndw(C) - 1);
+}
 // quarter warps + decision warps meet at the named barriers 1..3
 __host__ __device__ constexpr int tc_sync_threads(int C) { return 128 + 32 * tc_ndw(C); }
 // tiles per ring stage: clusters of 4 hold 64 replicas' state in shared memory and have room for
@@ -1000,7 +1009,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
         SG_ISTAMP(7);
         if (tid == 0 && n_chunks > 1) red_release_gpu_add(done_g + item.g, 1);
         }  // items
-    } else if (warp == 4) {
+    } else if (warp == (NTW ? 6 + NDW + 1 : 4)) {
         // ======================================================== PRODUCER (TMA)
         if (lane == 0) {
             int stage = 0;
@@ -1039,12 +1048,12 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                 }
             }
         }
-    } else if (warp >= 6 + NDW) {
+    } else if (NTW && (warp == 4 || warp == 6 + NDW)) {
         // ======================================================== THRESHOLD WARPS
         // thresholds of block kg -> theta_s[kg % 4]: unit (qq, r) covers attempts 4qq..4qq+3 of
         // replica r (one Philox call).  They depend on nothing but the counters; the only
         // constraint is the slot's previous user, block kg-4, having been decided.
-        const int tw = warp - (6 + NDW);
+        const int tw = (warp == 4) ? 0 : 1;
         TcBlockWalk wk;
         wk.start(items, cid);
         int kg = 0;
@@ -1083,7 +1092,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
             __syncwarp();
             if (lane == 0) mbar_arrive(&thbar[slot]);
         }
-    } else if (warp == 5 || warp >= 7) {
+    } else if (warp == 5 || (warp >= 7 && warp < 6 + NDW)) {
         // ======================================================== DECISION WARPS
         // (one per 32 replicas of the group: warp 5, and warps 7.. for the replicas beyond 32)
         const int dw = (warp == 5) ? 0 : warp - 6;
