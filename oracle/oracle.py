@@ -13,6 +13,8 @@ The sweeps run in C (``sg_oracle.c``); this file restates the control flow
 around them, citing the reference lines (paths relative to
 ``/root/reference/spin_glass_rl/``):
 
+* ``wolff_sweeps*``         <- core/spin_dynamics.py:193-262 (UpdateRule.WOLFF, dense branch), pinned
+  by ``tests/golden/wolff_*.npz`` (``tests/golden/make_wolff_golden.py``)
 * ``schedule_temperature``  <- annealing/temperature_scheduler.py:69-269
 * ``anneal``                <- annealing/gpu_annealer.py:96-183, 254-269
 * ``temperature_ladder``    <- annealing/parallel_tempering.py:146-173
@@ -78,6 +80,10 @@ def lib() -> ctypes.CDLL:
                                        ctypes.c_int, ctypes.c_double, ctypes.c_uint64, ctypes.c_int,
                                        c_dp]
         L.sgo_num_threads.restype = ctypes.c_int
+        L.sgo_wolff_sweeps.restype = ctypes.c_int
+        L.sgo_wolff_sweeps.argtypes = [c_fp, ctypes.c_int64, c_fp, c_fp, ctypes.c_int, c_dp, ctypes.c_int,
+                                       c_u32p, ctypes.c_int64, c_i64p, c_i32p, c_fp, ctypes.c_int64,
+                                       c_dp, c_i64p, c_i32p, c_fp, ctypes.c_int64, c_i32p, c_i64p]
         _lib = L
     return _lib
 
@@ -193,6 +199,75 @@ def sweeps_scheduled(J, h, spins: np.ndarray, temps, rule: str, sites, uniforms)
                                _p(uniforms, ctypes.c_float), _p(energies, ctypes.c_double),
                                _p(accepted, ctypes.c_int64))
     return energies, accepted
+
+
+# --------------------------------------------------------------------------- Wolff cluster updates
+def wolff_sweeps(J, h, spins: np.ndarray, temps, stream: RawStream, trace: bool = False):
+    """n = len(temps) reference sweeps with UpdateRule.WOLFF on ONE replica, in place on ``spins``
+    (core/spin_dynamics.py:73-94 with _wolff_cluster_dense, :211-262): every sweep is n cluster
+    updates, each from a start site drawn from the stream, the uniforms of the cluster growth
+    drawn from the same stream as they are needed.
+
+    Returns (energies[n], cluster_flips[n], trace) with trace = None or a dict: ``sites``
+    [n_sweeps, n] start sites, ``uniforms`` every uniform consumed in order, ``draws``
+    [n_sweeps, n] how many each update consumed."""
+    J, h = _f32(J), _f32(h)
+    assert spins.dtype == np.float32 and spins.flags.c_contiguous
+    n = spins.shape[0]
+    temps = np.ascontiguousarray(np.asarray(temps, dtype=np.float64))
+    ns = temps.shape[0]
+    energies = np.empty(ns, dtype=np.float64)
+    flips = np.empty(ns, dtype=np.int64)
+    cap = ns * n * n * n if trace else 0   # an update draws at most one uniform per (visited, other) pair
+    cap = min(cap, stream.raw.shape[0] - stream.pos)
+    tsite = np.empty(ns * n, dtype=np.int32) if trace else None
+    tu = np.empty(max(cap, 1), dtype=np.float32) if trace else None
+    draws = np.empty(ns * n, dtype=np.int32) if trace else None
+    pos = ctypes.c_int64(stream.pos)
+    used = ctypes.c_int64(0)
+    rc = lib().sgo_wolff_sweeps(_p(J, ctypes.c_float), J.shape[1], _p(h, ctypes.c_float),
+                                _p(spins, ctypes.c_float), n, _p(temps, ctypes.c_double), ns,
+                                _p(stream.raw, ctypes.c_uint32), stream.raw.shape[0], ctypes.byref(pos),
+                                _p(None, ctypes.c_int32), _p(None, ctypes.c_float), 0,
+                                _p(energies, ctypes.c_double), _p(flips, ctypes.c_int64),
+                                _p(tsite, ctypes.c_int32), _p(tu, ctypes.c_float), cap,
+                                _p(draws, ctypes.c_int32), ctypes.byref(used))
+    if rc != 0:
+        raise RuntimeError("raw stream exhausted inside sgo_wolff_sweeps")
+    stream.pos = pos.value
+    tr = None
+    if trace:
+        tr = {"sites": tsite.reshape(ns, n), "uniforms": tu[:used.value].copy(),
+              "draws": draws.reshape(ns, n)}
+    return energies, flips, tr
+
+
+def wolff_sweeps_scheduled(J, h, spins: np.ndarray, temps, sites, uniforms):
+    """The same sweeps driven by explicit start sites [n_sweeps, n] and a list of uniforms consumed
+    in order (the form the CUDA kernel takes in injected mode).  In place on ``spins``; returns
+    (energies, cluster_flips, uniforms_used)."""
+    J, h = _f32(J), _f32(h)
+    assert spins.dtype == np.float32 and spins.flags.c_contiguous
+    n = spins.shape[0]
+    temps = np.ascontiguousarray(np.asarray(temps, dtype=np.float64))
+    ns = temps.shape[0]
+    sites = np.ascontiguousarray(np.asarray(sites, dtype=np.int32).reshape(-1))
+    uniforms = np.ascontiguousarray(np.asarray(uniforms, dtype=np.float32).reshape(-1))
+    assert sites.shape[0] == ns * n
+    energies = np.empty(ns, dtype=np.float64)
+    flips = np.empty(ns, dtype=np.int64)
+    used = ctypes.c_int64(0)
+    rc = lib().sgo_wolff_sweeps(_p(J, ctypes.c_float), J.shape[1], _p(h, ctypes.c_float),
+                                _p(spins, ctypes.c_float), n, _p(temps, ctypes.c_double), ns,
+                                _p(None, ctypes.c_uint32), 0, ctypes.cast(None, ctypes.POINTER(ctypes.c_int64)),
+                                _p(sites, ctypes.c_int32), _p(uniforms, ctypes.c_float),
+                                uniforms.shape[0], _p(energies, ctypes.c_double),
+                                _p(flips, ctypes.c_int64), _p(None, ctypes.c_int32),
+                                _p(None, ctypes.c_float), 0, _p(None, ctypes.c_int32),
+                                ctypes.byref(used))
+    if rc != 0:
+        raise RuntimeError("uniform list exhausted inside sgo_wolff_sweeps")
+    return energies, flips, int(used.value)
 
 
 # --------------------------------------------------------------------------- operator API
@@ -371,13 +446,21 @@ def anneal(J, h, spins0, *, n_sweeps: int, T0: float, Tf: float, schedule: str =
         else:
             T = schedule_temperature(schedule, sweep, T0, Tf, n_sweeps, **sp)
         T = max(float(T), 1e-10)  # set_temperature clamp, core/spin_dynamics.py:57-59
-        es, acc, ts, tu = sweeps(J, h, spins, [T], rule, stream, trace=trace)
-        if trace:
-            tr_T.append(T)
-            tr_site.append(ts)
-            tr_u.append(tu)
-        n_acc += int(acc[0])
-        n_rej += spins.shape[0] - int(acc[0])
+        if rule == "wolff":   # every cluster site counts as accepted, nothing is ever rejected
+            es, acc, wtr = wolff_sweeps(J, h, spins, [T], stream, trace=trace)
+            if trace:
+                tr_T.append(T)
+                tr_site.append(wtr["sites"][0])
+                tr_u.append(wtr["uniforms"])
+            n_acc += int(acc[0])
+        else:
+            es, acc, ts, tu = sweeps(J, h, spins, [T], rule, stream, trace=trace)
+            if trace:
+                tr_T.append(T)
+                tr_site.append(ts)
+                tr_u.append(tu)
+            n_acc += int(acc[0])
+            n_rej += spins.shape[0] - int(acc[0])
         cur = float(es[0])
         sweep_energies.append(cur)
         if cur < best_e:  # :151-153
@@ -392,7 +475,9 @@ def anneal(J, h, spins0, *, n_sweeps: int, T0: float, Tf: float, schedule: str =
                        stream.pos - start_pos)
     if trace:
         res.extra = {"temps": np.array(tr_T, np.float64), "sites": np.stack(tr_site),
-                     "uniforms": np.stack(tr_u)}
+                     "uniforms": np.concatenate(tr_u) if rule == "wolff" else np.stack(tr_u)}
+        if rule == "wolff":   # the uniforms of sweep s are uniforms[offsets[s]:offsets[s + 1]]
+            res.extra["uniform_offsets"] = np.concatenate([[0], np.cumsum([len(u) for u in tr_u])])
     return res
 
 

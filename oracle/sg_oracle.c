@@ -36,6 +36,7 @@
 #define SGO_RULE_METROPOLIS 0
 #define SGO_RULE_GLAUBER 1
 #define SGO_RULE_HEAT_BATH 2
+/* UpdateRule.WOLFF has its own entry point (sgo_wolff_sweeps) */
 
 typedef struct {
     const uint32_t *raw; /* raw mt19937 outputs                           */
@@ -235,6 +236,123 @@ int sgo_sweeps_scheduled(const float *J, int64_t ld, const float *h, float *spin
     }
     free(scratch);
     return 0;
+}
+
+/*
+ * Wolff cluster updates -- core/spin_dynamics.py:193-262 (_wolff_update -> _wolff_cluster_dense;
+ * the dense branch is the one a dense model takes, :206-209).
+ *
+ * One update: breadth-first growth from `start` (:218-243).  The queue is FIFO (queue.pop(0)), the
+ * neighbours of the dequeued site are visited in index order, a neighbour already in the cluster
+ * is skipped WITHOUT a draw, and a uniform is drawn only for a neighbour with coupling < 0 whose
+ * spin equals the dequeued site's (:234-239):
+ *     prob_add = 1.0 - torch.exp(torch.tensor(2.0 * coupling / T))      float32 tensor arithmetic
+ *     torch.rand(1).item() < prob_add
+ * coupling = couplings[current, neighbour] (row of the dequeued site; J need not be symmetric).
+ * The spins tested are the clone taken before the cluster is flipped (:216).  Then every cluster
+ * site is flipped (:246-247) and n_accepted grows by the cluster size (:254); the update never
+ * counts as rejected.  External fields play no role in the move.  The two compute_energy() calls
+ * around it (:213, :250) only feed the returned delta, which sweep() ignores.
+ *
+ * The uniforms come either from the raw mt19937 stream (src->st) or, for replays, from an explicit
+ * list consumed in order (src->u_in); every uniform consumed can be logged (src->u_out).
+ */
+typedef struct {
+    sgo_stream *st;
+    const float *u_in;
+    int64_t u_len, u_pos;
+    float *u_out;
+    int64_t u_cap, u_cnt;
+    int overrun;
+} sgo_usource;
+
+static inline float sgo_usource_next(sgo_usource *s) {
+    float u;
+    if (s->st) {
+        u = sgo_rand(s->st);
+    } else if (s->u_pos < s->u_len) {
+        u = s->u_in[s->u_pos++];
+    } else {
+        s->overrun = 1;
+        u = 1.0f;
+    }
+    if (s->u_out) {
+        if (s->u_cnt < s->u_cap) s->u_out[s->u_cnt] = u;
+        else s->overrun = 1;
+    }
+    s->u_cnt++;
+    return u;
+}
+
+static int sgo_wolff_cluster(const float *J, int64_t ld, float *spins, int n, int start, double T,
+                             sgo_usource *src, int32_t *queue, uint8_t *in_cluster) {
+    memset(in_cluster, 0, (size_t)n);
+    int head = 0, tail = 0;
+    queue[tail++] = start;
+    in_cluster[start] = 1;
+    while (head < tail) {
+        const int cur = queue[head++];
+        const float cs = spins[cur];
+        const float *row = J + (int64_t)cur * ld;
+        for (int nb = 0; nb < n; ++nb) {
+            if (nb == cur || in_cluster[nb]) continue;
+            const float c = row[nb];
+            if (c < 0.0f && cs == spins[nb]) {
+                const float p = 1.0f - expf((float)(2.0 * (double)c / T));
+                const float u = sgo_usource_next(src);
+                if (u < p) {
+                    in_cluster[nb] = 1;
+                    queue[tail++] = nb;
+                }
+            }
+        }
+    }
+    for (int k = 0; k < tail; ++k) spins[queue[k]] = -spins[queue[k]];
+    return tail;
+}
+
+/*
+ * SpinDynamics.sweep() x n_sweeps with UpdateRule.WOLFF for ONE replica (core/spin_dynamics.py:73-94:
+ * n updates per sweep, each from a start site drawn with torch.randint, then compute_energy()).
+ *   raw != NULL : start sites and uniforms from the raw mt19937 stream (the reference's own order:
+ *                 one randint, then the cluster's uniforms); trace_site / trace_u / draws_per_update
+ *                 optionally record them for a replay
+ *   raw == NULL : start sites from sites[n_sweeps * n], uniforms from uniforms[0 .. n_uniforms) in
+ *                 consumption order (what the CUDA kernel takes in injected mode)
+ * accepted[s] = sum of the cluster sizes of sweep s; *uniforms_used = uniforms consumed.
+ * Returns 0, or -1 if a stream ran dry / a trace buffer was too small.
+ */
+int sgo_wolff_sweeps(const float *J, int64_t ld, const float *h, float *spins, int n,
+                     const double *temps, int n_sweeps, const uint32_t *raw, int64_t raw_len,
+                     int64_t *raw_pos, const int32_t *sites, const float *uniforms,
+                     int64_t n_uniforms, double *energies, int64_t *accepted, int32_t *trace_site,
+                     float *trace_u, int64_t trace_u_cap, int32_t *draws_per_update,
+                     int64_t *uniforms_used) {
+    sgo_stream st = {raw, raw_len, raw_pos ? *raw_pos : 0, 0};
+    sgo_usource src = {raw ? &st : NULL, uniforms, n_uniforms, 0, trace_u, trace_u_cap, 0, 0};
+    float *scratch = (float *)malloc(sizeof(float) * (size_t)n);
+    int32_t *queue = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
+    uint8_t *in_cluster = (uint8_t *)malloc((size_t)n);
+    for (int sw = 0; sw < n_sweeps; ++sw) {
+        const double T = temps[sw];
+        int64_t acc = 0;
+        for (int k = 0; k < n; ++k) {
+            const int64_t idx = (int64_t)sw * n + k;
+            const int start = raw ? sgo_randint(&st, n) : sites[idx];
+            const int64_t before = src.u_cnt;
+            acc += sgo_wolff_cluster(J, ld, spins, n, start, T, &src, queue, in_cluster);
+            if (trace_site) trace_site[idx] = start;
+            if (draws_per_update) draws_per_update[idx] = (int32_t)(src.u_cnt - before);
+        }
+        if (energies) energies[sw] = sgo_energy(J, ld, h, spins, n, scratch);
+        if (accepted) accepted[sw] = acc;
+    }
+    free(scratch);
+    free(queue);
+    free(in_cluster);
+    if (raw_pos) *raw_pos = st.pos;
+    if (uniforms_used) *uniforms_used = src.u_cnt;
+    return (st.overrun || src.overrun) ? -1 : 0;
 }
 
 /* Batched energies / local fields, one row per configuration:

@@ -53,6 +53,40 @@ def test_anneal_matches_reference(oracle, name):
     assert (-1 if conv is None else conv) == int(g["convergence_sweep"])
 
 
+@pytest.mark.parametrize("name", golden_names("wolff_"))
+def test_wolff_anneal_matches_reference(oracle, name):
+    """UpdateRule.WOLFF (core/spin_dynamics.py:193-262) through GPUAnnealer.anneal: same raw-stream
+    consumption (= same cluster growth decisions), spins, energies and acceptance bookkeeping."""
+    g = load_golden(name)
+    c = g["config"]
+    assert c["rule"] == "wolff"
+    stream = oracle.RawStream(oracle.mt_raw_stream(c["seed"], int(g["raw_consumed"]) + 4096))
+    res = oracle.anneal(g["J"], g["h"], g["spins0"], n_sweeps=c["n_sweeps"], T0=c["T0"],
+                        Tf=c["Tf"], schedule=c["schedule"], schedule_params=c["params"],
+                        record_interval=c["record_interval"], energy_tolerance=c["tol"],
+                        rule="wolff", stream=stream, trace=True)
+    exact = _is_integer(g)
+    assert res.raw_consumed == int(g["raw_consumed"])
+    assert res.n_sweeps == int(g["n_sweeps_done"])
+    assert np.array_equal(res.final_spins.astype(np.int8), g["final_spins"])
+    assert np.array_equal(res.best_configuration.astype(np.int8), g["best_configuration"])
+    _close(res.best_energy, g["best_energy"], exact)
+    _close(res.energy_history, g["energy_history"], exact)
+    _close(res.acceptance_rate_history, g["acceptance_rate_history"], True)
+    assert np.allclose(res.temperature_history, g["temperature_history"], rtol=1e-15, atol=0)
+    # the stream model: first start site and the first uniforms the reference drew
+    assert res.extra["sites"][0, 0] == g["head_sites"][0]
+    m = min(len(res.extra["uniforms"]), len(g["head_uniforms"]))
+    assert m > 0 and np.array_equal(res.extra["uniforms"][:m], g["head_uniforms"][:m])
+    # the scheduled form (what the CUDA kernel is fed) walks the same trajectory
+    spins = g["spins0"].astype(np.float32).copy()
+    es, flips, used = oracle.wolff_sweeps_scheduled(g["J"], g["h"], spins, res.extra["temps"],
+                                                    res.extra["sites"], res.extra["uniforms"])
+    assert used == len(res.extra["uniforms"])
+    assert np.array_equal(spins, res.final_spins)
+    assert np.array_equal(es, np.array(res.sweep_energies))
+
+
 @pytest.mark.parametrize("name", ["sa_pm1_n48", "sa_cfg1_float_n100", "sa_glauber_int_n32"])
 def test_stream_model_head(oracle, name):
     """The first recorded (site, uniform) draws equal the raw-stream model."""
