@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 4
+#define SG_ABI_VERSION 5
 
 typedef enum {
     SG_OK = 0,
@@ -41,10 +41,12 @@ typedef enum {
     SG_ERR_UNSUPPORTED = -4
 } sg_status;
 
-/* update rules: core/spin_dynamics.py:11-16 (UpdateRule; WOLFF is out of scope) */
+/* update rules: core/spin_dynamics.py:11-16 (UpdateRule) */
 #define SG_RULE_METROPOLIS 0 /* _metropolis_update  core/spin_dynamics.py:131-152 */
 #define SG_RULE_GLAUBER 1    /* _glauber_update     core/spin_dynamics.py:154-170 */
 #define SG_RULE_HEAT_BATH 2  /* _heat_bath_update   core/spin_dynamics.py:172-191 */
+#define SG_RULE_WOLFF 3      /* _wolff_update       core/spin_dynamics.py:193-262; a cluster move with
+                                its own entry point, sg_sweep_wolff (sg_sweep rejects it)        */
 
 /* where the acceptance randomness comes from */
 #define SG_RNG_PHILOX 0   /* in-kernel Philox4x32-10 counter RNG (production)          */
@@ -230,6 +232,48 @@ typedef struct {
  * (annealing/parallel_tempering.py:191-203) and the never-launched
  * CUDAKernelManager.metropolis_update_optimized (annealing/cuda_kernels.py:228-282). */
 int sg_sweep(sg_engine *e, const sg_sweep_params *p, void *stream);
+
+typedef struct {
+    uint32_t struct_size; /* = sizeof(sg_wolff_params)                                           */
+    int32_t n_sweeps;     /* one sweep = n cluster updates per replica (SpinDynamics.sweep)       */
+    int32_t rng_mode;     /* SG_RNG_*                                                             */
+    int32_t site_mode;    /* start sites: SG_SITES_SEQUENTIAL / _RANDOM (one list for all replicas)
+                             / _EXPLICIT                                                          */
+    /* temperature of replica r in sweep s, addressed like the temps of sg_sweep_params;
+     * NULL = the ladder temperatures */
+    const double *temps;
+    int64_t temps_sweep_stride;
+    int64_t temps_replica_stride;
+    uint64_t seed;        /* Philox key                                                           */
+    uint64_t sweep_base;  /* absolute index of the first sweep (Philox counter)                   */
+    /* SG_SITES_EXPLICIT: start site of update k of sweep s for replica r =
+     * sites[r*sites_replica_stride + s*sites_sweep_stride + k]   (dev, int32) */
+    const int32_t *sites;
+    int64_t sites_replica_stride;
+    int64_t sites_sweep_stride;
+    /* SG_RNG_INJECTED: replica r consumes uniforms[r*uniforms_replica_stride + c], c = cursor[r],
+     * cursor[r]+1, ... in the order the reference draws them (one per candidate neighbour: not in
+     * the cluster, coupling < 0, same spin -- walked in index order per dequeued site); at most
+     * uniforms_per_replica each (SG_ERR_INVALID when a replica needs more; the call then
+     * synchronises).  cursor (dev int64 [R], in/out) carries the position across calls. */
+    const float *uniforms;
+    int64_t uniforms_replica_stride;
+    int64_t uniforms_per_replica;
+    int64_t *cursor;
+    float *energy_trace;  /* optional dev out [n_sweeps][R]: exact energy after every sweep       */
+    int32_t track_best;   /* compare-and-keep best energy/configuration after every sweep         */
+    int32_t replica_base; /* global id of this engine's replica 0 (Philox key)                    */
+} sg_wolff_params;
+
+/* Sweeps of the reference's cluster move, UpdateRule.WOLFF: SpinDynamics.sweep() calling
+ * _wolff_update -> _wolff_cluster_dense (core/spin_dynamics.py:73-94, 193-262) n times per sweep,
+ * for all replicas (one thread block each, sg_wolff.cu).  Per update: breadth-first growth from
+ * the start site over the ROW of every dequeued site, a neighbour joins with probability
+ * 1 - exp(2 J / T) if its coupling is negative and its spin equal; the cluster is flipped; the
+ * acceptance counter grows by the cluster size (nothing is ever rejected, so the reference's
+ * acceptance rate is 1).  External fields do not enter the move.  After every sweep local fields
+ * and energies are recomputed exactly (as sg_refresh_fields does).  Dense single models only. */
+int sg_sweep_wolff(sg_engine *e, const sg_wolff_params *p, void *stream);
 
 /* Parallel tempering ladder: R replicas = n_ladders x n_rungs; rung 0 is the hottest
  * (ParallelTempering._generate_temperature_ladder, annealing/parallel_tempering.py:146-173).

@@ -16,12 +16,12 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SG_B200_LIB") or os.path.join(_PKG, "libsg_b200.so")   # (override: A/B builds)
 CSRC = os.path.join(_PKG, "csrc")
 
-SG_RULE = {"metropolis": 0, "glauber": 1, "heat_bath": 2}
+SG_RULE = {"metropolis": 0, "glauber": 1, "heat_bath": 2, "wolff": 3}
 SG_RNG_PHILOX, SG_RNG_INJECTED = 0, 1
 SG_SITES = {"sequential": 0, "random": 1, "explicit": 2, "random_per_block": 3, "checkerboard": 4}
 SG_KERNEL = {"auto": 0, "simt": 1, "tc": 2, "small": 3}
 SG_EXCHANGE = {"nearest_neighbor": 0, "all_pairs": 1}
-SG_ABI_VERSION = 4
+SG_ABI_VERSION = 5
 
 
 class SweepParams(Structure):
@@ -34,6 +34,18 @@ class SweepParams(Structure):
         ("uniforms", c_void_p), ("energy_trace", c_void_p),
         ("track_best", c_int32), ("kernel", c_int32), ("coupling_planes", c_int32),
         ("replica_base", c_int32), ("site_energy_changes", c_void_p),
+    ]
+
+
+class WolffParams(Structure):
+    _fields_ = [
+        ("struct_size", c_uint32), ("n_sweeps", c_int32), ("rng_mode", c_int32), ("site_mode", c_int32),
+        ("temps", c_void_p), ("temps_sweep_stride", c_int64), ("temps_replica_stride", c_int64),
+        ("seed", c_uint64), ("sweep_base", c_uint64),
+        ("sites", c_void_p), ("sites_replica_stride", c_int64), ("sites_sweep_stride", c_int64),
+        ("uniforms", c_void_p), ("uniforms_replica_stride", c_int64), ("uniforms_per_replica", c_int64),
+        ("cursor", c_void_p), ("energy_trace", c_void_p),
+        ("track_best", c_int32), ("replica_base", c_int32),
     ]
 
 
@@ -79,6 +91,7 @@ PROTOTYPES = {
     "sg_reset_best": (c_int, [c_void_p, c_void_p]),
     "sg_get_best": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "sg_sweep": (c_int, [c_void_p, POINTER(SweepParams), c_void_p]),
+    "sg_sweep_wolff": (c_int, [c_void_p, POINTER(WolffParams), c_void_p]),
     "sg_set_ladder": (c_int, [c_void_p, c_int, POINTER(c_double), c_void_p]),
     "sg_set_ladder_sharded": (c_int, [c_void_p, c_int, POINTER(c_double), c_int, c_int, c_void_p]),
     "sg_exchange": (c_int, [c_void_p, POINTER(ExchangeParams), c_void_p]),

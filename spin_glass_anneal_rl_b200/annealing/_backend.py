@@ -18,7 +18,7 @@ from ..utils.exceptions import DeviceError
 # sequential-FMA kernel (register-resident fields); beyond, the model goes to the sparse (CSR) kernel.
 DENSE_LIMIT = 7168
 
-RULE_NAMES = {"metropolis": "metropolis", "glauber": "glauber", "heat_bath": "heat_bath"}
+RULE_NAMES = {"metropolis": "metropolis", "glauber": "glauber", "heat_bath": "heat_bath", "wolff": "wolff"}
 
 
 def rule_name(update_rule) -> str:
@@ -26,8 +26,17 @@ def rule_name(update_rule) -> str:
     if name not in RULE_NAMES:
         raise NotImplementedError(
             f"update rule {name!r} is not available on the B200 sweep path "
-            "(Metropolis, Glauber and heat bath are; Wolff cluster updates are out of scope)")
+            "(Metropolis, Glauber, heat bath and Wolff are)")
     return name
+
+
+def require_dense_for_wolff(eng) -> None:
+    """The cluster move reads coupling rows of a dense model (the reference's sparse branch,
+    core/spin_dynamics.py:264-323, walks the COO entries and is not mirrored)."""
+    if getattr(eng, "kind", "dense") != "dense":
+        raise NotImplementedError(
+            f"UpdateRule.WOLFF needs a dense model (n <= {DENSE_LIMIT}); this model runs on the "
+            f"{eng.kind} kernel")
 
 
 class _Signature:

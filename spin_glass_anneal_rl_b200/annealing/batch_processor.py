@@ -169,6 +169,9 @@ class BatchProcessor:
         temp_hist = [cfg.initial_temp]
         acc_hist = [[0.0] for _ in range(M)]
         rule = rule_name(update_rule)
+        if rule == "wolff":
+            raise NotImplementedError("stacked small models run the single-spin rules; anneal a model with "
+                                      "UpdateRule.WOLFF through GPUAnnealer")
         done = 0
         while done < cfg.n_sweeps:
             last = done if done % interval == 0 else min(cfg.n_sweeps - 1, (done // interval + 1) * interval)

@@ -30,7 +30,8 @@ import numpy as np
 import torch
 
 from ..core.spin_dynamics import UpdateRule
-from ._backend import as_pm1_float, engine_for, mix_seed, random_spins, rule_name, site_order_for
+from ._backend import (as_pm1_float, engine_for, mix_seed, random_spins, require_dense_for_wolff, rule_name,
+                       site_order_for)
 from .result import AnnealingResult
 from .temperature_scheduler import ScheduleType, TemperatureScheduler
 
@@ -60,7 +61,9 @@ class GPUAnnealerConfig:
     # "philox": in-kernel counter RNG (production).  "replay": the (site, uniform) of every attempt
     # is injected from a recorded stream of the reference -- ``replay`` = {"sites": int [n_sweeps,
     # n], "uniforms": float32 [n_sweeps, n] (or [n_replicas, n_sweeps, n])}; anneal() then follows
-    # the reference's trajectory (bit for bit on integer couplings)
+    # the reference's trajectory (bit for bit on integer couplings).  For UpdateRule.WOLFF "sites"
+    # are the start sites of the n cluster updates of every sweep and "uniforms" is the flat list
+    # of the uniforms the run consumes, in order ([m], or [n_replicas, m])
     rng_mode: str = "philox"
     replay: Optional[Dict] = None
     kernel: str = "auto"             # "auto" | "simt" | "tc" | "small" (SG_KERNEL_*)
@@ -105,6 +108,9 @@ class GPUAnnealer:
         start = time.time()
         rule = rule_name(update_rule)
         eng = engine_for(model, cfg.device_index)
+        wolff = rule == "wolff"
+        if wolff:
+            require_dense_for_wolff(eng)
         n, R = model.n_spins, max(1, int(cfg.n_replicas))
         seed = cfg.random_seed if cfg.random_seed is not None else int(torch.initial_seed() & 0x7FFFFFFF)
         self._launch_seed += 1
@@ -125,6 +131,18 @@ class GPUAnnealer:
                 raise ValueError("rng_mode='replay' needs replay={'sites': ..., 'uniforms': ...}")
             replay_sites = torch.as_tensor(np.asarray(cfg.replay["sites"]), dtype=torch.int32,
                                            device=eng.device).reshape(-1, n)
+        wolff_cursor = None
+        if cfg.rng_mode == "replay" and wolff:
+            replay_uni = torch.as_tensor(np.asarray(cfg.replay["uniforms"], np.float32), dtype=torch.float32,
+                                         device=eng.device)
+            replay_uni = replay_uni.reshape(1, -1) if replay_uni.dim() == 1 else replay_uni
+            if replay_uni.shape[0] == 1 and R > 1:
+                replay_uni = replay_uni.expand(R, -1)
+            if replay_uni.shape[0] != R:
+                raise ValueError("replay stream: need uniforms [m] or [n_replicas, m] for UpdateRule.WOLFF")
+            replay_uni = replay_uni.contiguous()
+            wolff_cursor = torch.zeros(R, dtype=torch.int64, device=eng.device)
+        elif cfg.rng_mode == "replay":
             replay_uni = torch.as_tensor(np.nan_to_num(np.asarray(cfg.replay["uniforms"], np.float32), nan=0.5),
                                          dtype=torch.float32, device=eng.device)
             replay_uni = replay_uni.reshape(-1, replay_sites.shape[0], n)
@@ -135,6 +153,12 @@ class GPUAnnealer:
 
         def launch(k, temps, first):
             """k sweeps starting at absolute sweep `first`."""
+            if wolff:   # cluster updates: exact energies after every sweep, no kernel options
+                common = dict(temps_sweep_stride=1, sweep_base=first, energy_trace=True, track_best=True)
+                if replay_sites is not None:
+                    return eng.sweep_wolff(k, temps, sites=replay_sites[first:first + k].contiguous(),
+                                           uniforms=replay_uni, cursor=wolff_cursor, **common)
+                return eng.sweep_wolff(k, temps, site_order=cfg.site_order, seed=philox_seed, **common)
             common = dict(temps_sweep_stride=1, rule=rule, sweep_base=first, energy_trace=True,
                           track_best=True, kernel=cfg.kernel, coupling_planes=planes)
             if replay_sites is not None:
@@ -168,10 +192,17 @@ class GPUAnnealer:
             temps_all = np.maximum(schedule.precompute(cfg.n_sweeps), 1e-10)
             schedule.temperature_history.extend(temps_all.tolist())
 
+        def acceptance_rate(done):
+            """cumulative n_accepted / (n_accepted + n_rejected) of replica 0, as the reference counts"""
+            acc = eng.accepted()[0].item() - acc_base
+            if wolff:   # every cluster site counts as accepted, nothing as rejected (:254)
+                return 1.0 if acc > 0 else 0.0
+            return acc / (done * n) if done else 0.0
+
         sweep = 0
         done = 0  # sweeps executed
         stopped = False
-        if temps_all is None and not os.environ.get("SG_ADAPTIVE_HOST"):
+        if temps_all is None and not wolff and not os.environ.get("SG_ADAPTIVE_HOST"):
             # ADAPTIVE on the device: the geometric base schedule is precomputed, the feedback
             # step (running acceptance rate of replica 0 -> temperature of the next sweep) is a
             # one-thread kernel between two sweep launches, so the host only synchronises at the
@@ -208,9 +239,7 @@ class GPUAnnealer:
                 last = done if done % interval == 0 else min(cfg.n_sweeps - 1, (done // interval + 1) * interval)
                 chunk_t = temps_all[done:last + 1]
             else:  # ADAPTIVE: one sweep at a time, fed with the cumulative acceptance rate
-                attempts = done * n
-                rate = (eng.accepted()[0].item() - acc_base) / attempts if attempts else 0.0
-                chunk_t = np.array([max(schedule.update(done, acceptance_rate=rate), 1e-10)])
+                chunk_t = np.array([max(schedule.update(done, acceptance_rate=acceptance_rate(done)), 1e-10)])
                 last = done
             k = len(chunk_t)
             trace = launch(k, chunk_t, done)
@@ -221,10 +250,9 @@ class GPUAnnealer:
             sweep = last
             if sweep % interval == 0:
                 cur_e = float(eng.energies()[0].item())   # exact: fields were just refreshed
-                acc = eng.accepted()[0].item() - acc_base
                 energy_history.append(cur_e)
                 temperature_history.append(float(chunk_t[-1]))
-                acceptance_rate_history.append(acc / (done * n))
+                acceptance_rate_history.append(acceptance_rate(done))
                 if self._check_convergence(energy_history):
                     print(f"Converged at sweep {sweep}")
                     stopped = True

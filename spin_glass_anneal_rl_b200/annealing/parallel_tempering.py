@@ -34,7 +34,8 @@ import numpy as np
 import torch
 
 from ..core.spin_dynamics import UpdateRule
-from ._backend import as_pm1_float, engine_for, mix_seed, random_spins, rule_name, site_order_for
+from ._backend import (as_pm1_float, engine_for, mix_seed, random_spins, require_dense_for_wolff, rule_name,
+                       site_order_for)
 from .result import AnnealingResult
 
 
@@ -116,6 +117,11 @@ class ParallelTempering:
             raise ValueError(f"Unknown rng_mode: {c.rng_mode}")
         rule = rule_name(update_rule)
         eng = engine_for(model, c.device_index)
+        if rule == "wolff":
+            require_dense_for_wolff(eng)
+            if c.rng_mode == "replay":
+                raise NotImplementedError("rng_mode='replay' of parallel tempering covers the single-spin rules; "
+                                          "replay UpdateRule.WOLFF through GPUAnnealer / Engine.sweep_wolff")
         n, K, L = model.n_spins, c.n_replicas, max(1, int(c.n_ladders))
         Rg = K * L                               # replicas over all ranks
         sh = c.shard
@@ -237,6 +243,8 @@ class ParallelTempering:
             rung_acc = sum_over_ranks(rung_acc)
         # acceptance rate per TEMPERATURE (the reference's dynamics[k] stays with slot k, :137)
         rates = (rung_acc.double() / float(c.n_sweeps * n * L)).cpu().tolist()
+        if rule == "wolff":   # cluster sites all count as accepted, nothing as rejected (:254)
+            rates = [1.0 if r > 0 else 0.0 for r in rates]
         self._final_spins = eng.spins()
         self._rung_replica = rep_at.cpu().numpy()
         if replay is not None:

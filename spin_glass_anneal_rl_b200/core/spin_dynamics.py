@@ -5,7 +5,8 @@
 ``set_temperature``, ``get_acceptance_rate``, ``n_accepted/n_rejected``,
 ``energy_history``, ``run_dynamics``; :19-152, :325-359) but every sweep is one launch of
 the CUDA sweep kernel on one replica; the per-attempt Python loop of the reference
-(:73-94) does not exist here.  WOLFF is declared for API compatibility and rejected.
+(:73-94) does not exist here.  WOLFF (:193-262) runs the cluster kernel (csrc/sg_wolff.cu):
+n cluster updates per sweep, every cluster site counted as accepted, nothing as rejected.
 """
 from __future__ import annotations
 
@@ -44,8 +45,11 @@ class SpinDynamics:
 
     def sweep(self, n_sweeps: int = 1) -> float:
         """``n_sweeps`` Monte Carlo sweeps (n attempts each) on the GPU; returns the energy."""
-        from ..annealing._backend import engine_for, rule_name
+        from ..annealing._backend import engine_for, require_dense_for_wolff, rule_name
         eng = engine_for(self.model)
+        wolff = self.update_rule == UpdateRule.WOLFF
+        if wolff:
+            require_dense_for_wolff(eng)
         n = self.model.n_spins
         eng.alloc_replicas(1) if eng.n_replicas != 1 else None
         eng.set_spins(self.model.spins.reshape(1, n))
@@ -60,7 +64,7 @@ class SpinDynamics:
         self.model.spins = spins.to(self.model.device)
         self.model._invalidate_cache()
         self.n_accepted += acc
-        self.n_rejected += n_sweeps * n - acc
+        self.n_rejected += 0 if wolff else n_sweeps * n - acc
         energies = trace[:, 0].cpu().tolist()
         self.energy_history.extend(energies)
         self.magnetization_history.append(float(spins.sum().item()))

@@ -131,6 +131,9 @@ struct sg_engine {
     int planes_needed = 0;               // 0 = not read back yet
     unsigned char* best_out = nullptr;   // device: float energy, int replica, int8 spins[n]
     size_t best_out_cap = 0;
+    // Wolff cluster move: row-major copy of the couplings (built on first use), stream-dry flag
+    float* Jrow = nullptr;
+    int* wolff_status = nullptr;
 };
 
 namespace {
@@ -879,6 +882,8 @@ void sg_destroy(sg_engine* e) {
     cudaFree(e->up_stage[0]);
     cudaFree(e->up_stage[1]);
     cudaFree(e->best_out);
+    cudaFree(e->Jrow);
+    cudaFree(e->wolff_status);
     cudaFree(e->plane_flags);
     cudaFree(e->dig);
     cudaFree(e->scale);
@@ -924,6 +929,8 @@ int sg_set_model_dense(sg_engine* e, int n, const float* J, int64_t ldJ, const f
     e->stacked = false;
     e->n = n;
     e->n_pad = n_pad;
+    cudaFree(e->Jrow);
+    e->Jrow = nullptr;
     int rc;
     if ((rc = dev_alloc(&e->Jt, (size_t)n * n_pad)) != SG_OK) return rc;
     if ((rc = dev_alloc(&e->h, (size_t)n_pad)) != SG_OK) return rc;
@@ -1382,6 +1389,7 @@ int sg_sweep(sg_engine* e, const sg_sweep_params* p, void* stream) {
     SG_REQUIRE(p->struct_size == sizeof(sg_sweep_params), "sg_sweep: struct_size mismatch");
     SG_REQUIRE(e->R > 0 && e->fields_valid, "sg_sweep: call sg_init_fields first");
     SG_REQUIRE(p->n_sweeps >= 0, "sg_sweep: n_sweeps < 0");
+    SG_REQUIRE(p->rule != SG_RULE_WOLFF, "sg_sweep: the Wolff cluster move has its own entry point, sg_sweep_wolff");
     SG_REQUIRE(p->rule >= 0 && p->rule <= 2, "sg_sweep: unknown rule");
     SG_REQUIRE(p->rng_mode == SG_RNG_PHILOX || p->rng_mode == SG_RNG_INJECTED,
                "sg_sweep: unknown rng_mode");
@@ -1555,6 +1563,112 @@ int sg_sweep(sg_engine* e, const sg_sweep_params* p, void* stream) {
     SG_CUDA(sg::launch_sweep(a, inject, grid, static_cast<cudaStream_t>(stream)));
     if (e->profiling) e->timer.end(static_cast<cudaStream_t>(stream));
     e->launches++;
+    return SG_OK;
+}
+
+int sg_sweep_wolff(sg_engine* e, const sg_wolff_params* p, void* stream) {
+    SG_REQUIRE(e && p, "sg_sweep_wolff: NULL argument");
+    SG_REQUIRE(p->struct_size == sizeof(sg_wolff_params), "sg_sweep_wolff: struct_size mismatch");
+    if (e->csr || e->lat || e->stacked || !e->Jt)
+        return fail(SG_ERR_UNSUPPORTED, "sg_sweep_wolff: the cluster move takes one dense model (sg_set_model_dense)");
+    SG_REQUIRE(e->R > 0 && e->fields_valid, "sg_sweep_wolff: call sg_init_fields first");
+    SG_REQUIRE(p->n_sweeps >= 0, "sg_sweep_wolff: n_sweeps < 0");
+    SG_REQUIRE(p->rng_mode == SG_RNG_PHILOX || p->rng_mode == SG_RNG_INJECTED, "sg_sweep_wolff: unknown rng_mode");
+    SG_REQUIRE(p->site_mode == SG_SITES_SEQUENTIAL || p->site_mode == SG_SITES_RANDOM ||
+                   p->site_mode == SG_SITES_EXPLICIT,
+               "sg_sweep_wolff: site_mode must be SEQUENTIAL, RANDOM or EXPLICIT");
+    SG_REQUIRE(p->site_mode != SG_SITES_EXPLICIT || p->sites, "sg_sweep_wolff: explicit sites missing");
+    const bool inject = p->rng_mode == SG_RNG_INJECTED;
+    SG_REQUIRE(!inject || (p->uniforms && p->cursor && p->uniforms_per_replica >= 0),
+               "sg_sweep_wolff: injected mode needs uniforms, cursor and uniforms_per_replica");
+    SG_REQUIRE(p->temps || e->rep_temp, "sg_sweep_wolff: no temperatures (pass temps or set a ladder)");
+    SG_REQUIRE(p->replica_base >= 0, "sg_sweep_wolff: replica_base must be >= 0");
+    if (p->n_sweeps == 0) return SG_OK;
+    SG_REQUIRE((long long)p->n_sweeps * e->n < (1LL << 31) - 64,
+               "sg_sweep_wolff: n_sweeps * n must stay below 2^31 per call");
+    DeviceGuard g(e->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc;
+    if (!e->Jrow) {   // Jt[i][j] = J[j][i]; the growth reads rows of J
+        if ((rc = dev_alloc(&e->Jrow, (size_t)e->n * e->n_pad)) != SG_OK) return rc;
+        SG_CUDA(sg::launch_pad_transpose(e->Jt, e->n_pad, e->n, e->Jrow, e->n_pad, st));
+        e->launches++;
+    }
+    if (!e->wolff_status) {
+        if ((rc = dev_alloc(&e->wolff_status, (size_t)1)) != SG_OK) return rc;
+    }
+    if (inject) SG_CUDA(cudaMemsetAsync(e->wolff_status, 0, sizeof(int), st));
+    sg::WolffDev a{};
+    a.Jrow = e->Jrow;
+    a.spins = e->spins;
+    a.accepted = e->accepted;
+    if (p->temps) {
+        a.temps = p->temps;
+        a.t_ss = p->temps_sweep_stride;
+        a.t_rs = p->temps_replica_stride;
+    } else {
+        a.temps = e->rep_temp;
+        a.t_ss = 0;
+        a.t_rs = 1;
+    }
+    if (p->site_mode == SG_SITES_EXPLICIT) {
+        a.sites = p->sites;
+        a.s_rs = p->sites_replica_stride;
+        a.s_ss = p->sites_sweep_stride;
+    } else {   // one list per sweep for all replicas, from the same Philox stream as the other kernels
+        const size_t need = sg::csr_sites_bytes(e->n, p->n_sweeps);
+        if (need > e->c_sites_cap) {
+            SG_CUDA(cudaStreamSynchronize(st));
+            cudaFree(e->c_sites);
+            e->c_sites = nullptr;
+            e->c_sites_cap = 0;
+            cudaError_t ce = cudaMalloc(&e->c_sites, need);
+            if (ce != cudaSuccess) return fail(SG_ERR_NOMEM, "cudaMalloc(site tables)", ce);
+            e->c_sites_cap = need;
+        }
+        sg::SweepDev t{};
+        t.site_mode = p->site_mode;
+        t.seed = p->seed;
+        t.sweep_base = p->sweep_base;
+        t.n = e->n;
+        t.n_sweeps = p->n_sweeps;
+        SG_CUDA(sg::launch_sites_table(t, static_cast<int*>(e->c_sites), st));
+        e->launches++;
+        a.sites = static_cast<const int*>(e->c_sites);
+        a.s_rs = 0;
+        a.s_ss = e->n;
+    }
+    a.uniforms = p->uniforms;
+    a.u_rs = p->uniforms_replica_stride;
+    a.u_len = p->uniforms_per_replica;
+    a.cursor = reinterpret_cast<long long*>(p->cursor);
+    a.status = e->wolff_status;
+    a.seed = p->seed;
+    a.n = e->n;
+    a.n_pad = e->n_pad;
+    a.R = e->R;
+    a.rep_base = p->replica_base;
+    for (int s = 0; s < p->n_sweeps; ++s) {
+        a.sweep = s;
+        a.sweep_abs = p->sweep_base + (unsigned long long)s;
+        if (e->profiling) e->timer.begin(0, st);
+        SG_CUDA(sg::launch_wolff(a, inject, st));
+        if (e->profiling) e->timer.end(st);
+        e->launches++;
+        if ((rc = compute_fields(e, st)) != SG_OK) return rc;   // exact fields / energies
+        if (p->energy_trace || p->track_best) {
+            SG_CUDA(sg::launch_wolff_record(e->energy, e->best_energy, e->spins, e->best_spins,
+                                            p->energy_trace ? p->energy_trace + (size_t)s * e->R : nullptr,
+                                            e->n_pad, e->R, p->track_best ? 1 : 0, st));
+            e->launches++;
+        }
+    }
+    if (inject) {
+        int dry = 0;
+        SG_CUDA(cudaMemcpyAsync(&dry, e->wolff_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaStreamSynchronize(st));
+        if (dry) return fail(SG_ERR_INVALID, "sg_sweep_wolff: a replica needed more uniforms than uniforms_per_replica");
+    }
     return SG_OK;
 }
 

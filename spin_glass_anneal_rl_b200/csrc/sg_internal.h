@@ -210,6 +210,27 @@ cudaError_t launch_groups_energy(const GrpDev& m, const uint32_t* words, int n, 
 // int32 site table [n_sweeps][n] for the sparse / group kernels (same Philox stream as the others)
 cudaError_t launch_sites_table(const SweepDev& a, int* out, cudaStream_t st);
 
+// K1-WOLFF (sg_wolff.cu): the reference's cluster move, one CTA per replica, one launch per sweep
+struct WolffDev {
+    const float* Jrow;        // [n][n_pad] row-major couplings: Jrow[c][j] = J[c][j]
+    int8_t* spins;            // [R][n_pad]
+    unsigned long long* accepted;  // [R] += cluster sizes
+    const double* temps;      // T(s, r) = temps[s*t_ss + r*t_rs]
+    long long t_ss, t_rs;
+    const int* sites;         // start site of update k: sites[r*s_rs + s*s_ss + k]
+    long long s_rs, s_ss;
+    const float* uniforms;    // injected: replica r consumes uniforms[r*u_rs + cursor[r] ...] in order
+    long long u_rs, u_len;
+    long long* cursor;        // [R] in/out
+    int* status;              // set to 1 when a replica's stream ran dry
+    unsigned long long seed, sweep_abs;
+    int n, n_pad, R, sweep, rep_base;
+};
+cudaError_t launch_wolff(const WolffDev& a, bool inject, cudaStream_t st);
+cudaError_t launch_wolff_record(const float* energy, float* best_energy, const int8_t* spins,
+                                int8_t* best_spins, float* trace_row, int n_pad, int R, int track_best,
+                                cudaStream_t st);
+
 // K3 (sg_exchange.cu)
 struct ExchangeDev {
     int* rep_at;              // [L][K] (global) replica currently at rung k of ladder l

@@ -1,0 +1,304 @@
+// sg_wolff.cu -- K1-WOLFF: the reference's cluster move (UpdateRule.WOLFF,
+// core/spin_dynamics.py:193-262, dense branch _wolff_cluster_dense) for R replicas at once.
+//
+// What the reference does per update: breadth-first growth from a start site; the FIFO queue is a
+// Python list, every dequeued site walks ALL n columns of its coupling row in index order with
+// three .item() calls per column, and draws a uniform for each column that is not yet in the
+// cluster, has coupling < 0 and the same spin; accepted with probability 1 - exp(2 J / T).  The
+// whole cluster is flipped at the end; a sweep is n such updates.
+//
+// Here: ONE CTA PER REPLICA, the replica's spins, the cluster bitmap and the queue in shared
+// memory.  A dequeued site's row (n_pad floats of the row-major copy of J, L2 resident) is read
+// once by the 256 threads, four consecutive columns per thread and pass, all passes in flight
+// together.  Nothing in one row walk depends on another column of the same walk (a column is
+// visited once, cluster membership only changes for columns accepted in this very walk), so the
+// walk is evaluated in parallel and only the ORDER is restored afterwards:
+//   * injected uniforms (replay of the reference's stream): an ordered block-wide prefix count of
+//     the candidate columns gives every candidate the position of its uniform in the replica's
+//     stream -- candidate k of the walk consumes uniform cursor + k, exactly the reference's order;
+//   * a second ordered prefix count over the accepted columns appends them to the queue in index
+//     order (the reference's queue.append order), so the walks that follow are the reference's.
+// In Philox mode the uniform of column j in walk `visit` of update `upd` is a pure function of
+// (seed, replica, upd, visit, j): no candidate count is needed, one barrier per walk that grows
+// nothing.  Both counts ride on one packed warp scan (8 bits per pass) and __syncthreads_or.
+#include "sg_common.cuh"
+#include "sg_internal.h"
+
+namespace sg {
+
+namespace {
+
+constexpr int kWolffThreads = 256;
+constexpr int kWolffWarps = kWolffThreads / 32;
+constexpr int kWolffCols = kWolffThreads * 4;   // columns per pass
+constexpr uint32_t kWolffKeyTag = 0x574F4C46u;  // keeps the stream apart from the single-spin rules
+
+// ordered block-wide ranks of up to NP x 4 flags per thread (pass-major, then thread, then bit).
+// cnt[p] <= 4 per thread; a warp's sum per pass is <= 128 and fits a byte of the packed scan.
+template <int NP>
+struct OrderedCount {
+    uint32_t before[NP];   // flags ahead of this thread's first flag of pass p (whole block order)
+    uint32_t total;        // flags in the block
+};
+
+template <int NP>
+__device__ __forceinline__ void packed_warp_scan(const uint32_t (&cnt)[NP], uint32_t (&incl)[2]) {
+    incl[0] = incl[1] = 0u;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) incl[p >> 2] |= cnt[p] << (8 * (p & 3));
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t a0 = __shfl_up_sync(0xFFFFFFFFu, incl[0], d);
+        const uint32_t a1 = (NP > 4) ? __shfl_up_sync(0xFFFFFFFFu, incl[1], d) : 0u;
+        if (lane >= d) {
+            incl[0] += a0;
+            incl[1] += a1;
+        }
+    }
+}
+
+// wt: shared [kWolffWarps][2] packed warp totals, already published (barrier passed)
+template <int NP>
+__device__ __forceinline__ OrderedCount<NP> finish_count(const uint32_t (&cnt)[NP],
+                                                         const uint32_t (&incl)[2],
+                                                         const uint32_t (*wt)[2]) {
+    OrderedCount<NP> oc;
+    const int warp = threadIdx.x >> 5;
+    uint32_t run = 0u;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        const int sh = 8 * (p & 3), wd = p >> 2;
+        uint32_t below = 0u, all = 0u;
+#pragma unroll
+        for (int w = 0; w < kWolffWarps; ++w) {
+            const uint32_t t = (wt[w][wd] >> sh) & 0xFFu;
+            all += t;
+            below += (w < warp) ? t : 0u;
+        }
+        const uint32_t in_warp = ((incl[wd] >> sh) & 0xFFu) - cnt[p];   // exclusive
+        oc.before[p] = run + below + in_warp;
+        run += all;
+    }
+    oc.total = run;
+    return oc;
+}
+
+template <int NP, bool INJECT>
+__global__ void __launch_bounds__(kWolffThreads) wolff_kernel(const WolffDev a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int n = a.n, n_pad = a.n_pad;
+    int8_t* spin = reinterpret_cast<int8_t*>(smem);                          // [n_pad]
+    uint32_t* incl_bits = reinterpret_cast<uint32_t*>(smem + n_pad);         // [n_pad / 32]
+    int* queue = reinterpret_cast<int*>(smem + n_pad + (n_pad / 32) * 4);    // [n]
+    __shared__ uint32_t wt_cand[kWolffWarps][2], wt_acc[kWolffWarps][2];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rep = blockIdx.x;
+    int8_t* spins_g = a.spins + (size_t)rep * n_pad;
+    for (int i = tid; i < n_pad / 16; i += kWolffThreads)
+        reinterpret_cast<int4*>(spin)[i] = reinterpret_cast<const int4*>(spins_g)[i];
+
+    const double T = a.temps[(long long)a.sweep * a.t_ss + (long long)rep * a.t_rs];
+    const int* sites = a.sites + (long long)rep * a.s_rs + (long long)a.sweep * a.s_ss;
+    const float* ustream = INJECT ? a.uniforms + (long long)rep * a.u_rs : nullptr;
+    long long cur = INJECT ? a.cursor[rep] : 0;
+    const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32) ^ kWolffKeyTag);
+    const unsigned long long upd0 = a.sweep_abs * (unsigned long long)n;
+    unsigned long long flips = 0;
+    bool dry = false;
+
+#pragma unroll 1
+    for (int k = 0; k < n; ++k) {
+        const int start = sites[k];
+        for (int w = tid; w < n_pad / 32; w += kWolffThreads) incl_bits[w] = 0u;
+        __syncthreads();   // spins loaded / previous flips done, bitmap clear
+        if (tid == 0) {
+            queue[0] = start;
+            incl_bits[start >> 5] = 1u << (start & 31);
+        }
+        __syncthreads();
+        int head = 0, tail = 1;
+        const unsigned long long upd = upd0 + (unsigned long long)k;
+#pragma unroll 1
+        while (head < tail) {
+            const int c = queue[head];
+            const int8_t sc = spin[c];
+            const float4* row = reinterpret_cast<const float4*>(a.Jrow + (size_t)c * n_pad);
+            float4 v[NP];
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                const int j4 = p * kWolffCols + tid * 4;
+                v[p] = (j4 < n_pad) ? __ldg(row + (j4 >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            // candidates: not the site itself, not in the cluster, coupling < 0, same spin
+            uint32_t cand[NP], cnt[NP];
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                const int j4 = p * kWolffCols + tid * 4;
+                uint32_t m = 0u;
+                if (j4 < n) {
+                    const uint32_t inb = (incl_bits[j4 >> 5] >> (j4 & 31)) & 0xFu;
+                    const uint32_t sp = *reinterpret_cast<const uint32_t*>(spin + j4);
+                    const float jv[4] = {v[p].x, v[p].y, v[p].z, v[p].w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int j = j4 + i;
+                        const bool same = (int8_t)((sp >> (8 * i)) & 0xFFu) == sc;
+                        if (j < n && j != c && !((inb >> i) & 1u) && jv[i] < 0.0f && same) m |= 1u << i;
+                    }
+                }
+                cand[p] = m;
+                cnt[p] = __popc(m);
+            }
+            uint32_t mine = 0u;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) mine |= cand[p];
+
+            uint32_t n_cand = 0u;
+            OrderedCount<NP> oc_c;
+            if (INJECT) {
+                uint32_t inc[2];
+                packed_warp_scan<NP>(cnt, inc);
+                if (lane == 31) {
+                    wt_cand[warp][0] = inc[0];
+                    wt_cand[warp][1] = inc[1];
+                }
+                if (!__syncthreads_or(mine != 0u)) {   // nobody to ask: the walk draws nothing
+                    ++head;
+                    continue;
+                }
+                oc_c = finish_count<NP>(cnt, inc, wt_cand);
+                n_cand = oc_c.total;
+            }
+            // decisions
+            uint32_t acc[NP], acnt[NP];
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                uint32_t m = 0u;
+                if (cand[p]) {
+                    const int j4 = p * kWolffCols + tid * 4;
+                    const float jv[4] = {v[p].x, v[p].y, v[p].z, v[p].w};
+                    float u4[4];
+                    if (!INJECT) {
+                        const uint4 x = philox4x32_10(
+                            make_uint4((uint32_t)(rep + a.rep_base), (uint32_t)upd, (uint32_t)(upd >> 32),
+                                       ((uint32_t)head << 11) | (uint32_t)(j4 >> 2)), key);
+                        u4[0] = u01(x.x); u4[1] = u01(x.y); u4[2] = u01(x.z); u4[3] = u01(x.w);
+                    }
+                    uint32_t rank = INJECT ? oc_c.before[p] : 0u;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (!((cand[p] >> i) & 1u)) continue;
+                        float u;
+                        if (INJECT) {
+                            const long long at = cur + (long long)rank;
+                            ++rank;
+                            if (at < a.u_len) u = ustream[at];
+                            else { u = 2.0f; dry = true; }
+                        } else {
+                            u = u4[i];
+                        }
+                        // 1.0 - torch.exp(torch.tensor(2.0 * coupling / T)): double quotient rounded
+                        // to float32, exp and the subtraction in float32 (core/spin_dynamics.py:237)
+                        const float pr = 1.0f - expf((float)(2.0 * (double)jv[i] / T));
+                        if (u < pr) m |= 1u << i;
+                    }
+                }
+                acc[p] = m;
+                acnt[p] = __popc(m);
+            }
+            uint32_t grown = 0u;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) grown |= acc[p];
+            uint32_t inc2[2];
+            packed_warp_scan<NP>(acnt, inc2);
+            if (lane == 31) {
+                wt_acc[warp][0] = inc2[0];
+                wt_acc[warp][1] = inc2[1];
+            }
+            cur += (long long)n_cand;
+            ++head;
+            if (!__syncthreads_or(grown != 0u)) continue;   // the cluster did not grow in this walk
+            const OrderedCount<NP> oc_a = finish_count<NP>(acnt, inc2, wt_acc);
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                if (!acc[p]) continue;
+                const int j4 = p * kWolffCols + tid * 4;
+                int at = tail + (int)oc_a.before[p];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if ((acc[p] >> i) & 1u) queue[at++] = j4 + i;
+                atomicOr(&incl_bits[j4 >> 5], acc[p] << (j4 & 31));
+            }
+            tail += (int)oc_a.total;
+            __syncthreads();   // queue and bitmap of this walk visible to the next one
+        }
+        for (int q = tid; q < tail; q += kWolffThreads) {
+            const int j = queue[q];
+            spin[j] = (int8_t)-spin[j];
+        }
+        flips += (unsigned long long)tail;
+    }
+    __syncthreads();
+    for (int i = tid; i < n_pad / 16; i += kWolffThreads)
+        reinterpret_cast<int4*>(spins_g)[i] = reinterpret_cast<const int4*>(spin)[i];
+    if (tid == 0) {
+        a.accepted[rep] += flips;
+        if (INJECT) a.cursor[rep] = cur;
+    }
+    if (INJECT && dry) *a.status = 1;
+}
+
+// after the exact energy refresh of a sweep: trace row and compare-and-keep best
+__global__ void wolff_record_kernel(const float* __restrict__ energy, float* __restrict__ best_energy,
+                                    const int8_t* __restrict__ spins, int8_t* __restrict__ best_spins,
+                                    float* __restrict__ trace_row, int n_pad, int track_best) {
+    const int rep = blockIdx.x;
+    const float e = energy[rep];
+    if (trace_row && threadIdx.x == 0) trace_row[rep] = e;
+    if (!track_best) return;
+    const bool better = e < best_energy[rep];   // every thread reads before anyone writes: see barrier
+    __syncthreads();
+    if (!better) return;
+    if (threadIdx.x == 0) best_energy[rep] = e;
+    const int4* src = reinterpret_cast<const int4*>(spins + (size_t)rep * n_pad);
+    int4* dst = reinterpret_cast<int4*>(best_spins + (size_t)rep * n_pad);
+    for (int i = threadIdx.x; i < n_pad / 16; i += blockDim.x) dst[i] = src[i];
+}
+
+template <int NP>
+cudaError_t launch_np(const WolffDev& a, bool inject, size_t smem, cudaStream_t st) {
+    if (inject)
+        wolff_kernel<NP, true><<<a.R, kWolffThreads, smem, st>>>(a);
+    else
+        wolff_kernel<NP, false><<<a.R, kWolffThreads, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_wolff(const WolffDev& a, bool inject, cudaStream_t st) {
+    const size_t smem = (size_t)a.n_pad + (size_t)(a.n_pad / 32) * 4 + (size_t)a.n * 4;
+    const int np = (a.n_pad + kWolffCols - 1) / kWolffCols;
+    switch (np) {
+        case 1: return launch_np<1>(a, inject, smem, st);
+        case 2: return launch_np<2>(a, inject, smem, st);
+        case 3: return launch_np<3>(a, inject, smem, st);
+        case 4: return launch_np<4>(a, inject, smem, st);
+        case 5: return launch_np<5>(a, inject, smem, st);
+        case 6: return launch_np<6>(a, inject, smem, st);
+        case 7: return launch_np<7>(a, inject, smem, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_wolff_record(const float* energy, float* best_energy, const int8_t* spins,
+                                int8_t* best_spins, float* trace_row, int n_pad, int R, int track_best,
+                                cudaStream_t st) {
+    wolff_record_kernel<<<R, 128, 0, st>>>(energy, best_energy, spins, best_spins, trace_row, n_pad,
+                                           track_best);
+    return cudaGetLastError();
+}
+
+}  // namespace sg

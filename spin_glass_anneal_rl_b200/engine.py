@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import ExchangeParams, SweepParams, check
+from ._lib import ExchangeParams, SweepParams, WolffParams, check
 
 ArrayLike = Union[np.ndarray, torch.Tensor]
 
@@ -272,6 +272,16 @@ class Engine:
         (None = ladder temperatures).  ``uniforms`` switches to injected-uniform mode,
         ``sites`` to an explicit site list.  Returns the [n_sweeps, R] energy trace if asked.
         """
+        if rule == "wolff":
+            if replicas_per_block or kernel != "auto" or coupling_planes or site_energy_changes is not None:
+                raise ValueError("the Wolff cluster move has no kernel / block-shape options")
+            return self.sweep_wolff(n_sweeps, temps, temps_sweep_stride=temps_sweep_stride,
+                                    temps_replica_stride=temps_replica_stride, site_order=site_order,
+                                    seed=seed, sweep_base=sweep_base, sites=sites,
+                                    sites_replica_stride=sites_block_stride,
+                                    sites_sweep_stride=sites_sweep_stride, uniforms=uniforms,
+                                    energy_trace=energy_trace, track_best=track_best,
+                                    replica_base=replica_base)
         p = SweepParams()
         p.struct_size = ctypes.sizeof(SweepParams)
         p.n_sweeps = int(n_sweeps)
@@ -320,6 +330,69 @@ class Engine:
             keep.append(d)
             p.site_energy_changes = d.data_ptr()
         check(self._lib.sg_sweep(self._h, ctypes.byref(p), self.stream), "sg_sweep")
+        self._keep += keep
+        if len(self._keep) > 256:
+            self.synchronize()
+        return trace
+
+    def sweep_wolff(self, n_sweeps: int, temps: Optional[ArrayLike] = None, *,
+                    temps_sweep_stride: int = 0, temps_replica_stride: int = 0,
+                    site_order: str = "random", seed: int = 0, sweep_base: int = 0,
+                    sites: Optional[ArrayLike] = None, sites_replica_stride: int = 0,
+                    sites_sweep_stride: Optional[int] = None, uniforms: Optional[ArrayLike] = None,
+                    cursor: Optional[torch.Tensor] = None, energy_trace: bool = False,
+                    track_best: bool = True, replica_base: int = 0) -> Optional[torch.Tensor]:
+        """``n_sweeps`` sweeps of the Wolff cluster move (n cluster updates per sweep and replica),
+        exact energies after every sweep.
+
+        ``uniforms`` ([R, m] float32, or [m] for one replica) switches to injected mode: replica r
+        consumes its row in order, one value per candidate neighbour, starting at ``cursor[r]``
+        (device int64 [R], updated in place; None = start at 0, and ``self.wolff_cursor`` holds the
+        positions afterwards).  ``sites``: explicit start sites, addressed as
+        sites[r*sites_replica_stride + s*sites_sweep_stride + k]."""
+        p = WolffParams()
+        p.struct_size = ctypes.sizeof(WolffParams)
+        p.n_sweeps = int(n_sweeps)
+        p.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        p.sweep_base = int(sweep_base)
+        p.track_best = 1 if track_best else 0
+        p.replica_base = int(replica_base)
+        keep = []
+        if temps is not None:
+            t = self._dev(temps, torch.float64)
+            keep.append(t)
+            p.temps = t.data_ptr()
+            p.temps_sweep_stride = int(temps_sweep_stride)
+            p.temps_replica_stride = int(temps_replica_stride)
+        if sites is not None:
+            sd = self._dev(sites, torch.int32)
+            keep.append(sd)
+            p.sites = sd.data_ptr()
+            p.site_mode = _lib.SG_SITES["explicit"]
+            p.sites_replica_stride = int(sites_replica_stride)
+            p.sites_sweep_stride = int(self.n if sites_sweep_stride is None else sites_sweep_stride)
+        else:
+            p.site_mode = _lib.SG_SITES[site_order]
+        if uniforms is not None:
+            u = self._dev(uniforms, torch.float32).reshape(self.n_replicas, -1)
+            keep.append(u)
+            p.uniforms = u.data_ptr()
+            p.uniforms_replica_stride = int(u.shape[1])
+            p.uniforms_per_replica = int(u.shape[1])
+            if cursor is None:
+                cursor = torch.zeros(self.n_replicas, dtype=torch.int64, device=self.device)
+            if cursor.device != self.device or cursor.dtype != torch.int64 or cursor.numel() != self.n_replicas:
+                raise ValueError("cursor must be a device int64 [R] tensor")
+            self.wolff_cursor = cursor
+            p.cursor = cursor.data_ptr()
+            p.rng_mode = _lib.SG_RNG_INJECTED
+        else:
+            p.rng_mode = _lib.SG_RNG_PHILOX
+        trace = None
+        if energy_trace:
+            trace = torch.empty((n_sweeps, self.n_replicas), dtype=torch.float32, device=self.device)
+            p.energy_trace = trace.data_ptr()
+        check(self._lib.sg_sweep_wolff(self._h, ctypes.byref(p), self.stream), "sg_sweep_wolff")
         self._keep += keep
         if len(self._keep) > 256:
             self.synchronize()

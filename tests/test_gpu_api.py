@@ -152,8 +152,6 @@ def test_other_update_rules(rule, oracle):
                                               random_seed=5, n_replicas=64)).anneal(m, rule)
     assert oracle.energy(g["J"], g["h"], res.best_configuration.numpy()) == res.best_energy
     assert res.best_energy <= float(g["best_energy"]) + 8
-    with pytest.raises(NotImplementedError):
-        sg.GPUAnnealer(sg.GPUAnnealerConfig(n_sweeps=2)).anneal(m, UpdateRule.WOLFF)
 
 
 def test_early_stop_like_reference():

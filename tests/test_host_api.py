@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"libsg_b200.so lacks {name}"
     assert declared == set(_lib.PROTOTYPES), (declared ^ set(_lib.PROTOTYPES))
-    assert _lib.load().sg_abi_version() == _lib.SG_ABI_VERSION == 4
+    assert _lib.load().sg_abi_version() == _lib.SG_ABI_VERSION == 5
 
 
 def test_param_structs_match_header_layout(tmp_path):
@@ -36,12 +36,14 @@ def test_param_structs_match_header_layout(tmp_path):
     import subprocess
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include "sg_b200.h"\nint main(void){printf("%zu %zu\\n",'
-                   'sizeof(sg_sweep_params), sizeof(sg_exchange_params)); return 0;}\n')
+                   'sizeof(sg_sweep_params), sizeof(sg_exchange_params)); printf("%zu\\n", '
+                   'sizeof(sg_wolff_params)); return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
-    a, b = map(int, subprocess.check_output([str(exe)]).split())
+    a, b, c = map(int, subprocess.check_output([str(exe)]).split())
     assert ctypes.sizeof(_lib.SweepParams) == a
     assert ctypes.sizeof(_lib.ExchangeParams) == b
+    assert ctypes.sizeof(_lib.WolffParams) == c
 
 
 def test_no_gpu_fails_loudly():
