@@ -21,6 +21,8 @@
 // In Philox mode the uniform of column j in walk `visit` of update `upd` is a pure function of
 // (seed, replica, upd, visit, j): no candidate count is needed, one barrier per walk that grows
 // nothing.  Both counts ride on one packed warp scan (8 bits per pass) and __syncthreads_or.
+#include <cstdlib>
+
 #include "sg_common.cuh"
 #include "sg_internal.h"
 
@@ -32,6 +34,16 @@ constexpr int kWolffThreads = 256;
 constexpr int kWolffWarps = kWolffThreads / 32;
 constexpr int kWolffCols = kWolffThreads * 4;   // columns per pass
 constexpr uint32_t kWolffKeyTag = 0x574F4C46u;  // keeps the stream apart from the single-spin rules
+
+// probability that an aligned neighbour with coupling c < 0 joins the cluster.  Replay mode follows
+// the reference's arithmetic -- 1.0 - torch.exp(torch.tensor(2.0 * coupling / T)): double quotient
+// rounded to float32, exp and the subtraction in float32 (core/spin_dynamics.py:237); Philox mode
+// (its own random numbers anyway) stays in float32.
+template <bool INJECT>
+__device__ __forceinline__ float wolff_prob(float c, double T, float inv_t) {
+    if (INJECT) return 1.0f - expf((float)(2.0 * (double)c / T));
+    return 1.0f - __expf(2.0f * c * inv_t);
+}
 
 // ordered block-wide ranks of up to NP x 4 flags per thread (pass-major, then thread, then bit).
 // cnt[p] <= 4 per thread; a warp's sum per pass is <= 128 and fits a byte of the packed scan.
@@ -100,6 +112,7 @@ __global__ void __launch_bounds__(kWolffThreads) wolff_kernel(const WolffDev a) 
         reinterpret_cast<int4*>(spin)[i] = reinterpret_cast<const int4*>(spins_g)[i];
 
     const double T = a.temps[(long long)a.sweep * a.t_ss + (long long)rep * a.t_rs];
+    const float inv_t = (float)(1.0 / T);
     const int* sites = a.sites + (long long)rep * a.s_rs + (long long)a.sweep * a.s_ss;
     const float* ustream = INJECT ? a.uniforms + (long long)rep * a.u_rs : nullptr;
     long long cur = INJECT ? a.cursor[rep] : 0;
@@ -199,10 +212,7 @@ __global__ void __launch_bounds__(kWolffThreads) wolff_kernel(const WolffDev a) 
                         } else {
                             u = u4[i];
                         }
-                        // 1.0 - torch.exp(torch.tensor(2.0 * coupling / T)): double quotient rounded
-                        // to float32, exp and the subtraction in float32 (core/spin_dynamics.py:237)
-                        const float pr = 1.0f - expf((float)(2.0 * (double)jv[i] / T));
-                        if (u < pr) m |= 1u << i;
+                        if (u < wolff_prob<INJECT>(jv[i], T, inv_t)) m |= 1u << i;
                     }
                 }
                 acc[p] = m;
@@ -250,6 +260,209 @@ __global__ void __launch_bounds__(kWolffThreads) wolff_kernel(const WolffDev a) 
     if (INJECT && dry) *a.status = 1;
 }
 
+// ---------------------------------------------------------------------------------------------
+// n <= 1792: ONE WARP PER REPLICA (eight replicas per CTA).  A row walk of a small model is a
+// latency chain (one L2 round trip, then the two ordered counts); a whole CTA per replica leaves
+// the SM with four walks in flight.  Here a warp reads the row with coalesced float4 loads (pass q,
+// lane l: columns 128 q + 4 l ..), spins and cluster membership are bit masks in the registers of
+// the lane that owns the column, the candidates of a walk are three ANDs, and index order (pass,
+// lane, bit) is restored with a byte-per-pass shuffle scan: the walk needs no block barrier and no
+// shared memory but the queue, and an SM keeps up to 32 walks in flight.  Same Philox counters per (update, visit, column quad) as the CTA form: both
+// forms give the same spins in both RNG modes.
+// Ordered counts of a warp's flags in index order (pass q, lane, bit): per-pass counts ride as bytes
+// of one or two 64-bit words through a five-step shuffle scan (a pass holds at most 128 flags).
+template <int W4>
+struct PassCount {
+    unsigned long long inc[2], tot[2];   // inclusive over lanes / warp totals, a byte per pass
+    __device__ __forceinline__ void scan(const unsigned long long (&pk)[2], int lane) {
+        inc[0] = pk[0];
+        inc[1] = pk[1];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long t0 = __shfl_up_sync(0xFFFFFFFFu, inc[0], d);
+            const unsigned long long t1 = (W4 > 8) ? __shfl_up_sync(0xFFFFFFFFu, inc[1], d) : 0ull;
+            if (lane >= d) {
+                inc[0] += t0;
+                inc[1] += t1;
+            }
+        }
+        tot[0] = __shfl_sync(0xFFFFFFFFu, inc[0], 31);
+        tot[1] = (W4 > 8) ? __shfl_sync(0xFFFFFFFFu, inc[1], 31) : 0ull;
+    }
+    static __device__ __forceinline__ uint32_t byte_of(const unsigned long long (&w)[2], int q) {
+        const unsigned long long x = (W4 > 8 && q >= 8) ? w[1] : w[0];   // (no dynamic indexing: registers)
+        return (uint32_t)((x >> (8 * (q & 7))) & 0xFFull);
+    }
+    __device__ __forceinline__ uint32_t total() const {
+        uint32_t t = 0u;
+#pragma unroll
+        for (int q = 0; q < W4; ++q) t += byte_of(tot, q);
+        return t;
+    }
+};
+
+// walks one lane's flags in ascending order and returns each flag's position in the warp's order
+template <int W4>
+struct PassCursor {
+    int qc = 0, qlast = -1;
+    uint32_t base = 0u, within = 0u;
+    __device__ __forceinline__ uint32_t next(const PassCount<W4>& pc, const unsigned long long (&pk)[2], int q) {
+        while (qc < q) {
+            base += PassCount<W4>::byte_of(pc.tot, qc);
+            ++qc;
+        }
+        if (q != qlast) {
+            within = 0u;
+            qlast = q;
+        }
+        return base + PassCount<W4>::byte_of(pc.inc, q) - PassCount<W4>::byte_of(pk, q) + within++;
+    }
+};
+
+__device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t x, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, x, d);
+        if (lane >= d) x += t;
+    }
+    return x;
+}
+
+template <int W4, bool INJECT>   // W4 = float4 loads per lane and walk (7: n_pad 896, 14: n_pad 1792)
+__global__ void __launch_bounds__(kWolffThreads, W4 <= 7 ? 4 : 3) wolff_warp_kernel(const WolffDev a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int n = a.n, n_pad = a.n_pad;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rep = blockIdx.x * kWolffWarps + warp;
+    if (rep >= a.R) return;   // (no block-wide barrier below)
+    unsigned short* queue = reinterpret_cast<unsigned short*>(smem) + (size_t)warp * ((n + 7) & ~7);
+
+    // The replica's state lives in registers: lane l owns the columns 128 q + 4 l + i (the ones its
+    // float4 loads cover), bit 4 q + i of `sb` = spin up, of `ic` = in the cluster.  A lane only
+    // ever appends its own columns, so membership needs no shared bitmap, and flipping the cluster
+    // at the end of an update is sb ^= ic.
+    int8_t* spins_g = a.spins + (size_t)rep * n_pad;
+    unsigned long long sb = 0ull;
+#pragma unroll
+    for (int q = 0; q < W4; ++q) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(spins_g + 128 * q + 4 * lane);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if ((int8_t)((w >> (8 * i)) & 0xFFu) > 0) sb |= 1ull << (4 * q + i);
+    }
+    const double T = a.temps[(long long)a.sweep * a.t_ss + (long long)rep * a.t_rs];
+    const float inv_t = (float)(1.0 / T);
+    const int* sites = a.sites + (long long)rep * a.s_rs + (long long)a.sweep * a.s_ss;
+    const float* ustream = INJECT ? a.uniforms + (long long)rep * a.u_rs : nullptr;
+    long long cur = INJECT ? a.cursor[rep] : 0;
+    const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32) ^ kWolffKeyTag);
+    const unsigned long long upd0 = a.sweep_abs * (unsigned long long)n;
+    unsigned long long flips = 0;
+    bool dry = false;
+
+#pragma unroll 1
+    for (int k = 0; k < n; ++k) {
+        const int start = sites[k];
+        unsigned long long ic = 0ull;
+        if (((start & 127) >> 2) == lane) ic = 1ull << (4 * (start >> 7) + (start & 3));
+        if (lane == 0) queue[0] = (unsigned short)start;
+        __syncwarp();
+        int head = 0, tail = 1;
+        const unsigned long long upd = upd0 + (unsigned long long)k;
+#pragma unroll 1
+        while (head < tail) {
+            const int c = queue[head];
+            const bool c_up = (__shfl_sync(0xFFFFFFFFu, sb, (c & 127) >> 2) >> (4 * (c >> 7) + (c & 3))) & 1ull;
+            const float* rowf = a.Jrow + (size_t)c * n_pad;
+            // candidates: coupling < 0 (padding columns hold 0), same spin, not in the cluster (the
+            // dequeued site itself is).  The couplings are only needed again for the few candidates:
+            // re-read through L1 below, so the row leaves the registers here.
+            unsigned long long nm = 0ull;
+            {
+                const float4* row = reinterpret_cast<const float4*>(rowf) + lane;
+                float4 v[W4];
+#pragma unroll
+                for (int q = 0; q < W4; ++q)
+                    v[q] = (128 * q < n) ? __ldg(row + 32 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < W4; ++q) {
+                    const uint32_t m = (v[q].x < 0.0f ? 1u : 0u) | (v[q].y < 0.0f ? 2u : 0u) |
+                                       (v[q].z < 0.0f ? 4u : 0u) | (v[q].w < 0.0f ? 8u : 0u);
+                    nm |= (unsigned long long)m << (4 * q);
+                }
+            }
+            const unsigned long long cm = nm & (c_up ? sb : ~sb) & ~ic;
+            const int visit = head++;
+            if (!__any_sync(0xFFFFFFFFu, cm != 0ull)) continue;   // the walk draws nothing
+            PassCount<W4> pc;
+            unsigned long long pk[2] = {0ull, 0ull};   // flags per pass, a byte each
+            if (INJECT) {   // index order = pass, lane, bit
+#pragma unroll
+                for (int q = 0; q < W4; ++q)
+                    pk[q >> 3] += (unsigned long long)__popc((uint32_t)(cm >> (4 * q)) & 0xFu) << (8 * (q & 7));
+                pc.scan(pk, lane);
+            }
+            unsigned long long am = 0ull;
+            {
+                PassCursor<W4> pos;
+#pragma unroll 1
+                for (unsigned long long rest = cm; rest; rest &= rest - 1) {
+                    const int b = __ffsll((long long)rest) - 1;
+                    const int q = b >> 2, i = b & 3;
+                    const int col = 128 * q + 4 * lane + i;
+                    float u;
+                    if (INJECT) {
+                        const long long at = cur + (long long)pos.next(pc, pk, q);
+                        if (at < a.u_len) u = ustream[at];
+                        else { u = 2.0f; dry = true; }
+                    } else {   // the uniform of a column is a function of (update, visit, column quad)
+                        const uint4 x = philox4x32_10(
+                            make_uint4((uint32_t)(rep + a.rep_base), (uint32_t)upd, (uint32_t)(upd >> 32),
+                                       ((uint32_t)visit << 11) | (uint32_t)(col >> 2)), key);
+                        u = u01(i == 0 ? x.x : i == 1 ? x.y : i == 2 ? x.z : x.w);
+                    }
+                    if (u < wolff_prob<INJECT>(__ldg(rowf + col), T, inv_t)) am |= 1ull << b;
+                }
+            }
+            if (INJECT) cur += (long long)pc.total();
+            if (!__any_sync(0xFFFFFFFFu, am != 0ull)) continue;   // the cluster did not grow
+#pragma unroll
+            for (int q = 0; q < 2; ++q) pk[q] = 0ull;
+#pragma unroll
+            for (int q = 0; q < W4; ++q)
+                pk[q >> 3] += (unsigned long long)__popc((uint32_t)(am >> (4 * q)) & 0xFu) << (8 * (q & 7));
+            pc.scan(pk, lane);
+            {
+                PassCursor<W4> pos;
+#pragma unroll 1
+                for (unsigned long long rest = am; rest; rest &= rest - 1) {
+                    const int b = __ffsll((long long)rest) - 1;
+                    const int q = b >> 2;
+                    queue[tail + (int)pos.next(pc, pk, q)] = (unsigned short)(128 * q + 4 * lane + (b & 3));
+                }
+            }
+            ic |= am;
+            tail += (int)pc.total();
+            __syncwarp();   // queue entries of this walk visible to the next one
+        }
+        sb ^= ic;   // flip the cluster
+        flips += (unsigned long long)tail;
+        __syncwarp();   // every lane is done with the queue before the next update reuses it
+    }
+#pragma unroll
+    for (int q = 0; q < W4; ++q) {
+        uint32_t w = 0u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w |= (((sb >> (4 * q + i)) & 1ull) ? 0x01u : 0xFFu) << (8 * i);
+        *reinterpret_cast<uint32_t*>(spins_g + 128 * q + 4 * lane) = w;
+    }
+    if (lane == 0) {
+        a.accepted[rep] += flips;
+        if (INJECT) a.cursor[rep] = cur;
+    }
+    if (INJECT && dry) *a.status = 1;
+}
+
 // after the exact energy refresh of a sweep: trace row and compare-and-keep best
 __global__ void wolff_record_kernel(const float* __restrict__ energy, float* __restrict__ best_energy,
                                     const int8_t* __restrict__ spins, int8_t* __restrict__ best_spins,
@@ -276,9 +489,35 @@ cudaError_t launch_np(const WolffDev& a, bool inject, size_t smem, cudaStream_t 
     return cudaGetLastError();
 }
 
+template <int W4>
+cudaError_t launch_warp(const WolffDev& a, bool inject, cudaStream_t st) {
+    const size_t smem = (size_t)kWolffWarps * ((a.n + 7) & ~7) * sizeof(unsigned short);   // the queues
+    const int grid = (a.R + kWolffWarps - 1) / kWolffWarps;
+    cudaError_t e = inject ? cudaFuncSetAttribute(wolff_warp_kernel<W4, true>,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                           : cudaFuncSetAttribute(wolff_warp_kernel<W4, false>,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (inject)
+        wolff_warp_kernel<W4, true><<<grid, kWolffThreads, smem, st>>>(a);
+    else
+        wolff_warp_kernel<W4, false><<<grid, kWolffThreads, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
 }  // namespace
 
+// SG_WOLFF_FORM=cta forces the CTA-per-replica form for every size (tests, A/B timing)
+static bool wolff_force_cta() {
+    const char* f = getenv("SG_WOLFF_FORM");
+    return f && f[0] == 'c';
+}
+
 cudaError_t launch_wolff(const WolffDev& a, bool inject, cudaStream_t st) {
+    if (!wolff_force_cta()) {   // small models: a warp per replica
+        if (a.n_pad == 896) return launch_warp<7>(a, inject, st);
+        if (a.n_pad == 1792) return launch_warp<14>(a, inject, st);
+    }
     const size_t smem = (size_t)a.n_pad + (size_t)(a.n_pad / 32) * 4 + (size_t)a.n * 4;
     const int np = (a.n_pad + kWolffCols - 1) / kWolffCols;
     switch (np) {

@@ -144,13 +144,17 @@ def test_anneal_replay_reproduces_the_reference(oracle, name):
 
 
 # ------------------------------------------------------------------ wider shapes against the oracle
-@pytest.mark.parametrize("n,R,integer,asym,T", [
-    (300, 5, True, False, 5.0),      # one pass of 1024 columns
-    (1100, 3, True, True, 3.5),      # two passes, asymmetric couplings (row of the dequeued site)
-    (1000, 4, False, False, 3.0),    # float couplings
-    (4100, 2, True, False, 5.0),     # five passes (n_pad = 4480)
+@pytest.mark.parametrize("n,R,integer,asym,T,form", [
+    (300, 5, True, False, 5.0, "warp"),    # n_pad = 896: a warp per replica, 28 columns per lane
+    (300, 11, True, False, 5.0, "cta"),    # the same through the CTA-per-replica form (one pass)
+    (1100, 3, True, True, 3.5, "warp"),    # n_pad = 1792, asymmetric couplings (row of the dequeued site)
+    (1100, 3, True, True, 3.5, "cta"),     # two passes of 1024 columns
+    (1000, 4, False, False, 3.0, "warp"),  # float couplings
+    (4100, 2, True, False, 5.0, "cta"),    # five passes (n_pad = 4480; always the CTA form)
 ])
-def test_replicas_with_their_own_streams(oracle, n, R, integer, asym, T):
+def test_replicas_with_their_own_streams(oracle, monkeypatch, n, R, integer, asym, T, form):
+    if form == "cta":
+        monkeypatch.setenv("SG_WOLFF_FORM", "cta")
     J, h = _sparse_neg_model(n, 100 + n, integer=integer, asym=asym)
     rs = np.random.RandomState(n)
     ns = 2
@@ -247,6 +251,29 @@ def test_philox_mode_matches_the_oracle_distribution(oracle):
     half.sweep_wolff(ns, np.array([T]), site_order="random", seed=1234, replica_base=R // 2)
     assert torch.equal(half.spins(), first[R // 2:])
     assert len({tuple(r) for r in first.cpu().numpy()[:64].tolist()}) > 32   # replicas differ
+
+
+@pytest.mark.parametrize("n", [200, 1500])
+def test_both_kernel_forms_agree_in_philox_mode(monkeypatch, n):
+    """A warp per replica (n <= 1792) and a CTA per replica draw the same Philox numbers per
+    (update, visit, column quad): same clusters, same spins."""
+    J, h = _sparse_neg_model(n, 40 + n, integer=False)
+    R = 19
+    S0 = (np.random.RandomState(n).randint(0, 2, (R, n)) * 2 - 1).astype(np.int8)
+    out = []
+    for form in ("warp", "cta"):
+        if form == "cta":
+            monkeypatch.setenv("SG_WOLFF_FORM", "cta")
+        eng = Engine(0)
+        eng.set_model(J, h)
+        eng.alloc_replicas(R)
+        eng.set_spins(S0)
+        eng.init_fields()
+        tr = eng.sweep_wolff(2, np.array([3.0, 2.5]), temps_sweep_stride=1, seed=77, energy_trace=True)
+        out.append((eng.spins().cpu().numpy(), tr.cpu().numpy(), eng.accepted().cpu().numpy()))
+    assert out[0][2].sum() > 2 * R * n, "the case must exercise the cluster growth"
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
 
 
 def test_api_paths_take_wolff(oracle):
