@@ -252,6 +252,8 @@ def run_ours(args):
     q = eng.query()
     cluster = max(1, eng.tc_cluster_size()) if use_tc else 1
     R = R_main
+    # replicas the launch hands to cluster pairs on the SMs the clusters of 4 leave idle
+    r_pairs = eng.tc_side_replicas(sweeps, planes) if use_tc else 0
 
     # ---- end to end through the C ABI's host-buffer path, every step: pinned host spins ->
     # sg_upload_spins_async (side stream, double buffered) -> sg_set_spins_staged -> field init ->
@@ -406,7 +408,7 @@ def run_ours(args):
         # the C SMs of its cluster; peak = bandwidth of the same transport (TMA bulk copies of an
         # L2-resident buffer into a shared-memory ring, one block per SM) measured in this run
         ng = 16 * cluster
-        groups = (R + ng - 1) // ng
+        groups = (R - r_pairs + ng - 1) // ng + r_pairs // 32
         if use_tc:
             n_tc = (n + 127) // 128 * 128
             bytes_per_group_sweep = float(n) * n_tc * 2 * planes
@@ -472,10 +474,13 @@ def run_ours(args):
             slots = min(groups, max(1, (q["sm_count"] // cluster) * cluster // cluster)) * cluster
             if cluster == 4:
                 slots = min(groups, 33) * 4   # cudaOccupancyMaxActiveClusters: 33 clusters of 4 (132 SMs)
+                if r_pairs:
+                    slots = q["sm_count"]     # ... and cluster pairs on the other 16
             roofline["tensor_issue"] = {
                 "mma_per_launch": mma_per_launch, "clk_per_mma_isolated": clk_per_mma, "sms_used": slots,
                 "frac": mma_per_launch * clk_per_mma / slots / (ms_launch * 1e-3 * sm_clk),
-                "mma_tflops": mma_per_launch * 2.0 * 128 * (16 * cluster) * 16 / (ms_launch * 1e-3) / 1e12,
+                "mma_tflops": float(R) * sweeps * nblk * (n_tc // 128) * planes * args.steps / n_klaunch
+                              * 2.0 * 128 * 16 / (ms_launch * 1e-3) / 1e12,
                 "note": "share of the kernel's time that the tensor pipe of a used SM needs for its MMA "
                         "instructions at their isolated rate; the remainder is the two barrier round trips "
                         "per block between MMA completion, the raw field reads and the next issue"}
@@ -489,8 +494,11 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": workload_name(R, sweeps),
                        "kernel": (f"tensor-core (tcgen05, TMEM-resident fields, {16 * cluster} replicas per "
-                                  f"cluster of {cluster} SM(s), 1/{cluster} of the field columns each)")
+                                  f"cluster of {cluster} SM(s), 1/{cluster} of the field columns each"
+                                  + (f"; the last {r_pairs} replicas as cluster pairs of 32 on the 16 SMs the "
+                                     "clusters of 4 leave idle, in a concurrent launch" if r_pairs else "") + ")")
                        if use_tc else "simt",
+                       "replicas_on_cluster_pairs": r_pairs,
                        "coupling_planes": planes if use_tc else None,
                        "replicas_per_gpu": R, "replicas_total": R * world, "sweeps_per_step": sweeps,
                        "replicas_per_group": ng, "ctas_per_group": cluster, "replica_groups": groups,

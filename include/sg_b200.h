@@ -394,6 +394,12 @@ int sg_tc_selftest(sg_engine *e, int planes, const int32_t *sites16, const float
  * 2 = a thread-block cluster pair per 32 replicas, each CTA owning half of the field columns;
  * 1 = one CTA per 16 replicas; 0 = the tensor-core kernel does not take this model. */
 int sg_tc_cluster_size(sg_engine *e);
+/* With clusters of 4 a GPU keeps 33 of them resident (132 of 148 SMs).  When there are more replica
+ * groups than that, a launch of n_sweeps sweeps runs its LAST replicas as cluster pairs on the idle
+ * SMs, concurrently (same results: a replica draws the same random numbers and sees the same
+ * tensor-core updates in either form).  Returns how many replicas that is for the current model
+ * and replica count (0 = none; Philox mode only). */
+int sg_tc_side_replicas(sg_engine *e, int n_sweeps, int coupling_planes);
 
 int sg_query(sg_engine *e, int32_t *n, int32_t *n_pad, int32_t *n_replicas,
              int32_t *max_replicas_per_block, int32_t *sm_count);

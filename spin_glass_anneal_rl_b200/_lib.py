@@ -107,6 +107,7 @@ PROTOTYPES = {
     "sg_get_profile": (c_int, [c_void_p, POINTER(c_double), POINTER(c_uint64), POINTER(c_double),
                                POINTER(c_uint64)]),
     "sg_tc_cluster_size": (c_int, [c_void_p]),
+    "sg_tc_side_replicas": (c_int, [c_void_p, c_int, c_int]),
     "sg_query": (c_int, [c_void_p, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32),
                          POINTER(c_int32), POINTER(c_int32)]),
     "sg_launch_count": (c_uint64, [c_void_p]),

@@ -2082,6 +2082,13 @@ int sg_tc_cluster_size(sg_engine* e) {
     return sg::sweep_tc_cluster_size(e->n_tc, e->R);
 }
 
+int sg_tc_side_replicas(sg_engine* e, int n_sweeps, int coupling_planes) {
+    if (!e || !e->Jp || e->R <= 0 || n_sweeps <= 0) return 0;
+    DeviceGuard g(e->device);
+    const int planes = coupling_planes ? coupling_planes : (e->planes_needed ? e->planes_needed : 3);
+    return sg::sweep_tc_side_replicas(e->n, e->n_tc, planes, e->R, n_sweeps);
+}
+
 int sg_query(sg_engine* e, int32_t* n, int32_t* n_pad, int32_t* n_replicas,
              int32_t* max_replicas_per_block, int32_t* sm_count) {
     SG_REQUIRE(e, "sg_query: NULL engine");

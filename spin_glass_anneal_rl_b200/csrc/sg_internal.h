@@ -33,6 +33,7 @@ struct SweepDev {
     float* site_de;           // optional [R][n]: sum of the accepted energy changes per site
     int rpm;                  // stacked models (K1-SMALL): replicas per model, 0 = one model
     int rep_base;             // global id of replica 0 (Philox key of replica r = rep_base + r; sharded runs)
+    int trace_ld;             // row length of energy_trace (0 = R): a launch over a slice of the replicas
 };
 
 // Largest number of replicas one block can hold for this padded size (0 = unsupported).
@@ -115,6 +116,7 @@ cudaError_t launch_tc_mma_bench(int variant, int n_dim, int iters, long long* ou
 bool sweep_tc_supported(int n, int n_tc);
 size_t sweep_tc_sites_bytes(int n, int n_sweeps, int R);
 int sweep_tc_cluster_size(int n_tc, int R);
+int sweep_tc_side_replicas(int n, int n_tc, int planes, int R, int n_sweeps);
 size_t sweep_tc_stream_bytes_per_sweep(int n, int n_tc, int planes);
 // sites_buf: device scratch of sweep_tc_sites_bytes(); stream_buf: device scratch for the operand
 // stream, at least one sweep's worth (the launch is cut into sub-launches of as many sweeps as

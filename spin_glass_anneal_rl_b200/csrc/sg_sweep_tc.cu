@@ -1327,7 +1327,7 @@ sweep_tc_kernel(const SweepDev a, const __nv_bfloat16* __restrict__ Jp, const in
                     acc += (pr[0] + pr[NG]) + (pr[2 * NG] + pr[3 * NG]);
                 }
                 cur_e = -0.5f * acc;
-                if (a.energy_trace && crank == 0) a.energy_trace[(size_t)s * a.R + rep0 + rl] = cur_e;
+                if (a.energy_trace && crank == 0) a.energy_trace[(size_t)s * (a.trace_ld ? a.trace_ld : a.R) + rep0 + rl] = cur_e;
                 if (a.track_best && cur_e < best_e) {
                     best_e = cur_e;
                     improved = true;
@@ -1731,8 +1731,11 @@ size_t sweep_tc_stream_bytes_per_sweep(int n, int n_tc, int planes) {
 // Sweeps per work item for `groups` replica groups on `n_cta` persistent CTAs: the chunking whose
 // most loaded CTA finishes first (an item costs its sweeps plus ~3% of a sweep for moving the
 // group's state through HBM); ties go to the longer items.
-static int tc_pick_spi(int groups, int S, int n_sm) {
-    if (groups <= n_sm || S <= 1) return S;
+static int tc_pick_spi(int groups, int S, int n_sm, double* cost_out = nullptr) {
+    if (groups <= n_sm || S <= 1) {
+        if (cost_out) *cost_out = S + 0.03;
+        return S;
+    }
     int best_spi = S;
     double best_cost = 1e300;
     for (int spi = S; spi >= 1; --spi) {
@@ -1754,6 +1757,7 @@ static int tc_pick_spi(int groups, int S, int n_sm) {
             best_spi = spi;
         }
     }
+    if (cost_out) *cost_out = best_cost;
     return best_spi;
 }
 
@@ -1817,6 +1821,55 @@ struct TcItemGate {
 };
 static TcItemGate g_item_gate;
 
+// Clusters of 4 leave SMs idle (33 clusters = 132 of 148 SMs: a GPC holds a whole number of them).
+// A second launch of the SAME kernel family with cluster PAIRS runs the last replicas of the engine
+// on those SMs at the same time, on a side stream of its own (non-blocking: the caller's stream may
+// be the legacy default stream).  Replica r draws the same Philox numbers and sees the same MMAs in
+// either form, so the results do not depend on the split.
+struct TcSideStream {
+    std::mutex mu;
+    cudaStream_t st[64] = {};
+    cudaEvent_t ready[64] = {}, done[64] = {};
+    bool have[64] = {};
+};
+static TcSideStream g_side;
+
+// (call with g_side.mu held; the caller keeps it until its launches and event calls are enqueued, so
+// that two host threads never interleave their records of the shared events)
+static cudaError_t tc_side_stream(int dev, cudaStream_t* st, cudaEvent_t* ready, cudaEvent_t* done) {
+    if (!g_side.have[dev]) {
+        cudaError_t e = cudaStreamCreateWithFlags(&g_side.st[dev], cudaStreamNonBlocking);
+        if (e != cudaSuccess) return e;
+        e = cudaEventCreateWithFlags(&g_side.ready[dev], cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+        e = cudaEventCreateWithFlags(&g_side.done[dev], cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+        g_side.have[dev] = true;
+    }
+    *st = g_side.st[dev];
+    *ready = g_side.ready[dev];
+    *done = g_side.done[dev];
+    return cudaSuccess;
+}
+
+// the slice [r0, r0 + count) of the replicas as a launch of its own
+static SweepDev tc_slice(const SweepDev& a, int r0, int count) {
+    SweepDev b = a;
+    b.spins += (size_t)r0 * a.n_pad;
+    b.fields += (size_t)r0 * a.n_pad;
+    b.energy += r0;
+    b.best_energy += r0;
+    b.best_spins += (size_t)r0 * a.n_pad;
+    b.accepted += r0;
+    b.temps += (long long)r0 * a.t_rs;
+    if (b.energy_trace) b.energy_trace += r0;
+    b.trace_ld = a.trace_ld ? a.trace_ld : a.R;
+    b.rep_base = a.rep_base + r0;
+    b.R = count;
+    if (r0) b.dbg = nullptr;   // (the development timeline follows block 0 of the main launch)
+    return b;
+}
+
 // clusters of C CTAs that can be resident at the same time (the persistent work-item schedule must
 // not launch more: a waiting cluster would otherwise hold the SMs a cluster it depends on needs)
 template <int C>
@@ -1839,6 +1892,56 @@ static int tc_max_clusters(size_t smem) {
         return 0;
     }
     return ncl;
+}
+
+// The SMs the clusters of 4 leave idle take the last replicas as cluster pairs: m groups of 32 per
+// idle pair of SMs, m chosen so that neither launch waits for the other (a pair needs ~1.4 x the
+// time of a cluster of 4 per group and sweep).  Returns the number of replicas for the pairs
+// (SG_TC_HYBRID=0: none, SG_TC_HYBRID_M forces m).
+static int tc_side_split(int R, int S, int n_slots, int n_sm) {
+    const char* hy = getenv("SG_TC_HYBRID");
+    const int idle_pairs = (n_sm - 4 * n_slots) / 2;
+    const int groups4 = (R + 4 * kG - 1) / (4 * kG);
+    if ((hy && atoi(hy) == 0) || idle_pairs < 1 || groups4 <= n_slots) return 0;
+    const char* rt = getenv("SG_TC_HYBRID_RATIO");
+    const double ratio = rt ? atof(rt) : 1.4;
+    double best = 0.0;
+    tc_pick_spi(groups4, S, n_slots, &best);
+    int best_m = 0;
+    for (int m = 1; m <= 8; ++m) {
+        const int rb = m * idle_pairs * 2 * kG;
+        if (rb * 4 > R) break;
+        const int ga = (R - rb + 4 * kG - 1) / (4 * kG);
+        if (ga <= n_slots) break;
+        double ta = 0.0;
+        tc_pick_spi(ga, S, n_slots, &ta);
+        const double tb = m * (S * ratio + 0.03);
+        const double t = ta > tb ? ta : tb;
+        if (t < best * 0.985) {
+            best = t;
+            best_m = m;
+        }
+    }
+    if (const char* fm = getenv("SG_TC_HYBRID_M")) {
+        const int v = atoi(fm);
+        if (v >= 0 && v * idle_pairs * 2 * kG * 2 <= R) best_m = v;
+    }
+    return best_m * idle_pairs * 2 * kG;
+}
+
+// replicas a launch of n_sweeps sweeps hands to the pairs (0: everything runs on one cluster size)
+int sweep_tc_side_replicas(int n, int n_tc, int planes, int R, int n_sweeps) {
+    if (planes < 1 || planes > 3 || !sweep_tc_supported(n, n_tc) || sweep_tc_cluster_size(n_tc, R) != 4) return 0;
+    if (getenv("SG_TC_SM")) return 0;
+    int NS = kMaxStagesTc;
+    while (NS > 2 && tc_layout(n_tc, planes, NS, 4).total > 227 * 1024) --NS;
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    int n_slots = tc_max_clusters<4>(tc_layout(n_tc, planes, NS, 4).total);
+    if (n_slots > n_sm / 4) n_slots = n_sm / 4;
+    if (n_slots < 1) return 0;
+    return tc_side_split(R, n_sweeps, n_slots, n_sm);
 }
 
 cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int planes, bool inject,
@@ -1906,9 +2009,6 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
         const size_t units = (size_t)(s1 - s0) * q_per_sweep / 16;
         // persistent CTAs over (sweep chunk, replica group) items when there are more groups than
         // SMs: no partial last wave (SG_TC_SPI=0 forces one CTA per group for all sweeps)
-        const int groups = (a.R + kG * C - 1) / (kG * C);
-        int spi = s1 - s0, grid_groups = groups;
-        bool item_mode = false;
         // CTAs (C = 1) or clusters (C = 2, 4) resident at once
         int n_slots = n_sm;
         if (C > 1) {
@@ -1917,6 +2017,12 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
             if (sm_env_set && n_sm / C < n_slots) n_slots = n_sm / C > 0 ? n_sm / C : 1;
             if (n_slots < 1) n_slots = 1;
         }
+        const int r_side = (C == 4 && !inject && !sm_env_set && dev >= 0 && dev < 64)
+                               ? tc_side_split(a.R, s1 - s0, n_slots, n_sm) : 0;
+        const SweepDev a4 = r_side ? tc_slice(a, 0, a.R - r_side) : a;
+        const int groups = (a4.R + kG * C - 1) / (kG * C);
+        int spi = s1 - s0, grid_groups = groups;
+        bool item_mode = false;
         if (groups > n_slots) {
             spi = tc_pick_spi(groups, s1 - s0, n_slots);
             if (spi_env > 0) spi = spi_env < s1 - s0 ? spi_env : s1 - s0;
@@ -1938,6 +2044,21 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
                 if (err != cudaSuccess) return err;
             }
         }
+        cudaStream_t side_st = nullptr;
+        cudaEvent_t side_ready = nullptr, side_done = nullptr;
+        SweepDev a2 = a;
+        int NS2 = kMaxStagesTc;
+        size_t smem2 = 0;
+        std::unique_lock<std::mutex> side_lock(g_side.mu, std::defer_lock);
+        if (r_side) {
+            side_lock.lock();
+            err = tc_side_stream(dev, &side_st, &side_ready, &side_done);
+            if (err != cudaSuccess) return err;
+            a2 = tc_slice(a, a.R - r_side, r_side);
+            while (NS2 > 2 && tc_layout(n_tc, planes, NS2, 2).total > 227 * 1024) --NS2;
+            smem2 = tc_layout(n_tc, planes, NS2, 2).total;
+            if (smem2 > 227 * 1024) return cudaErrorInvalidValue;
+        }
         unsigned char* tabs = static_cast<unsigned char*>(stream_buf) + (size_t)sub * q_per_sweep;
         const unsigned char* Qc = static_cast<const unsigned char*>(stream_buf);
         int ggrid = (int)((units + 255) / 256 < (size_t)148 * 16 ? (units + 255) / 256 : (size_t)148 * 16);
@@ -1952,16 +2073,33 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
         err = cudaGetLastError();                                                              \
         if (err != cudaSuccess) return err;                                                    \
         if (timer) timer->begin(0, st);                                                        \
-        err = (C == 8) ? launch_tc_variant<P, INJ, 8>(a, J, n_tc, sites, n_s, NS, cols, Qc, tabs,\
+        if (r_side) {                                                                          \
+            err = cudaEventRecord(side_ready, st);                                             \
+            if (err != cudaSuccess) return err;                                                \
+        }                                                                                      \
+        err = (C == 8) ? launch_tc_variant<P, INJ, 8>(a4, J, n_tc, sites, n_s, NS, cols, Qc, tabs,\
                                                       s0, s1, spi, grid_groups, done, dbg, smem, st) \
-            : (C == 4) ? launch_tc_variant<P, INJ, 4>(a, J, n_tc, sites, n_s, NS, cols, Qc, tabs,\
+            : (C == 4) ? launch_tc_variant<P, INJ, 4>(a4, J, n_tc, sites, n_s, NS, cols, Qc, tabs,\
                                                       s0, s1, spi, grid_groups, done, dbg, smem, st) \
-            : (C == 2) ? launch_tc_variant<P, INJ, 2>(a, J, n_tc, sites, n_s, NS, cols, Qc, tabs,\
+            : (C == 2) ? launch_tc_variant<P, INJ, 2>(a4, J, n_tc, sites, n_s, NS, cols, Qc, tabs,\
                                                       s0, s1, spi, grid_groups, done, dbg, smem, st) \
-                       : launch_tc_variant<P, INJ, 1>(a, J, n_tc, sites, n_s, NS, cols, Qc, tabs,\
+                       : launch_tc_variant<P, INJ, 1>(a4, J, n_tc, sites, n_s, NS, cols, Qc, tabs,\
                                                       s0, s1, spi, grid_groups, done, dbg, smem, st); \
-        if (timer) timer->end(st);                                                             \
         if (err != cudaSuccess) return err;                                                    \
+        if (r_side) {   /* the pairs: one group of 32 replicas each for all sweeps, no item waits */ \
+            err = cudaStreamWaitEvent(side_st, side_ready, 0);                                 \
+            if (err != cudaSuccess) return err;                                                \
+            err = launch_tc_variant<P, INJ, 2>(a2, J, n_tc, sites, n_s, NS2, cols, Qc, tabs, s0, s1,\
+                                               s1 - s0, (a2.R + 2 * kG - 1) / (2 * kG),        \
+                                               done + groups, dbg, smem2, side_st);            \
+            if (err != cudaSuccess) return err;                                                \
+            err = cudaEventRecord(side_done, side_st);                                         \
+            if (err != cudaSuccess) return err;                                                \
+            err = cudaStreamWaitEvent(st, side_done, 0);                                       \
+            if (err != cudaSuccess) return err;                                                \
+            ++*launches;                                                                       \
+        }                                                                                      \
+        if (timer) timer->end(st);                                                             \
     }
         if (inject) {
             if (planes == 1) SG_TC(1, true) else if (planes == 2) SG_TC(2, true) else SG_TC(3, true)

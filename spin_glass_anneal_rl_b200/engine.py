@@ -536,6 +536,11 @@ class Engine:
         """CTAs per replica group of the tensor-core sweep (2 = cluster pairs, 1, or 0 = n/a)."""
         return int(self._lib.sg_tc_cluster_size(self._h))
 
+    def tc_side_replicas(self, n_sweeps: int, coupling_planes: int = 0) -> int:
+        """Replicas a tensor-core launch of ``n_sweeps`` sweeps runs as cluster pairs on the SMs the
+        clusters of 4 leave idle (0 = none)."""
+        return int(self._lib.sg_tc_side_replicas(self._h, int(n_sweeps), int(coupling_planes)))
+
     def set_profiling(self, enable: bool) -> None:
         check(self._lib.sg_set_profiling(self._h, 1 if enable else 0), "sg_set_profiling")
 

@@ -260,6 +260,49 @@ def test_tc_clusters_equal_single_cta_groups(engine, monkeypatch, n, R):
     assert outs[0][2].sum() > 0
 
 
+@pytest.mark.parametrize("n,R,planes,integer", [(1024, 2560 + 21, 3, False), (2048, 2560, 1, True)])
+def test_tc_pairs_on_the_idle_sms_are_invisible(engine, monkeypatch, n, R, planes, integer):
+    """More replica groups than resident clusters of 4: the SMs the clusters leave idle (16 of 148)
+    run the last replicas as cluster pairs in a concurrent launch on a side stream.  A replica draws
+    the same Philox numbers and sees the same MMAs in either form: nothing may depend on the split
+    (per-replica ladder temperatures, energy trace, best records, float couplings with 3 planes)."""
+    rng = np.random.default_rng(n + R)
+    J, h = _int_instance(rng, n) if integer else _sk(n)
+    S0 = (rng.integers(0, 2, size=(R, n)) * 2 - 1).astype(np.int8)
+    ns = 3
+    temps = np.tile(np.geomspace(2.0, 0.3, 64), R // 64 + 1)[:R].copy()
+    outs = []
+    for env in ({"SG_TC_HYBRID": "0"}, {"SG_TC_HYBRID_M": "1"}, {"SG_TC_HYBRID_M": "2"}, {}):
+        for k in ("SG_TC_HYBRID", "SG_TC_HYBRID_M"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        _setup(engine, J, h, S0)
+        n0 = engine.launch_count()
+        tr = engine.sweep(ns, temps, temps_replica_stride=1, seed=21, sweep_base=4, site_order="random",
+                          energy_trace=True, kernel="tc", coupling_planes=planes).cpu().numpy()
+        launches = engine.launch_count() - n0
+        outs.append((engine.spins().cpu().numpy(), tr, engine.accepted().cpu().numpy(),
+                     engine.best()[0].cpu().numpy(), engine.best()[1].cpu().numpy(),
+                     engine.fields().cpu().numpy(), engine.energies().cpu().numpy()))
+        if "SG_TC_HYBRID_M" in env:
+            assert launches == 5, "sites, gather, tables, clusters of 4, pairs"
+        if env.get("SG_TC_HYBRID") == "0":
+            assert launches == 4
+    names = ("spins", "energy trace", "accepted", "best energy", "best spins", "fields", "energies")
+    for o in outs[1:]:
+        for name, a, b in zip(names, outs[0], o):
+            if integer or name in ("spins", "accepted", "fields"):
+                assert np.array_equal(a, b), name
+            elif name == "best spins":
+                # the per-sweep energy is a sum over the cluster's column parts: its float rounding
+                # differs between pairs and clusters of 4, so a best record may change on a near tie
+                assert (a != b).any(axis=1).mean() < 0.01, name
+            else:
+                assert np.allclose(a, b, rtol=1e-5, atol=1e-4), (name, np.abs(a - b).max())
+    assert outs[0][2].min() > 0
+
+
 def test_tc_work_item_launches_on_two_streams_do_not_deadlock(monkeypatch):
     """Two engines, two CUDA streams, both launches in the persistent work-item mode (their CTAs
     spin-wait on each other's progress flags): the library chains such launches per device, so
