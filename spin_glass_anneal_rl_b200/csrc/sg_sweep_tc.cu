@@ -1894,10 +1894,12 @@ static int tc_max_clusters(size_t smem) {
     return ncl;
 }
 
-// The SMs the clusters of 4 leave idle take the last replicas as cluster pairs: m groups of 32 per
-// idle pair of SMs, m chosen so that neither launch waits for the other (a pair needs ~1.4 x the
-// time of a cluster of 4 per group and sweep).  Returns the number of replicas for the pairs
-// (SG_TC_HYBRID=0: none, SG_TC_HYBRID_M forces m).
+// The SMs the clusters of 4 leave idle take the last replicas as cluster pairs, in groups of 32: one
+// pair of CTAs per group for all sweeps of the launch, WITHOUT the work-item schedule -- the pairs
+// never wait for each other, so the two concurrent launches cannot hold SMs the other one's missing
+// CTAs need.  The number of groups is chosen so that neither launch waits for the other (a pair
+// needs ~1.4 x the time of a cluster of 4 per group and sweep).  Returns the number of replicas for
+// the pairs (SG_TC_HYBRID=0: none, SG_TC_HYBRID_M forces the number of groups per idle pair).
 static int tc_side_split(int R, int S, int n_slots, int n_sm) {
     const char* hy = getenv("SG_TC_HYBRID");
     const int idle_pairs = (n_sm - 4 * n_slots) / 2;
@@ -1907,26 +1909,30 @@ static int tc_side_split(int R, int S, int n_slots, int n_sm) {
     const double ratio = rt ? atof(rt) : 1.4;
     double best = 0.0;
     tc_pick_spi(groups4, S, n_slots, &best);
-    int best_m = 0;
-    for (int m = 1; m <= 8; ++m) {
-        const int rb = m * idle_pairs * 2 * kG;
+    int best_gb = 0;
+    for (int gb = 1; gb <= 8 * idle_pairs; ++gb) {
+        const int rb = gb * 2 * kG;
         if (rb * 4 > R) break;
         const int ga = (R - rb + 4 * kG - 1) / (4 * kG);
         if (ga <= n_slots) break;
         double ta = 0.0;
         tc_pick_spi(ga, S, n_slots, &ta);
-        const double tb = m * (S * ratio + 0.03);
+        const double tb = ((gb + idle_pairs - 1) / idle_pairs) * (S * ratio + 0.03);
         const double t = ta > tb ? ta : tb;
-        if (t < best * 0.985) {
+        if (t < best * 0.985 && (best_gb == 0 || t < best - 1e-9)) {
             best = t;
-            best_m = m;
+            best_gb = gb;
         }
     }
     if (const char* fm = getenv("SG_TC_HYBRID_M")) {
         const int v = atoi(fm);
-        if (v >= 0 && v * idle_pairs * 2 * kG * 2 <= R) best_m = v;
+        if (v >= 0 && v * idle_pairs * 2 * kG * 2 <= R) best_gb = v * idle_pairs;
     }
-    return best_m * idle_pairs * 2 * kG;
+    if (const char* fg = getenv("SG_TC_HYBRID_GROUPS")) {
+        const int v = atoi(fg);
+        if (v >= 0 && v * 2 * kG * 2 <= R) best_gb = v;
+    }
+    return best_gb * 2 * kG;
 }
 
 // replicas a launch of n_sweeps sweeps hands to the pairs (0: everything runs on one cluster size)
@@ -2047,7 +2053,7 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
         cudaStream_t side_st = nullptr;
         cudaEvent_t side_ready = nullptr, side_done = nullptr;
         SweepDev a2 = a;
-        int NS2 = kMaxStagesTc;
+        int NS2 = kMaxStagesTc, grid2 = 0, spi2 = 0;
         size_t smem2 = 0;
         std::unique_lock<std::mutex> side_lock(g_side.mu, std::defer_lock);
         if (r_side) {
@@ -2058,6 +2064,8 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
             while (NS2 > 2 && tc_layout(n_tc, planes, NS2, 2).total > 227 * 1024) --NS2;
             smem2 = tc_layout(n_tc, planes, NS2, 2).total;
             if (smem2 > 227 * 1024) return cudaErrorInvalidValue;
+            grid2 = r_side / (2 * kG);
+            spi2 = s1 - s0;
         }
         unsigned char* tabs = static_cast<unsigned char*>(stream_buf) + (size_t)sub * q_per_sweep;
         const unsigned char* Qc = static_cast<const unsigned char*>(stream_buf);
@@ -2090,8 +2098,7 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
             err = cudaStreamWaitEvent(side_st, side_ready, 0);                                 \
             if (err != cudaSuccess) return err;                                                \
             err = launch_tc_variant<P, INJ, 2>(a2, J, n_tc, sites, n_s, NS2, cols, Qc, tabs, s0, s1,\
-                                               s1 - s0, (a2.R + 2 * kG - 1) / (2 * kG),        \
-                                               done + groups, dbg, smem2, side_st);            \
+                                               spi2, grid2, done + groups, dbg, smem2, side_st);\
             if (err != cudaSuccess) return err;                                                \
             err = cudaEventRecord(side_done, side_st);                                         \
             if (err != cudaSuccess) return err;                                                \
