@@ -1907,6 +1907,19 @@ static int tc_side_split(int R, int S, int n_slots, int n_sm) {
     if ((hy && atoi(hy) == 0) || idle_pairs < 1 || groups4 <= n_slots) return 0;
     const char* rt = getenv("SG_TC_HYBRID_RATIO");
     const double ratio = rt ? atof(rt) : 1.4;
+    // the search below costs ~0.5 ms of host time: remember the answer for the shape (a launch that
+    // the host does not run ahead of would otherwise pay it on the device's clock)
+    static std::mutex memo_mu;
+    static struct { int R, S, n_slots, n_sm, gb; double ratio; } memo[8];
+    static int memo_n = 0;
+    const bool plain = !getenv("SG_TC_HYBRID_M") && !getenv("SG_TC_HYBRID_GROUPS");
+    if (plain) {
+        std::lock_guard<std::mutex> lock(memo_mu);
+        for (int i = 0; i < memo_n; ++i)
+            if (memo[i].R == R && memo[i].S == S && memo[i].n_slots == n_slots && memo[i].n_sm == n_sm &&
+                memo[i].ratio == ratio)
+                return memo[i].gb * 2 * kG;
+    }
     double best = 0.0;
     tc_pick_spi(groups4, S, n_slots, &best);
     int best_gb = 0;
@@ -1923,6 +1936,11 @@ static int tc_side_split(int R, int S, int n_slots, int n_sm) {
             best = t;
             best_gb = gb;
         }
+    }
+    if (plain) {
+        std::lock_guard<std::mutex> lock(memo_mu);
+        const int i = memo_n < 8 ? memo_n++ : 7;
+        memo[i] = {R, S, n_slots, n_sm, best_gb, ratio};
     }
     if (const char* fm = getenv("SG_TC_HYBRID_M")) {
         const int v = atoi(fm);
