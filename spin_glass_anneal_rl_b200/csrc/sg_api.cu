@@ -131,7 +131,6 @@ struct sg_engine {
     int planes_needed = 0;               // 0 = not read back yet
     unsigned char* best_out = nullptr;   // device: float energy, int replica, int8 spins[n]
     size_t best_out_cap = 0;
-    sg::TcAsync tc_async;                // ordering of the tensor-core sweep's preparation kernels
     // Wolff cluster move: row-major copy of the couplings (built on first use), stream-dry flag
     float* Jrow = nullptr;
     int* wolff_status = nullptr;
@@ -885,9 +884,6 @@ void sg_destroy(sg_engine* e) {
     cudaFree(e->best_out);
     cudaFree(e->Jrow);
     cudaFree(e->wolff_status);
-    if (e->tc_async.buf_free) cudaEventDestroy(e->tc_async.buf_free);
-    if (e->tc_async.model_ready) cudaEventDestroy(e->tc_async.model_ready);
-    if (e->tc_async.prep_done) cudaEventDestroy(e->tc_async.prep_done);
     cudaFree(e->plane_flags);
     cudaFree(e->dig);
     cudaFree(e->scale);
@@ -980,11 +976,6 @@ int sg_set_model_dense(sg_engine* e, int n, const float* J, int64_t ldJ, const f
         SG_CUDA(sg::launch_split_planes(e->Jt, n, n_pad, e->Jp, n_tc, e->plane_flags, st));
         e->planes_needed = 0;   // read back on the first sweep that leaves the choice to the engine
         e->launches++;
-        // the sweep's preparation kernels run on a side stream: they wait for this point
-        if (!e->tc_async.model_ready)
-            SG_CUDA(cudaEventCreateWithFlags(&e->tc_async.model_ready, cudaEventDisableTiming));
-        SG_CUDA(cudaEventRecord(e->tc_async.model_ready, st));
-        e->tc_async.have_model_ready = true;
     }
     if (tmp) {
         SG_CUDA(cudaStreamSynchronize(st));
@@ -1564,7 +1555,7 @@ int sg_sweep(sg_engine* e, const sg_sweep_params* p, void* stream) {
         SG_CUDA(sg::launch_sweep_tc(a, e->Jp, e->n_tc, planes, inject, e->tc_sites, e->tc_stream,
                                     e->tc_stream_cap, &e->launches,
                                     e->profiling ? &e->timer : nullptr,
-                                    static_cast<cudaStream_t>(stream), &e->tc_async));
+                                    static_cast<cudaStream_t>(stream)));
         return SG_OK;
     }
     const int grid = (e->R + G - 1) / G;

@@ -118,24 +118,12 @@ size_t sweep_tc_sites_bytes(int n, int n_sweeps, int R);
 int sweep_tc_cluster_size(int n_tc, int R);
 int sweep_tc_side_replicas(int n, int n_tc, int planes, int R, int n_sweeps);
 size_t sweep_tc_stream_bytes_per_sweep(int n, int n_tc, int planes);
-// Ordering of the tensor-core sweep's preparation kernels (site tables, operand gather, decision
-// tables) across calls: they depend on the couplings and on the scratch buffers being free, not on
-// the replica state, so they run on a side stream and overlap whatever the caller enqueued after
-// the previous sweep (the exact refresh, the exchange round).  One per engine.
-struct TcAsync {
-    cudaEvent_t buf_free = nullptr;     // after a sweep launch: operand stream / site tables may be rewritten
-    cudaEvent_t model_ready = nullptr;  // after the coupling planes were (re)built
-    cudaEvent_t prep_done = nullptr;    // after the preparation kernels of the current sub-launch
-    bool have_buf_free = false, have_model_ready = false;
-};
-
 // sites_buf: device scratch of sweep_tc_sites_bytes(); stream_buf: device scratch for the operand
 // stream, at least one sweep's worth (the launch is cut into sub-launches of as many sweeps as
 // fit).  Launches the site-table kernel, then (gather, sweep) per sub-launch; counts them.
 cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int planes, bool inject,
                             void* sites_buf, void* stream_buf, size_t stream_cap,
-                            uint64_t* launches, KernelTimer* timer, cudaStream_t st,
-                            TcAsync* async = nullptr);
+                            uint64_t* launches, KernelTimer* timer, cudaStream_t st);
 
 // K2-TC (sg_fields_tc.cu): exact field initialisation on the int8 tensor cores
 size_t fields_tc_digits_bytes(int n, int n_tc);

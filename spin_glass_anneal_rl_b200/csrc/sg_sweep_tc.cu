@@ -1970,58 +1970,17 @@ int sweep_tc_side_replicas(int n, int n_tc, int planes, int R, int n_sweeps) {
 
 cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int planes, bool inject,
                             void* sites_buf, void* stream_buf, size_t stream_cap,
-                            uint64_t* launches, KernelTimer* timer, cudaStream_t st, TcAsync* as) {
+                            uint64_t* launches, KernelTimer* timer, cudaStream_t st) {
     if (planes < 1 || planes > 3 || !sweep_tc_supported(a.n, n_tc)) return cudaErrorInvalidValue;
     if (a.site_mode == 3 || (a.site_mode == 2 && a.s_bs != 0)) return cudaErrorInvalidValue;
     const int n_s = (a.n + 15) / 16 * 16;
     uint16_t* sites = static_cast<uint16_t*>(sites_buf);
-    int dev = 0, n_sm = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t err = cudaSuccess;
-    // the side stream of this device (preparation kernels, cluster pairs); its mutex is held for the
-    // whole call so that two host threads never interleave their records of the shared events
-    const bool dev_ok = dev >= 0 && dev < 64;
-    std::unique_lock<std::mutex> side_lock(g_side.mu, std::defer_lock);
-    cudaStream_t side_st = nullptr;
-    cudaEvent_t side_ready = nullptr, side_done = nullptr;
-    if (dev_ok) {
-        side_lock.lock();
-        err = tc_side_stream(dev, &side_st, &side_ready, &side_done);
-        if (err != cudaSuccess) return err;
-    }
-    // Preparation kernels on the side stream (SG_TC_OVERLAP=0: on the caller's stream): they wait for
-    // the coupling planes and for the previous sweep to be done with the scratch buffers, not for
-    // what the caller enqueued since (explicit site lists come from the caller's stream: no overlap)
-    const char* ov_env = getenv("SG_TC_OVERLAP");
-    const bool overlap = as && dev_ok && a.site_mode != 2 && !(ov_env && atoi(ov_env) == 0);
-    if (as) {
-        if (!as->buf_free) {
-            err = cudaEventCreateWithFlags(&as->buf_free, cudaEventDisableTiming);
-            if (err != cudaSuccess) return err;
-        }
-        if (!as->prep_done) {
-            err = cudaEventCreateWithFlags(&as->prep_done, cudaEventDisableTiming);
-            if (err != cudaSuccess) return err;
-        }
-    }
-    cudaStream_t prep_st = overlap ? side_st : st;
-    if (overlap) {
-        if (as->have_model_ready) {
-            err = cudaStreamWaitEvent(side_st, as->model_ready, 0);
-            if (err != cudaSuccess) return err;
-        }
-        if (as->have_buf_free) {
-            err = cudaStreamWaitEvent(side_st, as->buf_free, 0);
-            if (err != cudaSuccess) return err;
-        }
-    }
     {
         const int total = a.n_sweeps * (n_s / 4);
         int grid = (total + 255) / 256;
         if (grid > 1184) grid = 1184;
-        tc_sites_kernel<<<grid, 256, 0, prep_st>>>(a.site_mode, a.seed, a.sweep_base, a.n, n_s,
-                                                   a.n_sweeps, a.sites, a.s_ss, sites);
+        tc_sites_kernel<<<grid, 256, 0, st>>>(a.site_mode, a.seed, a.sweep_base, a.n, n_s,
+                                              a.n_sweeps, a.sites, a.s_ss, sites);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         ++*launches;
@@ -2054,6 +2013,9 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
     const int dbg = dbg_env ? atoi(dbg_env) : 0;
     const char* spi_s = getenv("SG_TC_SPI");
     const int spi_env = spi_s ? atoi(spi_s) : -1;
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     bool sm_env_set = false;
     if (const char* sm_env = getenv("SG_TC_SM")) {   // tests: pretend the GPU has fewer SMs
         const int v = atoi(sm_env);
@@ -2065,6 +2027,7 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
     // per-group progress counters live behind the site tables
     int* done = reinterpret_cast<int*>(static_cast<unsigned char*>(sites_buf) +
                                        (((size_t)a.n_sweeps * n_s * sizeof(uint16_t) + 15) & ~(size_t)15));
+    cudaError_t err = cudaSuccess;
     for (int s0 = 0; s0 < a.n_sweeps; s0 += sub) {
         const int s1 = (s0 + sub < a.n_sweeps) ? s0 + sub : a.n_sweeps;
         const size_t units = (size_t)(s1 - s0) * q_per_sweep / 16;
@@ -2078,7 +2041,7 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
             if (sm_env_set && n_sm / C < n_slots) n_slots = n_sm / C > 0 ? n_sm / C : 1;
             if (n_slots < 1) n_slots = 1;
         }
-        const int r_side = (C == 4 && !inject && !sm_env_set && dev_ok)
+        const int r_side = (C == 4 && !inject && !sm_env_set && dev >= 0 && dev < 64)
                                ? tc_side_split(a.R, s1 - s0, n_slots, n_sm) : 0;
         const SweepDev a4 = r_side ? tc_slice(a, 0, a.R - r_side) : a;
         const int groups = (a4.R + kG * C - 1) / (kG * C);
@@ -2098,17 +2061,23 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
             }
         }
         std::unique_lock<std::mutex> gate(g_item_gate.mu, std::defer_lock);
-        if (item_mode && dev_ok) {
+        if (item_mode && dev >= 0 && dev < 64) {
             gate.lock();
             if (g_item_gate.have[dev]) {
                 err = cudaStreamWaitEvent(st, g_item_gate.ev[dev], 0);
                 if (err != cudaSuccess) return err;
             }
         }
+        cudaStream_t side_st = nullptr;
+        cudaEvent_t side_ready = nullptr, side_done = nullptr;
         SweepDev a2 = a;
         int NS2 = kMaxStagesTc, grid2 = 0, spi2 = 0;
         size_t smem2 = 0;
+        std::unique_lock<std::mutex> side_lock(g_side.mu, std::defer_lock);
         if (r_side) {
+            side_lock.lock();
+            err = tc_side_stream(dev, &side_st, &side_ready, &side_done);
+            if (err != cudaSuccess) return err;
             a2 = tc_slice(a, a.R - r_side, r_side);
             while (NS2 > 2 && tc_layout(n_tc, planes, NS2, 2).total > 227 * 1024) --NS2;
             smem2 = tc_layout(n_tc, planes, NS2, 2).total;
@@ -2119,26 +2088,16 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
         unsigned char* tabs = static_cast<unsigned char*>(stream_buf) + (size_t)sub * q_per_sweep;
         const unsigned char* Qc = static_cast<const unsigned char*>(stream_buf);
         int ggrid = (int)((units + 255) / 256 < (size_t)148 * 16 ? (units + 255) / 256 : (size_t)148 * 16);
-        if (overlap && s0 > 0) {   // the previous sub-launch still reads the operand stream
-            err = cudaStreamWaitEvent(side_st, as->buf_free, 0);
-            if (err != cudaSuccess) return err;
-        }
 #define SG_TC(P, INJ)                                                                          \
     {                                                                                          \
-        if (timer) timer->begin(1, prep_st);                                                   \
-        tc_gather_kernel<P><<<ggrid, 256, 0, prep_st>>>(J, a.n, n_tc, sites, n_s, s0, s1 - s0, \
-                                                        nblk, nchunk, static_cast<uint4*>(stream_buf)); \
-        tc_tables_kernel<P><<<(s1 - s0) * nblk, 256, 0, prep_st>>>(J, a.n, n_tc, sites, n_s, s0, \
-                                                                   nblk, tabs);                \
-        if (timer) timer->end(prep_st);                                                        \
+        if (timer) timer->begin(1, st);                                                        \
+        tc_gather_kernel<P><<<ggrid, 256, 0, st>>>(J, a.n, n_tc, sites, n_s, s0, s1 - s0, nblk,\
+                                                   nchunk, static_cast<uint4*>(stream_buf));   \
+        tc_tables_kernel<P><<<(s1 - s0) * nblk, 256, 0, st>>>(J, a.n, n_tc, sites, n_s, s0,    \
+                                                              nblk, tabs);                     \
+        if (timer) timer->end(st);                                                             \
         err = cudaGetLastError();                                                              \
         if (err != cudaSuccess) return err;                                                    \
-        if (overlap) {                                                                         \
-            err = cudaEventRecord(as->prep_done, side_st);                                     \
-            if (err != cudaSuccess) return err;                                                \
-            err = cudaStreamWaitEvent(st, as->prep_done, 0);                                   \
-            if (err != cudaSuccess) return err;                                                \
-        }                                                                                      \
         if (timer) timer->begin(0, st);                                                        \
         if (r_side) {                                                                          \
             err = cudaEventRecord(side_ready, st);                                             \
@@ -2175,11 +2134,6 @@ cudaError_t launch_sweep_tc(const SweepDev& a, const void* Jp, int n_tc, int pla
 #undef SG_TC
         err = cudaGetLastError();
         if (err != cudaSuccess) return err;
-        if (as) {   // from here on the scratch buffers may be rewritten
-            err = cudaEventRecord(as->buf_free, st);
-            if (err != cudaSuccess) return err;
-            as->have_buf_free = true;
-        }
         if (gate.owns_lock()) {
             if (!g_item_gate.have[dev]) {
                 err = cudaEventCreateWithFlags(&g_item_gate.ev[dev], cudaEventDisableTiming);

@@ -303,53 +303,6 @@ def test_tc_pairs_on_the_idle_sms_are_invisible(engine, monkeypatch, n, R, plane
     assert outs[0][2].min() > 0
 
 
-def test_tc_preparation_on_the_side_stream_is_invisible(monkeypatch):
-    """The site tables, the operand gather and the decision tables of a launch run on a side stream
-    (they only depend on the couplings and on the previous sweep being done with the scratch
-    buffers), overlapping the refresh / exchange the caller enqueued in between.  Same results as
-    with everything on the caller's stream (SG_TC_OVERLAP=0) -- for back-to-back launches, right
-    after a model upload, after a model change, and on a non-default stream."""
-    import torch
-    from spin_glass_anneal_rl_b200.engine import Engine
-    rng = np.random.default_rng(5)
-    n, R = 4096, 200
-    J1, h1 = _sk(n, 11)
-    J2, h2 = _sk(n, 12)
-    S0 = (rng.integers(0, 2, size=(R, n)) * 2 - 1).astype(np.int8)
-    Jd = [torch.from_numpy(J).cuda() for J in (J1, J2)]
-    hd = [torch.from_numpy(h).cuda() for h in (h1, h2)]
-    ladder = np.geomspace(2.0, 0.2, 8)
-
-    def run(stream):
-        eng = Engine(0)
-        out = []
-        with torch.cuda.stream(stream):
-            for m in (0, 1, 0):
-                eng.set_model(Jd[m], hd[m])          # device upload: the planes are split asynchronously
-                eng.alloc_replicas(R)
-                eng.set_spins(S0)
-                eng.init_fields()
-                eng.set_ladder(ladder)
-                for k in range(4):                   # a parallel-tempering loop, nothing synchronises
-                    eng.sweep(2, None, seed=3, sweep_base=2 * k, site_order="random", kernel="tc")
-                    eng.refresh_fields()
-                    eng.exchange(k & 1, seed=9, round=k)
-                out.append((eng.spins().cpu().numpy(), eng.energies().cpu().numpy(),
-                            eng.accepted().cpu().numpy(), eng.ladder_state()[0].cpu().numpy()))
-        torch.cuda.synchronize()
-        return out
-
-    monkeypatch.setenv("SG_TC_OVERLAP", "0")
-    ref = run(torch.cuda.default_stream())
-    monkeypatch.delenv("SG_TC_OVERLAP")
-    for stream in (torch.cuda.default_stream(), torch.cuda.Stream()):
-        got = run(stream)
-        for a, b in zip(ref, got):
-            for x, y in zip(a, b):
-                assert np.array_equal(x, y)
-    assert not np.array_equal(ref[0][0], ref[1][0])
-
-
 def test_tc_work_item_launches_on_two_streams_do_not_deadlock(monkeypatch):
     """Two engines, two CUDA streams, both launches in the persistent work-item mode (their CTAs
     spin-wait on each other's progress flags): the library chains such launches per device, so
