@@ -328,8 +328,8 @@ __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t x, int lane) {
     return x;
 }
 
-template <int W4, bool INJECT>   // W4 = float4 loads per lane and walk (7: n_pad 896, 14: n_pad 1792)
-__global__ void __launch_bounds__(kWolffThreads, W4 <= 7 ? 4 : 3) wolff_warp_kernel(const WolffDev a) {
+template <int W4, bool INJECT>   // W4 = float4 loads per lane and walk: 128 W4 >= n columns
+__global__ void __launch_bounds__(kWolffThreads, W4 <= 8 ? 4 : 3) wolff_warp_kernel(const WolffDev a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int n = a.n, n_pad = a.n_pad;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -382,8 +382,7 @@ __global__ void __launch_bounds__(kWolffThreads, W4 <= 7 ? 4 : 3) wolff_warp_ker
                 const float4* row = reinterpret_cast<const float4*>(rowf) + lane;
                 float4 v[W4];
 #pragma unroll
-                for (int q = 0; q < W4; ++q)
-                    v[q] = (128 * q < n) ? __ldg(row + 32 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int q = 0; q < W4; ++q) v[q] = __ldg(row + 32 * q);
 #pragma unroll
                 for (int q = 0; q < W4; ++q) {
                     const uint32_t m = (v[q].x < 0.0f ? 1u : 0u) | (v[q].y < 0.0f ? 2u : 0u) |
@@ -514,9 +513,14 @@ static bool wolff_force_cta() {
 }
 
 cudaError_t launch_wolff(const WolffDev& a, bool inject, cudaStream_t st) {
-    if (!wolff_force_cta()) {   // small models: a warp per replica
-        if (a.n_pad == 896) return launch_warp<7>(a, inject, st);
-        if (a.n_pad == 1792) return launch_warp<14>(a, inject, st);
+    if (!wolff_force_cta() && a.n_pad <= 1792) {   // small models: a warp per replica
+        const int q = (a.n + 127) / 128;            // float4 loads per lane that cover the n columns
+        if (q <= 2) return launch_warp<2>(a, inject, st);
+        if (q <= 4) return launch_warp<4>(a, inject, st);
+        if (q <= 7) return launch_warp<7>(a, inject, st);
+        if (q <= 8) return launch_warp<8>(a, inject, st);
+        if (q <= 10) return launch_warp<10>(a, inject, st);
+        return launch_warp<14>(a, inject, st);
     }
     const size_t smem = (size_t)a.n_pad + (size_t)(a.n_pad / 32) * 4 + (size_t)a.n * 4;
     const int np = (a.n_pad + kWolffCols - 1) / kWolffCols;
