@@ -7,8 +7,9 @@
 // cluster, has coupling < 0 and the same spin; accepted with probability 1 - exp(2 J / T).  The
 // whole cluster is flipped at the end; a sweep is n such updates.
 //
-// Here: ONE CTA PER REPLICA, the replica's spins, the cluster bitmap and the queue in shared
-// memory.  A dequeued site's row (n_pad floats of the row-major copy of J, L2 resident) is read
+// Two forms (launch_wolff picks): a WARP per replica for n <= 1792 (further down), and, for larger
+// dense models, ONE CTA PER REPLICA with the replica's spins, the cluster bitmap and the queue in shared
+// memory.  In the CTA form a dequeued site's row (n_pad floats of the row-major copy of J, L2 resident) is read
 // once by the 256 threads, four consecutive columns per thread and pass, all passes in flight
 // together.  Nothing in one row walk depends on another column of the same walk (a column is
 // visited once, cluster membership only changes for columns accepted in this very walk), so the
@@ -318,15 +319,6 @@ struct PassCursor {
         return base + PassCount<W4>::byte_of(pc.inc, q) - PassCount<W4>::byte_of(pk, q) + within++;
     }
 };
-
-__device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t x, int lane) {
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, x, d);
-        if (lane >= d) x += t;
-    }
-    return x;
-}
 
 template <int W4, bool INJECT>   // W4 = float4 loads per lane and walk: 128 W4 >= n columns
 __global__ void __launch_bounds__(kWolffThreads, W4 <= 8 ? 4 : 3) wolff_warp_kernel(const WolffDev a) {
