@@ -57,6 +57,24 @@ def test_no_gpu_fails_loudly():
         sg.GPUAnnealer(sg.GPUAnnealerConfig(n_sweeps=2)).anneal(m)
 
 
+def test_wolff_rule_is_routed_and_guarded():
+    """UpdateRule.WOLFF is a known rule of the sweep path; it needs a model the engine holds dense."""
+    from spin_glass_anneal_rl_b200.annealing import _backend
+    from spin_glass_anneal_rl_b200.core.spin_dynamics import UpdateRule
+    assert _backend.rule_name(UpdateRule.WOLFF) == "wolff" and _lib.SG_RULE["wolff"] == 3
+    with pytest.raises(NotImplementedError):
+        _backend.rule_name("swendsen_wang")
+
+    class _Eng:
+        kind = "csr"
+    with pytest.raises(NotImplementedError, match="dense"):
+        _backend.require_dense_for_wolff(_Eng())
+    _Eng.kind = "dense"
+    _backend.require_dense_for_wolff(_Eng())
+    header = open(os.path.join(ROOT, "include", "sg_b200.h")).read()
+    assert "#define SG_RULE_WOLFF 3" in header and "sg_sweep_wolff" in header
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "spin_glass_anneal_rl_b200")
     for base, _, files in os.walk(pkg):
