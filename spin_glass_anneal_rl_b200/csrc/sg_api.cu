@@ -134,6 +134,9 @@ struct sg_engine {
     // Wolff cluster move: row-major copy of the couplings (built on first use), stream-dry flag
     float* Jrow = nullptr;
     int* wolff_status = nullptr;
+    unsigned short* wolff_nb_col = nullptr;   // neighbour lists (rows with at most 32 negative couplings)
+    float* wolff_nb_val = nullptr;
+    int wolff_max_deg = -1;                    // -1: not counted yet for this model
 };
 
 namespace {
@@ -884,6 +887,8 @@ void sg_destroy(sg_engine* e) {
     cudaFree(e->best_out);
     cudaFree(e->Jrow);
     cudaFree(e->wolff_status);
+    cudaFree(e->wolff_nb_col);
+    cudaFree(e->wolff_nb_val);
     cudaFree(e->plane_flags);
     cudaFree(e->dig);
     cudaFree(e->scale);
@@ -931,6 +936,11 @@ int sg_set_model_dense(sg_engine* e, int n, const float* J, int64_t ldJ, const f
     e->n_pad = n_pad;
     cudaFree(e->Jrow);
     e->Jrow = nullptr;
+    cudaFree(e->wolff_nb_col);
+    e->wolff_nb_col = nullptr;
+    cudaFree(e->wolff_nb_val);
+    e->wolff_nb_val = nullptr;
+    e->wolff_max_deg = -1;
     int rc;
     if ((rc = dev_alloc(&e->Jt, (size_t)n * n_pad)) != SG_OK) return rc;
     if ((rc = dev_alloc(&e->h, (size_t)n_pad)) != SG_OK) return rc;
@@ -1597,9 +1607,26 @@ int sg_sweep_wolff(sg_engine* e, const sg_wolff_params* p, void* stream) {
     if (!e->wolff_status) {
         if ((rc = dev_alloc(&e->wolff_status, (size_t)1)) != SG_OK) return rc;
     }
+    if (e->wolff_max_deg < 0) {   // once per model: do the rows' negative couplings fit neighbour lists?
+        SG_CUDA(cudaMemsetAsync(e->wolff_status, 0, sizeof(int), st));
+        SG_CUDA(sg::launch_wolff_neg_count(e->Jrow, e->n, e->n_pad, e->wolff_status, st));
+        int max_deg = 0;
+        SG_CUDA(cudaMemcpyAsync(&max_deg, e->wolff_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaStreamSynchronize(st));
+        e->wolff_max_deg = max_deg;
+        e->launches++;
+        if (max_deg <= 32 && e->n < 65535) {
+            if ((rc = dev_alloc(&e->wolff_nb_col, (size_t)e->n * 32)) != SG_OK) return rc;
+            if ((rc = dev_alloc(&e->wolff_nb_val, (size_t)e->n * 32)) != SG_OK) return rc;
+            SG_CUDA(sg::launch_wolff_neg_fill(e->Jrow, e->n, e->n_pad, e->wolff_nb_col, e->wolff_nb_val, st));
+            e->launches++;
+        }
+    }
     if (inject) SG_CUDA(cudaMemsetAsync(e->wolff_status, 0, sizeof(int), st));
     sg::WolffDev a{};
     a.Jrow = e->Jrow;
+    a.nb_col = e->wolff_nb_col;
+    a.nb_val = e->wolff_nb_val;
     a.spins = e->spins;
     a.accepted = e->accepted;
     if (p->temps) {

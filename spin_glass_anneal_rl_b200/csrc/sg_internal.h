@@ -215,6 +215,8 @@ cudaError_t launch_sites_table(const SweepDev& a, int* out, cudaStream_t st);
 // K1-WOLFF (sg_wolff.cu): the reference's cluster move, one CTA per replica, one launch per sweep
 struct WolffDev {
     const float* Jrow;        // [n][n_pad] row-major couplings: Jrow[c][j] = J[c][j]
+    const unsigned short* nb_col;  // [n][32] ascending columns with a negative coupling (0xFFFF: none), or null
+    const float* nb_val;      // [n][32] their couplings
     int8_t* spins;            // [R][n_pad]
     unsigned long long* accepted;  // [R] += cluster sizes
     const double* temps;      // T(s, r) = temps[s*t_ss + r*t_rs]
@@ -229,6 +231,9 @@ struct WolffDev {
     int n, n_pad, R, sweep, rep_base;
 };
 cudaError_t launch_wolff(const WolffDev& a, bool inject, cudaStream_t st);
+cudaError_t launch_wolff_neg_count(const float* Jrow, int n, int n_pad, int* max_deg, cudaStream_t st);
+cudaError_t launch_wolff_neg_fill(const float* Jrow, int n, int n_pad, unsigned short* nb_col, float* nb_val,
+                                  cudaStream_t st);
 cudaError_t launch_wolff_record(const float* energy, float* best_energy, const int8_t* spins,
                                 int8_t* best_spins, float* trace_row, int n_pad, int R, int track_best,
                                 cudaStream_t st);

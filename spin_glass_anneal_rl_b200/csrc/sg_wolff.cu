@@ -454,6 +454,153 @@ __global__ void __launch_bounds__(kWolffThreads, W4 <= 8 ? 4 : 3) wolff_warp_ker
     if (INJECT && dry) *a.status = 1;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Models whose rows hold at most 32 NEGATIVE couplings (lattices, sparse graphs stored dense): only
+// those columns can ever be candidates, so a walk does not need the row at all.  The engine builds,
+// once per model, the ascending list of negative columns of every row (32 slots per row: column,
+// value); a walk is ONE LANE PER LIST ENTRY -- index order is lane order, the two ordered counts are
+// two ballots -- and touches 32 x 6 bytes instead of 4 n.  One warp per replica, any n the dense
+// engine takes; spins and cluster membership are bit arrays in shared memory (cleared / flipped per
+// cluster member, not per column).  Same Philox counters per (update, visit, column quad) as the
+// row-walking forms: all three give the same spins in both RNG modes.
+template <bool INJECT>
+__global__ void __launch_bounds__(kWolffThreads) wolff_list_kernel(const WolffDev a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int n = a.n, n_pad = a.n_pad;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rep = blockIdx.x * kWolffWarps + warp;
+    if (rep >= a.R) return;   // (no block-wide barrier below)
+    const int words = (n + 31) / 32;
+    const size_t per_warp = (((size_t)n * 2 + (size_t)words * 8) + 15) & ~(size_t)15;
+    unsigned char* base = smem + (size_t)warp * per_warp;
+    uint32_t* sbits = reinterpret_cast<uint32_t*>(base);              // [words] spin up
+    uint32_t* cbits = sbits + words;                                   // [words] in the cluster
+    unsigned short* queue = reinterpret_cast<unsigned short*>(cbits + words);   // [n]
+
+    int8_t* spins_g = a.spins + (size_t)rep * n_pad;
+    for (int w = lane; w < words; w += 32) {
+        uint32_t m = 0u;
+        for (int i = 0; i < 32; ++i) {
+            const int j = w * 32 + i;
+            if (j < n && spins_g[j] > 0) m |= 1u << i;
+        }
+        sbits[w] = m;
+        cbits[w] = 0u;
+    }
+    const double T = a.temps[(long long)a.sweep * a.t_ss + (long long)rep * a.t_rs];
+    const float inv_t = (float)(1.0 / T);
+    const int* sites = a.sites + (long long)rep * a.s_rs + (long long)a.sweep * a.s_ss;
+    const float* ustream = INJECT ? a.uniforms + (long long)rep * a.u_rs : nullptr;
+    long long cur = INJECT ? a.cursor[rep] : 0;
+    const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32) ^ kWolffKeyTag);
+    const unsigned long long upd0 = a.sweep_abs * (unsigned long long)n;
+    unsigned long long flips = 0;
+    bool dry = false;
+    const uint32_t lt = (1u << lane) - 1u;
+    __syncwarp();
+
+#pragma unroll 1
+    for (int k = 0; k < n; ++k) {
+        const int start = sites[k];
+        if (lane == 0) {
+            queue[0] = (unsigned short)start;
+            cbits[start >> 5] = 1u << (start & 31);   // (all other cluster bits are clear here)
+        }
+        __syncwarp();
+        int head = 0, tail = 1;
+        const unsigned long long upd = upd0 + (unsigned long long)k;
+#pragma unroll 1
+        while (head < tail) {
+            const int c = queue[head];
+            const bool c_up = (sbits[c >> 5] >> (c & 31)) & 1u;
+            const int j = a.nb_col[(size_t)c * 32 + lane];          // ascending; 0xFFFF beyond the row's list
+            bool cand = false;
+            if (j < n) {
+                const bool up = (sbits[j >> 5] >> (j & 31)) & 1u;
+                const bool in = (cbits[j >> 5] >> (j & 31)) & 1u;
+                cand = (up == c_up) && !in;                           // (j == c is in the cluster)
+            }
+            const uint32_t cmask = __ballot_sync(0xFFFFFFFFu, cand);
+            const int visit = head++;
+            if (cmask == 0u) continue;                                // the walk draws nothing
+            bool take = false;
+            if (cand) {
+                float u;
+                if (INJECT) {
+                    const long long at = cur + (long long)__popc(cmask & lt);
+                    if (at < a.u_len) u = ustream[at];
+                    else { u = 2.0f; dry = true; }
+                } else {
+                    const uint4 x = philox4x32_10(
+                        make_uint4((uint32_t)(rep + a.rep_base), (uint32_t)upd, (uint32_t)(upd >> 32),
+                                   ((uint32_t)visit << 11) | (uint32_t)(j >> 2)), key);
+                    const int i = j & 3;
+                    u = u01(i == 0 ? x.x : i == 1 ? x.y : i == 2 ? x.z : x.w);
+                }
+                take = u < wolff_prob<INJECT>(a.nb_val[(size_t)c * 32 + lane], T, inv_t);
+            }
+            if (INJECT) cur += (long long)__popc(cmask);
+            const uint32_t amask = __ballot_sync(0xFFFFFFFFu, take);
+            if (amask == 0u) continue;                                // the cluster did not grow
+            if (take) {
+                queue[tail + __popc(amask & lt)] = (unsigned short)j;
+                atomicOr(&cbits[j >> 5], 1u << (j & 31));
+            }
+            tail += __popc(amask);
+            __syncwarp();   // queue and bit arrays of this walk visible to the next one
+        }
+        for (int q = lane; q < tail; q += 32) {   // flip the cluster, take its members out again
+            const int j = queue[q];
+            atomicXor(&sbits[j >> 5], 1u << (j & 31));
+            atomicAnd(&cbits[j >> 5], ~(1u << (j & 31)));
+        }
+        flips += (unsigned long long)tail;
+        __syncwarp();
+    }
+    for (int j = lane; j < n; j += 32) spins_g[j] = ((sbits[j >> 5] >> (j & 31)) & 1u) ? (int8_t)1 : (int8_t)-1;
+    if (lane == 0) {
+        a.accepted[rep] += flips;
+        if (INJECT) a.cursor[rep] = cur;
+    }
+    if (INJECT && dry) *a.status = 1;
+}
+
+// number of negative couplings of every row and their maximum (one warp per row)
+__global__ void wolff_neg_count_kernel(const float* __restrict__ Jrow, int n, int n_pad, int* __restrict__ max_deg) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    int cnt = 0;
+    for (int j = lane; j < n; j += 32) cnt += Jrow[(size_t)row * n_pad + j] < 0.0f;
+    for (int d = 16; d; d >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, d);
+    if (lane == 0) atomicMax(max_deg, cnt);
+}
+
+// the ascending list of negative columns of every row, 32 slots per row (only called when they fit)
+__global__ void wolff_neg_fill_kernel(const float* __restrict__ Jrow, int n, int n_pad,
+                                      unsigned short* __restrict__ nb_col, float* __restrict__ nb_val) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    nb_col[(size_t)row * 32 + lane] = 0xFFFFu;
+    nb_val[(size_t)row * 32 + lane] = 0.0f;
+    __syncwarp();
+    int at = 0;
+    for (int j0 = 0; j0 < n; j0 += 32) {
+        const int j = j0 + lane;
+        const float v = (j < n) ? Jrow[(size_t)row * n_pad + j] : 0.0f;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, v < 0.0f);
+        if (v < 0.0f) {
+            const int slot = at + __popc(m & ((1u << lane) - 1u));
+            if (slot < 32) {
+                nb_col[(size_t)row * 32 + slot] = (unsigned short)j;
+                nb_val[(size_t)row * 32 + slot] = v;
+            }
+        }
+        at += __popc(m);
+    }
+}
+
 // after the exact energy refresh of a sweep: trace row and compare-and-keep best
 __global__ void wolff_record_kernel(const float* __restrict__ energy, float* __restrict__ best_energy,
                                     const int8_t* __restrict__ spins, int8_t* __restrict__ best_spins,
@@ -498,13 +645,44 @@ cudaError_t launch_warp(const WolffDev& a, bool inject, cudaStream_t st) {
 
 }  // namespace
 
-// SG_WOLFF_FORM=cta forces the CTA-per-replica form for every size (tests, A/B timing)
+// SG_WOLFF_FORM (tests, A/B timing): "cta" forces the CTA-per-replica form for every size, "row" the
+// row-walking forms (warp or CTA by size) also for models that have neighbour lists
 static bool wolff_force_cta() {
     const char* f = getenv("SG_WOLFF_FORM");
     return f && f[0] == 'c';
 }
+static bool wolff_force_row() {
+    const char* f = getenv("SG_WOLFF_FORM");
+    return f && (f[0] == 'c' || f[0] == 'r');
+}
+
+cudaError_t launch_wolff_neg_count(const float* Jrow, int n, int n_pad, int* max_deg, cudaStream_t st) {
+    wolff_neg_count_kernel<<<(n + 7) / 8, 256, 0, st>>>(Jrow, n, n_pad, max_deg);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_wolff_neg_fill(const float* Jrow, int n, int n_pad, unsigned short* nb_col, float* nb_val,
+                                  cudaStream_t st) {
+    wolff_neg_fill_kernel<<<(n + 7) / 8, 256, 0, st>>>(Jrow, n, n_pad, nb_col, nb_val);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_wolff(const WolffDev& a, bool inject, cudaStream_t st) {
+    if (a.nb_col && !wolff_force_row()) {   // at most 32 negative couplings per row: neighbour lists
+        const size_t per_warp = (((size_t)a.n * 2 + (size_t)((a.n + 31) / 32) * 8) + 15) & ~(size_t)15;
+        const size_t smem = per_warp * kWolffWarps;
+        const int grid = (a.R + kWolffWarps - 1) / kWolffWarps;
+        cudaError_t e = inject ? cudaFuncSetAttribute(wolff_list_kernel<true>,
+                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                               : cudaFuncSetAttribute(wolff_list_kernel<false>,
+                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (inject)
+            wolff_list_kernel<true><<<grid, kWolffThreads, smem, st>>>(a);
+        else
+            wolff_list_kernel<false><<<grid, kWolffThreads, smem, st>>>(a);
+        return cudaGetLastError();
+    }
     if (!wolff_force_cta() && a.n_pad <= 1792) {   // small models: a warp per replica
         const int q = (a.n + 127) / 128;            // float4 loads per lane that cover the n columns
         if (q <= 2) return launch_warp<2>(a, inject, st);

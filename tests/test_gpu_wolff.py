@@ -80,8 +80,19 @@ def _sparse_neg_model(n, seed, degree=3, integer=True, asym=False):
 
 
 # ------------------------------------------------------------------ replay of the reference's runs
+def _set_form(monkeypatch, form):
+    """list: neighbour lists (the default where every row has at most 32 negative couplings);
+    row: the row-walking forms (a warp per replica up to n = 1792, a CTA above); cta: a CTA always."""
+    if form == "list":
+        monkeypatch.delenv("SG_WOLFF_FORM", raising=False)
+    else:
+        monkeypatch.setenv("SG_WOLFF_FORM", form)
+
+
+@pytest.mark.parametrize("form", ["list", "row"])
 @pytest.mark.parametrize("name", golden_names("wolff_"))
-def test_engine_replay_walks_the_reference_clusters(oracle, name):
+def test_engine_replay_walks_the_reference_clusters(oracle, monkeypatch, name, form):
+    _set_form(monkeypatch, form)
     g = load_golden(name)
     ores = _oracle_run(oracle, g)
     n = g["J"].shape[0]
@@ -145,16 +156,19 @@ def test_anneal_replay_reproduces_the_reference(oracle, name):
 
 # ------------------------------------------------------------------ wider shapes against the oracle
 @pytest.mark.parametrize("n,R,integer,asym,T,form", [
-    (300, 5, True, False, 5.0, "warp"),    # n_pad = 896: a warp per replica, 28 columns per lane
+    (300, 5, True, False, 5.0, "list"),    # neighbour lists (rows with at most 32 negative couplings)
+    (300, 5, True, False, 5.0, "row"),     # n_pad = 896: a warp per replica walks the row
     (300, 11, True, False, 5.0, "cta"),    # the same through the CTA-per-replica form (one pass)
-    (1100, 3, True, True, 3.5, "warp"),    # n_pad = 1792, asymmetric couplings (row of the dequeued site)
+    (1100, 3, True, True, 3.5, "list"),    # asymmetric couplings (row of the dequeued site)
+    (1100, 3, True, True, 3.5, "row"),     # n_pad = 1792, 10 float4 loads per lane
     (1100, 3, True, True, 3.5, "cta"),     # two passes of 1024 columns
-    (1000, 4, False, False, 3.0, "warp"),  # float couplings
-    (4100, 2, True, False, 5.0, "cta"),    # five passes (n_pad = 4480; always the CTA form)
+    (1000, 4, False, False, 3.0, "list"),  # float couplings
+    (1000, 4, False, False, 3.0, "row"),
+    (4100, 2, True, False, 5.0, "list"),   # a model beyond the warp-per-replica row walk
+    (4100, 2, True, False, 5.0, "row"),    # five passes (n_pad = 4480: the CTA form)
 ])
 def test_replicas_with_their_own_streams(oracle, monkeypatch, n, R, integer, asym, T, form):
-    if form == "cta":
-        monkeypatch.setenv("SG_WOLFF_FORM", "cta")
+    _set_form(monkeypatch, form)
     J, h = _sparse_neg_model(n, 100 + n, integer=integer, asym=asym)
     rs = np.random.RandomState(n)
     ns = 2
@@ -253,27 +267,37 @@ def test_philox_mode_matches_the_oracle_distribution(oracle):
     assert len({tuple(r) for r in first.cpu().numpy()[:64].tolist()}) > 32   # replicas differ
 
 
-@pytest.mark.parametrize("n", [200, 1500])
-def test_both_kernel_forms_agree_in_philox_mode(monkeypatch, n):
-    """A warp per replica (n <= 1792) and a CTA per replica draw the same Philox numbers per
-    (update, visit, column quad): same clusters, same spins."""
-    J, h = _sparse_neg_model(n, 40 + n, integer=False)
+@pytest.mark.parametrize("n,dense", [(200, False), (1500, False), (200, True)])
+def test_kernel_forms_agree_in_philox_mode(monkeypatch, n, dense):
+    """Neighbour lists, a warp per replica and a CTA per replica draw the same Philox numbers per
+    (update, visit, column quad): same clusters, same spins.  A dense model (about n / 2 negative
+    couplings per row) has no neighbour lists: the default is then the row-walking form."""
+    if dense:
+        rs = np.random.RandomState(n)
+        G = rs.normal(0.0, 1.0, size=(n, n)).astype(np.float32)
+        J = ((G + G.T) / 2).astype(np.float32)
+        np.fill_diagonal(J, 0.0)
+        h = np.zeros(n, np.float32)
+        temps = np.array([100.0, 80.0])   # (clusters of a few sites)
+    else:
+        J, h = _sparse_neg_model(n, 40 + n, integer=False)
+        temps = np.array([3.0, 2.5])
     R = 19
     S0 = (np.random.RandomState(n).randint(0, 2, (R, n)) * 2 - 1).astype(np.int8)
     out = []
-    for form in ("warp", "cta"):
-        if form == "cta":
-            monkeypatch.setenv("SG_WOLFF_FORM", "cta")
+    for form in ("list", "row", "cta"):
+        _set_form(monkeypatch, form)
         eng = Engine(0)
         eng.set_model(J, h)
         eng.alloc_replicas(R)
         eng.set_spins(S0)
         eng.init_fields()
-        tr = eng.sweep_wolff(2, np.array([3.0, 2.5]), temps_sweep_stride=1, seed=77, energy_trace=True)
+        tr = eng.sweep_wolff(2, temps, temps_sweep_stride=1, seed=77, energy_trace=True)
         out.append((eng.spins().cpu().numpy(), tr.cpu().numpy(), eng.accepted().cpu().numpy()))
-    assert out[0][2].sum() > 2 * R * n, "the case must exercise the cluster growth"
-    for a, b in zip(out[0], out[1]):
-        assert np.array_equal(a, b)
+    assert out[0][2].sum() > 2.2 * R * n, "the case must exercise the cluster growth"
+    for o in out[1:]:
+        for a, b in zip(out[0], o):
+            assert np.array_equal(a, b)
 
 
 def test_api_paths_take_wolff(oracle):
