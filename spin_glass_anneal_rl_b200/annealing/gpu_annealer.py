@@ -136,10 +136,11 @@ class GPUAnnealer:
             replay_uni = torch.as_tensor(np.asarray(cfg.replay["uniforms"], np.float32), dtype=torch.float32,
                                          device=eng.device)
             replay_uni = replay_uni.reshape(1, -1) if replay_uni.dim() == 1 else replay_uni
-            if replay_uni.shape[0] == 1 and R > 1:
-                replay_uni = replay_uni.expand(R, -1)
             if replay_uni.shape[0] != R:
-                raise ValueError("replay stream: need uniforms [m] or [n_replicas, m] for UpdateRule.WOLFF")
+                # (a cluster run consumes as many uniforms as ITS clusters ask for: replicas that start
+                # elsewhere cannot share the recorded list of one run)
+                raise ValueError("replay stream: UpdateRule.WOLFF needs one uniform list per replica, "
+                                 "uniforms [m] for n_replicas = 1 or [n_replicas, m]")
             replay_uni = replay_uni.contiguous()
             wolff_cursor = torch.zeros(R, dtype=torch.int64, device=eng.device)
         elif cfg.rng_mode == "replay":
