@@ -105,6 +105,32 @@ class SpinDynamics:
         self.n_rejected = 0
         self.energy_history = []
 
+    # ---- analysis of the recorded histories (reference core/spin_dynamics.py:361-421; host side)
+    def get_autocorrelation_time(self, observable: str = "energy") -> float:
+        """First lag (in recorded sweeps) at which the normalised autocorrelation of the history
+        falls below 1/e; inf for fewer than 10 records, the history length if it never does."""
+        series = {"energy": self.energy_history, "magnetization": self.magnetization_history}.get(observable)
+        if series is None:
+            raise ValueError(f"Unknown observable: {observable}")
+        x = np.asarray(series, dtype=np.float64)
+        if x.size < 10:
+            return float("inf")
+        d = x - x.mean()
+        acf = np.correlate(d, d, mode="full")[x.size - 1:]
+        acf = acf / acf[0]
+        below = np.flatnonzero(acf < 1.0 / np.e)
+        return float(below[0]) if below.size else float(acf.size)
+
+    def thermal_equilibrium_check(self, window_size: int = 100) -> bool:
+        """Two-sample t-test between the last two windows of the energy history: True when their
+        means do not differ at the 5 % level (False while fewer than two windows are recorded)."""
+        if len(self.energy_history) < 2 * window_size:
+            return False
+        recent = np.asarray(self.energy_history[-window_size:], dtype=np.float64)
+        older = np.asarray(self.energy_history[-2 * window_size:-window_size], dtype=np.float64)
+        from scipy import stats
+        return bool(stats.ttest_ind(recent, older).pvalue > 0.05)
+
     def __repr__(self) -> str:
         return (f"SpinDynamics(temperature={self.temperature:.4f}, "
                 f"update_rule={self.update_rule.value}, "

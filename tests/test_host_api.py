@@ -75,6 +75,33 @@ def test_wolff_rule_is_routed_and_guarded():
     assert "#define SG_RULE_WOLFF 3" in header and "sg_sweep_wolff" in header
 
 
+def test_spin_dynamics_history_analysis():
+    """SpinDynamics.get_autocorrelation_time / thermal_equilibrium_check (reference
+    core/spin_dynamics.py:361-421) on histories with known answers; no device involved."""
+    from spin_glass_anneal_rl_b200.core.spin_dynamics import SpinDynamics, UpdateRule
+    m = sg.IsingModel(sg.IsingModelConfig(n_spins=8, use_sparse=False))
+    dyn = SpinDynamics(m, temperature=1.0, update_rule=UpdateRule.METROPOLIS, random_seed=1)
+    assert dyn.get_autocorrelation_time() == float("inf")          # fewer than 10 records
+    with pytest.raises(ValueError):
+        dyn.get_autocorrelation_time("susceptibility")
+    rs = np.random.RandomState(0)
+    # AR(1) with coefficient rho: the autocorrelation rho^k first falls below 1/e at ceil(1/-ln rho)
+    rho, x = 0.9, [0.0]
+    for _ in range(20000):
+        x.append(rho * x[-1] + rs.standard_normal())
+    dyn.energy_history = x
+    tau = dyn.get_autocorrelation_time("energy")
+    assert abs(tau - np.ceil(-1.0 / np.log(rho))) <= 2
+    dyn.magnetization_history = list(rs.standard_normal(500))       # white noise: below 1/e at lag 1
+    assert dyn.get_autocorrelation_time("magnetization") == 1.0
+    # equilibrium check: same distribution in both windows -> True; a drift -> False
+    assert dyn.thermal_equilibrium_check(window_size=50000) is False     # not enough records
+    dyn.energy_history = list(rs.standard_normal(400))
+    assert dyn.thermal_equilibrium_check(window_size=200) is True
+    dyn.energy_history = list(rs.standard_normal(200)) + list(5.0 + rs.standard_normal(200))
+    assert dyn.thermal_equilibrium_check(window_size=200) is False
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "spin_glass_anneal_rl_b200")
     for base, _, files in os.walk(pkg):
