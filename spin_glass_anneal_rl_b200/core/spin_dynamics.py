@@ -43,6 +43,13 @@ class SpinDynamics:
     def set_temperature(self, temperature: float) -> None:
         self.temperature = max(temperature, 1e-10)
 
+    def single_spin_update(self, site: Optional[int] = None):
+        """The reference's one-attempt entry point (core/spin_dynamics.py:61-71).  The device path has
+        no per-attempt call -- a kernel launch per spin is the pattern this package replaces -- so this
+        says so instead of quietly doing the attempt on the host."""
+        raise NotImplementedError("single_spin_update: one attempt per call is not offered on the GPU path; "
+                                  "use sweep() (n attempts per launch)")
+
     def sweep(self, n_sweeps: int = 1) -> float:
         """``n_sweeps`` Monte Carlo sweeps (n attempts each) on the GPU; returns the energy."""
         from ..annealing._backend import engine_for, require_dense_for_wolff, rule_name
