@@ -170,6 +170,36 @@ class MultiGPUAnnealer:
             return shard_replicas_split(self.config.n_replicas, self.world, self.rank, rungs)
         return shard_replicas(self.config.n_replicas, self.world, self.rank, rungs)
 
+    # the reference's per-strategy entry points (annealing/multi_gpu.py:121-307) on this design
+    def anneal_data_parallel(self, model, update_rule=None):
+        """Independent multi-start replicas on every GPU, best of all ranks (reference :121-176 runs
+        one full anneal per GPU in a thread)."""
+        return self._with_strategy("data_parallel", model, update_rule)
+
+    def anneal_replica_exchange(self, model, update_rule=None):
+        """Parallel tempering over all GPUs: whole ladders per GPU, or ladders that span GPUs with the
+        energies all-gathered every exchange round (reference :234-307 holds one temperature per GPU)."""
+        return self._with_strategy("replica_exchange", model, update_rule)
+
+    def anneal_model_parallel(self, model, update_rule=None):
+        """Not offered: the reference (:178-232) cuts the couplings into block-diagonal pieces, which
+        anneals a different model."""
+        raise NotImplementedError("model_parallel would split the couplings across GPUs, which changes "
+                                  "the model; use data_parallel or replica_exchange")
+
+    def _with_strategy(self, strategy, model, update_rule):
+        import copy
+        saved = self.config
+        self.config = copy.copy(saved)
+        self.config.strategy = strategy
+        try:
+            return self.anneal(model, update_rule)
+        finally:
+            self.config = saved
+
+    def cleanup(self) -> None:
+        """Nothing to release: the process group belongs to the launcher (torchrun)."""
+
     def anneal(self, model, update_rule=None):
         import copy
         from ..core.spin_dynamics import UpdateRule

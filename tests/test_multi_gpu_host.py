@@ -85,6 +85,14 @@ def test_multi_gpu_config_validation():
     a = MultiGPUAnnealer(MultiGPUConfig(n_replicas=128, strategy="replica_exchange", n_rungs=16))
     sh = a.shard()
     assert (a.world, a.rank, sh.count, sh.n_ladders) == (1, 0, 128, 8)
+    # the reference's per-strategy entry points run anneal() with that strategy and restore the config
+    seen = []
+    a.anneal = lambda model, rule=None: seen.append(a.config.strategy) or "result"
+    assert a.anneal_data_parallel(object()) == "result" and a.anneal_replica_exchange(object()) == "result"
+    assert seen == ["data_parallel", "replica_exchange"] and a.config.strategy == "replica_exchange"
+    with pytest.raises(NotImplementedError):
+        a.anneal_model_parallel(object())
+    a.cleanup()
 
 
 def _worker_c1(rank, world, port, out):
