@@ -121,7 +121,7 @@ class BatchProcessor:
 def install_as_spin_glass_rl(force: bool = False) -> None:
     """Alias this package's modules to the reference's import paths for the hot path."""
     from . import annealing, core
-    from .annealing import (batch_processor, cuda_kernels, gpu_annealer, parallel_tempering, result,
+    from .annealing import (batch_processor, cuda_kernels, gpu_annealer, multi_gpu, parallel_tempering, result,
                             temperature_scheduler)
     from .core import energy_computer, ising_model, spin_dynamics
     from .utils import exceptions
@@ -141,6 +141,7 @@ def install_as_spin_glass_rl(force: bool = False) -> None:
         "spin_glass_rl.annealing.cuda_kernels": cuda_kernels,
         "spin_glass_rl.annealing.batch_processor": batch_processor,
         "spin_glass_rl.annealing.parallel_tempering": parallel_tempering,
+        "spin_glass_rl.annealing.multi_gpu": multi_gpu,
         "spin_glass_rl.annealing.temperature_scheduler": temperature_scheduler,
         "spin_glass_rl.annealing.result": result,
     }

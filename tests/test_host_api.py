@@ -264,7 +264,9 @@ def test_install_as_spin_glass_rl():
     from spin_glass_rl.annealing.parallel_tempering import ParallelTempering as C
     from spin_glass_rl.core.spin_dynamics import UpdateRule as D
     assert A is sg.IsingModel and B is sg.GPUAnnealer and C is sg.ParallelTempering
-    assert D.METROPOLIS.value == "metropolis"
+    assert D.METROPOLIS.value == "metropolis" and D.WOLFF.value == "wolff"
+    from spin_glass_rl.annealing.multi_gpu import MultiGPUAnnealer, MultiGPUConfig
+    assert hasattr(MultiGPUAnnealer, "anneal_replica_exchange") and MultiGPUConfig().strategy == "data_parallel"
     for k in [k for k in sys.modules if k.startswith("spin_glass_rl")]:
         del sys.modules[k]
 
