@@ -6,8 +6,8 @@ only as the checker or the timed CPU baseline.  The product package
 ``spin_glass_anneal_rl_b200`` never imports it.
 
 Parity status: PINNED against traces recorded from the reference itself
-(``tests/golden/make_golden.py`` -> ``tests/golden/*.npz``; checked by
-``tests/test_oracle_golden.py``).
+(``tests/golden/make_golden.py`` / ``make_wolff_golden.py`` / ``make_operator_golden.py`` ->
+``tests/golden/*.npz``; checked by ``tests/test_oracle_golden.py``).
 
 The sweeps run in C (``sg_oracle.c``); this file restates the control flow
 around them, citing the reference lines (paths relative to

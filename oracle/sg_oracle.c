@@ -9,8 +9,9 @@
  *
  * Parity status: PINNED.  tests/test_oracle_golden.py checks this file
  * against traces recorded from the reference itself (device='cpu', dense
- * couplings) by tests/golden/make_golden.py: same seed => same energy
- * history, best energy, best configuration, final spins and RNG consumption.
+ * couplings) by tests/golden/make_golden.py and, for UpdateRule.WOLFF, by
+ * tests/golden/make_wolff_golden.py: same seed => same energy history, best
+ * energy, best configuration, final spins and RNG consumption.
  *
  * Every function cites the reference lines it restates (paths relative to
  * /root/reference/spin_glass_rl/).
