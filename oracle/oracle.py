@@ -540,8 +540,19 @@ def parallel_tempering(J, h, *, n_replicas: int, n_sweeps: int, temp_min: float,
             reps[i], reps[j] = reps[j], reps[i]  # :254-256 swap configurations
             accepts[min(i, j)] += 1
 
+    tr_wolff: List[List[np.ndarray]] = []   # rule "wolff": the uniforms of (sweep, slot), in order
     for sweep in range(n_sweeps):  # :108
+        if rule == "wolff":
+            tr_wolff.append([])
         for r in range(n_replicas):  # :193-196 (sequential, shared global stream)
+            if rule == "wolff":   # cluster sizes count as accepted, nothing as rejected
+                _, acc, wtr = wolff_sweeps(J, h, reps[r], [max(temps[r], 1e-10)], stream, trace=trace)
+                if trace:
+                    tr_sites[sweep, r] = wtr["sites"][0]
+                    tr_wolff[-1].append(wtr["uniforms"])
+                n_acc[r] += int(acc[0])
+                n_tot[r] += int(acc[0])
+                continue
             _, acc, ts, tu = sweeps(J, h, reps[r], [max(temps[r], 1e-10)], rule, stream, trace=trace)
             if trace:
                 tr_sites[sweep, r], tr_uni[sweep, r] = ts, tu
@@ -576,7 +587,7 @@ def parallel_tempering(J, h, *, n_replicas: int, n_sweeps: int, temp_min: float,
                        n_sweeps, np.stack(reps), [], stream.pos - start_pos)
     res.extra = {"temperatures": temps, "exchange_attempts": attempts, "exchange_accepts": accepts,
                  "energy_histories": e_hists, "spins0": spins0, "sites": tr_sites,
-                 "uniforms": tr_uni, "exchange_draws": draws}
+                 "uniforms": tr_wolff if rule == "wolff" else tr_uni, "exchange_draws": draws}
     return res
 
 

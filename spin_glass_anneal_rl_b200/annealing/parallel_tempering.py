@@ -119,9 +119,6 @@ class ParallelTempering:
         eng = engine_for(model, c.device_index)
         if rule == "wolff":
             require_dense_for_wolff(eng)
-            if c.rng_mode == "replay":
-                raise NotImplementedError("rng_mode='replay' of parallel tempering covers the single-spin rules; "
-                                          "replay UpdateRule.WOLFF through GPUAnnealer / Engine.sweep_wolff")
         n, K, L = model.n_spins, c.n_replicas, max(1, int(c.n_ladders))
         Rg = K * L                               # replicas over all ranks
         sh = c.shard
@@ -140,8 +137,12 @@ class ParallelTempering:
         if replay is not None:
             spins0 = torch.as_tensor(np.asarray(replay["spins0"]), device=eng.device).to(torch.int8)
             r_sites = torch.as_tensor(np.asarray(replay["sites"]), dtype=torch.int32, device=eng.device)
-            r_uni = torch.as_tensor(np.nan_to_num(np.asarray(replay["uniforms"], np.float32), nan=0.5),
-                                    dtype=torch.float32, device=eng.device)
+            if rule == "wolff":
+                # uniforms[s][k]: the list the cluster updates of temperature slot k consumed in sweep s
+                r_uni = [[np.asarray(u, np.float32).reshape(-1) for u in per_slot] for per_slot in replay["uniforms"]]
+            else:
+                r_uni = torch.as_tensor(np.nan_to_num(np.asarray(replay["uniforms"], np.float32), nan=0.5),
+                                        dtype=torch.float32, device=eng.device)
             draws = [list(d) for d in replay["exchange_draws"]]
         else:
             gen = torch.Generator(device=eng.device)
@@ -186,7 +187,20 @@ class ParallelTempering:
                 nxt += 1
             k = nxt - sweep + 1
             rep_at, rung_loc = rung_of_local()
-            if replay is not None:
+            if replay is not None and rule == "wolff":
+                # start sites and uniform lists of the slot (= rung) -> the replica sitting on it; a
+                # replica's list for the launch is the concatenation over the launch's sweeps
+                sl = r_sites[sweep:sweep + k]                       # [k, K, n]
+                sites_rep = sl[:, rung_loc, :].permute(1, 0, 2).contiguous()   # [R, k, n]
+                rungs = rung_loc.cpu().tolist()
+                lists = [np.concatenate([r_uni[s][rg] for s in range(sweep, sweep + k)]) for rg in rungs]
+                width = max(1, max(len(u) for u in lists))
+                uni_rep = np.full((R, width), 2.0, np.float32)
+                for i, u in enumerate(lists):
+                    uni_rep[i, :len(u)] = u
+                eng.sweep_wolff(k, None, sites=sites_rep, sites_replica_stride=k * n, sites_sweep_stride=n,
+                                uniforms=uni_rep, track_best=True)
+            elif replay is not None:
                 # slot (= rung) streams -> the replica that sits on the rung in this segment
                 sl = r_sites[sweep:sweep + k]                       # [k, K, n]
                 ul = r_uni[sweep:sweep + k]

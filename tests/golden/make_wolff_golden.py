@@ -17,7 +17,7 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from make_golden import run_sa, sym_gauss  # noqa: E402  (imports the reference)
+from make_golden import run_pt, run_sa, sym_gauss  # noqa: E402  (imports the reference)
 
 
 def lattice_couplings(L, rng, p_neg=0.8):
@@ -66,6 +66,12 @@ def main():
     sa = (rng.integers(0, 2, size=16) * 2 - 1).astype(np.float32)
     run_sa("wolff_asym_int_n16", Ja, np.zeros(16, np.float32), sa, seed=34, n_sweeps=8, T0=5.0,
            Tf=1.0, params={"alpha": 0.8}, record_interval=1, rule="wolff")
+
+    # parallel tempering with the cluster move (every replica's SpinDynamics runs _wolff_update);
+    # the "ptw_" prefix keeps it apart from the single-spin pt_* fixtures
+    Jl = lattice_couplings(5, rng, p_neg=0.7)
+    run_pt("ptw_lattice_int_n25_r4", Jl, np.zeros(25, np.float32), seed=35, n_replicas=4, n_sweeps=14,
+           tmin=1.5, tmax=6.0, exchange_interval=3, record_interval=2, rule="wolff")
 
 
 if __name__ == "__main__":

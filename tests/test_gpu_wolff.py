@@ -154,6 +154,40 @@ def test_anneal_replay_reproduces_the_reference(oracle, name):
     assert np.allclose(res.temperature_history, g["temperature_history"], rtol=1e-15, atol=0)
 
 
+@pytest.mark.parametrize("name", golden_names("ptw_"))
+def test_parallel_tempering_replay_with_the_cluster_move(oracle, name):
+    """ParallelTempering.run(model, UpdateRule.WOLFF) in replay mode == the reference's run whose
+    replicas all use _wolff_update (n_threads=1, device='cpu'): configurations per temperature slot,
+    exchange statistics, per-slot energy histories, best configuration, acceptance rates."""
+    g = load_golden(name)
+    c = g["config"]
+    n, K = g["J"].shape[0], c["n_replicas"]
+    stream = oracle.RawStream(oracle.mt_raw_stream(c["seed"], int(g["raw_consumed"]) + 4096))
+    ores = oracle.parallel_tempering(
+        g["J"], g["h"], n_replicas=K, n_sweeps=c["n_sweeps"], temp_min=c["tmin"], temp_max=c["tmax"],
+        temp_distribution=c["dist"], exchange_interval=c["exchange_interval"],
+        record_interval=c["record_interval"], rule="wolff", stream=stream,
+        np_rng=np.random.RandomState(c["seed"]), trace=True)
+    assert ores.raw_consumed == int(g["raw_consumed"])
+    cfg = sg.ParallelTemperingConfig(
+        n_replicas=K, n_sweeps=c["n_sweeps"], temp_min=c["tmin"], temp_max=c["tmax"],
+        temp_distribution=c["dist"], exchange_interval=c["exchange_interval"],
+        record_interval=c["record_interval"], random_seed=c["seed"], rng_mode="replay",
+        replay={k: ores.extra[k] for k in ("spins0", "sites", "uniforms", "exchange_draws")})
+    pt = sg.ParallelTempering(cfg)
+    res = pt.run(_model(g["J"], g["h"]), UpdateRule.WOLFF)
+    exact = _is_integer(g["J"], g["h"])
+    assert np.array_equal(pt.exchange_attempts, g["exchange_attempts"])
+    assert np.array_equal(pt.exchange_accepts, g["exchange_accepts"])
+    slot_spins = pt._final_spins.cpu().numpy()[pt._rung_replica[:K]]
+    assert np.array_equal(slot_spins, g["final_spins"]), "configurations per temperature slot differ"
+    assert np.array_equal(res.best_configuration.numpy().astype(np.int8), g["best_configuration"])
+    _close(res.best_energy, g["best_energy"], exact, "best energy")
+    _close(np.array(pt.energy_histories), g["energy_histories"], exact, "per-slot energy histories")
+    assert np.allclose(res.acceptance_rate_history, g["acceptance_rate_history"], rtol=0, atol=1e-12)
+    assert g["exchange_accepts"].sum() > 0
+
+
 # ------------------------------------------------------------------ wider shapes against the oracle
 @pytest.mark.parametrize("n,R,integer,asym,T,form", [
     (300, 5, True, False, 5.0, "list"),    # neighbour lists (rows with at most 32 negative couplings)

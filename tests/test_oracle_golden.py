@@ -127,13 +127,14 @@ def test_exp_model_matches_reference_probs(oracle):
     assert tot > 1000 and worst < 1e-5
 
 
-@pytest.mark.parametrize("name", golden_names("pt_"))
+@pytest.mark.parametrize("name", golden_names("pt_") + golden_names("ptw_"))
 def test_parallel_tempering_matches_reference(oracle, name):
+    """(ptw_*: parallel tempering whose replicas run the cluster move, UpdateRule.WOLFF)"""
     g = load_golden(name)
     c = g["config"]
     n = g["J"].shape[0]
     R = c["n_replicas"]
-    stream = oracle.RawStream(oracle.mt_raw_stream(c["seed"], 2 * n * R * (c["n_sweeps"] + 1) + 16))
+    stream = oracle.RawStream(oracle.mt_raw_stream(c["seed"], int(g["raw_consumed"]) + 4096))
     res = oracle.parallel_tempering(
         g["J"], g["h"], n_replicas=R, n_sweeps=c["n_sweeps"], temp_min=c["tmin"],
         temp_max=c["tmax"], temp_distribution=c["dist"], exchange_interval=c["exchange_interval"],
